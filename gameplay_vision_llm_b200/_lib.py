@@ -1,0 +1,88 @@
+"""ctypes binding of libgvl_sm100a.so (include/gvl.h).
+
+The library is built in-tree by `__graft_entry__.build()` / `make -C gameplay_vision_llm_b200/csrc`.
+There is no fallback: if the shared object is missing or a call fails, a RuntimeError is raised.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from ctypes import POINTER, c_char_p, c_float, c_int, c_int16, c_int32, c_size_t, c_ulonglong, c_void_p
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libgvl_sm100a.so")
+
+c_float_p = POINTER(c_float)
+
+
+class VitLayer(ctypes.Structure):
+    _fields_ = [(n, c_void_p) for n in (
+        "ln1_g", "ln1_b", "w_qkv", "b_qkv", "w_o", "b_o", "ln2_g", "ln2_b", "w_fc1", "b_fc1", "w_fc2", "b_fc2")]
+
+
+class VitWeights(ctypes.Structure):
+    _fields_ = (
+        [(n, c_int32) for n in ("D", "I", "H", "hd", "L", "T", "patch_k", "patch_ld")]
+        + [("eps", c_float), ("act", c_int32)]
+        + [("w_patch", c_void_p), ("b_patch", c_void_p), ("pos", c_void_p), ("layers", POINTER(VitLayer)),
+           ("post_g", c_void_p), ("post_b", c_void_p), ("probe_q", c_void_p), ("w_kv", c_void_p), ("b_kv", c_void_p),
+           ("w_ho", c_void_p), ("b_ho", c_void_p), ("hln_g", c_void_p), ("hln_b", c_void_p), ("w_hfc1", c_void_p),
+           ("b_hfc1", c_void_p), ("w_hfc2", c_void_p), ("b_hfc2", c_void_p)]
+    )
+
+
+# name -> (restype, argtypes); every symbol include/gvl.h declares
+SIGNATURES = {
+    "gvl_last_error": (c_char_p, []),
+    "gvl_abi_version": (c_int, []),
+    "gvl_launch_count": (c_ulonglong, []),
+    "gvl_check_device": (c_int, [c_int]),
+    "gvl_resize_taps": (c_int, [c_int, c_int, c_int, c_int, POINTER(c_int32), POINTER(c_int32), POINTER(c_int16),
+                                POINTER(c_int), POINTER(c_int)]),
+    "gvl_preprocess_u8": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_float_p, c_float_p, c_void_p,
+                                  c_int, c_int, c_int, c_void_p]),
+    "gvl_gemm_bf16": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_void_p, c_int,
+                              c_int, c_int, c_int, c_int, c_int, c_void_p]),
+    "gvl_layernorm_bf16": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_float,
+                                   c_void_p]),
+    "gvl_attention_bf16": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_float, c_void_p]),
+    "gvl_probe_attention_bf16": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
+    "gvl_siglip_workspace_bytes": (c_size_t, [POINTER(VitWeights), c_int]),
+    "gvl_siglip_forward": (c_int, [POINTER(VitWeights), c_void_p, c_int, c_void_p, c_size_t, c_void_p, c_void_p,
+                                   c_void_p]),
+    "gvl_project": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                            c_int, c_void_p]),
+    "gvl_topk_cosine": (c_int, [c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_float, c_void_p, c_void_p, c_void_p,
+                                c_void_p]),
+}
+
+_LIB = None
+
+
+def lib() -> ctypes.CDLL:
+    """Load (once) and return the shared library; raises if it has not been built."""
+    global _LIB
+    if _LIB is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(or `make -C gameplay_vision_llm_b200/csrc`). There is no CPU/PyTorch fallback for this path.")
+        handle = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(handle, name)
+            fn.restype = res
+            fn.argtypes = args
+        if handle.gvl_abi_version() != 1:
+            raise RuntimeError("libgvl_sm100a.so ABI version mismatch; rebuild the extension")
+        _LIB = handle
+    return _LIB
+
+
+def check(rc: int, what: str = "gvl") -> None:
+    if rc != 0:
+        msg = lib().gvl_last_error().decode("utf-8", "replace")
+        raise RuntimeError(f"{what} failed (status {rc}): {msg}")
+
+
+def launch_count() -> int:
+    return int(lib().gvl_launch_count())

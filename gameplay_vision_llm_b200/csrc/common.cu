@@ -1,0 +1,94 @@
+// common.cu — host-side plumbing of libgvl_sm100a.so: thread-local error string, launch counter,
+// device checks and the TMA descriptor helper.
+#include "common.cuh"
+
+#include <mutex>
+
+namespace gvl {
+
+static thread_local char t_err[512] = "";
+std::atomic<unsigned long long> g_launches{0};
+
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(t_err, sizeof(t_err), fmt, ap);
+    va_end(ap);
+}
+
+int sm_count() {
+    static int cached[64] = {0};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+    if (cached[dev] == 0) {
+        int n = 0;
+        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+        cached[dev] = n;
+    }
+    return cached[dev];
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_tiled_fn() {
+    static EncodeTiledFn fn = nullptr;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    });
+    return fn;
+}
+
+int make_tmap_2d_bf16(CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols, uint64_t ld,
+                      uint32_t box_rows, uint32_t box_cols, bool swizzle128) {
+    EncodeTiledFn fn = encode_tiled_fn();
+    if (!fn) {
+        set_error("cuTensorMapEncodeTiled unavailable (no CUDA driver?)");
+        return 4;
+    }
+    cuuint64_t gdim[2] = {cols, rows};
+    cuuint64_t gstride[1] = {ld * 2};
+    cuuint32_t box[2] = {box_cols, box_rows};
+    cuuint32_t estride[2] = {1, 1};
+    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstride, box, estride,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
+                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("cuTensorMapEncodeTiled failed (CUresult %d): base=%p rows=%llu cols=%llu ld=%llu box=%ux%u", (int)r,
+                  base, (unsigned long long)rows, (unsigned long long)cols, (unsigned long long)ld, box_rows, box_cols);
+        return 4;
+    }
+    return 0;
+}
+
+}  // namespace gvl
+
+extern "C" {
+
+const char* gvl_last_error(void) { return gvl::t_err; }
+int gvl_abi_version(void) { return GVL_ABI_VERSION; }
+unsigned long long gvl_launch_count(void) { return gvl::g_launches.load(); }
+
+int gvl_check_device(int dev) {
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0) {
+        gvl::set_error("no CUDA device: %s", cudaGetErrorString(e));
+        return 2;
+    }
+    cudaDeviceProp prop;
+    GVL_CUDA(cudaGetDeviceProperties(&prop, dev));
+    if (prop.major != 10) {
+        gvl::set_error("device %d is sm_%d%d; libgvl_sm100a needs sm_100 (B200)", dev, prop.major, prop.minor);
+        return 5;
+    }
+    return 0;
+}
+
+}  // extern "C"

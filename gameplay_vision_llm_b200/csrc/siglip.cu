@@ -1,0 +1,106 @@
+// siglip.cu — K6/K7: the whole SigLIP2 vision tower as one stream-ordered call, and the projector.
+//
+// The composite only sequences the kernels of this library on the caller's stream (no allocation,
+// no synchronisation): patch GEMM (+bias +position embedding) -> L x [LN, QKV GEMM, attention,
+// out-proj GEMM (+residual), LN, fc1 GEMM (+GELU), fc2 GEMM (+residual)] -> post-LN -> MAP head.
+// The residual stream is updated in place by the GEMM epilogues.
+#include "common.cuh"
+
+namespace gvl {
+
+struct Workspace {
+    uint8_t* base;
+    size_t off, cap;
+    void* take(size_t bytes) {
+        size_t a = (off + 255) & ~(size_t)255;
+        off = a + bytes;
+        return base ? base + a : nullptr;
+    }
+};
+
+struct VitBuffers {
+    void *x, *xn, *qkv, *attn, *h, *pa, *hx, *hxn, *hh;
+};
+
+static size_t carve(const gvl_vit_weights* w, int B, uint8_t* base, VitBuffers& vb) {
+    const size_t M = (size_t)B * w->T, D = w->D, I = w->I;
+    Workspace ws{base, 0, 0};
+    vb.x = ws.take(M * D * 2);
+    vb.xn = ws.take(M * D * 2);
+    vb.qkv = ws.take(M * 3 * D * 2);
+    vb.attn = ws.take(M * D * 2);
+    vb.h = ws.take(M * I * 2);
+    vb.pa = ws.take((size_t)B * D * 2);
+    vb.hx = ws.take((size_t)B * D * 2);
+    vb.hxn = ws.take((size_t)B * D * 2);
+    vb.hh = ws.take((size_t)B * I * 2);
+    return ws.off + 256;
+}
+
+}  // namespace gvl
+
+extern "C" size_t gvl_siglip_workspace_bytes(const gvl_vit_weights* w, int B) {
+    if (!w || B <= 0) return 0;
+    gvl::VitBuffers vb;
+    return gvl::carve(w, B, nullptr, vb);
+}
+
+#define GVL_TRY(call)          \
+    do {                       \
+        int rc__ = (call);     \
+        if (rc__) return rc__; \
+    } while (0)
+
+extern "C" int gvl_siglip_forward(const gvl_vit_weights* w, const void* patches, int B, void* workspace,
+                                  size_t workspace_bytes, void* pooled, void* last_hidden, void* stream) {
+    using namespace gvl;
+    GVL_CHECK_ARG(w && patches && workspace && pooled, "gvl_siglip_forward: null pointer");
+    GVL_CHECK_ARG(B > 0, "gvl_siglip_forward: bad batch %d", B);
+    GVL_CHECK_ARG(w->D == w->H * w->hd && w->L > 0 && w->layers, "gvl_siglip_forward: inconsistent weight pack");
+    GVL_CHECK_ARG((uintptr_t)workspace % 256 == 0, "gvl_siglip_forward: workspace must be 256-byte aligned");
+    VitBuffers vb;
+    const size_t need = carve(w, B, reinterpret_cast<uint8_t*>(workspace), vb);
+    GVL_CHECK_ARG(workspace_bytes >= need, "gvl_siglip_forward: workspace %zu < required %zu bytes", workspace_bytes, need);
+
+    const int D = w->D, I = w->I, T = w->T, H = w->H, hd = w->hd;
+    const int M = B * T;
+    const float scale = 1.0f / sqrtf((float)hd);
+
+    // embeddings: conv-as-GEMM + bias + learned position embedding (row % T)
+    GVL_TRY(gvl_gemm_bf16(patches, w->patch_ld, w->w_patch, w->patch_ld, w->b_patch, w->pos, D, T, vb.x, D, 0, M, D,
+                          w->patch_ld, GVL_ACT_NONE, stream));
+    for (int l = 0; l < w->L; ++l) {
+        const gvl_vit_layer& ly = w->layers[l];
+        GVL_TRY(gvl_layernorm_bf16(vb.x, D, ly.ln1_g, ly.ln1_b, vb.xn, D, M, D, w->eps, stream));
+        GVL_TRY(gvl_gemm_bf16(vb.xn, D, ly.w_qkv, D, ly.b_qkv, nullptr, 0, 0, vb.qkv, 3 * D, 0, M, 3 * D, D,
+                              GVL_ACT_NONE, stream));
+        GVL_TRY(gvl_attention_bf16(vb.qkv, vb.attn, B, T, H, hd, scale, stream));
+        GVL_TRY(gvl_gemm_bf16(vb.attn, D, ly.w_o, D, ly.b_o, vb.x, D, 0, vb.x, D, 0, M, D, D, GVL_ACT_NONE, stream));
+        GVL_TRY(gvl_layernorm_bf16(vb.x, D, ly.ln2_g, ly.ln2_b, vb.xn, D, M, D, w->eps, stream));
+        GVL_TRY(gvl_gemm_bf16(vb.xn, D, ly.w_fc1, D, ly.b_fc1, nullptr, 0, 0, vb.h, I, 0, M, I, D, w->act, stream));
+        GVL_TRY(gvl_gemm_bf16(vb.h, I, ly.w_fc2, I, ly.b_fc2, vb.x, D, 0, vb.x, D, 0, M, D, I, GVL_ACT_NONE, stream));
+    }
+    void* tokens = last_hidden ? last_hidden : vb.xn;
+    GVL_TRY(gvl_layernorm_bf16(vb.x, D, w->post_g, w->post_b, tokens, D, M, D, w->eps, stream));
+
+    // MAP head: K/V projections of all tokens, probe attention, out-proj, LN, MLP with residual
+    GVL_TRY(gvl_gemm_bf16(tokens, D, w->w_kv, D, w->b_kv, nullptr, 0, 0, vb.qkv, 2 * D, 0, M, 2 * D, D, GVL_ACT_NONE,
+                          stream));
+    GVL_TRY(gvl_probe_attention_bf16(w->probe_q, vb.qkv, vb.pa, B, T, H, hd, stream));
+    GVL_TRY(gvl_gemm_bf16(vb.pa, D, w->w_ho, D, w->b_ho, nullptr, 0, 0, vb.hx, D, 0, B, D, D, GVL_ACT_NONE, stream));
+    GVL_TRY(gvl_layernorm_bf16(vb.hx, D, w->hln_g, w->hln_b, vb.hxn, D, B, D, w->eps, stream));
+    GVL_TRY(gvl_gemm_bf16(vb.hxn, D, w->w_hfc1, D, w->b_hfc1, nullptr, 0, 0, vb.hh, I, 0, B, I, D, w->act, stream));
+    GVL_TRY(gvl_gemm_bf16(vb.hh, I, w->w_hfc2, I, w->b_hfc2, vb.hx, D, 0, pooled, D, 0, B, D, I, GVL_ACT_NONE, stream));
+    return 0;
+}
+
+extern "C" int gvl_project(const void* x, int M, int enc_dim, int llm_dim, const void* w1, const float* b1,
+                           const void* w2, const float* b2, void* hidden, void* out, int out_f32, void* stream) {
+    using namespace gvl;
+    GVL_CHECK_ARG(x && w1 && w2 && hidden && out, "gvl_project: null pointer");
+    GVL_TRY(gvl_gemm_bf16(x, enc_dim, w1, enc_dim, b1, nullptr, 0, 0, hidden, llm_dim, 0, M, llm_dim, enc_dim,
+                          GVL_ACT_GELU_ERF, stream));
+    GVL_TRY(gvl_gemm_bf16(hidden, llm_dim, w2, llm_dim, b2, nullptr, 0, 0, out, llm_dim, out_f32, M, llm_dim, llm_dim,
+                          GVL_ACT_NONE, stream));
+    return 0;
+}

@@ -1,0 +1,197 @@
+"""Tensor-level wrappers over the C ABI (include/gvl.h).  PyTorch is used for device memory and
+streams only; every function below launches hand-written kernels from libgvl_sm100a.so on the current
+CUDA stream and raises RuntimeError on any failure (there is no eager/PyTorch fallback).
+"""
+from __future__ import annotations
+
+import ctypes
+
+import numpy as np
+import torch
+
+from . import _lib
+from .weights import ProjectorPack, SiglipPack
+
+LAYOUT_U8_CHW, LAYOUT_F32_CHW, LAYOUT_BF16_CHW, LAYOUT_BF16_PATCH = 0, 1, 2, 3
+ACT_NONE, ACT_GELU_TANH, ACT_GELU_ERF = 0, 1, 2
+BILINEAR, BICUBIC = 2, 3
+
+
+def _stream() -> int:
+    return int(torch.cuda.current_stream().cuda_stream)
+
+
+def _need_cuda(*tensors: torch.Tensor) -> None:
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError("gvl ops take CUDA tensors only (no CPU fallback exists for this path)")
+
+
+def _ptr(t: torch.Tensor | None) -> int | None:
+    return None if t is None else t.data_ptr()
+
+
+def resize_taps(in_size: int, out_size: int, resample: int = BILINEAR, max_taps: int = 64):
+    """Host-only: the integer tap tables the preprocessing kernel uses (for parity checks on CPU)."""
+    xmin = (ctypes.c_int32 * out_size)()
+    xsize = (ctypes.c_int32 * out_size)()
+    w = (ctypes.c_int16 * (out_size * max_taps))()
+    prec, used = ctypes.c_int(0), ctypes.c_int(0)
+    _lib.check(_lib.lib().gvl_resize_taps(in_size, out_size, resample, max_taps, xmin, xsize, w, ctypes.byref(prec),
+                                          ctypes.byref(used)), "gvl_resize_taps")
+    wn = np.ctypeslib.as_array(w).reshape(out_size, max_taps)[:, : used.value].copy()
+    return np.ctypeslib.as_array(xmin).copy(), np.ctypeslib.as_array(xsize).copy(), wn, prec.value
+
+
+def fused_sub_div(image_mean=(0.5, 0.5, 0.5), image_std=(0.5, 0.5, 0.5), rescale_factor: float = 1.0 / 255.0):
+    """The fp32 constants HF's fused rescale+normalize uses: fp32(mean) * fp32(1/rescale_factor)
+    (HF: image_processing_backends.py:292-310)."""
+    inv = 1.0 / rescale_factor
+    sub = (torch.tensor(list(image_mean), dtype=torch.float32) * inv).numpy().astype(np.float32)
+    div = (torch.tensor(list(image_std), dtype=torch.float32) * inv).numpy().astype(np.float32)
+    return sub, div
+
+
+def preprocess(frames: torch.Tensor, out_h: int = 384, out_w: int = 384, resample: int = BILINEAR,
+               image_mean=(0.5, 0.5, 0.5), image_std=(0.5, 0.5, 0.5), layout: int = LAYOUT_BF16_PATCH, patch: int = 14,
+               ld: int | None = None, out: torch.Tensor | None = None) -> torch.Tensor:
+    """uint8 [B,H,W,3] frames -> resized / normalized / patchified tensor (see GVL_LAYOUT_*)."""
+    _need_cuda(frames)
+    if frames.dtype != torch.uint8 or frames.dim() != 4 or frames.shape[-1] != 3 or not frames.is_contiguous():
+        raise RuntimeError("frames must be a contiguous uint8 [B,H,W,3] tensor")
+    B, H, W, _ = frames.shape
+    dev = frames.device
+    if layout == LAYOUT_BF16_PATCH:
+        gh, gw = out_h // patch, out_w // patch
+        ld = ld or (3 * patch * patch + 7) // 8 * 8
+        shape, dtype = (B * gh * gw, ld), torch.bfloat16
+    else:
+        shape = (B, 3, out_h, out_w)
+        dtype = {LAYOUT_U8_CHW: torch.uint8, LAYOUT_F32_CHW: torch.float32, LAYOUT_BF16_CHW: torch.bfloat16}[layout]
+        ld = 0
+    if out is None:
+        out = torch.empty(shape, dtype=dtype, device=dev)
+    elif tuple(out.shape) != shape or out.dtype != dtype or not out.is_contiguous():
+        raise RuntimeError(f"preprocess: `out` must be contiguous {dtype} {shape}")
+    sub, div = fused_sub_div(image_mean, image_std)
+    _lib.check(_lib.lib().gvl_preprocess_u8(
+        frames.data_ptr(), B, H, W, out_h, out_w, resample, sub.ctypes.data_as(_lib.c_float_p),
+        div.ctypes.data_as(_lib.c_float_p), out.data_ptr(), layout, patch, ld, _stream()), "gvl_preprocess_u8")
+    return out
+
+
+def gemm(a: torch.Tensor, w: torch.Tensor, bias: torch.Tensor | None = None, residual: torch.Tensor | None = None,
+         res_row_mod: int = 0, act: int = ACT_NONE, out: torch.Tensor | None = None,
+         out_dtype: torch.dtype = torch.bfloat16) -> torch.Tensor:
+    """act(a @ w.T + bias) + residual; a [M,K] bf16, w [N,K] bf16, bias fp32 [N], residual bf16."""
+    _need_cuda(a, w, bias, residual, out)
+    M, K = a.shape
+    N, K2 = w.shape
+    if K != K2 or a.dtype != torch.bfloat16 or w.dtype != torch.bfloat16:
+        raise RuntimeError("gemm: a [M,K] and w [N,K] must be bf16 with matching K")
+    if a.stride(1) != 1 or w.stride(1) != 1:
+        raise RuntimeError("gemm: operands must be K-contiguous")
+    if bias is not None and (bias.dtype != torch.float32 or bias.numel() != N):
+        raise RuntimeError("gemm: bias must be fp32 [N]")
+    if out is None:
+        out = torch.empty((M, N), dtype=out_dtype, device=a.device)
+    if out.dtype not in (torch.bfloat16, torch.float32) or out.stride(1) != 1:
+        raise RuntimeError("gemm: out must be bf16 or fp32, row-major")
+    ldr = 0
+    if residual is not None:
+        if residual.dtype != torch.bfloat16 or residual.stride(1) != 1:
+            raise RuntimeError("gemm: residual must be bf16, row-major")
+        ldr = residual.stride(0)
+    _lib.check(_lib.lib().gvl_gemm_bf16(
+        a.data_ptr(), a.stride(0), w.data_ptr(), w.stride(0), _ptr(bias), _ptr(residual), ldr, res_row_mod,
+        out.data_ptr(), out.stride(0), 1 if out.dtype == torch.float32 else 0, M, N, K, act, _stream()), "gvl_gemm_bf16")
+    return out
+
+
+def layernorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: float,
+              out: torch.Tensor | None = None) -> torch.Tensor:
+    _need_cuda(x, gamma, beta, out)
+    if x.dtype != torch.bfloat16 or x.dim() != 2 or x.stride(1) != 1:
+        raise RuntimeError("layernorm: x must be bf16 [rows, D], row-major")
+    rows, D = x.shape
+    if out is None:
+        out = torch.empty_like(x)
+    _lib.check(_lib.lib().gvl_layernorm_bf16(x.data_ptr(), x.stride(0), gamma.data_ptr(), beta.data_ptr(),
+                                             out.data_ptr(), out.stride(0), rows, D, float(eps), _stream()),
+               "gvl_layernorm_bf16")
+    return out
+
+
+def attention(qkv: torch.Tensor, B: int, T: int, H: int, hd: int, scale: float | None = None,
+              out: torch.Tensor | None = None) -> torch.Tensor:
+    """qkv bf16 [B*T, 3*H*hd] -> bf16 [B*T, H*hd]."""
+    _need_cuda(qkv, out)
+    if qkv.dtype != torch.bfloat16 or tuple(qkv.shape) != (B * T, 3 * H * hd) or not qkv.is_contiguous():
+        raise RuntimeError("attention: qkv must be contiguous bf16 [B*T, 3*H*hd]")
+    if out is None:
+        out = torch.empty((B * T, H * hd), dtype=torch.bfloat16, device=qkv.device)
+    scale = float(hd) ** -0.5 if scale is None else float(scale)
+    _lib.check(_lib.lib().gvl_attention_bf16(qkv.data_ptr(), out.data_ptr(), B, T, H, hd, scale, _stream()),
+               "gvl_attention_bf16")
+    return out
+
+
+def probe_attention(q: torch.Tensor, kv: torch.Tensor, B: int, T: int, H: int, hd: int) -> torch.Tensor:
+    """q fp32 [H*hd] (pre-scaled), kv bf16 [B*T, 2*H*hd] -> bf16 [B, H*hd]."""
+    _need_cuda(q, kv)
+    if q.dtype != torch.float32 or kv.dtype != torch.bfloat16 or not kv.is_contiguous():
+        raise RuntimeError("probe_attention: q fp32, kv contiguous bf16")
+    out = torch.empty((B, H * hd), dtype=torch.bfloat16, device=kv.device)
+    _lib.check(_lib.lib().gvl_probe_attention_bf16(q.data_ptr(), kv.data_ptr(), out.data_ptr(), B, T, H, hd, _stream()),
+               "gvl_probe_attention_bf16")
+    return out
+
+
+def siglip_forward(pack: SiglipPack, patches: torch.Tensor, workspace: torch.Tensor | None = None,
+                   return_tokens: bool = False):
+    """bf16 patches [B*T, patch_ld] -> pooled bf16 [B, D] (and post-LN tokens [B*T, D] if asked)."""
+    _need_cuda(patches)
+    spec = pack.spec
+    if patches.dtype != torch.bfloat16 or patches.shape[1] != spec.patch_ld or patches.shape[0] % spec.tokens:
+        raise RuntimeError("siglip_forward: patches must be bf16 [B*T, patch_ld]")
+    B = patches.shape[0] // spec.tokens
+    need = pack.workspace_bytes(B)
+    if workspace is None:
+        workspace = torch.empty(need, dtype=torch.uint8, device=patches.device)
+    pooled = torch.empty((B, spec.hidden), dtype=torch.bfloat16, device=patches.device)
+    tokens = torch.empty((B * spec.tokens, spec.hidden), dtype=torch.bfloat16, device=patches.device) if return_tokens else None
+    _lib.check(_lib.lib().gvl_siglip_forward(ctypes.byref(pack.struct), patches.data_ptr(), B, workspace.data_ptr(),
+                                             workspace.numel(), pooled.data_ptr(), _ptr(tokens), _stream()),
+               "gvl_siglip_forward")
+    return (pooled, tokens) if return_tokens else pooled
+
+
+def project(pp: ProjectorPack, x: torch.Tensor, out_dtype: torch.dtype = torch.float32,
+            hidden: torch.Tensor | None = None) -> torch.Tensor:
+    """MultiModalProjector: bf16 [M, enc] -> [M, llm] (fp32 like the reference, or bf16 for the index)."""
+    _need_cuda(x)
+    if x.dtype != torch.bfloat16 or x.dim() != 2 or not x.is_contiguous() or x.shape[1] != pp.encoder_dim:
+        raise RuntimeError("project: x must be contiguous bf16 [M, encoder_dim]")
+    M = x.shape[0]
+    if hidden is None:
+        hidden = torch.empty((M, pp.llm_dim), dtype=torch.bfloat16, device=x.device)
+    out = torch.empty((M, pp.llm_dim), dtype=out_dtype, device=x.device)
+    _lib.check(_lib.lib().gvl_project(x.data_ptr(), M, pp.encoder_dim, pp.llm_dim, pp.w1.data_ptr(), pp.b1.data_ptr(),
+                                      pp.w2.data_ptr(), pp.b2.data_ptr(), hidden.data_ptr(), out.data_ptr(),
+                                      1 if out_dtype == torch.float32 else 0, _stream()), "gvl_project")
+    return out
+
+
+def topk_cosine(index: torch.Tensor, queries: torch.Tensor, k: int, eps: float = 1e-12):
+    """index bf16 [N,D], queries bf16 [Q,D] -> (scores fp32 [Q,k], idx int32 [Q,k]), score desc / idx asc."""
+    _need_cuda(index, queries)
+    if index.dtype != torch.bfloat16 or queries.dtype != torch.bfloat16 or not index.is_contiguous() or not queries.is_contiguous():
+        raise RuntimeError("topk_cosine: index and queries must be contiguous bf16")
+    N, D = index.shape
+    Q = queries.shape[0]
+    scratch = torch.empty((Q, N), dtype=torch.float32, device=index.device)
+    scores = torch.empty((Q, k), dtype=torch.float32, device=index.device)
+    idx = torch.empty((Q, k), dtype=torch.int32, device=index.device)
+    _lib.check(_lib.lib().gvl_topk_cosine(index.data_ptr(), N, D, queries.data_ptr(), Q, k, float(eps), scratch.data_ptr(),
+                                          scores.data_ptr(), idx.data_ptr(), _stream()), "gvl_topk_cosine")
+    return scores, idx

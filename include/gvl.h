@@ -1,0 +1,201 @@
+/*
+ * gvl.h — C ABI of libgvl_sm100a.so: the B200-native per-frame perception embedding path.
+ *
+ * Scope: decoded uint8 frames -> SigLIP2-so400m-patch14-384 vision tower (MAP-pooled
+ * 1152-d embedding) -> ProjectorBank MLP (1152 -> 4096 -> 4096) -> timeline index + cosine top-k.
+ *
+ * The reference (chasemetoyer/gameplay-vision-llm) is pure Python and has NO FFI for this path: its
+ * seam is a set of Python call signatures whose arithmetic runs inside HuggingFace `transformers`
+ * and `torch.nn`.  Every entry point below cites the reference call it replaces (paths relative to
+ * the reference root; `HF:` = transformers 5.5.0, `TV:` = torchvision 0.26, `ATen:` = torch 2.11).
+ *
+ * Conventions
+ *  - plain pointers + sizes, no torch types; every `const void*` / `void*` data pointer is a DEVICE
+ *    pointer unless the parameter name starts with `h_` (host).
+ *  - `stream` is a `cudaStream_t` passed as `void*` (0 = legacy default stream).  All work is
+ *    stream-ordered; no entry point synchronises the device.
+ *  - return value 0 = ok; non-zero = error, message via gvl_last_error() (thread-local).
+ *  - no CPU fallback exists: on a machine without an sm_100 GPU every compute entry point fails.
+ *  - bf16 = raw uint16_t storage of IEEE bfloat16.
+ */
+#ifndef GVL_H_
+#define GVL_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GVL_ABI_VERSION 1
+
+#if defined(__GNUC__)
+#define GVL_API __attribute__((visibility("default")))
+#else
+#define GVL_API
+#endif
+
+/* ---- status / introspection --------------------------------------------------------------- */
+
+/* Last error message of the calling thread ("" if none). */
+GVL_API const char* gvl_last_error(void);
+/* Returns GVL_ABI_VERSION. Host only. */
+GVL_API int gvl_abi_version(void);
+/* Number of kernel launches issued by this library since load (all threads). Host only.
+ * bench.py reports the delta over the timed region as `gpu_launches`. */
+GVL_API unsigned long long gvl_launch_count(void);
+/* 0 if device `dev` is an sm_100 GPU this library can run on. */
+GVL_API int gvl_check_device(int dev);
+
+/* ---- K1: frame preprocessing --------------------------------------------------------------- */
+/*
+ * Replaces `self.encoder._processor(images=[image], return_tensors="pt")`
+ * (src/perception/siglip_semantic_encoder.py:474-477) = HF SiglipImageProcessor, torchvision
+ * backend: uint8 antialiased resize (HF:image_processing_backends.py:200-251 ->
+ * TV:v2/functional/_geometry.py:271-340 -> ATen:native/cpu/UpSampleKernelAVXAntialias.h:304-437,
+ * integer two-pass, horizontal then vertical, int16 weights, uint8 intermediate) followed by the fused
+ * rescale+normalize `(float(u8) - sub) / div` (HF:image_processing_backends.py:292-331), and — for
+ * GVL_LAYOUT_BF16_PATCH — the cast to bf16 and the im2col of the stride-14 patch-embedding Conv2d
+ * (HF:models/siglip/modeling_siglip.py:177-179).
+ */
+enum {
+    GVL_RESAMPLE_BILINEAR = 2, /* PIL.Image.BILINEAR */
+    GVL_RESAMPLE_BICUBIC = 3   /* PIL.Image.BICUBIC (a = -0.5) */
+};
+enum {
+    GVL_LAYOUT_U8_CHW = 0,    /* uint8  [B,3,out_h,out_w]  resized image (exactness checks) */
+    GVL_LAYOUT_F32_CHW = 1,   /* float  [B,3,out_h,out_w]  == HF `pixel_values` */
+    GVL_LAYOUT_BF16_CHW = 2,  /* bf16   [B,3,out_h,out_w]  == pixel_values.to(bfloat16) */
+    GVL_LAYOUT_BF16_PATCH = 3 /* bf16   [B*gh*gw, ld]; row = b*gh*gw + py*gw + px, col = c*p*p + ky*p + kx,
+                                 gh = out_h / p, gw = out_w / p; cols [3*p*p, ld) are written as zero */
+};
+
+/* Host only: integer tap tables of one axis, exactly as ATen builds them
+ * (ATen:native/cpu/UpSampleKernel.cpp `_compute_index_ranges_int16_weights`).
+ * h_xmin/h_xsize: [out_size]; h_weights: [out_size*max_taps] (zero padded); *h_precision: shift. */
+GVL_API int gvl_resize_taps(int in_size, int out_size, int resample, int max_taps,
+                    int32_t* h_xmin, int32_t* h_xsize, int16_t* h_weights, int* h_precision,
+                    int* h_taps_used);
+
+/* frames: uint8 [B,H,W,3] (HWC RGB).  sub/div: host float[3], value = (u8 - sub[c]) / div[c] in fp32.
+ * patch / ld are used by GVL_LAYOUT_BF16_PATCH only (ld in elements, ld >= 3*patch*patch, ld % 8 == 0). */
+GVL_API int gvl_preprocess_u8(const uint8_t* frames, int B, int H, int W, int out_h, int out_w, int resample,
+                      const float* h_sub, const float* h_div, void* out, int layout, int patch, int ld,
+                      void* stream);
+
+/* ---- K2: tcgen05 GEMM with fused epilogue ---------------------------------------------------- */
+/*
+ * out[M,N] = act(A[M,K] . W[N,K]^T + bias[N]) + residual[(row % res_row_mod), N]
+ * Replaces every nn.Linear / Conv2d-as-GEMM on the path:
+ *   patch embedding + position embedding   HF:models/siglip/modeling_siglip.py:124-130,175-186
+ *   q/k/v/out projections                  HF:models/siglip/modeling_siglip.py:270-273,285-287,309
+ *   MLP fc1 + GELU(tanh) + fc2 + residual  HF:models/siglip/modeling_siglip.py:315-327,354-359
+ *   MAP head in_proj/out_proj/MLP          HF:models/siglip/modeling_siglip.py:628-649
+ *   projector Linear-GELU(erf)-Linear      src/agent_core/qwen_reasoning_core.py:1009-1013
+ * A, W: bf16 row-major (K contiguous), lda/ldw in elements (multiples of 8), 16-byte aligned.
+ * bias: float[N] or NULL.  residual: bf16, ldr elements, or NULL; res_row_mod = 0 -> row index as is.
+ * out: bf16 (out_f32 = 0) or float (out_f32 = 1), ldo elements.  N % 8 == 0, K % 8 == 0.
+ * fp32 accumulation in tensor memory; one rounding to the output type.
+ */
+enum { GVL_ACT_NONE = 0, GVL_ACT_GELU_TANH = 1, GVL_ACT_GELU_ERF = 2 };
+
+GVL_API int gvl_gemm_bf16(const void* A, int lda, const void* W, int ldw, const float* bias,
+                  const void* residual, int ldr, int res_row_mod, void* out, int ldo, int out_f32,
+                  int M, int N, int K, int act, void* stream);
+
+/* ---- K3: LayerNorm -------------------------------------------------------------------------- */
+/* y = (x - mean) / sqrt(var + eps) * gamma + beta over the last dim, fp32 statistics.
+ * Replaces nn.LayerNorm (HF:models/siglip/modeling_siglip.py:334-336,596,636). x,y bf16; D % 4 == 0. */
+GVL_API int gvl_layernorm_bf16(const void* x, int ldx, const float* gamma, const float* beta, void* y, int ldy,
+                       int rows, int D, float eps, void* stream);
+
+/* ---- K4: self-attention ---------------------------------------------------------------------- */
+/* qkv: bf16 [B*T, 3*H*hd] (q | k | v, head-major inside each third); out: bf16 [B*T, H*hd].
+ * softmax(q k^T * scale) v, non-causal, no mask, fp32 softmax.
+ * Replaces SiglipAttention's SDPA call (HF:models/siglip/modeling_siglip.py:293-306; eager
+ * definition :229-249).  hd % 8 == 0, hd <= 80. */
+GVL_API int gvl_attention_bf16(const void* qkv, void* out, int B, int T, int H, int hd, float scale,
+                       void* stream);
+
+/* ---- K5: MAP-head probe attention -------------------------------------------------------------- */
+/* One query (the learned probe, already projected and pre-scaled: q float[H*hd]) attends over the T
+ * keys/values of each image.  kv: bf16 [B*T, 2*H*hd] (k | v).  out: bf16 [B, H*hd].
+ * Replaces nn.MultiheadAttention(probe, h, h) inside SiglipMultiheadAttentionPoolingHead
+ * (HF:models/siglip/modeling_siglip.py:639-643); the q/k/v/out projections run through gvl_gemm_bf16. */
+GVL_API int gvl_probe_attention_bf16(const float* q, const void* kv, void* out, int B, int T, int H, int hd,
+                             void* stream);
+
+/* ---- K6: whole-tower forward -------------------------------------------------------------------- */
+/* Device-pointer weight pack, repacked by the host from the HF state_dict
+ * (names: SURVEY.md §8a row M1; src/perception/siglip_semantic_encoder.py:195-204 loads them). */
+typedef struct gvl_vit_layer {
+    const float *ln1_g, *ln1_b;
+    const void* w_qkv;  /* bf16 [3D, D]  = cat(q_proj, k_proj, v_proj).weight */
+    const float* b_qkv; /* [3D] */
+    const void* w_o;    /* bf16 [D, D] */
+    const float* b_o;
+    const float *ln2_g, *ln2_b;
+    const void* w_fc1; /* bf16 [I, D] */
+    const float* b_fc1;
+    const void* w_fc2; /* bf16 [D, I] */
+    const float* b_fc2;
+} gvl_vit_layer;
+
+typedef struct gvl_vit_weights {
+    int32_t D, I, H, hd, L, T, patch_k, patch_ld; /* hidden, intermediate, heads, head dim, layers,
+                                                    tokens/image, 3*p*p, padded patch row length */
+    float eps;
+    int32_t act; /* GVL_ACT_* of the encoder MLPs */
+    const void* w_patch;  /* bf16 [D, patch_ld] (zero padded beyond patch_k) */
+    const float* b_patch; /* [D] */
+    const void* pos;      /* bf16 [T, D] */
+    const gvl_vit_layer* layers; /* HOST array of L entries */
+    const float *post_g, *post_b;
+    /* MAP head */
+    const float* probe_q;  /* [D] = (probe . Wq^T + bq) * hd^-0.5, precomputed on the host in fp32 */
+    const void* w_kv;      /* bf16 [2D, D] = in_proj_weight[D:3D] */
+    const float* b_kv;     /* [2D] */
+    const void* w_ho;      /* bf16 [D, D]  = attention.out_proj.weight */
+    const float* b_ho;
+    const float *hln_g, *hln_b;
+    const void* w_hfc1; /* bf16 [I, D] */
+    const float* b_hfc1;
+    const void* w_hfc2; /* bf16 [D, I] */
+    const float* b_hfc2;
+} gvl_vit_weights;
+
+/* Bytes of scratch gvl_siglip_forward needs for a batch of B images. Host only. */
+GVL_API size_t gvl_siglip_workspace_bytes(const gvl_vit_weights* w, int B);
+
+/* patches: bf16 [B*T, patch_ld] (GVL_LAYOUT_BF16_PATCH output).  pooled: bf16 [B, D].
+ * last_hidden: optional bf16 [B*T, D] (post-layernorm tokens) or NULL.
+ * Replaces `self.encoder._model.get_image_features(**inputs)`
+ * (src/perception/siglip_semantic_encoder.py:479-481 -> HF:models/siglip/modeling_siglip.py:787-816,
+ * 604-625). */
+GVL_API int gvl_siglip_forward(const gvl_vit_weights* w, const void* patches, int B, void* workspace,
+                       size_t workspace_bytes, void* pooled, void* last_hidden, void* stream);
+
+/* ---- K7: projector ------------------------------------------------------------------------------ */
+/* out = W2 . gelu_erf(W1 . x + b1) + b2.  Replaces MultiModalProjector.forward
+ * (src/agent_core/qwen_reasoning_core.py:1007-1027) as used by ProjectorBank.project_region (:1076).
+ * x bf16 [M, enc]; w1 bf16 [llm, enc]; w2 bf16 [llm, llm]; hidden: scratch bf16 [M, llm];
+ * out: bf16 or float [M, llm]. */
+GVL_API int gvl_project(const void* x, int M, int enc_dim, int llm_dim, const void* w1, const float* b1,
+                const void* w2, const float* b2, void* hidden, void* out, int out_f32, void* stream);
+
+/* ---- K8: cosine top-k over the timeline index ------------------------------------------------------ */
+/* For each of Q queries: score_n = <q, e_n> / (max(|q|,eps) * max(|e_n|,eps)), fp32; returns the k
+ * best in (score descending, index ascending) order.  Replaces TimelineRetriever.retrieve_by_semantic
+ * (src/agent_core/qwen_reasoning_core.py:1492-1528: cos_sim + argsort(descending)[:k]) and
+ * SigLIPSemanticEncoder.find_similar_regions (src/perception/siglip_semantic_encoder.py:616-638:
+ * stable sort => ties keep the lower index first).
+ * index: bf16 [N, D] (ld = D); queries: bf16 [Q, D]; scratch: float [Q*N];
+ * out_scores: float [Q,k]; out_idx: int32 [Q,k]; k <= 64; D % 8 == 0. */
+GVL_API int gvl_topk_cosine(const void* index, int N, int D, const void* queries, int Q, int k, float eps,
+                    float* scratch, float* out_scores, int32_t* out_idx, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GVL_H_ */

@@ -1,0 +1,195 @@
+"""Per-kernel parity: every CUDA kernel, called through the C ABI (ops -> ctypes -> libgvl_sm100a.so),
+against the oracle (integer work: bit-exact; floating point: stated tolerances vs fp32 math on the same
+bf16 inputs)."""
+import math
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from gameplay_vision_llm_b200 import ops, synth  # noqa: E402
+from oracle import preprocess_ref, siglip_ref  # noqa: E402
+
+DEV = "cuda:0"
+
+
+def _rel_err(out: torch.Tensor, ref: torch.Tensor):
+    out, ref = out.double().cpu(), ref.double().cpu()
+    err = (out - ref).abs()
+    return err.max().item(), (err.max() / ref.abs().max().clamp_min(1e-30)).item(), err.mean().item()
+
+
+# ------------------------------------------------------------------------------------------------ GEMM
+GEMM_CASES = [
+    # M, N, K, act, residual(0 none, 1 full, T = row modulo), out_fp32
+    (128, 128, 64, 0, 0, False),
+    (128, 256, 128, 0, 0, True),
+    (300, 1152, 1152, 0, 1, False),      # out-proj: bias + residual, ragged M
+    (1458, 3456, 1152, 0, 0, False),     # QKV, BN=192
+    (520, 4304, 1152, 1, 0, False),      # fc1 + GELU-tanh, ragged N (4304 = 16*269)
+    (260, 1152, 4304, 0, 1, False),      # fc2: ragged K (4304 = 67*64 + 16)
+    (1458, 1152, 592, 0, 729, False),    # patch embedding + position embedding (row % 729)
+    (64, 4096, 1152, 2, 0, False),       # projector fc1 + GELU-erf
+    (64, 4096, 4096, 0, 0, True),        # projector fc2, fp32 out
+    (5000, 2304, 1152, 0, 0, False),     # MAP-head K/V projection, many tiles per CTA? (40 x 12)
+    (46656, 1152, 1152, 0, 1, False),    # full batch-64 out-proj: > 148 tiles, persistent loop + phases
+]
+
+
+@pytest.mark.parametrize("M,N,K,act,res,f32", GEMM_CASES)
+def test_gemm(M, N, K, act, res, f32):
+    g = torch.Generator(device="cpu").manual_seed(M * 7 + N * 3 + K)
+    a = (torch.randn(M, K, generator=g)).to(torch.bfloat16).to(DEV)
+    w = (torch.randn(N, K, generator=g) / math.sqrt(K)).to(torch.bfloat16).to(DEV)
+    bias = torch.randn(N, generator=g).to(DEV)
+    residual = None
+    mod = 0
+    if res == 1:
+        residual = torch.randn(M, N, generator=g).to(torch.bfloat16).to(DEV)
+    elif res > 1:
+        residual = torch.randn(res, N, generator=g).to(torch.bfloat16).to(DEV)
+        mod = res
+    out = ops.gemm(a, w, bias, residual, res_row_mod=mod, act=act,
+                   out_dtype=torch.float32 if f32 else torch.bfloat16)
+    torch.cuda.synchronize()
+    ref = a.float() @ w.float().T + bias
+    if act == 1:
+        ref = siglip_ref.gelu_tanh(ref)
+    elif act == 2:
+        ref = siglip_ref.gelu_erf(ref)
+    if residual is not None:
+        rr = residual.float()
+        ref = ref + (rr[torch.arange(M, device=DEV) % mod] if mod else rr)
+    mx, rel, mean = _rel_err(out, ref)
+    print(f"gemm M={M} N={N} K={K} act={act} res={res} f32={f32}: max_abs={mx:.3e} rel={rel:.3e} mean={mean:.3e}")
+    assert torch.isfinite(out.float()).all()
+    tol = 2e-5 if f32 else 6e-3  # fp32 out: accumulation-order noise only; bf16 out: one rounding (2^-8 relative)
+    assert rel < tol, f"relative error {rel}"
+
+
+def test_gemm_strided_views():
+    """A and out as column slices of wider buffers (lda/ldo > logical width), in-place residual."""
+    g = torch.Generator().manual_seed(5)
+    big = torch.randn(400, 2304, generator=g).to(torch.bfloat16).to(DEV)
+    a = big[:, 1152:]                                # lda = 2304
+    w = (torch.randn(1152, 1152, generator=g) / 34).to(torch.bfloat16).to(DEV)
+    x = torch.randn(400, 1152, generator=g).to(torch.bfloat16).to(DEV)
+    ref = a.float() @ w.float().T + x.float()
+    ops.gemm(a, w, None, residual=x, out=x)         # x += a @ w.T, in place
+    torch.cuda.synchronize()
+    _, rel, _ = _rel_err(x, ref)
+    assert rel < 6e-3
+
+
+# ------------------------------------------------------------------------------------------- LayerNorm
+@pytest.mark.parametrize("rows,D", [(7, 1152), (1458, 1152), (33, 768), (5, 144), (9, 4096)])
+def test_layernorm(rows, D):
+    g = torch.Generator().manual_seed(rows + D)
+    x = (torch.randn(rows, D, generator=g) * 3 + 0.5).to(torch.bfloat16).to(DEV)
+    gamma = (1 + 0.1 * torch.randn(D, generator=g)).to(DEV)
+    beta = (0.1 * torch.randn(D, generator=g)).to(DEV)
+    out = ops.layernorm(x, gamma, beta, 1e-6)
+    torch.cuda.synchronize()
+    ref = torch.nn.functional.layer_norm(x.float(), (D,), gamma, beta, 1e-6)
+    mx, rel, _ = _rel_err(out, ref)
+    print(f"layernorm {rows}x{D}: max_abs={mx:.3e} rel={rel:.3e}")
+    assert rel < 5e-3
+
+
+# ------------------------------------------------------------------------------------------- attention
+@pytest.mark.parametrize("B,T,H,hd", [(1, 16, 2, 72), (2, 729, 16, 72), (1, 200, 3, 64), (3, 129, 2, 72), (1, 1568, 12, 64)])
+def test_attention(B, T, H, hd):
+    g = torch.Generator().manual_seed(B * 100 + T)
+    D = H * hd
+    qkv = (torch.randn(B * T, 3 * D, generator=g) * 1.5).to(torch.bfloat16).to(DEV)
+    out = ops.attention(qkv, B, T, H, hd)
+    torch.cuda.synchronize()
+    q, k, v = qkv.float().view(B, T, 3, H, hd).permute(2, 0, 3, 1, 4)
+    s = (q @ k.transpose(-1, -2)) * hd ** -0.5
+    ref = (torch.softmax(s, -1) @ v).transpose(1, 2).reshape(B * T, D)
+    mx, rel, mean = _rel_err(out, ref)
+    print(f"attention B={B} T={T} H={H} hd={hd}: max_abs={mx:.3e} rel={rel:.3e} mean={mean:.3e}")
+    assert torch.isfinite(out.float()).all()
+    assert rel < 1.5e-2 and mean < 2e-3  # P is rounded to bf16 before PV (as HF eager/SDPA do)
+
+
+def test_probe_attention():
+    B, T, H, hd = 3, 729, 16, 72
+    D = H * hd
+    g = torch.Generator().manual_seed(11)
+    kv = torch.randn(B * T, 2 * D, generator=g).to(torch.bfloat16).to(DEV)
+    q = (torch.randn(D, generator=g) * hd ** -0.5).to(DEV)
+    out = ops.probe_attention(q, kv, B, T, H, hd)
+    torch.cuda.synchronize()
+    k, v = kv.float().view(B, T, 2, H, hd).permute(2, 0, 3, 1, 4)  # [B,H,T,hd]
+    s = torch.einsum("hd,bhtd->bht", q.view(H, hd), k)
+    ref = torch.einsum("bht,bhtd->bhd", torch.softmax(s, -1), v).reshape(B, D)
+    _, rel, _ = _rel_err(out, ref)
+    assert rel < 5e-3
+
+
+# --------------------------------------------------------------------------------------- preprocessing
+PRE_CASES = [(1080, 1920, 384, 384, 2), (1080, 1920, 384, 384, 3), (123, 211, 56, 56, 2), (270, 480, 96, 112, 3),
+             (720, 1280, 384, 384, 2), (1080, 1920, 224, 398, 2)]
+
+
+@pytest.mark.parametrize("H,W,oh,ow,rs", PRE_CASES)
+def test_preprocess_resize_bit_exact(H, W, oh, ow, rs):
+    frames = synth.noise_frames(3, H, W, seed=H + rs)
+    want = preprocess_ref.resize_u8(frames.numpy(), oh, ow, rs)
+    got = ops.preprocess(frames.to(DEV), oh, ow, rs, layout=ops.LAYOUT_U8_CHW).cpu().numpy()
+    nd = int((got != want).sum())
+    print(f"resize {H}x{W}->{oh}x{ow} rs={rs}: mismatching bytes {nd}/{want.size}")
+    assert nd == 0
+
+
+@pytest.mark.parametrize("H,W,size,rs", [(1080, 1920, 384, 2), (123, 211, 56, 2), (1080, 1920, 384, 3)])
+def test_preprocess_layouts_bit_exact(H, W, size, rs):
+    frames = synth.scene_frames_np(3, 2, H, W)
+    pv = preprocess_ref.pixel_values(frames, size, size, rs)
+    dev_frames = torch.from_numpy(frames).to(DEV)
+    got_f32 = ops.preprocess(dev_frames, size, size, rs, layout=ops.LAYOUT_F32_CHW).cpu().numpy()
+    assert np.array_equal(got_f32.view(np.uint32), pv.view(np.uint32)), "fp32 pixel_values differ"
+    want_bf16 = torch.from_numpy(pv).to(torch.bfloat16)
+    got_bf16 = ops.preprocess(dev_frames, size, size, rs, layout=ops.LAYOUT_BF16_CHW).cpu()
+    assert torch.equal(got_bf16.view(torch.int16), want_bf16.view(torch.int16)), "bf16 CHW differs"
+    ld = (3 * 14 * 14 + 7) // 8 * 8
+    want_patch = torch.from_numpy(preprocess_ref.patchify(pv, 14, ld)).to(torch.bfloat16)
+    got_patch = ops.preprocess(dev_frames, size, size, rs, layout=ops.LAYOUT_BF16_PATCH, patch=14).cpu()
+    assert got_patch.shape == want_patch.shape
+    assert torch.equal(got_patch.view(torch.int16), want_patch.view(torch.int16)), "bf16 patches differ"
+
+
+def test_preprocess_unaligned_base_pointer():
+    """Frames whose base address is not 16-byte aligned take the byte-copy staging path."""
+    H, W = 60, 101
+    frames = synth.noise_frames(2, H, W, seed=3)
+    buf = torch.empty(frames.numel() + 1, dtype=torch.uint8, device=DEV)
+    view = buf[1:].view(2, H, W, 3)
+    view.copy_(frames)
+    want = preprocess_ref.resize_u8(frames.numpy(), 28, 28, 2)
+    got = ops.preprocess(view, 28, 28, 2, layout=ops.LAYOUT_U8_CHW).cpu().numpy()
+    assert np.array_equal(got, want)
+
+
+# ----------------------------------------------------------------------------------------------- top-k
+def test_topk_matches_oracle_with_ties():
+    g = torch.Generator().manual_seed(21)
+    N, D, Q, k = 5000, 4096, 11, 16
+    index = torch.randn(N, D, generator=g).to(torch.bfloat16)
+    index[4000] = index[17]          # exact duplicates -> exact ties, lower index must come first
+    index[4500] = index[17]
+    queries = torch.randn(Q, D, generator=g).to(torch.bfloat16)
+    queries[0] = index[17]           # query 0 hits the tie group
+    queries[1] = 0                   # zero query: all scores 0 -> indices 0..k-1
+    want_s, want_i, margins = siglip_ref.cosine_topk(index.float().numpy(), queries.float().numpy(), k)
+    got_s, got_i = ops.topk_cosine(index.to(DEV), queries.to(DEV), k)
+    torch.cuda.synchronize()
+    got_i, got_s = got_i.cpu().numpy(), got_s.cpu().numpy()
+    print("top-k min margin", float(np.min(margins[2:])))
+    assert np.array_equal(got_i, want_i), f"indices differ\n{got_i}\n{want_i}"
+    assert np.allclose(got_s, want_s, atol=2e-6)
+    assert list(got_i[0][:3]) == [17, 4000, 4500]
+    assert list(got_i[1]) == list(range(k))

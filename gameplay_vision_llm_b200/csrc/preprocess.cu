@@ -358,7 +358,55 @@ preprocess_kernel(const PreParams p) {
     }
 }
 
+// pixel_values fp32 [B,3,H,W] -> bf16 im2col rows (the drop-in `get_image_features(pixel_values=...)` seam).
+// One thread per 8 output elements (16-byte stores); reads are 4-byte, L1/L2 resident.
+__global__ void __launch_bounds__(256)
+patchify_f32_kernel(const float* __restrict__ pv, int B, int H, int W, int patch, int ld, int gh, int gw,
+                    __nv_bfloat16* __restrict__ out) {
+    const int chunks = ld >> 3;
+    const size_t total = (size_t)B * gh * gw * chunks;
+    const int PP = patch * patch, K = 3 * PP;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const int ch = (int)(i % chunks);
+        const size_t row = i / chunks;
+        const int px = (int)(row % gw), py = (int)((row / gw) % gh), b = (int)(row / ((size_t)gw * gh));
+        float v[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            const int k = ch * 8 + e;
+            if (k < K) {
+                const int c = k / PP, r = k - c * PP, ky = r / patch, kx = r - ky * patch;
+                v[e] = pv[(((size_t)b * 3 + c) * H + py * patch + ky) * W + px * patch + kx];
+            } else {
+                v[e] = 0.f;
+            }
+        }
+        uint4 o;
+        o.x = pack_bf16x2(v[0], v[1]);
+        o.y = pack_bf16x2(v[2], v[3]);
+        o.z = pack_bf16x2(v[4], v[5]);
+        o.w = pack_bf16x2(v[6], v[7]);
+        reinterpret_cast<uint4*>(out + row * ld)[ch] = o;
+    }
+}
+
 }  // namespace gvl
+
+extern "C" int gvl_patchify_f32(const float* pixel_values, int B, int H, int W, int patch, int ld, void* out,
+                                void* stream) {
+    using namespace gvl;
+    GVL_CHECK_ARG(pixel_values && out, "gvl_patchify_f32: null pointer");
+    GVL_CHECK_ARG(B > 0 && patch >= 1 && H >= patch && W >= patch && ld >= 3 * patch * patch && ld % 8 == 0,
+                  "gvl_patchify_f32: bad shape B=%d H=%d W=%d patch=%d ld=%d", B, H, W, patch, ld);
+    GVL_CHECK_ARG((uintptr_t)out % 16 == 0, "gvl_patchify_f32: output must be 16-byte aligned");
+    const int gh = H / patch, gw = W / patch;
+    const size_t total = (size_t)B * gh * gw * (ld / 8);
+    int grid = (int)std::min<size_t>((total + 255) / 256, (size_t)sm_count() * 16);
+    patchify_f32_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+        pixel_values, B, H, W, patch, ld, gh, gw, reinterpret_cast<__nv_bfloat16*>(out));
+    GVL_LAUNCH_CHECK("patchify_f32_kernel");
+    return 0;
+}
 
 extern "C" int gvl_resize_taps(int in_size, int out_size, int resample, int max_taps, int32_t* h_xmin, int32_t* h_xsize,
                                int16_t* h_weights, int* h_precision, int* h_taps_used) {

@@ -80,6 +80,20 @@ def preprocess(frames: torch.Tensor, out_h: int = 384, out_w: int = 384, resampl
     return out
 
 
+def patchify(pixel_values: torch.Tensor, patch: int = 14, ld: int | None = None) -> torch.Tensor:
+    """fp32 pixel_values [B,3,H,W] -> bf16 patch rows [B*gh*gw, ld] (the get_image_features seam)."""
+    _need_cuda(pixel_values)
+    if pixel_values.dtype != torch.float32 or pixel_values.dim() != 4 or pixel_values.shape[1] != 3:
+        raise RuntimeError("patchify: pixel_values must be fp32 [B,3,H,W]")
+    pixel_values = pixel_values.contiguous()
+    B, _, H, W = pixel_values.shape
+    ld = ld or (3 * patch * patch + 7) // 8 * 8
+    out = torch.empty((B * (H // patch) * (W // patch), ld), dtype=torch.bfloat16, device=pixel_values.device)
+    _lib.check(_lib.lib().gvl_patchify_f32(pixel_values.data_ptr(), B, H, W, patch, ld, out.data_ptr(), _stream()),
+               "gvl_patchify_f32")
+    return out
+
+
 def gemm(a: torch.Tensor, w: torch.Tensor, bias: torch.Tensor | None = None, residual: torch.Tensor | None = None,
          res_row_mod: int = 0, act: int = ACT_NONE, out: torch.Tensor | None = None,
          out_dtype: torch.dtype = torch.bfloat16) -> torch.Tensor:

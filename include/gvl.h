@@ -84,6 +84,12 @@ GVL_API int gvl_preprocess_u8(const uint8_t* frames, int B, int H, int W, int ou
                       const float* h_sub, const float* h_div, void* out, int layout, int patch, int ld,
                       void* stream);
 
+/* pixel_values: float [B,3,H,W] (what the HF processor returns) -> bf16 im2col rows [B*gh*gw, ld], i.e. the
+ * `.to(bfloat16)` + patch extraction at the head of `get_image_features(pixel_values=...)`
+ * (HF:models/siglip/modeling_siglip.py:175-179).  Same row/column order as GVL_LAYOUT_BF16_PATCH. */
+GVL_API int gvl_patchify_f32(const float* pixel_values, int B, int H, int W, int patch, int ld, void* out,
+                             void* stream);
+
 /* ---- K2: tcgen05 GEMM with fused epilogue ---------------------------------------------------- */
 /*
  * out[M,N] = act(A[M,K] . W[N,K]^T + bias[N]) + residual[(row % res_row_mod), N]

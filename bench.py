@@ -1,0 +1,283 @@
+#!/usr/bin/env python
+"""bench.py — frames/s of the SigLIP2-so400m + ProjectorBank embedding path on N B200s (BASELINE.json).
+
+    python bench.py --gpus 1 --steps 57 --warmup 3            # our arm (default)
+    python bench.py --impl reference --steps 1 --warmup 1     # the reference's CPU path, same metric
+    torchrun ... bench.py --gpus N ...                        # one rank per GPU
+
+A *step* is one pass of the hot path over one batch of 64 synthetic 1080p frames per GPU
+(preprocess -> 27-layer tower -> MAP head -> projector -> row of the timeline index).  The default 57
+steps are BASELINE.json configs[1]: one hour of 1 fps gameplay (3600 frames) rounded up to whole
+batches (57 x 64 = 3648).  With N > 1 each rank owns a contiguous chunk of the timeline with the same
+per-rank work ("weak" scaling) and the projected index is all-gathered over NCCL inside the timed
+region.  Rank 0 prints ONE JSON line.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+FRAME_H, FRAME_W = 1080, 1920
+FRAME_BYTES = FRAME_H * FRAME_W * 3
+PRE_BYTES_PER_FRAME = FRAME_BYTES + 729 * 588 * 2  # BASELINE.md §3 (patch layout written directly)
+
+
+def load_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            p = json.load(f)
+        return {"hbm_gbs": p["hbm_gbs"], "bf16_tflops": p["bf16_tflops"],
+                "bf16_tflops_sustained": p.get("bf16_tflops_sustained", p["bf16_tflops"]), "source": "measured"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
+
+
+class ClockSampler:
+    """Samples nvidia-smi clocks / throttle reasons of one GPU while the timed region runs."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu, self.proc, self.lines = gpu_index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            parts = [x.strip() for x in ln.split(",")]
+            if len(parts) < 7:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                mx = float(parts[1])
+            except ValueError:
+                continue
+            for name, val in zip(names, parts[3:7]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------ reference arm
+def cpu_reference(n_frames: int, batch: int = 8, warmup_batches: int = 1) -> dict:
+    """The reference's CPU path for this metric on the host cores (oracle/hf_baseline.py)."""
+    from oracle import hf_baseline
+    return hf_baseline.run(n_frames=n_frames, batch=batch, warmup_batches=warmup_batches, frame_hw=(FRAME_H, FRAME_W))
+
+
+def main_reference(args) -> None:
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    n = min(64, max(1, args.steps) * 8)  # bounded sample: at most 8 batches of 8 frames (~2 min on 8 cores)
+    res = cpu_reference(n_frames=n, batch=8, warmup_batches=1 if args.warmup > 0 else 0)
+    line = {
+        "impl": "reference", "metric": "frames/s SigLIP2+ProjectorBank", "value": res["frames_per_s"], "unit": "frames/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": res["seconds"] / (n / 8) * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "fp32", "data": "synthetic",
+        "config": {"workload": "SigLIP2-so400m-patch14-384 + ProjectorBank 1152->4096, synthetic 1080p frames, fp32 on "
+                               "host CPU, batch 8 (BASELINE.json configs[0] procedure), bounded sample",
+                   "frames": n, "batch": 8},
+        "cpu_baseline": {"value": res["frames_per_s"], "unit": "frames/s", "cores": res["cores"], "kind": res["kind"],
+                         "sample": res["sample"]},
+        "e2e": {"value": res["frames_per_s"], "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------ our arm
+def main_ours(args) -> None:
+    import torch
+    import torch.distributed as dist
+
+    from gameplay_vision_llm_b200 import _lib, synth
+    from gameplay_vision_llm_b200.pipeline import EmbeddingPipeline
+    from gameplay_vision_llm_b200.weights import (SiglipVisionSpec, synth_projector_state_dict,
+                                                    synth_siglip_state_dict)
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if world != args.gpus and world > 1:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    _lib.check(_lib.lib().gvl_check_device(local_rank), "gvl_check_device")
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    peaks = load_peaks()
+    spec = SiglipVisionSpec.so400m()
+    B, K, W = args.batch, args.steps, args.warmup
+    pipe = EmbeddingPipeline(synth_siglip_state_dict(spec, seed=0), synth_projector_state_dict(spec.hidden, 4096, seed=1),
+                             spec, dev, batch=B)
+
+    # this rank's chunk of the timeline, resident in HBM: K batches of B frames (22.7 GB at K=57, B=64)
+    n_local = K * B
+    first = rank * n_local
+    frames = torch.empty((n_local, FRAME_H, FRAME_W, 3), dtype=torch.uint8, device=dev)
+    for i0 in range(0, n_local, 16):
+        n = min(16, n_local - i0)
+        frames[i0:i0 + n] = synth.scene_frames(first + i0, n, FRAME_H, FRAME_W, device=dev)
+    index_local = torch.empty((n_local, 4096), dtype=torch.bfloat16, device=dev)
+    index_full = torch.empty((world * n_local, 4096), dtype=torch.bfloat16, device=dev) if world > 1 else index_local
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def run_region(steps: int):
+        for s in range(steps):
+            pipe.embed(frames[s * B:(s + 1) * B], out_index=index_local[s * B:(s + 1) * B])
+        if world > 1:
+            dist.all_gather_into_tensor(index_full, index_local)
+
+    for s in range(W):  # warm-up: W batches (+ one all-gather)
+        pipe.embed(frames[(s % K) * B:(s % K + 1) * B], out_index=index_local[(s % K) * B:(s % K + 1) * B])
+    if world > 1:
+        dist.all_gather_into_tensor(index_full, index_local)
+    barrier()
+
+    # ---- timed region 1: device-resident inputs (value) ----
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    launches0 = _lib.launch_count()
+    barrier()
+    e0.record()
+    run_region(K)
+    e1.record()
+    barrier()
+    launches = _lib.launch_count() - launches0
+    clocks = sampler.stop()
+    ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms = float(ms.item())
+    total_frames = world * n_local
+    value = total_frames / (ms * 1e-3)
+
+    # ---- timed region 2: same steps with per-launch CUDA events (roofline of the dominant kernel) ----
+    _lib.prof_enable(True)
+    run_region(K)
+    torch.cuda.synchronize()
+    _lib.prof_enable(False)
+    prof = _lib.prof_summary()
+    gemm = prof.get("gemm", {"ms": 0.0, "launches": 0, "work": 0.0})
+    gemm_tflops = gemm["work"] / (gemm["ms"] * 1e-3) / 1e12 if gemm["ms"] else 0.0
+    prof_total_ms = sum(v["ms"] for v in prof.values()) or 1.0
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "gemm_traffic.json")
+    if os.path.exists(tpath):
+        with open(tpath) as f:
+            traffic = json.load(f).get("dram_bytes_per_launch")
+    roofline = {"kernel": "gemm_bf16_tcgen05_kernel", "bound": "tensor", "achieved": round(gemm_tflops, 2),
+                "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
+                "frac": round(gemm_tflops / peaks["bf16_tflops_sustained"], 4), "traffic": traffic,
+                "peak_source": f"{peaks['source']} (sustained; burst {peaks['bf16_tflops']})",
+                "launches": gemm["launches"], "avg_launch_ms": round(gemm["ms"] / max(1, gemm["launches"]), 4),
+                "share_of_step": round(gemm["ms"] / prof_total_ms, 4)}
+    kernels = {k: {"ms_per_step": round(v["ms"] / K, 4), "launches_per_step": round(v["launches"] / K, 2),
+                   "share": round(v["ms"] / prof_total_ms, 4)} for k, v in prof.items()}
+    if "preprocess" in prof and prof["preprocess"]["ms"]:
+        gbs = prof["preprocess"]["work"] / (prof["preprocess"]["ms"] * 1e-3) / 1e9
+        kernels["preprocess"].update({"achieved_gbs": round(gbs, 1), "hbm_frac": round(gbs / peaks["hbm_gbs"], 4)})
+    if "attention" in prof and prof["attention"]["ms"]:
+        kernels["attention"]["achieved_tflops"] = round(prof["attention"]["work"] / (prof["attention"]["ms"] * 1e-3) / 1e12, 2)
+    model_tflops = value / world * spec.flops_per_frame() / 1e12
+
+    # ---- timed region 3: end to end through the public API with HOST frames (e2e) ----
+    ring = [frames[i * B:(i + 1) * B].cpu().pin_memory() for i in range(min(4, K))]
+    host_out = torch.empty((n_local, 4096), dtype=torch.bfloat16).pin_memory()
+
+    def host_batches(steps):
+        for s in range(steps):
+            yield ring[s % len(ring)]
+
+    pipe.embed_stream(host_batches(min(W, 2)), index_local, host_out)
+    barrier()
+    e0.record()
+    pipe.embed_stream(host_batches(K), index_local, host_out)
+    if world > 1:
+        dist.all_gather_into_tensor(index_full, index_local)
+    e1.record()
+    barrier()
+    ms_e2e = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        dist.all_reduce(ms_e2e, op=dist.ReduceOp.MAX)
+    e2e_value = total_frames / (float(ms_e2e.item()) * 1e-3)
+
+    if rank == 0:
+        cpu = None
+        if world == 1 and not args.no_cpu_baseline:
+            cpu = cpu_reference(n_frames=8, batch=8, warmup_batches=1)
+        line = {
+            "metric": "frames/s SigLIP2+ProjectorBank", "value": round(value, 2), "unit": "frames/s", "n_gpus": world,
+            "steps": K, "warmup": W, "ms_per_step": round(ms / K, 3), "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": "1 h synthetic 1080p gameplay @1 fps (BASELINE.json configs[1]: 3600 frames, rounded up "
+                                   "to 57 batches of 64) through SigLIP2-so400m-patch14-384 + ProjectorBank 1152->4096->4096",
+                       "frames_per_gpu": n_local, "batch": B, "frame": [FRAME_H, FRAME_W, 3],
+                       "weights": "random init, seeds 0/1", "sharding": "contiguous timeline chunk per rank, "
+                       "NCCL all-gather of the projected index inside the timed region" if world > 1 else "single GPU",
+                       "l2": "inputs larger than L2 (398 MB of frames per step, never reused)"},
+            "model_tflops_per_gpu": round(model_tflops, 1),
+            "model_frac_of_sustained_peak": round(model_tflops / peaks["bf16_tflops_sustained"], 4),
+            "roofline": roofline, "kernels": kernels, "clocks": clocks,
+            "e2e": {"value": round(e2e_value, 2), "unit": "frames/s", "h2d_bytes_per_step": B * FRAME_BYTES,
+                    "d2h_bytes_per_step": B * 4096 * 2},
+            "gpu_launches": int(launches),
+        }
+        if cpu is not None:
+            line["cpu_baseline"] = {"value": cpu["frames_per_s"], "unit": "frames/s", "cores": cpu["cores"],
+                                    "kind": cpu["kind"], "sample": cpu["sample"]}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=57)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--batch", type=int, default=64)
+    ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    a = ap.parse_args()
+    if a.impl == "reference":
+        main_reference(a)
+    else:
+        main_ours(a)

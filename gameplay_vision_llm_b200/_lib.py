@@ -37,6 +37,8 @@ SIGNATURES = {
     "gvl_abi_version": (c_int, []),
     "gvl_launch_count": (c_ulonglong, []),
     "gvl_check_device": (c_int, [c_int]),
+    "gvl_prof_enable": (c_int, [c_int]),
+    "gvl_prof_summary": (c_int, [c_int, POINTER(ctypes.c_double), POINTER(c_ulonglong), POINTER(ctypes.c_double)]),
     "gvl_resize_taps": (c_int, [c_int, c_int, c_int, c_int, POINTER(c_int32), POINTER(c_int32), POINTER(c_int16),
                                 POINTER(c_int), POINTER(c_int)]),
     "gvl_preprocess_u8": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_float_p, c_float_p, c_void_p,
@@ -87,3 +89,22 @@ def check(rc: int, what: str = "gvl") -> None:
 
 def launch_count() -> int:
     return int(lib().gvl_launch_count())
+
+
+KERNEL_IDS = {"preprocess": 0, "gemm": 1, "layernorm": 2, "attention": 3, "probe_attention": 4, "topk_scores": 5,
+              "topk_select": 6, "patchify": 7}
+
+
+def prof_enable(on: bool) -> None:
+    check(lib().gvl_prof_enable(1 if on else 0), "gvl_prof_enable")
+
+
+def prof_summary() -> dict:
+    """{kernel family: {"ms": total device ms, "launches": n, "work": algorithmic FLOPs or bytes}} of the session."""
+    out = {}
+    for name, kid in KERNEL_IDS.items():
+        ms, n, work = ctypes.c_double(0), c_ulonglong(0), ctypes.c_double(0)
+        check(lib().gvl_prof_summary(kid, ctypes.byref(ms), ctypes.byref(n), ctypes.byref(work)), "gvl_prof_summary")
+        if n.value:
+            out[name] = {"ms": ms.value, "launches": int(n.value), "work": work.value}
+    return out

@@ -328,6 +328,7 @@ static int launch_attention(const void* qkv, void* out, int B, int T, int H, flo
     GVL_CUDA(cudaFuncSetAttribute(attention_bf16_kernel<HD>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   Cfg::SMEM_BYTES));
     dim3 grid((T + ATT_BQ - 1) / ATT_BQ, H, B);
+    ProfScope prof(GVL_K_ATTENTION, 4.0 * B * (double)H * T * (double)T * HD, s);
     attention_bf16_kernel<HD><<<grid, ATT_THREADS, Cfg::SMEM_BYTES, s>>>(
         reinterpret_cast<const __nv_bfloat16*>(qkv), reinterpret_cast<__nv_bfloat16*>(out), T, H,
         scale * 1.4426950408889634f);
@@ -359,6 +360,7 @@ extern "C" int gvl_probe_attention_bf16(const float* q, const void* kv, void* ou
     GVL_CHECK_ARG((uintptr_t)kv % 16 == 0, "gvl_probe_attention_bf16: misaligned pointer");
     cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
     dim3 grid(H, B);
+    ProfScope prof(GVL_K_PROBE_ATTENTION, 4.0 * B * (double)T * H * hd, s);
     probe_attention_kernel<<<grid, PROBE_THREADS, 0, s>>>(q, reinterpret_cast<const __nv_bfloat16*>(kv),
                                                           reinterpret_cast<__nv_bfloat16*>(out), T, H, hd);
     GVL_LAUNCH_CHECK("probe_attention_kernel");

@@ -3,6 +3,7 @@
 #include "common.cuh"
 
 #include <mutex>
+#include <vector>
 
 namespace gvl {
 
@@ -26,6 +27,41 @@ int sm_count() {
         cached[dev] = n;
     }
     return cached[dev];
+}
+
+// ---- per-launch profiling ----
+struct ProfRec {
+    int kid;
+    double work;
+    cudaEvent_t e0, e1;
+};
+static std::mutex g_prof_mu;
+static bool g_prof_on = false;
+static std::vector<ProfRec*> g_prof_recs;   // records of the current session
+static std::vector<ProfRec*> g_prof_pool;   // recycled records (events are reused)
+
+ProfScope::ProfScope(int kernel_id, double work, cudaStream_t s) : rec(nullptr), stream(s) {
+    if (!g_prof_on) return;
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    ProfRec* r = nullptr;
+    if (!g_prof_pool.empty()) {
+        r = g_prof_pool.back();
+        g_prof_pool.pop_back();
+    } else {
+        r = new ProfRec();
+        if (cudaEventCreate(&r->e0) != cudaSuccess || cudaEventCreate(&r->e1) != cudaSuccess) {
+            delete r;
+            return;
+        }
+    }
+    r->kid = kernel_id;
+    r->work = work;
+    cudaEventRecord(r->e0, s);
+    g_prof_recs.push_back(r);
+    rec = r;
+}
+ProfScope::~ProfScope() {
+    if (rec) cudaEventRecord(static_cast<ProfRec*>(rec)->e1, stream);
 }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -74,6 +110,33 @@ extern "C" {
 const char* gvl_last_error(void) { return gvl::t_err; }
 int gvl_abi_version(void) { return GVL_ABI_VERSION; }
 unsigned long long gvl_launch_count(void) { return gvl::g_launches.load(); }
+
+int gvl_prof_enable(int on) {
+    std::lock_guard<std::mutex> lk(gvl::g_prof_mu);
+    for (gvl::ProfRec* r : gvl::g_prof_recs) gvl::g_prof_pool.push_back(r);
+    gvl::g_prof_recs.clear();
+    gvl::g_prof_on = on != 0;
+    return 0;
+}
+
+int gvl_prof_summary(int kernel_id, double* total_ms, unsigned long long* launches, double* total_work) {
+    std::lock_guard<std::mutex> lk(gvl::g_prof_mu);
+    double ms = 0.0, work = 0.0;
+    unsigned long long n = 0;
+    for (gvl::ProfRec* r : gvl::g_prof_recs) {
+        if (r->kid != kernel_id) continue;
+        GVL_CUDA(cudaEventSynchronize(r->e1));
+        float t = 0.f;
+        GVL_CUDA(cudaEventElapsedTime(&t, r->e0, r->e1));
+        ms += t;
+        work += r->work;
+        ++n;
+    }
+    if (total_ms) *total_ms = ms;
+    if (launches) *launches = n;
+    if (total_work) *total_work = work;
+    return 0;
+}
 
 int gvl_check_device(int dev) {
     int n = 0;

@@ -52,6 +52,15 @@ inline void count_launch(int n = 1) { g_launches.fetch_add((unsigned long long)n
 
 int sm_count();  // SMs of the current device (cached)
 
+// Optional per-launch timing (gvl_prof_enable): CUDA events recorded on the launch stream around every
+// kernel, summed per kernel family by gvl_prof_summary.  `work` = algorithmic FLOPs or bytes of the launch.
+struct ProfScope {
+    void* rec;
+    cudaStream_t stream;
+    ProfScope(int kernel_id, double work, cudaStream_t s);
+    ~ProfScope();
+};
+
 // cuTensorMapEncodeTiled through the runtime's driver entry point (no link-time libcuda dependency).
 // 2-D bf16 row-major tensor [rows, cols] with row stride ld (elements); box = [box_rows, box_cols];
 // 128-byte swizzle when box_cols*2 == 128, OOB reads fill zero, OOB writes are clipped.

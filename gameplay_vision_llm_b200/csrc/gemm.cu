@@ -237,6 +237,7 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const Gem
                                   Cfg::SMEM_BYTES));
     const int tiles = p.m_tiles * p.n_tiles;
     const int grid = tiles < sm_count() ? tiles : sm_count();
+    ProfScope prof(GVL_K_GEMM, 2.0 * p.M * (double)p.N * p.K, stream);
     gemm_bf16_tcgen05_kernel<BN><<<grid, kGemmThreads, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, p);
     GVL_LAUNCH_CHECK("gemm_bf16_tcgen05_kernel");
     return 0;

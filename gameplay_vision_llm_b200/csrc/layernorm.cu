@@ -87,6 +87,7 @@ extern "C" int gvl_layernorm_bf16(const void* x, int ldx, const float* gamma, co
     const auto* xp = reinterpret_cast<const __nv_bfloat16*>(x);
     auto* yp = reinterpret_cast<__nv_bfloat16*>(y);
     const int nv = (D / 4 + 31) / 32;
+    ProfScope prof(GVL_K_LAYERNORM, 4.0 * rows * (double)D, s);
     if (nv <= 6)
         layernorm_bf16_kernel<6><<<grid, kLnWarps * 32, 0, s>>>(xp, ldx, gamma, beta, yp, ldy, rows, D, eps);
     else if (nv <= 9)

@@ -402,6 +402,7 @@ extern "C" int gvl_patchify_f32(const float* pixel_values, int B, int H, int W, 
     const int gh = H / patch, gw = W / patch;
     const size_t total = (size_t)B * gh * gw * (ld / 8);
     int grid = (int)std::min<size_t>((total + 255) / 256, (size_t)sm_count() * 16);
+    ProfScope prof(GVL_K_PATCHIFY, (double)B * gh * gw * 3 * patch * patch * 6, reinterpret_cast<cudaStream_t>(stream));
     patchify_f32_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
         pixel_values, B, H, W, patch, ld, gh, gw, reinterpret_cast<__nv_bfloat16*>(out));
     GVL_LAUNCH_CHECK("patchify_f32_kernel");
@@ -496,6 +497,9 @@ extern "C" int gvl_preprocess_u8(const uint8_t* frames, int B, int H, int W, int
                   smem);
     cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
     dim3 grid((p.eff_w + TX - 1) / TX, (p.eff_h + TY - 1) / TY, B);
+    const double out_bytes = layout == GVL_LAYOUT_BF16_PATCH ? (double)p.gh * p.gw * 3 * patch * patch * 2
+                                                              : (double)3 * out_h * out_w * esize;
+    ProfScope prof(GVL_K_PREPROCESS, (double)B * ((double)H * W * 3 + out_bytes), s);
     auto launch = [&](auto kernel) -> int {
         GVL_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         kernel<<<grid, PRE_THREADS, smem, s>>>(p);

@@ -156,11 +156,13 @@ extern "C" int gvl_topk_cosine(const void* index, int N, int D, const void* quer
     if (grid > max_grid) grid = max_grid;
     for (int q0 = 0; q0 < Q; q0 += TOPK_QB) {
         const int nq = Q - q0 < TOPK_QB ? Q - q0 : TOPK_QB;
+        ProfScope prof(GVL_K_TOPK_SCORES, (double)N * D * 2, s);
         cos_scores_kernel<<<grid, TOPK_THREADS, smem, s>>>(
             reinterpret_cast<const __nv_bfloat16*>(index), N, D,
             reinterpret_cast<const __nv_bfloat16*>(queries) + (size_t)q0 * D, nq, eps, scratch + (size_t)q0 * N);
         GVL_LAUNCH_CHECK("cos_scores_kernel");
     }
+    ProfScope prof(GVL_K_TOPK_SELECT, (double)Q * N * 4 * k, s);
     topk_select_kernel<<<Q, TOPK_THREADS, 0, s>>>(scratch, N, k, out_scores, out_idx);
     GVL_LAUNCH_CHECK("topk_select_kernel");
     return 0;

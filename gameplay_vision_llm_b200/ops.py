@@ -181,7 +181,7 @@ def siglip_forward(pack: SiglipPack, patches: torch.Tensor, workspace: torch.Ten
 
 
 def project(pp: ProjectorPack, x: torch.Tensor, out_dtype: torch.dtype = torch.float32,
-            hidden: torch.Tensor | None = None) -> torch.Tensor:
+            hidden: torch.Tensor | None = None, out: torch.Tensor | None = None) -> torch.Tensor:
     """MultiModalProjector: bf16 [M, enc] -> [M, llm] (fp32 like the reference, or bf16 for the index)."""
     _need_cuda(x)
     if x.dtype != torch.bfloat16 or x.dim() != 2 or not x.is_contiguous() or x.shape[1] != pp.encoder_dim:
@@ -189,7 +189,11 @@ def project(pp: ProjectorPack, x: torch.Tensor, out_dtype: torch.dtype = torch.f
     M = x.shape[0]
     if hidden is None:
         hidden = torch.empty((M, pp.llm_dim), dtype=torch.bfloat16, device=x.device)
-    out = torch.empty((M, pp.llm_dim), dtype=out_dtype, device=x.device)
+    if out is None:
+        out = torch.empty((M, pp.llm_dim), dtype=out_dtype, device=x.device)
+    elif tuple(out.shape) != (M, pp.llm_dim) or not out.is_contiguous() or out.dtype not in (torch.float32, torch.bfloat16):
+        raise RuntimeError("project: `out` must be contiguous fp32/bf16 [M, llm_dim]")
+    out_dtype = out.dtype
     _lib.check(_lib.lib().gvl_project(x.data_ptr(), M, pp.encoder_dim, pp.llm_dim, pp.w1.data_ptr(), pp.b1.data_ptr(),
                                       pp.w2.data_ptr(), pp.b2.data_ptr(), hidden.data_ptr(), out.data_ptr(),
                                       1 if out_dtype == torch.float32 else 0, _stream()), "gvl_project")

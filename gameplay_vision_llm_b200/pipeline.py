@@ -1,0 +1,122 @@
+"""The hot path as one object: uint8 frames -> SigLIP2 embedding (1152) -> projected embedding (4096) ->
+timeline index, batched, stream-ordered, one process per GPU.
+
+Replaces the reference's per-frame loop (scripts/extract_features.py:590-607 `run_siglip_encoder`, twin
+scripts/realtime_inference.py:313-324): there every frame costs a CPU preprocess, one H2D, a batch-1
+forward and a D2H sync; here a chunk of the timeline is resident (or streamed through a double-buffered
+pinned-memory feed), each batch is three C-ABI calls (preprocess, tower, projector) on one stream, and
+the only host synchronisation is at the end of the chunk.
+"""
+from __future__ import annotations
+
+from typing import Iterable, Iterator
+
+import numpy as np
+import torch
+
+from . import ops
+from .weights import ProjectorPack, SiglipPack, SiglipVisionSpec
+
+
+def shard_range(n_items: int, rank: int, world: int, align: int = 1) -> tuple[int, int]:
+    """Contiguous timeline chunk of `rank`: [r*ceil(n/world), min(n, (r+1)*ceil(n/world))), chunk size rounded
+    up to a multiple of `align` (16 for VideoMAE clips) so timestamps stay ordered after the gather."""
+    per = -(-n_items // world)
+    per = -(-per // align) * align
+    lo = min(n_items, rank * per)
+    return lo, min(n_items, lo + per)
+
+
+class EmbeddingPipeline:
+    def __init__(self, siglip_sd: dict, projector_sd: dict, spec: SiglipVisionSpec | None = None,
+                 device: str | torch.device = "cuda:0", batch: int = 64, resample: int = ops.BILINEAR,
+                 image_mean=(0.5, 0.5, 0.5), image_std=(0.5, 0.5, 0.5)):
+        self.spec = spec or SiglipVisionSpec.so400m()
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise RuntimeError("EmbeddingPipeline needs a CUDA device: this path has no CPU fallback")
+        self.batch = int(batch)
+        self.resample = resample
+        self.image_mean, self.image_std = tuple(image_mean), tuple(image_std)
+        with torch.cuda.device(self.device):
+            self.pack = SiglipPack(siglip_sd, self.spec, self.device)
+            self.proj = ProjectorPack(projector_sd, self.device)
+            s = self.spec
+            self.workspace = torch.empty(self.pack.workspace_bytes(self.batch), dtype=torch.uint8, device=self.device)
+            self.patches = torch.empty((self.batch * s.tokens, s.patch_ld), dtype=torch.bfloat16, device=self.device)
+            self.hidden = torch.empty((self.batch, self.proj.llm_dim), dtype=torch.bfloat16, device=self.device)
+        self.llm_dim = self.proj.llm_dim
+
+    # ---- one batch, everything already on the device ------------------------------------------------
+    def embed(self, frames: torch.Tensor, out_index: torch.Tensor | None = None):
+        """frames uint8 [B,H,W,3] on the device (B <= batch) -> (pooled bf16 [B,D], projected bf16 [B,llm]).
+        `out_index` (bf16 [B, llm], e.g. a slice of the timeline index) receives the projection in place."""
+        B = frames.shape[0]
+        if B > self.batch:
+            raise RuntimeError(f"batch of {B} frames exceeds the pipeline's capacity {self.batch}")
+        s = self.spec
+        patches = self.patches[: B * s.tokens]
+        ops.preprocess(frames, s.image, s.image, self.resample, self.image_mean, self.image_std,
+                       layout=ops.LAYOUT_BF16_PATCH, patch=s.patch, ld=s.patch_ld, out=patches)
+        pooled = ops.siglip_forward(self.pack, patches, workspace=self.workspace)
+        projected = ops.project(self.proj, pooled, out_dtype=torch.bfloat16, hidden=self.hidden[:B], out=out_index)
+        return pooled, projected
+
+    # ---- a resident chunk of the timeline ---------------------------------------------------------
+    def embed_resident(self, frames: torch.Tensor, index: torch.Tensor | None = None) -> torch.Tensor:
+        """frames uint8 [N,H,W,3] resident in HBM -> projected index bf16 [N, llm] (timestamp order)."""
+        N = frames.shape[0]
+        if index is None:
+            index = torch.empty((N, self.llm_dim), dtype=torch.bfloat16, device=self.device)
+        for i0 in range(0, N, self.batch):
+            i1 = min(N, i0 + self.batch)
+            self.embed(frames[i0:i1], out_index=index[i0:i1])
+        return index
+
+    # ---- host frames streamed through pinned memory -----------------------------------------------
+    def embed_stream(self, host_batches: Iterable[torch.Tensor], index: torch.Tensor,
+                     host_out: torch.Tensor | None = None) -> int:
+        """The call a user makes with decoded frames in host memory.
+
+        host_batches yields pinned uint8 [b,H,W,3] tensors (b <= batch) in timeline order; rows of `index`
+        (bf16 [>=N, llm], device) are filled in order; if `host_out` (pinned bf16 [>=N, llm]) is given, every
+        batch's result is also copied device->host asynchronously.  H2D copies run on a side stream and
+        overlap the previous batch's compute (two device frame buffers).  Returns the number of frames; the
+        caller synchronises (e.g. `torch.cuda.current_stream().synchronize()`).
+        """
+        compute = torch.cuda.current_stream(self.device)
+        if not hasattr(self, "_copy_stream"):
+            self._copy_stream = torch.cuda.Stream(self.device)
+            self._dev_frames = [None, None]
+            self._copied = [torch.cuda.Event(), torch.cuda.Event()]
+            self._consumed = [torch.cuda.Event(), torch.cuda.Event()]
+        done = 0
+        for step, hb in enumerate(host_batches):
+            slot = step & 1
+            b = hb.shape[0]
+            buf = self._dev_frames[slot]
+            if buf is None or buf.shape[1:] != hb.shape[1:] or buf.shape[0] < b:
+                buf = torch.empty((self.batch,) + tuple(hb.shape[1:]), dtype=torch.uint8, device=self.device)
+                self._dev_frames[slot] = buf
+            with torch.cuda.stream(self._copy_stream):
+                if step >= 2:
+                    self._copy_stream.wait_event(self._consumed[slot])
+                else:
+                    self._copy_stream.wait_stream(compute)
+                buf[:b].copy_(hb, non_blocking=True)
+                self._copied[slot].record(self._copy_stream)
+            compute.wait_event(self._copied[slot])
+            _, proj = self.embed(buf[:b], out_index=index[done:done + b])
+            self._consumed[slot].record(compute)
+            if host_out is not None:
+                host_out[done:done + b].copy_(proj, non_blocking=True)
+            done += b
+        return done
+
+
+def pinned_batches(frames: np.ndarray | torch.Tensor, batch: int) -> Iterator[torch.Tensor]:
+    """Convenience: slice a host frame array into pinned batches."""
+    t = torch.as_tensor(frames)
+    for i0 in range(0, t.shape[0], batch):
+        chunk = t[i0:i0 + batch]
+        yield chunk if chunk.is_pinned() else chunk.contiguous().pin_memory()

@@ -48,6 +48,17 @@ GVL_API unsigned long long gvl_launch_count(void);
 /* 0 if device `dev` is an sm_100 GPU this library can run on. */
 GVL_API int gvl_check_device(int dev);
 
+/* Per-launch timing for bench.py's roofline: while enabled, every kernel launch of this library is bracketed
+ * by CUDA events on its own stream.  gvl_prof_enable(1) starts a fresh session, gvl_prof_enable(0) stops
+ * recording (the session stays readable); gvl_prof_summary sums one kernel family (it waits for the
+ * recorded events).  total_work = algorithmic FLOPs (GEMM, attention) or bytes (the others). */
+enum {
+    GVL_K_PREPROCESS = 0, GVL_K_GEMM = 1, GVL_K_LAYERNORM = 2, GVL_K_ATTENTION = 3, GVL_K_PROBE_ATTENTION = 4,
+    GVL_K_TOPK_SCORES = 5, GVL_K_TOPK_SELECT = 6, GVL_K_PATCHIFY = 7, GVL_K_COUNT = 8
+};
+GVL_API int gvl_prof_enable(int on);
+GVL_API int gvl_prof_summary(int kernel_id, double* total_ms, unsigned long long* launches, double* total_work);
+
 /* ---- K1: frame preprocessing --------------------------------------------------------------- */
 /*
  * Replaces `self.encoder._processor(images=[image], return_tensors="pt")`

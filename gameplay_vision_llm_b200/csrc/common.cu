@@ -113,8 +113,10 @@ unsigned long long gvl_launch_count(void) { return gvl::g_launches.load(); }
 
 int gvl_prof_enable(int on) {
     std::lock_guard<std::mutex> lk(gvl::g_prof_mu);
-    for (gvl::ProfRec* r : gvl::g_prof_recs) gvl::g_prof_pool.push_back(r);
-    gvl::g_prof_recs.clear();
+    if (on) {  // a new session recycles the previous one's records; disabling keeps them readable
+        for (gvl::ProfRec* r : gvl::g_prof_recs) gvl::g_prof_pool.push_back(r);
+        gvl::g_prof_recs.clear();
+    }
     gvl::g_prof_on = on != 0;
     return 0;
 }

@@ -1,0 +1,314 @@
+"""Drop-in for the hot-path half of the reference's `src/perception/siglip_semantic_encoder.py`.
+
+Same names, argument meaning and error behaviour as the reference for everything on the path
+(SURVEY.md §8b): `NaFlexConfig` (:59-83), `SemanticEmbedding` (:37-56), `SigLIPEncoder._load_model`
+(:178-210) with its `_model` / `_processor` seam, `SigLIPSemanticEncoder.encode_image` (:445-483),
+`compute_similarity` / `find_similar_regions` (:604-638).  The arithmetic runs in libgvl_sm100a.so:
+
+* `_processor(images=[...], return_tensors="pt")`  -> preprocess kernel (bit-exact with HF's CPU path)
+* `_model.get_image_features(pixel_values=...)`    -> patchify + tcgen05 tower + MAP head
+* `encode_frames(uint8 [B,H,W,3])`                 -> the batched fast entry the reference lacks
+
+Differences, on purpose: a model that cannot be loaded raises (the reference silently degrades to a
+random `Placeholder`, :206-210 — a CPU/placeholder fallback would void every parity claim);
+`encode_masked_regions` and the REN `projection` head are out of scope (not reached from
+`extract_features.main`).
+"""
+from __future__ import annotations
+
+import logging
+import os
+from dataclasses import dataclass
+from typing import Optional, Sequence
+
+import numpy as np
+import torch
+
+from . import ops
+from .weights import SiglipPack, SiglipVisionSpec, synth_siglip_state_dict
+
+logger = logging.getLogger(__name__)
+
+
+@dataclass
+class SemanticEmbedding:
+    """Semantic embedding of a region / frame (reference :37-56)."""
+
+    embedding: torch.Tensor  # (embedding_dim,)
+    entity_id: Optional[str] = None
+    confidence: float = 1.0
+    original_bbox: Optional[tuple[float, float, float, float]] = None
+    aspect_ratio: Optional[float] = None
+
+    def __repr__(self) -> str:
+        return f"SemanticEmbedding(dim={self.embedding.shape[-1]}, entity={self.entity_id}, conf={self.confidence:.2f})"
+
+
+@dataclass
+class NaFlexConfig:
+    """Reference fields (:59-83) first; the fields after `use_tf32` are this build's additions."""
+
+    model_name: str = "google/siglip2-so400m-patch14-384"
+    device: str = "cuda"
+    dtype: torch.dtype = torch.bfloat16
+    base_resolution: int = 384
+    min_resolution: int = 128
+    max_resolution: int = 768
+    preserve_aspect_ratio: bool = True
+    embedding_dim: int = 1152
+    use_cls_token: bool = True
+    pool_strategy: str = "mean"
+    batch_size: int = 16
+    use_amp: bool = True
+    use_tf32: bool = True
+    # --- additions ---
+    resample: int = 2  # PIL BILINEAR; the checkpoint's preprocessor_config.json value (unknowable offline)
+    image_mean: tuple = (0.5, 0.5, 0.5)
+    image_std: tuple = (0.5, 0.5, 0.5)
+    synthetic_seed: Optional[int] = None  # random-init weights in the HF layout (no network here)
+    state_dict: Optional[dict] = None  # an already loaded HF state_dict (vision_model.* keys)
+
+
+class BatchFeature(dict):
+    """Minimal stand-in for transformers.BatchFeature: a dict with `.to(device)` and attribute access."""
+
+    def to(self, device=None, *args, **kwargs):
+        return BatchFeature({k: (v.to(device, *args, **kwargs) if torch.is_tensor(v) else v) for k, v in self.items()})
+
+    def __getattr__(self, name):
+        try:
+            return self[name]
+        except KeyError as exc:
+            raise AttributeError(name) from exc
+
+
+def _to_uint8_hwc(image) -> np.ndarray:
+    """PIL image / numpy array / tensor -> uint8 [H,W,3] (`convert_rgb` + `pil_to_tensor` of the HF processor)."""
+    if hasattr(image, "convert"):  # PIL
+        return np.asarray(image.convert("RGB"), dtype=np.uint8)
+    arr = image.detach().cpu().numpy() if torch.is_tensor(image) else np.asarray(image)
+    if arr.dtype != np.uint8 or arr.ndim != 3 or arr.shape[-1] != 3:
+        raise ValueError("images must be PIL RGB images or uint8 [H,W,3] arrays")
+    return arr
+
+
+class GvlSiglipProcessor:
+    """`AutoProcessor` seam: `processor(images=[...], return_tensors="pt") -> {"pixel_values": fp32 [B,3,S,S]}`.
+
+    The result lives on the GPU already (the reference moves it there right after, :477) and is bit-identical
+    to HF SiglipImageProcessor's CPU output for the same `resample` / mean / std."""
+
+    def __init__(self, size: int, resample: int, image_mean, image_std, device: torch.device):
+        self.size = {"height": size, "width": size}
+        self.resample, self.image_mean, self.image_std = resample, tuple(image_mean), tuple(image_std)
+        self.device = device
+
+    def __call__(self, images=None, return_tensors: str = "pt", **kwargs) -> BatchFeature:
+        if images is None:
+            raise ValueError("images is required")
+        if not isinstance(images, (list, tuple)):
+            images = [images]
+        arrays = [_to_uint8_hwc(im) for im in images]
+        s = self.size["height"]
+        outs = []
+        # frames of equal shape go through one launch (HF groups by shape the same way)
+        i = 0
+        while i < len(arrays):
+            j = i
+            while j < len(arrays) and arrays[j].shape == arrays[i].shape:
+                j += 1
+            batch = torch.from_numpy(np.stack(arrays[i:j])).to(self.device, non_blocking=False)
+            outs.append(ops.preprocess(batch, s, s, self.resample, self.image_mean, self.image_std,
+                                       layout=ops.LAYOUT_F32_CHW))
+            i = j
+        pv = outs[0] if len(outs) == 1 else torch.cat(outs, 0)
+        return BatchFeature({"pixel_values": pv})
+
+
+class GvlSiglipModel:
+    """`AutoModel` seam: `.device`, `.eval()`, `.get_image_features(pixel_values=...) -> Tensor [B, D]` (the
+    transformers-4.57 return type the reference's `.squeeze(0)` expects, :483)."""
+
+    def __init__(self, pack: SiglipPack):
+        self.pack = pack
+        self.spec = pack.spec
+        self.device = pack.device
+        self.dtype = torch.bfloat16
+        self._workspace: Optional[torch.Tensor] = None
+
+    def eval(self):
+        return self
+
+    def _ws(self, batch: int) -> torch.Tensor:
+        need = self.pack.workspace_bytes(batch)
+        if self._workspace is None or self._workspace.numel() < need:
+            self._workspace = torch.empty(need, dtype=torch.uint8, device=self.device)
+        return self._workspace
+
+    def forward_patches(self, patches: torch.Tensor) -> torch.Tensor:
+        return ops.siglip_forward(self.pack, patches, workspace=self._ws(patches.shape[0] // self.spec.tokens))
+
+    def get_image_features(self, pixel_values: torch.Tensor = None, **kwargs) -> torch.Tensor:
+        if pixel_values is None:
+            raise ValueError("pixel_values is required")
+        pv = pixel_values.to(self.device, torch.float32)
+        if pv.shape[-1] != self.spec.image or pv.shape[-2] != self.spec.image:
+            raise RuntimeError(f"pixel_values must be {self.spec.image}x{self.spec.image} (fixed position embedding)")
+        return self.forward_patches(ops.patchify(pv, self.spec.patch, self.spec.patch_ld))
+
+
+def _load_state_dict(model_name: str) -> dict:
+    """A local HF checkpoint directory or file (safetensors / torch).  There is no hub access."""
+    path = model_name
+    if os.path.isdir(path):
+        for cand in ("model.safetensors", "pytorch_model.bin"):
+            if os.path.exists(os.path.join(path, cand)):
+                path = os.path.join(path, cand)
+                break
+    if not os.path.isfile(path):
+        raise RuntimeError(
+            f"cannot load SigLIP weights '{model_name}': not a local checkpoint (no network in this build). Pass a "
+            "local path, NaFlexConfig.state_dict, or NaFlexConfig.synthetic_seed for random-init weights.")
+    if path.endswith(".safetensors"):
+        from safetensors.torch import load_file
+        return load_file(path)
+    return torch.load(path, map_location="cpu", weights_only=True)
+
+
+class SigLIPEncoder:
+    """Lazy loader with the reference's attribute seam (`_model`, `_processor`, `_load_model`)."""
+
+    def __init__(self, config: NaFlexConfig):
+        self.config = config
+        self._model: Optional[GvlSiglipModel] = None
+        self._processor: Optional[GvlSiglipProcessor] = None
+
+    def _load_model(self) -> None:
+        if self._model is not None:
+            return
+        cfg = self.config
+        device = torch.device(cfg.device if cfg.device != "cuda" else "cuda:0")
+        if device.type != "cuda":
+            raise RuntimeError("SigLIPEncoder runs on a CUDA (sm_100a) device only; there is no CPU fallback")
+        if cfg.state_dict is not None:
+            sd = cfg.state_dict
+        elif cfg.synthetic_seed is not None:
+            sd = None
+        else:
+            sd = _load_state_dict(cfg.model_name)
+        spec = SiglipVisionSpec.so400m() if sd is None else spec_from_state_dict(sd, cfg.base_resolution)
+        if sd is None:
+            sd = synth_siglip_state_dict(spec, cfg.synthetic_seed)
+        logger.info("Loading SigLIP encoder: %s (%d layers, hidden %d)", cfg.model_name, spec.layers, spec.hidden)
+        self._model = GvlSiglipModel(SiglipPack(sd, spec, device))
+        self._processor = GvlSiglipProcessor(spec.image, cfg.resample, cfg.image_mean, cfg.image_std, device)
+
+    def forward(self, pixel_values: torch.Tensor):
+        """(sequence_output, pooled_output) like the reference's `SigLIPEncoder.forward` (:246-289)."""
+        self._load_model()
+        m = self._model
+        patches = ops.patchify(pixel_values.to(m.device, torch.float32), m.spec.patch, m.spec.patch_ld)
+        pooled, tokens = ops.siglip_forward(m.pack, patches, workspace=m._ws(pixel_values.shape[0]), return_tokens=True)
+        return tokens.view(pixel_values.shape[0], m.spec.tokens, m.spec.hidden), pooled
+
+    __call__ = forward
+
+
+def spec_from_state_dict(sd: dict, image: int = 384) -> SiglipVisionSpec:
+    pre = "vision_model." if any(k.startswith("vision_model.") for k in sd) else ""
+    w = sd[pre + "embeddings.patch_embedding.weight"]
+    hidden, patch = w.shape[0], w.shape[-1]
+    tokens = sd[pre + "embeddings.position_embedding.weight"].shape[0]
+    grid = int(round(tokens ** 0.5))
+    layers = 1 + max(int(k[len(pre):].split(".")[2]) for k in sd if k.startswith(pre + "encoder.layers."))
+    inter = sd[pre + "encoder.layers.0.mlp.fc1.weight"].shape[0]
+    # so400m: 1152 / 16 heads = 72; other SigLIP towers use head dim 64
+    heads = hidden // 72 if hidden % 72 == 0 else hidden // 64
+    img = image if image // patch == grid else grid * patch
+    return SiglipVisionSpec(hidden=hidden, intermediate=inter, layers=layers, heads=heads, image=img, patch=patch)
+
+
+class SigLIPSemanticEncoder:
+    """Main interface (reference :370-638), hot-path subset."""
+
+    def __init__(self, config: Optional[NaFlexConfig] = None, device: Optional[str] = None):
+        self.config = config or NaFlexConfig()
+        if device:
+            self.config.device = device
+        self.encoder = SigLIPEncoder(self.config)
+        logger.info("SigLIPSemanticEncoder initialized with device=%s", self.config.device)
+
+    # ---- the reference's per-frame entry ----------------------------------------------------------
+    def encode_image(self, image) -> torch.Tensor:
+        """PIL image -> embedding (embedding_dim,) bf16 on the device; same call sequence as the reference
+        (:462-483): processor -> `.to(model.device)` -> `get_image_features(**inputs)` under no_grad."""
+        self.encoder._load_model()
+        inputs = self.encoder._processor(images=[image], return_tensors="pt").to(self.encoder._model.device)
+        with torch.no_grad():
+            embedding = self.encoder._model.get_image_features(**inputs)
+        return embedding.squeeze(0)
+
+    # ---- batched fast entry -----------------------------------------------------------------------
+    def encode_frames(self, frames) -> torch.Tensor:
+        """uint8 frames [B,H,W,3] (tensor on any device, or numpy) -> embeddings bf16 [B, D] on the device.
+        One fused resize/normalize/patchify launch + one tower pass per `config.batch_size` frames."""
+        self.encoder._load_model()
+        m = self.encoder._model
+        t = torch.as_tensor(frames)
+        if t.dtype != torch.uint8 or t.dim() != 4 or t.shape[-1] != 3:
+            raise ValueError("frames must be uint8 [B,H,W,3]")
+        t = t.to(m.device).contiguous()
+        outs = []
+        bs = max(1, int(self.config.batch_size))
+        for i in range(0, t.shape[0], bs):
+            patches = ops.preprocess(t[i:i + bs], m.spec.image, m.spec.image, self.config.resample, self.config.image_mean,
+                                     self.config.image_std, layout=ops.LAYOUT_BF16_PATCH, patch=m.spec.patch,
+                                     ld=m.spec.patch_ld)
+            outs.append(m.forward_patches(patches))
+        return outs[0] if len(outs) == 1 else torch.cat(outs, 0)
+
+    def encode_masked_regions(self, *args, **kwargs):
+        raise NotImplementedError(
+            "encode_masked_regions (NaFlex masked-region path) is outside this build's scope: it is not reached from "
+            "scripts/extract_features.py and fails in the reference with the fixed 729-position checkpoint")
+
+    # ---- similarity (reference :604-638) ------------------------------------------------------------
+    def compute_similarity(self, emb1: SemanticEmbedding, emb2: SemanticEmbedding) -> float:
+        e1 = emb1.embedding.to(self._sim_device(emb1.embedding)).to(torch.bfloat16).reshape(1, -1).contiguous()
+        e2 = emb2.embedding.to(e1.device).to(torch.bfloat16).reshape(1, -1).contiguous()
+        scores, _ = ops.topk_cosine(e2, e1, 1, eps=1e-8)
+        return float(scores.item())
+
+    def find_similar_regions(self, query: SemanticEmbedding, candidates: Sequence[SemanticEmbedding],
+                             top_k: int = 5) -> list[tuple[SemanticEmbedding, float]]:
+        """Cosine similarity of `query` to every candidate, best first; equal scores keep the lower index first
+        (the reference's stable `list.sort(reverse=True)`, :637)."""
+        if not candidates:
+            return []
+        dev = self._sim_device(query.embedding)
+        index = torch.stack([c.embedding.to(dev).to(torch.bfloat16).reshape(-1) for c in candidates]).contiguous()
+        q = query.embedding.to(dev).to(torch.bfloat16).reshape(1, -1).contiguous()
+        out = []
+        k_total = min(top_k, len(candidates))
+        # the selection kernel returns up to 64 per call
+        scores, idx = ops.topk_cosine(index, q, min(k_total, 64), eps=1e-8)
+        for s, i in zip(scores[0].tolist(), idx[0].tolist()):
+            out.append((candidates[i], float(s)))
+        if k_total > 64:
+            raise RuntimeError("find_similar_regions: top_k > 64 is not supported by the selection kernel")
+        return out
+
+    def _sim_device(self, t: torch.Tensor) -> torch.device:
+        if t.is_cuda:
+            return t.device
+        d = torch.device(self.config.device if self.config.device != "cuda" else "cuda:0")
+        if d.type != "cuda":
+            raise RuntimeError("similarity search runs on the GPU only (no CPU fallback)")
+        return d
+
+
+def create_siglip_encoder(model_name: str = "google/siglip2-so400m-patch14-384", device: str = "cuda",
+                          preserve_aspect_ratio: bool = True, **kwargs) -> SigLIPSemanticEncoder:
+    """Factory with the reference's signature (:641-662)."""
+    return SigLIPSemanticEncoder(NaFlexConfig(model_name=model_name, device=device,
+                                              preserve_aspect_ratio=preserve_aspect_ratio, **kwargs))

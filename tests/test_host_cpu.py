@@ -1,0 +1,123 @@
+"""Host-side logic that needs no GPU: drop-in construction and error behaviour, cache layouts, sharding."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from gameplay_vision_llm_b200 import feature_cache as fc
+from gameplay_vision_llm_b200.pipeline import shard_range
+from gameplay_vision_llm_b200.projector import MultiModalProjector, ProjectorBank, ReasoningCoreConfig
+from gameplay_vision_llm_b200.siglip_semantic_encoder import (BatchFeature, NaFlexConfig, SigLIPSemanticEncoder,
+                                                               spec_from_state_dict)
+from gameplay_vision_llm_b200.weights import SiglipVisionSpec, synth_projector_state_dict, synth_siglip_state_dict
+
+
+def test_flops_per_frame_matches_baseline_md():
+    assert SiglipVisionSpec.so400m().flops_per_frame() == 670_389_441_536
+    assert SiglipVisionSpec.so400m().flops_per_frame(None) == 670_389_441_536 - 42_991_616
+
+
+def test_naflex_config_defaults_match_reference():
+    c = NaFlexConfig()
+    assert (c.model_name, c.device, c.dtype, c.base_resolution, c.embedding_dim, c.batch_size) == (
+        "google/siglip2-so400m-patch14-384", "cuda", torch.bfloat16, 384, 1152, 16)
+
+
+def test_encoder_raises_instead_of_placeholder():
+    enc = SigLIPSemanticEncoder(NaFlexConfig(device="cpu", synthetic_seed=0))
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        enc.encode_image(np.zeros((8, 8, 3), np.uint8))
+    enc2 = SigLIPSemanticEncoder(NaFlexConfig(model_name="/nonexistent/checkpoint", device="cuda"))
+    with pytest.raises(RuntimeError):
+        enc2.encoder._load_model()
+    with pytest.raises(NotImplementedError):
+        enc.encode_masked_regions(None, [])
+
+
+def test_spec_from_state_dict_roundtrip():
+    spec = SiglipVisionSpec.tiny()
+    assert spec_from_state_dict(synth_siglip_state_dict(spec, 0), 384) == spec
+
+
+def test_batchfeature_seam():
+    bf = BatchFeature({"pixel_values": torch.zeros(1, 3, 4, 4)})
+    moved = bf.to("cpu")
+    assert set(dict(**moved)) == {"pixel_values"} and moved.pixel_values.shape == (1, 3, 4, 4)
+
+
+def test_projector_bank_construction_and_state_dict_layout(tmp_path):
+    bank = ProjectorBank(ReasoningCoreConfig(device="cpu")).to("cpu")  # what the reference's tests construct
+    assert bank.siglip_proj.net[0].weight.shape == (4096, 1152)
+    assert bank.videomae_proj.net[0].weight.shape == (4096, 768)
+    assert bank.video_proj.net[0].weight.shape == (4096, 1408) and bank.audio_proj.net[0].weight.shape == (4096, 1024)
+    p = tmp_path / "projector_weights.pt"
+    bank.save_weights(str(p))
+    sd = torch.load(p, weights_only=False)
+    assert set(sd) == {"siglip", "videomae", "audio", "video"}
+    assert set(sd["siglip"]) == {"net.0.weight", "net.0.bias", "net.2.weight", "net.2.bias"}
+    bank2 = ProjectorBank(ReasoningCoreConfig(device="cpu"))
+    bank2.load_weights(str(p))
+    assert torch.equal(bank2.siglip_proj.net[2].weight, bank.siglip_proj.net[2].weight)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        bank.project_region(torch.zeros(2, 1152))
+
+
+def test_projector_accepts_reference_state_dict():
+    m = MultiModalProjector(1152, 4096)
+    m.load_state_dict(synth_projector_state_dict(1152, 4096, 1))
+    assert list(m.state_dict()) == ["net.0.weight", "net.0.bias", "net.2.weight", "net.2.bias"]
+
+
+def test_shard_range_covers_timeline_in_order():
+    for n, w in ((3600, 8), (3600, 1), (10, 4), (72000, 8), (5, 8)):
+        spans = [shard_range(n, r, w) for r in range(w)]
+        assert spans[0][0] == 0 and spans[-1][1] == n
+        for (a, b), (c, d) in zip(spans, spans[1:]):
+            assert b == c and a <= b
+    lo, hi = shard_range(100, 1, 3, align=16)
+    assert lo % 16 == 0
+
+
+def test_feature_cache_layout_and_eviction(tmp_path):
+    video = tmp_path / "clip.mp4"
+    video.write_bytes(os.urandom(3 * 1024 * 1024 + 17))
+    cache = fc.FeatureCache(str(tmp_path / "cache"), max_cache_size_gb=1.0)
+    h = cache._get_video_hash(str(video))
+    assert len(h) == 16 and cache._get_cache_path(str(video)).name == f"clip_{h}.pt"
+    # same recipe as the reference: sha256(str(size) + first MiB + last MiB)
+    import hashlib
+    raw = video.read_bytes()
+    want = hashlib.sha256(str(len(raw)).encode() + raw[: 1 << 20] + raw[-(1 << 20):]).hexdigest()[:16]
+    assert h == want
+    emb = torch.randn(3, 1152).to(torch.bfloat16)
+    payload = {"siglip": fc.siglip_cache_entries([0.0, 1.0, 2.0], emb), "videomae": []}
+    assert not cache.has_features(str(video))
+    cache.save_features(str(video), payload)
+    assert cache.has_features(str(video))
+    fresh = fc.FeatureCache(str(tmp_path / "cache"))
+    got = fresh.load_features(str(video))
+    assert got["siglip"][1]["timestamp"] == 1.0 and torch.equal(got["siglip"][2]["embedding"], emb[2])
+    # corrupt file -> unlinked, None
+    fresh2 = fc.FeatureCache(str(tmp_path / "cache"))
+    fresh2._get_cache_path(str(video)).write_bytes(b"garbage")
+    assert fresh2.load_features(str(video)) is None and not fresh2._get_cache_path(str(video)).exists()
+    assert cache._get_video_hash(str(tmp_path / "missing.mp4")) == ""
+
+
+def test_embeddings_pt_and_npz_layouts(tmp_path):
+    emb = torch.randn(4, 1152).to(torch.bfloat16)
+    recs = fc.siglip_embedding_records([0.0, 1.0, 2.0, 3.0], emb)
+    assert recs[0]["entity_type"] == "full_frame" and recs[3]["embedding_shape"] == [1152]
+    data = fc.write_embeddings_pt(str(tmp_path / "v_embeddings.pt"), recs)
+    back = torch.load(tmp_path / "v_embeddings.pt", weights_only=False)
+    assert set(back) >= {"siglip", "videomae", "wav2vec2", "hico", "visual_events", "audio_transcripts"}
+    assert back["siglip"][2]["shape"] == [1152] and back["siglip"][2]["embedding"].dtype == torch.bfloat16
+    stacked = torch.stack([e["embedding"] for e in back["siglip"]])  # what demo_projector_inference.py does
+    assert stacked.shape == (4, 1152) and data["siglip"][0]["timestamp"] == 0.0
+    video = tmp_path / "v.mp4"
+    video.write_bytes(b"x" * 100)
+    d = fc.write_perception_npz(str(tmp_path / "pc"), str(video), siglip=emb, timestamps=np.arange(4.0),
+                                frame_indices=np.arange(4))
+    z = np.load(os.path.join(d, "siglip.npz"))
+    assert z["embeddings"].shape == (4, 1152) and z["embeddings"].dtype == np.float32

@@ -4,24 +4,30 @@
 //
 // Both operands are K-major bf16, so a [rows x 64] box lands in shared memory as rows of 128 bytes —
 // exactly one SWIZZLE_128B atom wide — and the same bytes are addressed by the UMMA shared-memory
-// descriptor.  One CTA per SM loops over output tiles (m-major order: the CTAs running at the same
-// time share one A panel and the whole weight stays in the 126 MB L2):
+// descriptor.  The grid is one 2-CTA cluster per SM pair; a cluster loops over "super tiles" of
+// 256 x BN outputs (m-major order: clusters running at the same time share A panels, the whole weight
+// stays in the 126 MB L2).  Inside a cluster the two CTAs own the two 128-row halves and SHARE the
+// weight tile: each CTA fetches one half of the BN x 64 weight box and TMA-multicasts it into both
+// CTAs' shared memory, which cuts the L2->SM operand traffic per FLOP by a third (v1 of this kernel was
+// operand-feed bound: 15 TB/s of L2 reads at 64 % tensor-pipe utilisation, profiles/r01_v1_*).
 //
-//   warp 0    TMA producer: A box 128x64, W box BNx64 per stage, mbarrier expect_tx
-//   warp 1    tcgen05.mma issuer (one elected lane): 4 x (128 x BN x 16) per stage, accumulating in TMEM;
-//             tcgen05.commit releases the smem stage / publishes the accumulator
-//   warps 2-5 epilogue: tcgen05.ld 32 lanes x 32 columns -> bias, GELU, residual -> bf16/fp32 stores
+//   warp 0     TMA producer: own A box 128x64 + half W box (BN/2)x64 multicast to the pair, expect_tx
+//   warp 1     tcgen05.mma issuer (one elected lane): 4 x (128 x BN x 16) per stage into TMEM;
+//              tcgen05.commit (multicast) releases the stage in BOTH CTAs / publishes the accumulator
+//   warps 2-9  epilogue, two warps per TMEM lane quadrant (each takes half of the columns):
+//              tcgen05.ld 32 lanes x 32 columns -> bias, GELU, residual -> bf16/fp32 stores
 //
 // The accumulator is double-buffered in TMEM (2 x BN columns), so the epilogue of tile i overlaps the
-// MMAs of tile i+1.  Ragged M / N / K edges are handled by TMA (out-of-bounds reads are zero) and by
-// row / column guards on the stores.
+// MMAs of tile i+1.  Ragged M / N / K edges are handled by TMA (out-of-bounds reads are zero, including
+// the phantom second half of an odd last super tile) and by row / column guards on the stores.
 #include "common.cuh"
 
 namespace gvl {
 
 constexpr int BM = 128;
 constexpr int BK = 64;
-constexpr int kGemmThreads = 192;
+constexpr int kEpiWarps = 8;
+constexpr int kGemmThreads = 64 + kEpiWarps * 32;
 constexpr int A_STAGE_BYTES = BM * BK * 2;
 
 struct GemmParams {
@@ -34,35 +40,33 @@ struct GemmParams {
     int out_f32;
     int M, N, K;
     int act;
-    int m_tiles, n_tiles, k_blocks;
+    int m_pairs, n_tiles, k_blocks;
 };
 
 template <int BN>
 struct GemmCfg {
     static constexpr int B_STAGE_BYTES = BN * BK * 2;
+    static constexpr int B_HALF_BYTES = B_STAGE_BYTES / 2;
     static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
     static constexpr int STAGES = BN == 256 ? 4 : (BN == 192 ? 5 : 6);
     static constexpr int TMEM_COLS = (2 * BN <= 256) ? 256 : 512;
-    static constexpr int BIAS_BYTES = 4 * BN * 4;
+    static constexpr int CHUNKS = BN / 32;               // 32-column epilogue chunks per tile
+    static constexpr int CHUNKS_PER_WARP = CHUNKS / 2;   // two epilogue warps share a lane quadrant
+    static constexpr int BIAS_BYTES = kEpiWarps * CHUNKS_PER_WARP * 32 * 4;
     static constexpr int BAR_BYTES = (2 * STAGES + 4) * 8 + 16;
     static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + BIAS_BYTES + BAR_BYTES + 1024 /*alignment slack*/;
 };
 
-template <int ACT>
-__device__ __forceinline__ float apply_act(float x) {
-    if (ACT == GVL_ACT_GELU_TANH) return gelu_tanh_f(x);
-    if (ACT == GVL_ACT_GELU_ERF) return gelu_erf_f(x);
-    return x;
-}
-
 template <int BN>
-__global__ void __launch_bounds__(kGemmThreads, 1)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
 gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                          const GemmParams p) {
     using Cfg = GemmCfg<BN>;
     constexpr int STAGES = Cfg::STAGES;
 
     extern __shared__ uint8_t smem_raw[];
+    // the dynamic smem window starts at the same CTA-relative offset in both CTAs of the cluster, so the
+    // aligned carve-up below is identical in both (required by the multicast writes / remote arrives)
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* sA = smem;
     uint8_t* sB = smem + STAGES * A_STAGE_BYTES;
@@ -76,40 +80,44 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
+    const uint32_t cta_rank = cluster_ctarank();
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmA);
         tma_prefetch_desc(&tmB);
         for (int s = 0; s < STAGES; ++s) {
-            mbar_init(&full_bar[s], 1);
-            mbar_init(&empty_bar[s], 1);
+            mbar_init(&full_bar[s], 1);   // own producer's arrive.expect_tx (+ tx bytes from both CTAs' TMA)
+            mbar_init(&empty_bar[s], 2);  // one tcgen05.commit from each CTA of the pair
         }
         for (int s = 0; s < 2; ++s) {
             mbar_init(&tmem_full_bar[s], 1);
-            mbar_init(&tmem_empty_bar[s], 4);
+            mbar_init(&tmem_empty_bar[s], kEpiWarps);
         }
         fence_barrier_init();
     }
     if (warp == 1) tmem_alloc<Cfg::TMEM_COLS>(tmem_ptr_smem);
     tcgen05_fence_before();
-    __syncthreads();
+    cluster_sync_all();  // barriers of both CTAs initialised before any multicast / remote arrive
     tcgen05_fence_after();
     const uint32_t tmem_base = *tmem_ptr_smem;
 
-    const int num_tiles = p.m_tiles * p.n_tiles;
+    const int num_super = p.m_pairs * p.n_tiles;
+    const int cluster_id = blockIdx.x >> 1;
+    const int num_clusters = gridDim.x >> 1;
 
     if (warp == 0) {
         // ===== TMA producer =====
         if (elect_one()) {
             int stage = 0;
             uint32_t phase = 0;
-            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-                const int m_blk = tile / p.n_tiles, n_blk = tile % p.n_tiles;
+            for (int st = cluster_id; st < num_super; st += num_clusters) {
+                const int m_blk = (st / p.n_tiles) * 2 + (int)cta_rank, n_blk = st % p.n_tiles;
                 for (int kb = 0; kb < p.k_blocks; ++kb) {
-                    mbar_wait(&empty_bar[stage], phase ^ 1);
+                    mbar_wait(&empty_bar[stage], phase ^ 1);  // both CTAs are done reading this stage
                     mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
                     tma_load_2d(sA + stage * A_STAGE_BYTES, &tmA, &full_bar[stage], kb * BK, m_blk * BM);
-                    tma_load_2d(sB + stage * Cfg::B_STAGE_BYTES, &tmB, &full_bar[stage], kb * BK, n_blk * BN);
+                    tma_load_2d_mc(sB + stage * Cfg::B_STAGE_BYTES + cta_rank * Cfg::B_HALF_BYTES, &tmB, &full_bar[stage],
+                                   kb * BK, n_blk * BN + (int)cta_rank * (BN / 2), (uint16_t)0x3);
                     if (++stage == STAGES) {
                         stage = 0;
                         phase ^= 1;
@@ -125,7 +133,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
             uint32_t phase = 0;
             int as = 0;
             uint32_t aphase = 0;
-            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+            for (int st = cluster_id; st < num_super; st += num_clusters) {
                 mbar_wait(&tmem_empty_bar[as], aphase ^ 1);
                 tcgen05_fence_after();
                 const uint32_t d_tmem = tmem_base + (uint32_t)(as * BN);
@@ -139,7 +147,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
                         umma_bf16_ss(d_tmem, umma_desc_sw128(a_addr + k * 32), umma_desc_sw128(b_addr + k * 32), idesc,
                                      (uint32_t)((kb | k) != 0));
                     }
-                    umma_commit(&empty_bar[stage]);
+                    umma_commit_mc(&empty_bar[stage], (uint16_t)0x3);  // frees the stage in both CTAs
                     if (++stage == STAGES) {
                         stage = 0;
                         phase ^= 1;
@@ -152,50 +160,69 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
         }
     } else {
         // ===== epilogue warps =====
-        const int q = warp & 3;  // TMEM lane quadrant this warp may read
-        float* myBias = sBias + q * BN;
+        const int ew = warp - 2;
+        const int q = warp & 3;   // TMEM lane quadrant this warp may read
+        const int half = ew >> 2; // which half of the tile's column chunks
+        float* myBias = sBias + ew * (Cfg::CHUNKS_PER_WARP * 32);
         int as = 0;
         uint32_t aphase = 0;
-        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-            const int m_blk = tile / p.n_tiles, n_blk = tile % p.n_tiles;
-            const int n0 = n_blk * BN;
-            for (int c = lane; c < BN; c += 32) myBias[c] = (p.bias != nullptr && n0 + c < p.N) ? p.bias[n0 + c] : 0.0f;
+        for (int st = cluster_id; st < num_super; st += num_clusters) {
+            const int m_blk = (st / p.n_tiles) * 2 + (int)cta_rank, n_blk = st % p.n_tiles;
+            const int n0 = n_blk * BN + half * (Cfg::CHUNKS_PER_WARP * 32);
+            for (int c = lane; c < Cfg::CHUNKS_PER_WARP * 32; c += 32)
+                myBias[c] = (p.bias != nullptr && n0 + c < p.N) ? p.bias[n0 + c] : 0.0f;
             __syncwarp();
             mbar_wait(&tmem_full_bar[as], aphase);
             tcgen05_fence_after();
             const int row = m_blk * BM + q * 32 + lane;
             const bool row_ok = row < p.M;
             const int rrow = p.res_row_mod > 0 ? (row % p.res_row_mod) : row;
-            const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BN);
+            const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) +
+                                    (uint32_t)(as * BN + half * (Cfg::CHUNKS_PER_WARP * 32));
+            const bool has_res = p.residual != nullptr;
 #pragma unroll 1
-            for (int chunk = 0; chunk < BN / 32; ++chunk) {
+            for (int chunk = 0; chunk < Cfg::CHUNKS_PER_WARP; ++chunk) {
                 const int c0 = n0 + chunk * 32;
                 if (c0 >= p.N) break;  // warp-uniform
                 uint32_t r[32];
                 tmem_ld_32x32(t_addr + (uint32_t)(chunk * 32), r);
+                // residual loads are issued before waiting on TMEM so their latency overlaps it
+                uint4 rv[4];
+                if (has_res && row_ok) {
+                    const __nv_bfloat16* rp = p.residual + (size_t)rrow * p.ldr + c0;
+#pragma unroll
+                    for (int g = 0; g < 4; ++g)
+                        rv[g] = (c0 + g * 8 < p.N) ? *reinterpret_cast<const uint4*>(rp + g * 8) : make_uint4(0, 0, 0, 0);
+                }
                 tmem_ld_wait();
                 if (row_ok) {
 #pragma unroll
                     for (int g = 0; g < 4; ++g) {
                         const int col = c0 + g * 8;
                         if (col < p.N) {
+                            const float4 b0 = *reinterpret_cast<const float4*>(myBias + chunk * 32 + g * 8);
+                            const float4 b1 = *reinterpret_cast<const float4*>(myBias + chunk * 32 + g * 8 + 4);
                             float v[8];
+                            v[0] = __uint_as_float(r[g * 8 + 0]) + b0.x;
+                            v[1] = __uint_as_float(r[g * 8 + 1]) + b0.y;
+                            v[2] = __uint_as_float(r[g * 8 + 2]) + b0.z;
+                            v[3] = __uint_as_float(r[g * 8 + 3]) + b0.w;
+                            v[4] = __uint_as_float(r[g * 8 + 4]) + b1.x;
+                            v[5] = __uint_as_float(r[g * 8 + 5]) + b1.y;
+                            v[6] = __uint_as_float(r[g * 8 + 6]) + b1.z;
+                            v[7] = __uint_as_float(r[g * 8 + 7]) + b1.w;
+                            if (p.act == GVL_ACT_GELU_TANH) {
 #pragma unroll
-                            for (int j = 0; j < 8; ++j) {
-                                float x = __uint_as_float(r[g * 8 + j]) + myBias[chunk * 32 + g * 8 + j];
-                                if (p.act == GVL_ACT_GELU_TANH)
-                                    x = gelu_tanh_f(x);
-                                else if (p.act == GVL_ACT_GELU_ERF)
-                                    x = gelu_erf_f(x);
-                                v[j] = x;
+                                for (int j = 0; j < 8; ++j) v[j] = gelu_tanh_f(v[j]);
+                            } else if (p.act == GVL_ACT_GELU_ERF) {
+#pragma unroll
+                                for (int j = 0; j < 8; ++j) v[j] = gelu_erf_f(v[j]);
                             }
-                            if (p.residual != nullptr) {
-                                const uint4 rv =
-                                    *reinterpret_cast<const uint4*>(p.residual + (size_t)rrow * p.ldr + col);
-                                v[0] += bf16_lo(rv.x); v[1] += bf16_hi(rv.x);
-                                v[2] += bf16_lo(rv.y); v[3] += bf16_hi(rv.y);
-                                v[4] += bf16_lo(rv.z); v[5] += bf16_hi(rv.z);
-                                v[6] += bf16_lo(rv.w); v[7] += bf16_hi(rv.w);
+                            if (has_res) {
+                                v[0] += bf16_lo(rv[g].x); v[1] += bf16_hi(rv[g].x);
+                                v[2] += bf16_lo(rv[g].y); v[3] += bf16_hi(rv[g].y);
+                                v[4] += bf16_lo(rv[g].z); v[5] += bf16_hi(rv[g].z);
+                                v[6] += bf16_lo(rv[g].w); v[7] += bf16_hi(rv[g].w);
                             }
                             if (p.out_f32) {
                                 float* o = reinterpret_cast<float*>(p.out) + (size_t)row * p.ldo + col;
@@ -222,8 +249,9 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
         }
     }
 
+    // no CTA may exit while its peer can still multicast into its smem or arrive on its barriers
     tcgen05_fence_before();
-    __syncthreads();
+    cluster_sync_all();
     if (warp == 1) {
         tcgen05_fence_after();
         tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
@@ -235,10 +263,11 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const Gem
     using Cfg = GemmCfg<BN>;
     GVL_CUDA(cudaFuncSetAttribute(gemm_bf16_tcgen05_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   Cfg::SMEM_BYTES));
-    const int tiles = p.m_tiles * p.n_tiles;
-    const int grid = tiles < sm_count() ? tiles : sm_count();
+    const int super_tiles = p.m_pairs * p.n_tiles;
+    const int max_clusters = sm_count() / 2;
+    const int clusters = super_tiles < max_clusters ? super_tiles : max_clusters;
     ProfScope prof(GVL_K_GEMM, 2.0 * p.M * (double)p.N * p.K, stream);
-    gemm_bf16_tcgen05_kernel<BN><<<grid, kGemmThreads, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, p);
+    gemm_bf16_tcgen05_kernel<BN><<<2 * clusters, kGemmThreads, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, p);
     GVL_LAUNCH_CHECK("gemm_bf16_tcgen05_kernel");
     return 0;
 }
@@ -289,14 +318,14 @@ extern "C" int gvl_gemm_bf16(const void* A, int lda, const void* W, int ldw, con
     p.N = N;
     p.K = K;
     p.act = act;
-    p.m_tiles = (M + BM - 1) / BM;
+    p.m_pairs = ((M + BM - 1) / BM + 1) / 2;
     p.n_tiles = (N + bn - 1) / bn;
     p.k_blocks = (K + BK - 1) / BK;
 
     CUtensorMap tmA, tmB;
     int rc = make_tmap_2d_bf16(&tmA, A, (uint64_t)M, (uint64_t)K, (uint64_t)lda, BM, BK, true);
     if (rc) return rc;
-    rc = make_tmap_2d_bf16(&tmB, W, (uint64_t)N, (uint64_t)K, (uint64_t)ldw, (uint32_t)bn, BK, true);
+    rc = make_tmap_2d_bf16(&tmB, W, (uint64_t)N, (uint64_t)K, (uint64_t)ldw, (uint32_t)(bn / 2), BK, true);
     if (rc) return rc;
 
     cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);

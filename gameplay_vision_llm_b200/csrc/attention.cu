@@ -9,6 +9,8 @@
 // TODO(round 2): move S/O accumulators to TMEM with tcgen05.mma (this version uses the legacy HMMA path).
 #include "common.cuh"
 
+#include <cstdlib>
+
 namespace gvl {
 
 constexpr int ATT_BQ = 128;  // query rows per CTA (8 warps x 16)
@@ -336,6 +338,9 @@ static int launch_attention(const void* qkv, void* out, int B, int T, int H, flo
     return 0;
 }
 
+template <int HD>
+int launch_attention_tc(const void* qkv, void* out, int B, int T, int H, float scale, cudaStream_t s);  // attention_tc.cu
+
 }  // namespace gvl
 
 extern "C" int gvl_attention_bf16(const void* qkv, void* out, int B, int T, int H, int hd, float scale, void* stream) {
@@ -345,8 +350,18 @@ extern "C" int gvl_attention_bf16(const void* qkv, void* out, int B, int T, int 
     GVL_CHECK_ARG(B <= 65535 && H <= 65535, "gvl_attention_bf16: B/H exceed grid limits");
     GVL_CHECK_ARG((uintptr_t)qkv % 16 == 0 && (uintptr_t)out % 16 == 0, "gvl_attention_bf16: misaligned pointer");
     cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
-    if (hd == 72) return launch_attention<72>(qkv, out, B, T, H, scale, s);
-    if (hd == 64) return launch_attention<64>(qkv, out, B, T, H, scale, s);
+    // GVL_ATTN_LEGACY=1 selects the round-1 mma.sync kernel (kept for A/B measurements only)
+    static const bool legacy = [] {
+        const char* e = getenv("GVL_ATTN_LEGACY");
+        return e && e[0] == '1';
+    }();
+    if (!legacy) {
+        if (hd == 72) return launch_attention_tc<72>(qkv, out, B, T, H, scale, s);
+        if (hd == 64) return launch_attention_tc<64>(qkv, out, B, T, H, scale, s);
+    } else {
+        if (hd == 72) return launch_attention<72>(qkv, out, B, T, H, scale, s);
+        if (hd == 64) return launch_attention<64>(qkv, out, B, T, H, scale, s);
+    }
     set_error("gvl_attention_bf16: unsupported head dim %d (built for 72 and 64)", hd);
     return 1;
 }

@@ -135,6 +135,8 @@ def main_ours(args) -> None:
     dev = torch.device("cuda", local_rank)
     _lib.check(_lib.lib().gvl_check_device(local_rank), "gvl_check_device")
     if world > 1:
+        if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"  # keep stdout to the single JSON line
         dist.init_process_group("nccl", device_id=dev)
 
     peaks = load_peaks()

@@ -1,0 +1,104 @@
+"""The reference-facing classes on the GPU: same call sequence as the reference's scripts, checked against
+the oracle; plus the streaming pipeline and the timeline index."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from gameplay_vision_llm_b200 import ops, synth  # noqa: E402
+from gameplay_vision_llm_b200.pipeline import EmbeddingPipeline, pinned_batches  # noqa: E402
+from gameplay_vision_llm_b200.projector import ProjectorBank, ReasoningCoreConfig, project_embeddings  # noqa: E402
+from gameplay_vision_llm_b200.siglip_semantic_encoder import (NaFlexConfig, SemanticEmbedding,  # noqa: E402
+                                                               SigLIPSemanticEncoder)
+from gameplay_vision_llm_b200.timeline import TimelineEmbeddingIndex  # noqa: E402
+from gameplay_vision_llm_b200.weights import (SiglipVisionSpec, synth_projector_state_dict,  # noqa: E402
+                                                synth_siglip_state_dict)
+from oracle import preprocess_ref, siglip_ref  # noqa: E402
+
+DEV = "cuda:0"
+SPEC = SiglipVisionSpec(hidden=216, intermediate=400, layers=2, heads=3, image=140, patch=14)
+
+
+def _encoder():
+    sd = synth_siglip_state_dict(SPEC, seed=0)
+    enc = SigLIPSemanticEncoder(NaFlexConfig(device=DEV, state_dict=sd, base_resolution=SPEC.image, embedding_dim=SPEC.hidden,
+                                             batch_size=4))
+    return enc, sd
+
+
+def test_encode_image_reference_call_sequence():
+    from PIL import Image
+    enc, sd = _encoder()
+    frames = synth.scene_frames_np(0, 3, 270, 480)
+    want = siglip_ref.vision_forward(sd, torch.from_numpy(preprocess_ref.pixel_values(frames, SPEC.image, SPEC.image, 2)),
+                                     SPEC.heads, SPEC.patch, SPEC.eps)
+    for i in range(3):
+        emb = enc.encode_image(Image.fromarray(frames[i]))          # extract_features.py:595
+        assert emb.shape == (SPEC.hidden,) and emb.dtype == torch.bfloat16 and emb.is_cuda
+        cos = torch.nn.functional.cosine_similarity(emb.float().cpu(), want[i], dim=0)
+        assert cos > 0.999
+    # the inner seam the reference uses (:474-481)
+    inputs = enc.encoder._processor(images=[Image.fromarray(frames[0])], return_tensors="pt").to(enc.encoder._model.device)
+    pv = inputs["pixel_values"]
+    assert np.array_equal(pv.cpu().numpy(), preprocess_ref.pixel_values(frames[:1], SPEC.image, SPEC.image, 2))
+    batched = enc.encode_frames(frames)
+    single = torch.stack([enc.encode_image(Image.fromarray(f)) for f in frames])
+    assert torch.nn.functional.cosine_similarity(batched.float(), single.float(), dim=1).min() > 0.9999
+
+
+def test_find_similar_regions_order_and_ties():
+    enc, _ = _encoder()
+    g = torch.Generator().manual_seed(0)
+    vecs = torch.randn(20, SPEC.hidden, generator=g)
+    vecs[7] = vecs[2]
+    cands = [SemanticEmbedding(embedding=v.to(torch.bfloat16), entity_id=str(i)) for i, v in enumerate(vecs)]
+    res = enc.find_similar_regions(cands[2], cands, top_k=5)
+    assert [r[0].entity_id for r in res[:2]] == ["2", "7"] and abs(res[0][1] - 1.0) < 1e-3
+    want = siglip_ref.cosine_topk(vecs.to(torch.bfloat16).float().numpy(), vecs[2:3].to(torch.bfloat16).float().numpy(), 5)[1][0]
+    assert [int(r[0].entity_id) for r in res] == want.tolist()
+    assert abs(enc.compute_similarity(cands[0], cands[1]) -
+               float(torch.nn.functional.cosine_similarity(vecs[0].bfloat16().float(), vecs[1].bfloat16().float(), dim=0))) < 1e-4
+
+
+def test_projector_bank_matches_reference_module(tmp_path):
+    bank = ProjectorBank(ReasoningCoreConfig(device=DEV))
+    bank.siglip_proj.load_state_dict(synth_projector_state_dict(1152, 4096, 1))
+    bank.videomae_proj.load_state_dict(synth_projector_state_dict(768, 4096, 2))
+    path = tmp_path / "projector_weights.pt"
+    bank.save_weights(str(path))
+    bank2 = ProjectorBank(ReasoningCoreConfig(device=DEV)).to(DEV)
+    bank2.load_weights(str(path))
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn(10, 1152, generator=g).to(torch.bfloat16)          # embeddings as stored in *_embeddings.pt
+    out = project_embeddings(bank2, region_embeddings=x, videomae_embeddings=torch.randn(2, 5, 768, generator=g))
+    assert out["siglip"].shape == (10, 4096) and out["siglip"].dtype == torch.float32
+    assert out["videomae"].shape == (2, 5, 4096)
+    want = siglip_ref.projector_forward(synth_projector_state_dict(1152, 4096, 1), x.float())
+    cos = torch.nn.functional.cosine_similarity(out["siglip"].cpu(), want, dim=1)
+    assert cos.min() > 0.9999 and (out["siglip"].cpu() - want).abs().max() < 0.05
+
+
+def test_pipeline_stream_equals_resident_and_index_search():
+    sd = synth_siglip_state_dict(SPEC, seed=0)
+    psd = synth_projector_state_dict(SPEC.hidden, 512, seed=1)
+    pipe = EmbeddingPipeline(sd, psd, SPEC, DEV, batch=4)
+    frames = synth.scene_frames_np(0, 10, 180, 320, frames_per_scene=5)
+    idx = TimelineEmbeddingIndex(10, 512, fps=2.0, device=DEV)
+    pipe.embed_resident(torch.from_numpy(frames).to(DEV), index=idx.local_rows())
+    resident = idx.index().clone()
+    host_out = torch.empty((10, 512), dtype=torch.bfloat16).pin_memory()
+    streamed = torch.zeros((10, 512), dtype=torch.bfloat16, device=DEV)
+    n = pipe.embed_stream(pinned_batches(frames, 4), streamed, host_out)
+    torch.cuda.synchronize()
+    assert n == 10 and torch.equal(streamed, resident) and torch.equal(host_out, resident.cpu())
+    # oracle embeddings -> same nearest neighbours
+    want = siglip_ref.projector_forward(psd, siglip_ref.vision_forward(
+        sd, torch.from_numpy(preprocess_ref.pixel_values(frames, SPEC.image, SPEC.image, 2)), SPEC.heads, SPEC.patch, SPEC.eps))
+    assert torch.nn.functional.cosine_similarity(resident.float().cpu(), want, dim=1).min() > 0.999
+    scores, ids = idx.search(resident[3:4], top_k=3)
+    assert ids[0, 0].item() == 3
+    hits = idx.retrieve_by_semantic(resident[6], top_k=2)
+    assert hits[0][0] == 3.0  # frame 6 at 2 fps
+    sel, emb = idx.window(2.0, window_sec=1.0)
+    assert sel.tolist() == [3, 4, 5] and emb.shape == (3, 512)

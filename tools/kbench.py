@@ -1,0 +1,88 @@
+#!/usr/bin/env python
+"""Per-kernel microbenchmark at the batch-64 shapes of the headline workload (CUDA events, isolated kernels).
+Not the bench of record (bench.py is) — a tuning aid: python tools/kbench.py [gemm|attn|ln|pre|all]"""
+import math
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from gameplay_vision_llm_b200 import ops, synth  # noqa: E402
+
+DEV = "cuda:0"
+M = 64 * 729
+
+
+def timeit(fn, reps=20, warm=3):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / reps
+
+
+def gemm_cases():
+    shapes = [("patch", M, 1152, 592, 0, 729), ("qkv", M, 3456, 1152, 0, 0), ("out", M, 1152, 1152, 0, 1),
+              ("fc1", M, 4304, 1152, 1, 0), ("fc2", M, 1152, 4304, 0, 1), ("kv", M, 2304, 1152, 0, 0),
+              ("proj1", 64, 4096, 1152, 2, 0), ("proj2", 64, 4096, 4096, 0, 0)]
+    tot = 0.0
+    for name, m, n, k, act, res in shapes:
+        a = torch.randn(m, k, device=DEV).to(torch.bfloat16)
+        w = (torch.randn(n, k, device=DEV) / math.sqrt(k)).to(torch.bfloat16)
+        bias = torch.randn(n, device=DEV)
+        out = torch.empty(m, n, device=DEV, dtype=torch.bfloat16)
+        r, mod = None, 0
+        if res == 1:
+            r = out  # in-place residual like the tower
+        elif res > 1:
+            r, mod = torch.randn(res, n, device=DEV).to(torch.bfloat16), res
+        ms = timeit(lambda: ops.gemm(a, w, bias, r, res_row_mod=mod, act=act, out=out))
+        tf = 2.0 * m * n * k / ms / 1e9
+        per_step = {"qkv": 27, "out": 27, "fc1": 27, "fc2": 27}.get(name, 1)
+        tot += ms * per_step
+        print(f"gemm {name:6s} M={m} N={n} K={k} act={act} res={res}: {ms*1e3:8.1f} us  {tf:7.1f} TFLOP/s  (x{per_step}/step)")
+    print(f"gemm total per step ~ {tot:.2f} ms")
+
+
+def attn_case():
+    B, T, H, hd = 64, 729, 16, 72
+    qkv = torch.randn(B * T, 3 * H * hd, device=DEV).to(torch.bfloat16)
+    out = torch.empty(B * T, H * hd, device=DEV, dtype=torch.bfloat16)
+    ms = timeit(lambda: ops.attention(qkv, B, T, H, hd, out=out))
+    print(f"attention B={B} T={T}: {ms*1e3:.1f} us  {4.0*B*H*T*T*hd/ms/1e9:.1f} TFLOP/s  (x27/step = {ms*27:.2f} ms)")
+
+
+def ln_case():
+    x = torch.randn(M, 1152, device=DEV).to(torch.bfloat16)
+    g = torch.ones(1152, device=DEV)
+    b = torch.zeros(1152, device=DEV)
+    out = torch.empty_like(x)
+    ms = timeit(lambda: ops.layernorm(x, g, b, 1e-6, out=out))
+    print(f"layernorm {M}x1152: {ms*1e3:.1f} us  {M*1152*4/ms/1e6:.0f} GB/s  (x56/step = {ms*56:.2f} ms)")
+
+
+def pre_case():
+    frames = synth.noise_frames(64, seed=1).to(DEV)
+    out = torch.empty(64 * 729, 592, device=DEV, dtype=torch.bfloat16)
+    for rs in (2, 3):
+        ms = timeit(lambda: ops.preprocess(frames, 384, 384, rs, out=out))
+        gb = 64 * (1080 * 1920 * 3 + 729 * 588 * 2) / ms / 1e6
+        print(f"preprocess 64x1080p rs={rs}: {ms*1e3:.1f} us  {gb:.0f} GB/s ({gb/6552.6*100:.1f}% of measured HBM peak)")
+
+
+if __name__ == "__main__":
+    what = sys.argv[1] if len(sys.argv) > 1 else "all"
+    if what in ("gemm", "all"):
+        gemm_cases()
+    if what in ("attn", "all"):
+        attn_case()
+    if what in ("ln", "all"):
+        ln_case()
+    if what in ("pre", "all"):
+        pre_case()

@@ -6,15 +6,21 @@
 // then `(float(u8) - sub) / div` in fp32 (IEEE division) and, for the patch layout, a round-to-nearest
 // bf16 cast scattered into im2col order for the stride-P patch-embedding GEMM.
 //
-// One CTA produces a tile of TY output rows x TX output columns.  The source rows it needs stream
-// through a double-buffered cp.async staging ring in groups of RG rows (16-byte coalesced loads; each
-// frame byte is fetched from HBM once, the ~7 % halo between vertically adjacent tiles hits L2); the
-// horizontal pass writes the uint8 intermediate to shared memory, the vertical pass reads it back
-// and the finished tile is staged in its final element type so the global stores are full
-// contiguous segments (whole 592-element patch rows / whole CHW row pieces).
+// Two kernels.  `preprocess_planar_kernel` is the production path (v2): a CTA owns a tile of TY x TX
+// output pixels; the source rows stream through registers in groups of 8 (three coalesced 128-bit loads
+// per 16-pixel chunk, next group in flight while the current one is filtered), are de-interleaved with
+// byte permutes into channel-planar shared memory, and both filter passes run on IDP.2A (two u8 x s16
+// taps per instruction): every thread keeps its column's taps as zero-padded 16-bit weight pairs aligned
+// to the 32-bit words it loads, so no per-byte extraction is ever needed.  The horizontal pass writes
+// the uint8 intermediate TRANSPOSED (four consecutive source rows of one column per word), which makes
+// the vertical taps contiguous bytes as well.  Finished bands are staged in their final element type
+// and leave as full contiguous segments (whole 592-element patch rows / whole CHW row pieces).
+// `preprocess_kernel` (v1, one byte per shared-memory load) remains as the fallback for geometries
+// outside the planar kernel's limits and for A/B runs (GVL_PRE_LEGACY=1).
 #include "common.cuh"
 
 #include <cmath>
+#include <cstdlib>
 #include <map>
 #include <mutex>
 #include <tuple>
@@ -100,6 +106,10 @@ struct DevTables {
     int max_seg_bytes = 0;  // staging bytes per source row (16-byte aligned span) over all x tiles
     int max_rows = 0;       // source rows per y tile
     int TX = 0, TY = 0;
+    // planar kernel
+    float* lut = nullptr;   // [3][256] (u8 - sub) / div, built per call signature below
+    int nch_max = 0;        // 16-pixel chunks per staged source row (max over x tiles)
+    int max_hsize = 0, max_vsize = 0;  // largest tap count actually used per axis
 };
 
 static std::mutex g_tab_mu;
@@ -141,7 +151,10 @@ static int get_tables(int H, int W, int eff_h, int eff_w, int out_h, int out_w, 
         const int c_lo = th.xmin[x0], c_hi = th.xmin[x1 - 1] + th.xsize[x1 - 1];
         const int a_lo = (3 * c_lo) & ~15, a_hi = (3 * c_hi + 15) & ~15;
         d.max_seg_bytes = std::max(d.max_seg_bytes, a_hi - a_lo);
+        d.nch_max = std::max(d.nch_max, ((c_hi + 15) >> 4) - (c_lo >> 4));
     }
+    for (int i = 0; i < eff_w; ++i) d.max_hsize = std::max(d.max_hsize, (int)th.xsize[i]);
+    for (int i = 0; i < eff_h; ++i) d.max_vsize = std::max(d.max_vsize, (int)tv.xsize[i]);
     for (int y0 = 0; y0 < eff_h; y0 += TY) {
         const int y1 = std::min(y0 + TY, eff_h);
         d.max_rows = std::max(d.max_rows, tv.xmin[y1 - 1] + tv.xsize[y1 - 1] - tv.xmin[y0]);
@@ -358,6 +371,455 @@ preprocess_kernel(const PreParams p) {
     }
 }
 
+// ---- v2: planar / IDP.2A kernel ---------------------------------------------------------------------
+
+constexpr int PL_THREADS = 256;
+constexpr int PL_RG = 8;  // source rows per staged group = two row quads of the transposed intermediate
+
+struct PlanarParams {
+    const uint8_t* frames;
+    int B, H, W;
+    int out_h, out_w, eff_h, eff_w;
+    const int32_t *h_min, *h_size, *v_min, *v_size;
+    const int16_t *h_w, *v_w;
+    int h_taps, v_taps, h_prec, v_prec;
+    int TX, TY, VB;   // tile and band (rows finished per staging round) sizes
+    int pw;           // bytes per planar staged row (multiple of 16)
+    int g_max;        // row quads of the intermediate
+    int stage_bytes;  // max(planar staging, output band staging), multiple of 16
+    const float* lut; // [3][256]
+    void* out;
+    int layout, patch, ld, gh, gw;
+    int fast_rows;    // every frame row starts 16-byte aligned and W % 16 == 0
+};
+
+__device__ __forceinline__ int dp2a_lo(uint32_t w2, uint32_t px4, int acc) {
+    int d;
+    asm("dp2a.lo.s32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(w2), "r"(px4), "r"(acc));
+    return d;
+}
+__device__ __forceinline__ int dp2a_hi(uint32_t w2, uint32_t px4, int acc) {
+    int d;
+    asm("dp2a.hi.s32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(w2), "r"(px4), "r"(acc));
+    return d;
+}
+// {sat_u8(v3), sat_u8(v2), sat_u8(v1), sat_u8(v0)} with v0 in the low byte
+__device__ __forceinline__ uint32_t pack4_sat_u8(int v0, int v1, int v2, int v3) {
+    uint32_t hi, d;
+    asm("cvt.pack.sat.u8.s32.b32 %0, %1, %2, %3;" : "=r"(hi) : "r"(v3), "r"(v2), "r"(0));
+    asm("cvt.pack.sat.u8.s32.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(v1), "r"(v0), "r"(hi));
+    return d;
+}
+// 16-bit weight pair for the bytes (2h, 2h+1) of a word run whose first tap sits at byte `o`
+__device__ __forceinline__ uint32_t weight_pair(const int16_t* w, int taps, int h, int o) {
+    const int j0 = 2 * h - o, j1 = j0 + 1;
+    const uint32_t lo = (j0 >= 0 && j0 < taps) ? (uint32_t)(uint16_t)w[j0] : 0u;
+    const uint32_t hi = (j1 >= 0 && j1 < taps) ? (uint32_t)(uint16_t)w[j1] : 0u;
+    return lo | (hi << 16);
+}
+
+// 16 interleaved RGB pixels (12 words) -> 4 words per colour plane
+__device__ __forceinline__ void deinterleave16(const uint32_t (&a)[12], uint4& r, uint4& g, uint4& b) {
+    uint32_t rr[4], gg[4], bb[4];
+#pragma unroll
+    for (int m = 0; m < 4; ++m) {
+        const uint32_t w0 = a[3 * m], w1 = a[3 * m + 1], w2 = a[3 * m + 2];
+        rr[m] = __byte_perm(__byte_perm(w0, w1, 0x0630), w2, 0x5210);  // bytes 0,3,6,9
+        gg[m] = __byte_perm(__byte_perm(w0, w1, 0x0741), w2, 0x6210);  // bytes 1,4,7,10
+        bb[m] = __byte_perm(__byte_perm(w0, w1, 0x0052), w2, 0x7410);  // bytes 2,5,8,11
+    }
+    r = make_uint4(rr[0], rr[1], rr[2], rr[3]);
+    g = make_uint4(gg[0], gg[1], gg[2], gg[3]);
+    b = make_uint4(bb[0], bb[1], bb[2], bb[3]);
+}
+
+// Horizontal filter of one row quad (4 staged rows x 3 planes) for this thread's column.  NWE = words per
+// window actually loaded; SKIP_FIRST / SKIP_LAST drop the IDP of the first low / last high byte pair when it
+// is zero-weighted for the whole warp (all three are warp-uniform, chosen once per warp at start-up).
+template <int NWMAX, int NWE, bool SKIP_FIRST, bool SKIP_LAST>
+__device__ __forceinline__ void h_pass_quad(const uint8_t* src_base, int pw, const uint32_t (&wq)[2 * NWMAX],
+                                            int h_round, int h_prec, uint32_t* dst, int plane_stride) {
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        int u[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const uint32_t* src = reinterpret_cast<const uint32_t*>(src_base + (size_t)(c * PL_RG + i) * pw);
+            int acc = h_round;
+#pragma unroll
+            for (int k = 0; k < NWE; ++k) {
+                const uint32_t w = src[k];
+                if (!(SKIP_FIRST && k == 0)) acc = dp2a_lo(wq[2 * k], w, acc);
+                if (!(SKIP_LAST && k == NWE - 1)) acc = dp2a_hi(wq[2 * k + 1], w, acc);
+            }
+            u[i] = acc >> h_prec;
+        }
+        dst[c * plane_stride] = pack4_sat_u8(u[0], u[1], u[2], u[3]);
+    }
+}
+
+// NW / NWV: 32-bit words a thread loads per horizontal / vertical window (o + taps <= 4 * words);
+// LPT: 16-pixel chunks a thread fetches per staged group.
+// FAST: every row is 16-byte aligned with W % 16 == 0 (128-bit loads only; the guarded byte loader is compiled out).
+template <int NW, int NWV, int LPT, bool FAST>
+__global__ void __launch_bounds__(PL_THREADS, FAST ? 3 : 2)
+preprocess_planar_kernel(const PlanarParams p) {
+    extern __shared__ __align__(16) uint8_t pl_smem[];
+    // [stage: 3 planes x 8 rows x pw | aliased by the output band] [sH: 3 x g_max x 4 x 32 words (+ NWV quads pad)]
+    // [sWV: TY x 2*NWV weight pairs] [sVinfo: TY first quads] [lut: 768 floats]
+    uint8_t* sP = pl_smem;
+    uint8_t* sOut = pl_smem;
+    uint32_t* sH = reinterpret_cast<uint32_t*>(pl_smem + p.stage_bytes);
+    uint32_t* sWV = sH + (3 * p.g_max + NWV) * 128;
+    int* sVinfo = reinterpret_cast<int*>(sWV + p.TY * 2 * NWV);
+    float* sLut = reinterpret_cast<float*>(sVinfo + p.TY);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int b = blockIdx.z;
+    const int x0 = blockIdx.x * p.TX, x1 = min(x0 + p.TX, p.eff_w);
+    const int y0 = blockIdx.y * p.TY, y1 = min(y0 + p.TY, p.eff_h);
+    const int ntx = x1 - x0, nty = y1 - y0;
+    const int r_lo = p.v_min[y0];
+    const int r_hi = p.v_min[y1 - 1] + p.v_size[y1 - 1];
+    const int nrows = r_hi - r_lo;
+    const int c_lo = p.h_min[x0];
+    const int c_hi = p.h_min[x1 - 1] + p.h_size[x1 - 1];
+    const int chunk0 = c_lo >> 4;                     // first 16-pixel chunk of the staged rows
+    const int nch = ((c_hi + 15) >> 4) - chunk0;      // chunks per staged row
+    const int row_chunks = p.W >> 4;                  // whole chunks in a frame row
+    const size_t row_bytes = (size_t)p.W * 3;
+    const uint8_t* fbase = p.frames + ((size_t)b * p.H + r_lo) * row_bytes;
+
+    // ---- per-thread horizontal setup: column x0 + 4*lane + (warp & 3), row quad (warp >> 2) of each group
+    const int xm = warp & 3, slot = warp >> 2;
+    const int xx = 4 * lane + xm;
+    const bool x_active = xx < ntx;
+    uint32_t wq[2 * NW];
+    int my_off, variant;
+    {
+        const int x = x0 + (x_active ? xx : 0);
+        const int rel = p.h_min[x] - (chunk0 << 4);
+        int o = rel & 3;
+        my_off = rel & ~3;
+        const int16_t* wp = p.h_w + (size_t)x * p.h_taps;
+        // first / last byte pair with a non-zero weight, over the active lanes of the warp
+        int first = 2 * NW, last = 0;
+#pragma unroll
+        for (int h = 0; h < 2 * NW; ++h) {
+            if (x_active && weight_pair(wp, p.h_taps, h, o) != 0u) {
+                first = min(first, h);
+                last = h + 1;
+            }
+        }
+        first = __reduce_min_sync(0xffffffffu, first);
+        last = __reduce_max_sync(0xffffffffu, last);
+        if (last <= first) first = 0, last = 1;  // warp without columns
+        const int skip = first >> 1;              // leading words nobody needs
+        my_off += 4 * skip;
+        o -= 4 * skip;
+        const int hb = first - 2 * skip, he = last - 2 * skip;
+        const int nwe = (he + 1) >> 1 <= NW - 1 ? NW - 1 : NW;
+        variant = (nwe == NW ? 4 : 0) | (hb == 1 ? 2 : 0) | (he <= 2 * nwe - 1 ? 1 : 0);
+#pragma unroll
+        for (int h = 0; h < 2 * NW; ++h) wq[h] = weight_pair(wp, p.h_taps, h, o);
+    }
+    // ---- vertical tables for this tile's rows
+    for (int i = tid; i < nty * 2 * NWV; i += PL_THREADS) {
+        const int yy = i / (2 * NWV), h = i - yy * (2 * NWV);
+        const int y = y0 + yy;
+        sWV[i] = weight_pair(p.v_w + (size_t)y * p.v_taps, p.v_taps, h, (p.v_min[y] - r_lo) & 3);
+    }
+    for (int yy = tid; yy < nty; yy += PL_THREADS) sVinfo[yy] = (p.v_min[y0 + yy] - r_lo) >> 2;
+    for (int i = tid; i < 768; i += PL_THREADS) sLut[i] = p.lut[i];
+
+    // ---- staging: global -> registers (next group) while the current group is filtered.  A thread owns the same
+    // LPT (row, chunk) slots of every group, so the address arithmetic is done once.
+    uint32_t pre[LPT][12];
+    int src_off[LPT], dst_off[LPT], item_rr[LPT];
+#pragma unroll
+    for (int k = 0; k < LPT; ++k) {
+        const int i = tid + k * PL_THREADS;
+        const int rr = i / nch, ch = i - rr * nch;
+        const bool ok = rr < PL_RG && (!FAST || chunk0 + ch < row_chunks);
+        item_rr[k] = ok ? rr : 0x40000000;  // never < rows_left
+        src_off[k] = rr * (int)row_bytes + (chunk0 + ch) * 48;
+        dst_off[k] = rr * p.pw + ch * 16;
+    }
+    auto fetch_group = [&](int g) {
+        const int rows_left = min(nrows, p.H - r_lo) - g * PL_RG;  // staged rows of this group that exist
+        const uint8_t* gbase = fbase + (size_t)g * PL_RG * row_bytes;
+#pragma unroll
+        for (int k = 0; k < LPT; ++k) {
+            const bool in = item_rr[k] < rows_left;
+            if (FAST) {
+                uint4 v0 = make_uint4(0, 0, 0, 0), v1 = v0, v2 = v0;
+                if (in) {
+                    const uint4* src = reinterpret_cast<const uint4*>(gbase + src_off[k]);
+                    v0 = __ldg(src);
+                    v1 = __ldg(src + 1);
+                    v2 = __ldg(src + 2);
+                }
+                pre[k][0] = v0.x; pre[k][1] = v0.y; pre[k][2] = v0.z; pre[k][3] = v0.w;
+                pre[k][4] = v1.x; pre[k][5] = v1.y; pre[k][6] = v1.z; pre[k][7] = v1.w;
+                pre[k][8] = v2.x; pre[k][9] = v2.y; pre[k][10] = v2.z; pre[k][11] = v2.w;
+            } else {
+                // ragged / unaligned rows: guarded byte loads (zero beyond the row end)
+                const int rr = item_rr[k];
+                const uint8_t* rowp = gbase + (size_t)(in ? rr : 0) * row_bytes;
+                const int byte0 = src_off[k] - rr * (int)row_bytes;
+#pragma unroll
+                for (int w = 0; w < 12; ++w) {
+                    uint32_t v = 0;
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        const int o = byte0 + 4 * w + e;
+                        if (in && o < (int)row_bytes) v |= (uint32_t)rowp[o] << (8 * e);
+                    }
+                    pre[k][w] = v;
+                }
+            }
+        }
+    };
+    auto store_group = [&]() {
+#pragma unroll
+        for (int k = 0; k < LPT; ++k) {
+            if (tid + k * PL_THREADS < PL_RG * nch) {
+                uint4 r, g, bl;
+                deinterleave16(pre[k], r, g, bl);
+                uint8_t* d = sP + dst_off[k];
+                *reinterpret_cast<uint4*>(d) = r;
+                *reinterpret_cast<uint4*>(d + (size_t)PL_RG * p.pw) = g;
+                *reinterpret_cast<uint4*>(d + (size_t)2 * PL_RG * p.pw) = bl;
+            }
+        }
+    };
+
+    const int ngroups = (nrows + PL_RG - 1) / PL_RG;
+    const int h_round = 1 << (p.h_prec - 1);
+    const uint8_t* h_src = sP + (size_t)slot * 4 * p.pw + my_off;
+    uint32_t* h_dst = sH + (slot * 4 + xm) * 32 + lane;
+    const int plane_stride = p.g_max * 128;
+    fetch_group(0);
+    store_group();
+    __syncthreads();
+    for (int g = 0; g < ngroups; ++g) {
+        if (g + 1 < ngroups) fetch_group(g + 1);
+        // horizontal pass: 4 rows x 3 planes of this thread's column -> one transposed word per plane
+        if (x_active) {
+            uint32_t* dst = h_dst + g * 256;
+            switch (variant) {
+                case 0: h_pass_quad<NW, NW - 1, false, false>(h_src, p.pw, wq, h_round, p.h_prec, dst, plane_stride); break;
+                case 1: h_pass_quad<NW, NW - 1, false, true>(h_src, p.pw, wq, h_round, p.h_prec, dst, plane_stride); break;
+                case 2: h_pass_quad<NW, NW - 1, true, false>(h_src, p.pw, wq, h_round, p.h_prec, dst, plane_stride); break;
+                case 3: h_pass_quad<NW, NW - 1, true, true>(h_src, p.pw, wq, h_round, p.h_prec, dst, plane_stride); break;
+                case 4: h_pass_quad<NW, NW, false, false>(h_src, p.pw, wq, h_round, p.h_prec, dst, plane_stride); break;
+                case 5: h_pass_quad<NW, NW, false, true>(h_src, p.pw, wq, h_round, p.h_prec, dst, plane_stride); break;
+                case 6: h_pass_quad<NW, NW, true, false>(h_src, p.pw, wq, h_round, p.h_prec, dst, plane_stride); break;
+                default: h_pass_quad<NW, NW, true, true>(h_src, p.pw, wq, h_round, p.h_prec, dst, plane_stride); break;
+            }
+        }
+        __syncthreads();  // everyone is done reading the staged group
+        if (g + 1 < ngroups) store_group();
+        __syncthreads();
+    }
+
+    // ---- vertical pass + normalise, one band (VB output rows) at a time through the staging buffer.
+    // Work item = (column 4*lane + xm, output row): all three planes share the row's weight pairs; the two
+    // warps with the same xm alternate rows.  Words beyond a row's window carry zero weights (the pad quads
+    // after sH keep the reads in bounds), so the tap loop needs no guards.
+    const int v_round = 1 << (p.v_prec - 1);
+    const int PP = p.patch * p.patch;
+    const bool patch_layout = p.layout == GVL_LAYOUT_BF16_PATCH;
+    const int my_o = patch_layout ? (xx / p.patch) * p.ld + xx % p.patch : xx;
+    const int c_stride = patch_layout ? PP : p.VB * p.TX;  // elements between planes inside the staged band
+    const int y_stride = patch_layout ? p.patch : p.TX;
+    const int esize = p.layout == GVL_LAYOUT_U8_CHW ? 1 : (p.layout == GVL_LAYOUT_F32_CHW ? 4 : 2);
+    const uint32_t* v_src = sH + xm * 32 + lane;
+    for (int band0 = 0; band0 < nty; band0 += p.VB) {
+        const int nb = min(p.VB, nty - band0);
+        if (patch_layout) {
+            const int padc = p.ld - 3 * PP, npatch = ntx / p.patch;
+            for (int i = tid; i < npatch * padc; i += PL_THREADS)
+                reinterpret_cast<uint16_t*>(sOut)[(size_t)(i / padc) * p.ld + 3 * PP + i % padc] = 0;
+        }
+        for (int yl = slot; yl < nb; yl += 2) {
+            uint32_t wv[2 * NWV];
+#pragma unroll
+            for (int h = 0; h < 2 * NWV; ++h) wv[h] = sWV[(band0 + yl) * 2 * NWV + h];
+            const uint32_t* src = v_src + sVinfo[band0 + yl] * 128;
+            int u[3];
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                int acc = v_round;
+#pragma unroll
+                for (int k = 0; k < NWV; ++k) {
+                    const uint32_t w = src[c * plane_stride + k * 128];
+                    acc = dp2a_lo(wv[2 * k], w, acc);
+                    acc = dp2a_hi(wv[2 * k + 1], w, acc);
+                }
+                u[c] = min(max(acc >> p.v_prec, 0), 255);
+            }
+            if (x_active) {
+                const int o = my_o + yl * y_stride;
+#pragma unroll
+                for (int c = 0; c < 3; ++c) {
+                    if (p.layout == GVL_LAYOUT_U8_CHW)
+                        sOut[o + c * c_stride] = (uint8_t)u[c];
+                    else if (p.layout == GVL_LAYOUT_F32_CHW)
+                        reinterpret_cast<float*>(sOut)[o + c * c_stride] = sLut[c * 256 + u[c]];
+                    else
+                        reinterpret_cast<__nv_bfloat16*>(sOut)[o + c * c_stride] = __float2bfloat16_rn(sLut[c * 256 + u[c]]);
+                }
+            }
+        }
+        __syncthreads();
+        // copy-out: contiguous segments
+        if (patch_layout) {
+            const size_t prow = ((size_t)b * p.gh + (y0 + band0) / p.patch) * p.gw + x0 / p.patch;
+            uint4* gdst = reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(p.out) + prow * p.ld * 2);
+            const int n16 = (ntx / p.patch) * p.ld * 2 / 16;
+            for (int i = tid; i < n16; i += PL_THREADS) gdst[i] = reinterpret_cast<const uint4*>(sOut)[i];
+        } else {
+            const int seg_bytes = ntx * esize;
+            for (int s = warp; s < 3 * nb; s += PL_THREADS / 32) {
+                const int c = s / nb, yl = s - c * nb;
+                uint8_t* gdst = reinterpret_cast<uint8_t*>(p.out) +
+                                ((((size_t)b * 3 + c) * p.out_h + y0 + band0 + yl) * p.out_w + x0) * esize;
+                const uint8_t* ssrc = sOut + (size_t)((c * p.VB + yl) * p.TX) * esize;
+                if (((reinterpret_cast<uintptr_t>(gdst) | (uintptr_t)seg_bytes | reinterpret_cast<uintptr_t>(ssrc)) & 15) == 0) {
+                    for (int i = lane; i < (seg_bytes >> 4); i += 32)
+                        reinterpret_cast<uint4*>(gdst)[i] = reinterpret_cast<const uint4*>(ssrc)[i];
+                } else {
+                    for (int i = lane; i < seg_bytes; i += 32) gdst[i] = ssrc[i];
+                }
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// (u8 - sub[c]) / div[c] in fp32 (IEEE division on the host), cached per (device, sub, div)
+static std::map<std::tuple<int, float, float, float, float, float, float>, float*> g_luts;
+static int get_lut(const float* sub, const float* div, float** out) {
+    int dev = 0;
+    GVL_CUDA(cudaGetDevice(&dev));
+    std::lock_guard<std::mutex> lk(g_tab_mu);
+    auto key = std::make_tuple(dev, sub[0], sub[1], sub[2], div[0], div[1], div[2]);
+    auto it = g_luts.find(key);
+    if (it != g_luts.end()) {
+        *out = it->second;
+        return 0;
+    }
+    std::vector<float> h(768);
+    for (int c = 0; c < 3; ++c)
+        for (int u = 0; u < 256; ++u) {
+            volatile float num = (float)u - sub[c];
+            volatile float q = num / div[c];
+            h[c * 256 + u] = q;
+        }
+    float* d = nullptr;
+    if (upload(h, &d)) return 2;
+    g_luts[key] = d;
+    *out = d;
+    return 0;
+}
+
+// returns -1 when the geometry is outside the planar kernel's limits (caller falls back to v1)
+static int launch_planar(const uint8_t* frames, int B, int H, int W, int out_h, int out_w, int resample,
+                         const float* h_sub, const float* h_div, void* out, int layout, int patch, int ld,
+                         cudaStream_t s) {
+    PlanarParams p;
+    memset(&p, 0, sizeof(p));
+    p.eff_h = out_h;
+    p.eff_w = out_w;
+    int TX = 128, VB = 8, ty_unit = 8, ty_mult = 4;
+    const int esize = layout == GVL_LAYOUT_U8_CHW ? 1 : (layout == GVL_LAYOUT_F32_CHW ? 4 : 2);
+    if (layout == GVL_LAYOUT_BF16_PATCH) {
+        p.gh = out_h / patch;
+        p.gw = out_w / patch;
+        p.eff_h = p.gh * patch;
+        p.eff_w = p.gw * patch;
+        TX = patch * (128 / patch);
+        VB = patch;
+        ty_unit = patch;
+        ty_mult = 3;
+    }
+    DevTables tb;
+    int nw = 0, nwv = 0, lpt = 0;
+    size_t smem = 0;
+    int TY = 0, pw = 0, g_max = 0, stage_bytes = 0;
+    for (; ty_mult >= 1; --ty_mult) {
+        TY = ty_unit * ty_mult;
+        int rc = get_tables(H, W, p.eff_h, p.eff_w, out_h, out_w, resample, TX, TY, tb);
+        if (rc) return rc;
+        nw = tb.max_hsize + 3 <= 16 ? 4 : (tb.max_hsize + 3 <= 24 ? 6 : (tb.max_hsize + 3 <= 32 ? 8 : 0));
+        nwv = tb.max_vsize + 3 <= 12 ? 3 : (tb.max_vsize + 3 <= 16 ? 4 : (tb.max_vsize + 3 <= 32 ? 8 : 0));
+        lpt = PL_RG * tb.nch_max <= 2 * PL_THREADS ? 2 : (PL_RG * tb.nch_max <= 3 * PL_THREADS ? 3 : 0);
+        if (!nw || !nwv || !lpt) return -1;
+        const bool fast_rows = W % 16 == 0 && (uintptr_t)frames % 16 == 0;
+        if (!fast_rows || (!(nw <= 4 && nwv <= 3 && lpt <= 2) && !(nw <= 6 && nwv <= 4 && lpt <= 2))) nw = 8, nwv = 8, lpt = 3;
+        else if (!(nw <= 4 && nwv <= 3)) nw = 6, nwv = 4;
+        pw = tb.nch_max * 16 + 32;
+        g_max = 2 * ((tb.max_rows + PL_RG - 1) / PL_RG);
+        const int band_bytes = layout == GVL_LAYOUT_BF16_PATCH ? (TX / patch) * ld * 2 : 3 * VB * TX * esize;
+        stage_bytes = (std::max(3 * PL_RG * pw, band_bytes) + 15) & ~15;
+        smem = (size_t)stage_bytes + (size_t)(3 * g_max + nwv) * 128 * 4 + (size_t)TY * 2 * nwv * 4 + (size_t)TY * 4 +
+               768 * 4;
+        if (smem <= 74 * 1024) break;  // three CTAs per SM
+    }
+    if (smem > 200 * 1024) return -1;
+    float* lut = nullptr;
+    int rc = get_lut(h_sub, h_div, &lut);
+    if (rc) return rc;
+    p.frames = frames;
+    p.B = B;
+    p.H = H;
+    p.W = W;
+    p.out_h = out_h;
+    p.out_w = out_w;
+    p.h_min = tb.h_min;
+    p.h_size = tb.h_size;
+    p.v_min = tb.v_min;
+    p.v_size = tb.v_size;
+    p.h_w = tb.h_w;
+    p.v_w = tb.v_w;
+    p.h_taps = tb.h_taps;
+    p.v_taps = tb.v_taps;
+    p.h_prec = tb.h_prec;
+    p.v_prec = tb.v_prec;
+    p.TX = TX;
+    p.TY = TY;
+    p.VB = VB;
+    p.pw = pw;
+    p.g_max = g_max;
+    p.stage_bytes = stage_bytes;
+    p.lut = lut;
+    p.out = out;
+    p.layout = layout;
+    p.patch = patch > 0 ? patch : 1;
+    p.ld = ld;
+    p.fast_rows = (W % 16 == 0 && (uintptr_t)frames % 16 == 0) ? 1 : 0;
+    dim3 grid((p.eff_w + TX - 1) / TX, (p.eff_h + TY - 1) / TY, B);
+    const double out_bytes = layout == GVL_LAYOUT_BF16_PATCH ? (double)p.gh * p.gw * 3 * patch * patch * 2
+                                                              : (double)3 * out_h * out_w * esize;
+    ProfScope prof(GVL_K_PREPROCESS, (double)B * ((double)H * W * 3 + out_bytes), s);
+    auto launch = [&](auto kernel) -> int {
+        GVL_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kernel<<<grid, PL_THREADS, smem, s>>>(p);
+        return 0;
+    };
+    if (p.fast_rows) {
+        if (nw == 4) rc = launch(preprocess_planar_kernel<4, 3, 2, true>);
+        else if (nw == 6) rc = launch(preprocess_planar_kernel<6, 4, 2, true>);
+        else rc = launch(preprocess_planar_kernel<8, 8, 3, true>);
+    } else {
+        rc = launch(preprocess_planar_kernel<8, 8, 3, false>);
+    }
+    if (rc) return rc;
+    GVL_LAUNCH_CHECK("preprocess_planar_kernel");
+    return 0;
+}
+
 // pixel_values fp32 [B,3,H,W] -> bf16 im2col rows (the drop-in `get_image_features(pixel_values=...)` seam).
 // One thread per 8 output elements (16-byte stores); reads are 4-byte, L1/L2 resident.
 __global__ void __launch_bounds__(256)
@@ -434,6 +896,20 @@ extern "C" int gvl_preprocess_u8(const uint8_t* frames, int B, int H, int W, int
     GVL_CHECK_ARG(layout >= 0 && layout <= 3, "gvl_preprocess_u8: bad layout %d", layout);
     GVL_CHECK_ARG(H >= out_h && W >= out_w, "gvl_preprocess_u8: only downscaling is supported (%dx%d -> %dx%d)", H, W,
                   out_h, out_w);
+    if (layout == GVL_LAYOUT_BF16_PATCH) {
+        GVL_CHECK_ARG(patch >= 4 && patch <= 32 && ld >= 3 * patch * patch && ld % 8 == 0,
+                      "gvl_preprocess_u8: bad patch/ld %d/%d", patch, ld);
+        GVL_CHECK_ARG((uintptr_t)out % 16 == 0, "gvl_preprocess_u8: output must be 16-byte aligned");
+        GVL_CHECK_ARG(out_h >= patch && out_w >= patch, "gvl_preprocess_u8: output smaller than one patch");
+    }
+    {
+        const char* legacy = getenv("GVL_PRE_LEGACY");
+        if (!(legacy && legacy[0] == '1')) {
+            const int prc = launch_planar(frames, B, H, W, out_h, out_w, resample, h_sub, h_div, out, layout, patch, ld,
+                                          reinterpret_cast<cudaStream_t>(stream));
+            if (prc != -1) return prc;
+        }
+    }
     PreParams p;
     memset(&p, 0, sizeof(p));
     int TX = 128, TY = 16;

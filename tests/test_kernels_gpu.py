@@ -132,7 +132,10 @@ def test_probe_attention():
 
 # --------------------------------------------------------------------------------------- preprocessing
 PRE_CASES = [(1080, 1920, 384, 384, 2), (1080, 1920, 384, 384, 3), (123, 211, 56, 56, 2), (270, 480, 96, 112, 3),
-             (720, 1280, 384, 384, 2), (1080, 1920, 224, 398, 2)]
+             (720, 1280, 384, 384, 2), (1080, 1920, 224, 398, 2),
+             (2160, 3840, 384, 384, 2),   # 4K: 20 horizontal taps -> widest planar-kernel instantiation
+             (1440, 2560, 384, 384, 3),   # bicubic 1440p: 27 horizontal taps
+             (384, 384, 384, 384, 2)]     # identity scale
 
 
 @pytest.mark.parametrize("H,W,oh,ow,rs", PRE_CASES)
@@ -160,6 +163,22 @@ def test_preprocess_layouts_bit_exact(H, W, size, rs):
     got_patch = ops.preprocess(dev_frames, size, size, rs, layout=ops.LAYOUT_BF16_PATCH, patch=14).cpu()
     assert got_patch.shape == want_patch.shape
     assert torch.equal(got_patch.view(torch.int16), want_patch.view(torch.int16)), "bf16 patches differ"
+
+
+def test_preprocess_rejects_out_of_range_geometry():
+    """A 16x downscale needs 35 horizontal taps: beyond both kernels' windows -> a clean error, not garbage."""
+    frames = synth.noise_frames(1, 400, 1000, seed=1).to(DEV)
+    with pytest.raises(RuntimeError, match="taps"):
+        ops.preprocess(frames, 37, 61, 2, layout=ops.LAYOUT_U8_CHW)
+
+
+def test_preprocess_legacy_kernel_matches(monkeypatch):
+    """The v1 kernel (GVL_PRE_LEGACY=1) stays bit-exact: it is the fallback for out-of-range geometries."""
+    frames = synth.noise_frames(2, 1080, 1920, seed=11)
+    want = preprocess_ref.resize_u8(frames.numpy(), 384, 384, 2)
+    monkeypatch.setenv("GVL_PRE_LEGACY", "1")
+    got = ops.preprocess(frames.to(DEV), 384, 384, 2, layout=ops.LAYOUT_U8_CHW).cpu().numpy()
+    assert np.array_equal(got, want)
 
 
 def test_preprocess_unaligned_base_pointer():

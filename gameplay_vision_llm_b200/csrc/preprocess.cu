@@ -167,6 +167,71 @@ static int get_tables(int H, int W, int eff_h, int eff_w, int out_h, int out_w, 
     return 0;
 }
 
+// ---- planar-kernel tables: taps pre-packed as 16-bit weight pairs aligned to the 32-bit words a thread loads ----
+
+static uint32_t host_weight_pair(const int16_t* w, int taps, int h, int o) {
+    const int j0 = 2 * h - o, j1 = j0 + 1;
+    const uint32_t lo = (j0 >= 0 && j0 < taps) ? (uint32_t)(uint16_t)w[j0] : 0u;
+    const uint32_t hi = (j1 >= 0 && j1 < taps) ? (uint32_t)(uint16_t)w[j1] : 0u;
+    return lo | (hi << 16);
+}
+
+struct PlanarTables {
+    // hq: per output column, 4*nw + 4 words: [0, 2nw) weight pairs of the window starting at the word holding the
+    //     first tap, [2nw, 4nw) zeros (so a warp can slide its window start), [4nw] = first | last << 16 (non-zero
+    //     pair range), [4nw + 1] = source pixel of the window's first word (xmin & ~3).
+    // vq: per output row, vq_stride words: [0, 2nwv) weight pairs relative to the row quads of the row's y tile,
+    //     [2nwv] = first quad.
+    uint32_t *hq = nullptr, *vq = nullptr;
+    int vq_stride = 0;
+};
+static std::map<std::tuple<int, int, int, int, int, int, int, int, int, int, int>, PlanarTables> g_ptabs;
+
+static int get_planar_tables(int H, int W, int eff_h, int eff_w, int out_h, int out_w, int resample, int TY, int nw,
+                             int nwv, PlanarTables& out) {
+    int dev = 0;
+    GVL_CUDA(cudaGetDevice(&dev));
+    std::lock_guard<std::mutex> lk(g_tab_mu);
+    auto key = std::make_tuple(dev, H, W, out_h, out_w, resample, TY, eff_h, eff_w, nw, nwv);
+    auto it = g_ptabs.find(key);
+    if (it != g_ptabs.end()) {
+        out = it->second;
+        return 0;
+    }
+    AxisTaps th, tv;
+    if (compute_axis_taps(W, out_w, resample, th) || compute_axis_taps(H, out_h, resample, tv)) return 1;
+    PlanarTables t;
+    const int hs = 4 * nw + 4;
+    std::vector<uint32_t> hq((size_t)eff_w * hs, 0u);
+    for (int x = 0; x < eff_w; ++x) {
+        uint32_t* row = hq.data() + (size_t)x * hs;
+        const int o = th.xmin[x] & 3;
+        int first = 2 * nw, last = 0;
+        for (int h = 0; h < 2 * nw; ++h) {
+            row[h] = host_weight_pair(th.w.data() + (size_t)x * th.taps, th.taps, h, o);
+            if (row[h]) {
+                first = std::min(first, h);
+                last = h + 1;
+            }
+        }
+        row[4 * nw] = (uint32_t)first | ((uint32_t)last << 16);
+        row[4 * nw + 1] = (uint32_t)(th.xmin[x] & ~3);
+    }
+    t.vq_stride = (2 * nwv + 1 + 3) & ~3;
+    std::vector<uint32_t> vq((size_t)eff_h * t.vq_stride, 0u);
+    for (int y = 0; y < eff_h; ++y) {
+        uint32_t* row = vq.data() + (size_t)y * t.vq_stride;
+        const int rel = tv.xmin[y] - tv.xmin[(y / TY) * TY];
+        for (int h = 0; h < 2 * nwv; ++h)
+            row[h] = host_weight_pair(tv.w.data() + (size_t)y * tv.taps, tv.taps, h, rel & 3);
+        row[2 * nwv] = (uint32_t)(rel >> 2);
+    }
+    if (upload(hq, &t.hq) || upload(vq, &t.vq)) return 2;
+    g_ptabs[key] = t;
+    out = t;
+    return 0;
+}
+
 // ---- kernel ----
 
 constexpr int PRE_THREADS = 256;
@@ -388,6 +453,8 @@ struct PlanarParams {
     int g_max;        // row quads of the intermediate
     int stage_bytes;  // max(planar staging, output band staging), multiple of 16
     const float* lut; // [3][256]
+    const uint32_t *hq, *vq;  // packed weight-pair tables (PlanarTables)
+    int vq_stride;
     void* out;
     int layout, patch, ld, gh, gw;
     int fast_rows;    // every frame row starts 16-byte aligned and W % 16 == 0
@@ -410,14 +477,6 @@ __device__ __forceinline__ uint32_t pack4_sat_u8(int v0, int v1, int v2, int v3)
     asm("cvt.pack.sat.u8.s32.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(v1), "r"(v0), "r"(hi));
     return d;
 }
-// 16-bit weight pair for the bytes (2h, 2h+1) of a word run whose first tap sits at byte `o`
-__device__ __forceinline__ uint32_t weight_pair(const int16_t* w, int taps, int h, int o) {
-    const int j0 = 2 * h - o, j1 = j0 + 1;
-    const uint32_t lo = (j0 >= 0 && j0 < taps) ? (uint32_t)(uint16_t)w[j0] : 0u;
-    const uint32_t hi = (j1 >= 0 && j1 < taps) ? (uint32_t)(uint16_t)w[j1] : 0u;
-    return lo | (hi << 16);
-}
-
 // 16 interleaved RGB pixels (12 words) -> 4 words per colour plane
 __device__ __forceinline__ void deinterleave16(const uint32_t (&a)[12], uint4& r, uint4& g, uint4& b) {
     uint32_t rr[4], gg[4], bb[4];
@@ -465,14 +524,13 @@ template <int NW, int NWV, int LPT, bool FAST>
 __global__ void __launch_bounds__(PL_THREADS, FAST ? 3 : 2)
 preprocess_planar_kernel(const PlanarParams p) {
     extern __shared__ __align__(16) uint8_t pl_smem[];
-    // [stage: 3 planes x 8 rows x pw | aliased by the output band] [sH: 3 x g_max x 4 x 32 words (+ NWV quads pad)]
-    // [sWV: TY x 2*NWV weight pairs] [sVinfo: TY first quads] [lut: 768 floats]
+    // [stage: 3 planes x 8 rows x pw | aliased by the output band]
+    // [sH: 3 planes x g_max quads x 2 column pairs x 32 x 2 words (+ NWV pad quads)] [sWV] [lut: 768 floats]
     uint8_t* sP = pl_smem;
     uint8_t* sOut = pl_smem;
     uint32_t* sH = reinterpret_cast<uint32_t*>(pl_smem + p.stage_bytes);
-    uint32_t* sWV = sH + (3 * p.g_max + NWV) * 128;
-    int* sVinfo = reinterpret_cast<int*>(sWV + p.TY * 2 * NWV);
-    float* sLut = reinterpret_cast<float*>(sVinfo + p.TY);
+    uint32_t* sWV = sH + (3 * p.g_max + NWV) * 128;   // [TY][vq_stride]
+    float* sLut = reinterpret_cast<float*>(sWV + p.TY * p.vq_stride);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int b = blockIdx.z;
@@ -490,46 +548,36 @@ preprocess_planar_kernel(const PlanarParams p) {
     const size_t row_bytes = (size_t)p.W * 3;
     const uint8_t* fbase = p.frames + ((size_t)b * p.H + r_lo) * row_bytes;
 
-    // ---- per-thread horizontal setup: column x0 + 4*lane + (warp & 3), row quad (warp >> 2) of each group
+    // ---- per-thread horizontal setup: column x0 + 4*lane + (warp & 3), row quad (warp >> 2) of each group.
+    // The warp slides its window start past the leading words none of its columns need and picks the
+    // h_pass_quad variant that skips the byte pairs that are zero-weighted for all of them.
     const int xm = warp & 3, slot = warp >> 2;
     const int xx = 4 * lane + xm;
     const bool x_active = xx < ntx;
     uint32_t wq[2 * NW];
     int my_off, variant;
     {
-        const int x = x0 + (x_active ? xx : 0);
-        const int rel = p.h_min[x] - (chunk0 << 4);
-        int o = rel & 3;
-        my_off = rel & ~3;
-        const int16_t* wp = p.h_w + (size_t)x * p.h_taps;
-        // first / last byte pair with a non-zero weight, over the active lanes of the warp
-        int first = 2 * NW, last = 0;
-#pragma unroll
-        for (int h = 0; h < 2 * NW; ++h) {
-            if (x_active && weight_pair(wp, p.h_taps, h, o) != 0u) {
-                first = min(first, h);
-                last = h + 1;
-            }
-        }
+        const uint32_t* hrow = p.hq + (size_t)(x0 + (x_active ? xx : 0)) * (4 * NW + 4);
+        const uint2 info = *reinterpret_cast<const uint2*>(hrow + 4 * NW);
+        int first = x_active ? (int)(info.x & 0xffffu) : 2 * NW;
+        int last = x_active ? (int)(info.x >> 16) : 0;
         first = __reduce_min_sync(0xffffffffu, first);
         last = __reduce_max_sync(0xffffffffu, last);
         if (last <= first) first = 0, last = 1;  // warp without columns
         const int skip = first >> 1;              // leading words nobody needs
-        my_off += 4 * skip;
-        o -= 4 * skip;
+        my_off = (int)info.y - (chunk0 << 4) + 4 * skip;
         const int hb = first - 2 * skip, he = last - 2 * skip;
         const int nwe = (he + 1) >> 1 <= NW - 1 ? NW - 1 : NW;
         variant = (nwe == NW ? 4 : 0) | (hb == 1 ? 2 : 0) | (he <= 2 * nwe - 1 ? 1 : 0);
 #pragma unroll
-        for (int h = 0; h < 2 * NW; ++h) wq[h] = weight_pair(wp, p.h_taps, h, o);
+        for (int k = 0; k < NW; ++k) {
+            const uint2 w2 = *reinterpret_cast<const uint2*>(hrow + 2 * skip + 2 * k);
+            wq[2 * k] = w2.x;
+            wq[2 * k + 1] = w2.y;
+        }
     }
-    // ---- vertical tables for this tile's rows
-    for (int i = tid; i < nty * 2 * NWV; i += PL_THREADS) {
-        const int yy = i / (2 * NWV), h = i - yy * (2 * NWV);
-        const int y = y0 + yy;
-        sWV[i] = weight_pair(p.v_w + (size_t)y * p.v_taps, p.v_taps, h, (p.v_min[y] - r_lo) & 3);
-    }
-    for (int yy = tid; yy < nty; yy += PL_THREADS) sVinfo[yy] = (p.v_min[y0 + yy] - r_lo) >> 2;
+    // ---- vertical tables of this tile's rows, LUT
+    for (int i = tid; i < nty * p.vq_stride; i += PL_THREADS) sWV[i] = p.vq[(size_t)y0 * p.vq_stride + i];
     for (int i = tid; i < 768; i += PL_THREADS) sLut[i] = p.lut[i];
 
     // ---- staging: global -> registers (next group) while the current group is filtered.  A thread owns the same
@@ -597,7 +645,7 @@ preprocess_planar_kernel(const PlanarParams p) {
     const int ngroups = (nrows + PL_RG - 1) / PL_RG;
     const int h_round = 1 << (p.h_prec - 1);
     const uint8_t* h_src = sP + (size_t)slot * 4 * p.pw + my_off;
-    uint32_t* h_dst = sH + (slot * 4 + xm) * 32 + lane;
+    uint32_t* h_dst = sH + (slot * 2 + (xm >> 1)) * 64 + lane * 2 + (xm & 1);
     const int plane_stride = p.g_max * 128;
     fetch_group(0);
     store_group();
@@ -624,17 +672,23 @@ preprocess_planar_kernel(const PlanarParams p) {
     }
 
     // ---- vertical pass + normalise, one band (VB output rows) at a time through the staging buffer.
-    // Work item = (column 4*lane + xm, output row): all three planes share the row's weight pairs; the two
-    // warps with the same xm alternate rows.  Words beyond a row's window carry zero weights (the pad quads
-    // after sH keep the reads in bounds), so the tap loop needs no guards.
+    // Work item = (column pair 4*lane + 2*xp + {0,1}, output row): one 64-bit load per row quad and plane
+    // fetches both columns, all planes share the row's weight pairs; four warps per xp alternate rows.
+    // Words beyond a row's window carry zero weights (the pad quads after sH keep the reads in bounds).
     const int v_round = 1 << (p.v_prec - 1);
     const int PP = p.patch * p.patch;
     const bool patch_layout = p.layout == GVL_LAYOUT_BF16_PATCH;
-    const int my_o = patch_layout ? (xx / p.patch) * p.ld + xx % p.patch : xx;
+    const int xp = warp & 1, vslot = warp >> 1;
+    const int xa = 4 * lane + 2 * xp;
+    const bool a_on = xa < ntx, b_on = xa + 1 < ntx;
+    const int oa = patch_layout ? (xa / p.patch) * p.ld + xa % p.patch : xa;
+    const int ob = patch_layout ? ((xa + 1) / p.patch) * p.ld + (xa + 1) % p.patch : xa + 1;
+    const bool pair_store = b_on && ob == oa + 1 && (oa & 1) == 0 && (p.patch & 1) == 0;
     const int c_stride = patch_layout ? PP : p.VB * p.TX;  // elements between planes inside the staged band
     const int y_stride = patch_layout ? p.patch : p.TX;
     const int esize = p.layout == GVL_LAYOUT_U8_CHW ? 1 : (p.layout == GVL_LAYOUT_F32_CHW ? 4 : 2);
-    const uint32_t* v_src = sH + xm * 32 + lane;
+    const uint2* v_src = reinterpret_cast<const uint2*>(sH) + xp * 32 + lane;
+    constexpr int VS = (2 * NWV + 1 + 3) & ~3;
     for (int band0 = 0; band0 < nty; band0 += p.VB) {
         const int nb = min(p.VB, nty - band0);
         if (patch_layout) {
@@ -642,33 +696,48 @@ preprocess_planar_kernel(const PlanarParams p) {
             for (int i = tid; i < npatch * padc; i += PL_THREADS)
                 reinterpret_cast<uint16_t*>(sOut)[(size_t)(i / padc) * p.ld + 3 * PP + i % padc] = 0;
         }
-        for (int yl = slot; yl < nb; yl += 2) {
-            uint32_t wv[2 * NWV];
+        for (int yl = vslot; yl < nb; yl += 4) {
+            uint32_t wv[VS];
 #pragma unroll
-            for (int h = 0; h < 2 * NWV; ++h) wv[h] = sWV[(band0 + yl) * 2 * NWV + h];
-            const uint32_t* src = v_src + sVinfo[band0 + yl] * 128;
-            int u[3];
+            for (int h = 0; h < VS / 4; ++h) {
+                const uint4 t = reinterpret_cast<const uint4*>(sWV + (band0 + yl) * VS)[h];
+                wv[4 * h] = t.x; wv[4 * h + 1] = t.y; wv[4 * h + 2] = t.z; wv[4 * h + 3] = t.w;
+            }
+            const uint2* src = v_src + wv[2 * NWV] * 64;
+            int ua[3], ub[3];
 #pragma unroll
             for (int c = 0; c < 3; ++c) {
-                int acc = v_round;
+                int acc_a = v_round, acc_b = v_round;
 #pragma unroll
                 for (int k = 0; k < NWV; ++k) {
-                    const uint32_t w = src[c * plane_stride + k * 128];
-                    acc = dp2a_lo(wv[2 * k], w, acc);
-                    acc = dp2a_hi(wv[2 * k + 1], w, acc);
+                    const uint2 w = src[(c * p.g_max + k) * 64];
+                    acc_a = dp2a_lo(wv[2 * k], w.x, acc_a);
+                    acc_b = dp2a_lo(wv[2 * k], w.y, acc_b);
+                    acc_a = dp2a_hi(wv[2 * k + 1], w.x, acc_a);
+                    acc_b = dp2a_hi(wv[2 * k + 1], w.y, acc_b);
                 }
-                u[c] = min(max(acc >> p.v_prec, 0), 255);
+                ua[c] = min(max(acc_a >> p.v_prec, 0), 255);
+                ub[c] = min(max(acc_b >> p.v_prec, 0), 255);
             }
-            if (x_active) {
-                const int o = my_o + yl * y_stride;
+            if (a_on) {
+                const int o = oa + yl * y_stride, o2 = ob + yl * y_stride;
 #pragma unroll
                 for (int c = 0; c < 3; ++c) {
-                    if (p.layout == GVL_LAYOUT_U8_CHW)
-                        sOut[o + c * c_stride] = (uint8_t)u[c];
-                    else if (p.layout == GVL_LAYOUT_F32_CHW)
-                        reinterpret_cast<float*>(sOut)[o + c * c_stride] = sLut[c * 256 + u[c]];
-                    else
-                        reinterpret_cast<__nv_bfloat16*>(sOut)[o + c * c_stride] = __float2bfloat16_rn(sLut[c * 256 + u[c]]);
+                    if (p.layout == GVL_LAYOUT_U8_CHW) {
+                        sOut[o + c * c_stride] = (uint8_t)ua[c];
+                        if (b_on) sOut[o2 + c * c_stride] = (uint8_t)ub[c];
+                    } else if (p.layout == GVL_LAYOUT_F32_CHW) {
+                        reinterpret_cast<float*>(sOut)[o + c * c_stride] = sLut[c * 256 + ua[c]];
+                        if (b_on) reinterpret_cast<float*>(sOut)[o2 + c * c_stride] = sLut[c * 256 + ub[c]];
+                    } else if (pair_store) {
+                        *reinterpret_cast<uint32_t*>(reinterpret_cast<uint16_t*>(sOut) + o + c * c_stride) =
+                            pack_bf16x2(sLut[c * 256 + ua[c]], sLut[c * 256 + ub[c]]);
+                    } else {
+                        reinterpret_cast<__nv_bfloat16*>(sOut)[o + c * c_stride] = __float2bfloat16_rn(sLut[c * 256 + ua[c]]);
+                        if (b_on)
+                            reinterpret_cast<__nv_bfloat16*>(sOut)[o2 + c * c_stride] =
+                                __float2bfloat16_rn(sLut[c * 256 + ub[c]]);
+                    }
                 }
             }
         }
@@ -763,14 +832,20 @@ static int launch_planar(const uint8_t* frames, int B, int H, int W, int out_h, 
         g_max = 2 * ((tb.max_rows + PL_RG - 1) / PL_RG);
         const int band_bytes = layout == GVL_LAYOUT_BF16_PATCH ? (TX / patch) * ld * 2 : 3 * VB * TX * esize;
         stage_bytes = (std::max(3 * PL_RG * pw, band_bytes) + 15) & ~15;
-        smem = (size_t)stage_bytes + (size_t)(3 * g_max + nwv) * 128 * 4 + (size_t)TY * 2 * nwv * 4 + (size_t)TY * 4 +
-               768 * 4;
+        const int vq_stride = (2 * nwv + 1 + 3) & ~3;
+        smem = (size_t)stage_bytes + (size_t)(3 * g_max + nwv) * 128 * 4 + (size_t)TY * vq_stride * 4 + 768 * 4;
         if (smem <= 74 * 1024) break;  // three CTAs per SM
     }
     if (smem > 200 * 1024) return -1;
     float* lut = nullptr;
     int rc = get_lut(h_sub, h_div, &lut);
     if (rc) return rc;
+    PlanarTables pt;
+    rc = get_planar_tables(H, W, p.eff_h, p.eff_w, out_h, out_w, resample, TY, nw, nwv, pt);
+    if (rc) return rc;
+    p.hq = pt.hq;
+    p.vq = pt.vq;
+    p.vq_stride = pt.vq_stride;
     p.frames = frames;
     p.B = B;
     p.H = H;

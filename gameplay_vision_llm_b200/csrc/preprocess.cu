@@ -440,6 +440,8 @@ preprocess_kernel(const PreParams p) {
 
 constexpr int PL_THREADS = 256;
 constexpr int PL_RG = 8;  // source rows per staged group = two row quads of the transposed intermediate
+constexpr int PL_PF = 3;  // L2 prefetch distance in groups
+constexpr int PL_HALF = PL_THREADS / 2;
 
 struct PlanarParams {
     const uint8_t* frames;
@@ -582,16 +584,19 @@ preprocess_planar_kernel(const PlanarParams p) {
 
     // ---- staging: global -> registers (next group) while the current group is filtered.  A thread owns the same
     // LPT (row, chunk) slots of every group, so the address arithmetic is done once.
+    // The two row-quad halves of the CTA (warps 0-3 / 4-7) stage and filter their own 4 rows of every group and
+    // synchronise among themselves only (named barriers), so one half's loads overlap the other half's math.
     uint32_t pre[LPT][12];
     int src_off[LPT], dst_off[LPT], item_rr[LPT];
+    const int htid = tid & (PL_HALF - 1);
 #pragma unroll
     for (int k = 0; k < LPT; ++k) {
-        const int i = tid + k * PL_THREADS;
+        const int i = htid + k * PL_HALF;
         const int rr = i / nch, ch = i - rr * nch;
-        const bool ok = rr < PL_RG && (!FAST || chunk0 + ch < row_chunks);
-        item_rr[k] = ok ? rr : 0x40000000;  // never < rows_left
-        src_off[k] = rr * (int)row_bytes + (chunk0 + ch) * 48;
-        dst_off[k] = rr * p.pw + ch * 16;
+        const bool ok = rr < 4 && (!FAST || chunk0 + ch < row_chunks);
+        item_rr[k] = ok ? slot * 4 + rr : 0x40000000;  // never < rows_left
+        src_off[k] = (slot * 4 + rr) * (int)row_bytes + (chunk0 + ch) * 48;
+        dst_off[k] = (slot * 4 + rr) * p.pw + ch * 16;
     }
     auto fetch_group = [&](int g) {
         const int rows_left = min(nrows, p.H - r_lo) - g * PL_RG;  // staged rows of this group that exist
@@ -631,7 +636,7 @@ preprocess_planar_kernel(const PlanarParams p) {
     auto store_group = [&]() {
 #pragma unroll
         for (int k = 0; k < LPT; ++k) {
-            if (tid + k * PL_THREADS < PL_RG * nch) {
+            if (htid + k * PL_HALF < 4 * nch) {
                 uint4 r, g, bl;
                 deinterleave16(pre[k], r, g, bl);
                 uint8_t* d = sP + dst_off[k];
@@ -644,13 +649,30 @@ preprocess_planar_kernel(const PlanarParams p) {
 
     const int ngroups = (nrows + PL_RG - 1) / PL_RG;
     const int h_round = 1 << (p.h_prec - 1);
+    // DRAM latency is taken off the critical path with bulk L2 prefetches PL_PF groups ahead (one per source
+    // row, no registers, no shared memory): the register loads of fetch_group then hit L2.
+    auto prefetch_group = [&](int g) {
+        if (FAST && g < ngroups && htid < 4) {
+            const int row = g * PL_RG + slot * 4 + htid;
+            if (row < min(nrows, p.H - r_lo)) {
+                const int nb = min(nch, row_chunks - chunk0) * 48;
+                const uint8_t* src = fbase + (size_t)row * row_bytes + (size_t)chunk0 * 48;
+                asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(nb) : "memory");
+            }
+        }
+    };
+#pragma unroll
+    for (int g = 1; g <= PL_PF; ++g) prefetch_group(g);
     const uint8_t* h_src = sP + (size_t)slot * 4 * p.pw + my_off;
     uint32_t* h_dst = sH + (slot * 2 + (xm >> 1)) * 64 + lane * 2 + (xm & 1);
     const int plane_stride = p.g_max * 128;
+    auto half_sync = [&]() { asm volatile("bar.sync %0, %1;" ::"r"(1 + slot), "n"(PL_HALF) : "memory"); };
+    __syncthreads();  // tables / LUT visible
     fetch_group(0);
     store_group();
-    __syncthreads();
+    half_sync();
     for (int g = 0; g < ngroups; ++g) {
+        prefetch_group(g + 1 + PL_PF);
         if (g + 1 < ngroups) fetch_group(g + 1);
         // horizontal pass: 4 rows x 3 planes of this thread's column -> one transposed word per plane
         if (x_active) {
@@ -666,10 +688,11 @@ preprocess_planar_kernel(const PlanarParams p) {
                 default: h_pass_quad<NW, NW, true, true>(h_src, p.pw, wq, h_round, p.h_prec, dst, plane_stride); break;
             }
         }
-        __syncthreads();  // everyone is done reading the staged group
+        half_sync();  // this half is done reading its staged rows
         if (g + 1 < ngroups) store_group();
-        __syncthreads();
+        half_sync();
     }
+    __syncthreads();  // both halves' intermediate rows complete; the staging buffer becomes the output band
 
     // ---- vertical pass + normalise, one band (VB output rows) at a time through the staging buffer.
     // Work item = (column pair 4*lane + 2*xp + {0,1}, output row): one 64-bit load per row quad and plane
@@ -823,7 +846,7 @@ static int launch_planar(const uint8_t* frames, int B, int H, int W, int out_h, 
         if (rc) return rc;
         nw = tb.max_hsize + 3 <= 16 ? 4 : (tb.max_hsize + 3 <= 24 ? 6 : (tb.max_hsize + 3 <= 32 ? 8 : 0));
         nwv = tb.max_vsize + 3 <= 12 ? 3 : (tb.max_vsize + 3 <= 16 ? 4 : (tb.max_vsize + 3 <= 32 ? 8 : 0));
-        lpt = PL_RG * tb.nch_max <= 2 * PL_THREADS ? 2 : (PL_RG * tb.nch_max <= 3 * PL_THREADS ? 3 : 0);
+        lpt = 4 * tb.nch_max <= 2 * PL_HALF ? 2 : (4 * tb.nch_max <= 3 * PL_HALF ? 3 : 0);
         if (!nw || !nwv || !lpt) return -1;
         const bool fast_rows = W % 16 == 0 && (uintptr_t)frames % 16 == 0;
         if (!fast_rows || (!(nw <= 4 && nwv <= 3 && lpt <= 2) && !(nw <= 6 && nwv <= 4 && lpt <= 2))) nw = 8, nwv = 8, lpt = 3;

@@ -228,6 +228,78 @@ __device__ __forceinline__ void umma_commit_mc(uint64_t* bar, uint16_t cta_mask)
         "h"(cta_mask)
         : "memory");
 }
+// ---- CTA-pair (cta_group::2) forms: one MMA spans the tensor cores / TMEM of both CTAs of a 2-CTA cluster ----
+template <uint32_t kCols>
+__device__ __forceinline__ void tmem_alloc_cg2(uint32_t* dst_smem) {  // one warp in EACH CTA of the pair
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)),
+                 "n"(kCols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+template <uint32_t kCols>
+__device__ __forceinline__ void tmem_dealloc_cg2(uint32_t taddr) {
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "n"(kCols) : "memory");
+}
+// D[tmem of both CTAs, 256 rows] (+)= A[each CTA's 128 rows] . B[each CTA holds half of the N rows]^T.
+// Issued by one thread of the leader CTA (cluster rank 0); descriptors are CTA-relative and apply to both.
+__device__ __forceinline__ void umma_bf16_ss_cg2(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                                 uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t"
+        "}\n" ::"r"(tmem_d),
+        "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit_mc_cg2(uint64_t* bar, uint16_t cta_mask) {
+    asm volatile(
+        "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+            smem_u32(bar)),
+        "h"(cta_mask)
+        : "memory");
+}
+// shared::cluster address of `addr` (a shared::cta address of this CTA) in the CTA with cluster rank `rank`
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t addr, uint32_t rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+    return r;
+}
+// 2-D tile load into THIS CTA's shared memory whose completion is signalled on an mbarrier that may live in the
+// peer CTA of the pair (bar_cluster_addr is a shared::cluster address).
+__device__ __forceinline__ void tma_load_2d_cg2(void* smem_dst, const CUtensorMap* m, uint32_t bar_cluster_addr,
+                                                int32_t c0, int32_t c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes"
+        " [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar_cluster_addr), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar_cluster_addr) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar_cluster_addr) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait_cluster(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred P;\n\t"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 P, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, P;\n\t"
+        "}\n"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
+    if (mbar_try_wait_cluster(bar, parity)) return;
+    const uint64_t t0 = global_timer_ns();
+    while (!mbar_try_wait_cluster(bar, parity)) {
+        if (global_timer_ns() - t0 > 4000000000ull) mbar_timeout_trap();
+    }
+}
+
 // 32 lanes x 32 consecutive fp32 columns: thread t of the warp receives lane (taddr.lane + t).
 __device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t (&r)[32]) {
     asm volatile(

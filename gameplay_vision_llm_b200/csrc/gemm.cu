@@ -22,6 +22,8 @@
 // the phantom second half of an odd last super tile) and by row / column guards on the stores.
 #include "common.cuh"
 
+#include <cstdlib>
+
 namespace gvl {
 
 constexpr int BM = 128;
@@ -56,6 +58,80 @@ struct GemmCfg {
     static constexpr int BAR_BYTES = (2 * STAGES + 4) * 8 + 16;
     static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + BIAS_BYTES + BAR_BYTES + 1024 /*alignment slack*/;
 };
+
+// Epilogue of one 128 x BN accumulator tile for one warp: TMEM lane quadrant q, column half `half`.
+template <int BN>
+__device__ __forceinline__ void epilogue_tile(const GemmParams& p, const float* myBias, uint32_t tmem_base, int as,
+                                              int m_blk, int n0, int q, int half, int lane) {
+    using Cfg = GemmCfg<BN>;
+    const int row = m_blk * BM + q * 32 + lane;
+    const bool row_ok = row < p.M;
+    const int rrow = p.res_row_mod > 0 ? (row % p.res_row_mod) : row;
+    const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) +
+                            (uint32_t)(as * BN + half * (Cfg::CHUNKS_PER_WARP * 32));
+    const bool has_res = p.residual != nullptr;
+#pragma unroll 1
+    for (int chunk = 0; chunk < Cfg::CHUNKS_PER_WARP; ++chunk) {
+        const int c0 = n0 + chunk * 32;
+        if (c0 >= p.N) break;  // warp-uniform
+        uint32_t r[32];
+        tmem_ld_32x32(t_addr + (uint32_t)(chunk * 32), r);
+        // residual loads are issued before waiting on TMEM so their latency overlaps it
+        uint4 rv[4];
+        if (has_res && row_ok) {
+            const __nv_bfloat16* rp = p.residual + (size_t)rrow * p.ldr + c0;
+#pragma unroll
+            for (int g = 0; g < 4; ++g)
+                rv[g] = (c0 + g * 8 < p.N) ? *reinterpret_cast<const uint4*>(rp + g * 8) : make_uint4(0, 0, 0, 0);
+        }
+        tmem_ld_wait();
+        if (row_ok) {
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+                const int col = c0 + g * 8;
+                if (col < p.N) {
+                    const float4 b0 = *reinterpret_cast<const float4*>(myBias + chunk * 32 + g * 8);
+                    const float4 b1 = *reinterpret_cast<const float4*>(myBias + chunk * 32 + g * 8 + 4);
+                    float v[8];
+                    v[0] = __uint_as_float(r[g * 8 + 0]) + b0.x;
+                    v[1] = __uint_as_float(r[g * 8 + 1]) + b0.y;
+                    v[2] = __uint_as_float(r[g * 8 + 2]) + b0.z;
+                    v[3] = __uint_as_float(r[g * 8 + 3]) + b0.w;
+                    v[4] = __uint_as_float(r[g * 8 + 4]) + b1.x;
+                    v[5] = __uint_as_float(r[g * 8 + 5]) + b1.y;
+                    v[6] = __uint_as_float(r[g * 8 + 6]) + b1.z;
+                    v[7] = __uint_as_float(r[g * 8 + 7]) + b1.w;
+                    if (p.act == GVL_ACT_GELU_TANH) {
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) v[j] = gelu_tanh_f(v[j]);
+                    } else if (p.act == GVL_ACT_GELU_ERF) {
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) v[j] = gelu_erf_f(v[j]);
+                    }
+                    if (has_res) {
+                        v[0] += bf16_lo(rv[g].x); v[1] += bf16_hi(rv[g].x);
+                        v[2] += bf16_lo(rv[g].y); v[3] += bf16_hi(rv[g].y);
+                        v[4] += bf16_lo(rv[g].z); v[5] += bf16_hi(rv[g].z);
+                        v[6] += bf16_lo(rv[g].w); v[7] += bf16_hi(rv[g].w);
+                    }
+                    if (p.out_f32) {
+                        float* o = reinterpret_cast<float*>(p.out) + (size_t)row * p.ldo + col;
+                        *reinterpret_cast<float4*>(o) = make_float4(v[0], v[1], v[2], v[3]);
+                        *reinterpret_cast<float4*>(o + 4) = make_float4(v[4], v[5], v[6], v[7]);
+                    } else {
+                        __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + (size_t)row * p.ldo + col;
+                        uint4 ov;
+                        ov.x = pack_bf16x2(v[0], v[1]);
+                        ov.y = pack_bf16x2(v[2], v[3]);
+                        ov.z = pack_bf16x2(v[4], v[5]);
+                        ov.w = pack_bf16x2(v[6], v[7]);
+                        *reinterpret_cast<uint4*>(o) = ov;
+                    }
+                }
+            }
+        }
+    }
+}
 
 template <int BN>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
@@ -174,73 +250,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
             __syncwarp();
             mbar_wait(&tmem_full_bar[as], aphase);
             tcgen05_fence_after();
-            const int row = m_blk * BM + q * 32 + lane;
-            const bool row_ok = row < p.M;
-            const int rrow = p.res_row_mod > 0 ? (row % p.res_row_mod) : row;
-            const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) +
-                                    (uint32_t)(as * BN + half * (Cfg::CHUNKS_PER_WARP * 32));
-            const bool has_res = p.residual != nullptr;
-#pragma unroll 1
-            for (int chunk = 0; chunk < Cfg::CHUNKS_PER_WARP; ++chunk) {
-                const int c0 = n0 + chunk * 32;
-                if (c0 >= p.N) break;  // warp-uniform
-                uint32_t r[32];
-                tmem_ld_32x32(t_addr + (uint32_t)(chunk * 32), r);
-                // residual loads are issued before waiting on TMEM so their latency overlaps it
-                uint4 rv[4];
-                if (has_res && row_ok) {
-                    const __nv_bfloat16* rp = p.residual + (size_t)rrow * p.ldr + c0;
-#pragma unroll
-                    for (int g = 0; g < 4; ++g)
-                        rv[g] = (c0 + g * 8 < p.N) ? *reinterpret_cast<const uint4*>(rp + g * 8) : make_uint4(0, 0, 0, 0);
-                }
-                tmem_ld_wait();
-                if (row_ok) {
-#pragma unroll
-                    for (int g = 0; g < 4; ++g) {
-                        const int col = c0 + g * 8;
-                        if (col < p.N) {
-                            const float4 b0 = *reinterpret_cast<const float4*>(myBias + chunk * 32 + g * 8);
-                            const float4 b1 = *reinterpret_cast<const float4*>(myBias + chunk * 32 + g * 8 + 4);
-                            float v[8];
-                            v[0] = __uint_as_float(r[g * 8 + 0]) + b0.x;
-                            v[1] = __uint_as_float(r[g * 8 + 1]) + b0.y;
-                            v[2] = __uint_as_float(r[g * 8 + 2]) + b0.z;
-                            v[3] = __uint_as_float(r[g * 8 + 3]) + b0.w;
-                            v[4] = __uint_as_float(r[g * 8 + 4]) + b1.x;
-                            v[5] = __uint_as_float(r[g * 8 + 5]) + b1.y;
-                            v[6] = __uint_as_float(r[g * 8 + 6]) + b1.z;
-                            v[7] = __uint_as_float(r[g * 8 + 7]) + b1.w;
-                            if (p.act == GVL_ACT_GELU_TANH) {
-#pragma unroll
-                                for (int j = 0; j < 8; ++j) v[j] = gelu_tanh_f(v[j]);
-                            } else if (p.act == GVL_ACT_GELU_ERF) {
-#pragma unroll
-                                for (int j = 0; j < 8; ++j) v[j] = gelu_erf_f(v[j]);
-                            }
-                            if (has_res) {
-                                v[0] += bf16_lo(rv[g].x); v[1] += bf16_hi(rv[g].x);
-                                v[2] += bf16_lo(rv[g].y); v[3] += bf16_hi(rv[g].y);
-                                v[4] += bf16_lo(rv[g].z); v[5] += bf16_hi(rv[g].z);
-                                v[6] += bf16_lo(rv[g].w); v[7] += bf16_hi(rv[g].w);
-                            }
-                            if (p.out_f32) {
-                                float* o = reinterpret_cast<float*>(p.out) + (size_t)row * p.ldo + col;
-                                *reinterpret_cast<float4*>(o) = make_float4(v[0], v[1], v[2], v[3]);
-                                *reinterpret_cast<float4*>(o + 4) = make_float4(v[4], v[5], v[6], v[7]);
-                            } else {
-                                __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + (size_t)row * p.ldo + col;
-                                uint4 ov;
-                                ov.x = pack_bf16x2(v[0], v[1]);
-                                ov.y = pack_bf16x2(v[2], v[3]);
-                                ov.z = pack_bf16x2(v[4], v[5]);
-                                ov.w = pack_bf16x2(v[6], v[7]);
-                                *reinterpret_cast<uint4*>(o) = ov;
-                            }
-                        }
-                    }
-                }
-            }
+            epilogue_tile<BN>(p, myBias, tmem_base, as, m_blk, n0, q, half, lane);
             tcgen05_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&tmem_empty_bar[as]);
@@ -256,6 +266,174 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
         tcgen05_fence_after();
         tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
     }
+}
+
+// ---- CTA-pair kernel (cta_group::2): one MMA = 256 x BN x 16 over both CTAs' tensor cores ------------------------
+//
+// Same roles and pipelines as above, but the pair now runs ONE tcgen05.mma.cta_group::2 per k-step: each CTA
+// stages only its own 128 A rows and HALF of the W tile (BN/2 rows), the hardware reads the other half from the
+// peer's shared memory.  Per CTA and k-block that is 16 KB + BN*64 B of shared-memory writes and reads instead of
+// 16 KB + BN*128 B, which takes the kernel off the operand-feed limit (SS-mode at 128x256 reads 96 B/clk of the
+// 128 B/clk the SM has) and frees room for a 6-8 stage ring.
+//   - full barriers live in the leader CTA (cluster rank 0): both CTAs' TMA loads complete_tx on them
+//   - the leader's MMA thread issues for the pair; tcgen05.commit multicasts to both CTAs' empty / tmem_full barriers
+//   - both CTAs' epilogue warps arrive on the leader's tmem_empty barrier (remote arrive from the peer)
+template <int BN>
+struct Gemm2Cfg {
+    static constexpr int B_HALF_BYTES = (BN / 2) * BK * 2;
+    static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_HALF_BYTES;  // per CTA
+    static constexpr int STAGES = BN == 256 ? 6 : (BN == 192 ? 7 : 8);
+    static constexpr int TMEM_COLS = (2 * BN <= 256) ? 256 : 512;
+    static constexpr int BAR_BYTES = (2 * STAGES + 4) * 8 + 16;
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + GemmCfg<BN>::BIAS_BYTES + BAR_BYTES + 1024;
+};
+
+template <int BN>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
+gemm_bf16_cg2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                     const GemmParams p) {
+    using Cfg = GemmCfg<BN>;
+    using Cfg2 = Gemm2Cfg<BN>;
+    constexpr int STAGES = Cfg2::STAGES;
+
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* sA = smem;
+    uint8_t* sB = smem + STAGES * A_STAGE_BYTES;
+    float* sBias = reinterpret_cast<float*>(smem + STAGES * Cfg2::STAGE_BYTES);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg2::STAGE_BYTES + Cfg::BIAS_BYTES);
+    uint64_t* full_bar = bars;                       // used in the leader only
+    uint64_t* empty_bar = bars + STAGES;             // per CTA: "this stage may be overwritten"
+    uint64_t* tmem_full_bar = bars + 2 * STAGES;     // per CTA: accumulator stage ready
+    uint64_t* tmem_empty_bar = bars + 2 * STAGES + 2;  // leader only: both CTAs' epilogues drained the stage
+    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const uint32_t cta_rank = cluster_ctarank();
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmA);
+        tma_prefetch_desc(&tmB);
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(&full_bar[s], 1);   // leader producer's arrive.expect_tx (+ tx bytes of both CTAs' loads)
+            mbar_init(&empty_bar[s], 1);  // one multicast tcgen05.commit
+        }
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(&tmem_full_bar[s], 1);
+            mbar_init(&tmem_empty_bar[s], 2 * kEpiWarps);
+        }
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc_cg2<Cfg2::TMEM_COLS>(tmem_ptr_smem);
+    tcgen05_fence_before();
+    cluster_sync_all();
+    tcgen05_fence_after();
+    const uint32_t tmem_base = *tmem_ptr_smem;
+
+    const int num_super = p.m_pairs * p.n_tiles;
+    const int cluster_id = blockIdx.x >> 1;
+    const int num_clusters = gridDim.x >> 1;
+
+    if (warp == 0) {
+        // ===== TMA producer (both CTAs): own A rows + own half of the W tile, completion on the LEADER's barrier =====
+        if (elect_one()) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int st = cluster_id; st < num_super; st += num_clusters) {
+                const int m_blk = (st / p.n_tiles) * 2 + (int)cta_rank, n_blk = st % p.n_tiles;
+                for (int kb = 0; kb < p.k_blocks; ++kb) {
+                    mbar_wait_cluster(&empty_bar[stage], phase ^ 1);
+                    if (cta_rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * Cfg2::STAGE_BYTES);
+                    const uint32_t fb = mapa_u32(smem_u32(&full_bar[stage]), 0);
+                    tma_load_2d_cg2(sA + stage * A_STAGE_BYTES, &tmA, fb, kb * BK, m_blk * BM);
+                    tma_load_2d_cg2(sB + stage * Cfg2::B_HALF_BYTES, &tmB, fb, kb * BK,
+                                    n_blk * BN + (int)cta_rank * (BN / 2));
+                    if (++stage == STAGES) {
+                        stage = 0;
+                        phase ^= 1;
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer (leader CTA only) =====
+        if (cta_rank == 0 && elect_one()) {
+            constexpr uint32_t idesc = umma_idesc_bf16(2 * BM, BN);
+            int stage = 0;
+            uint32_t phase = 0;
+            int as = 0;
+            uint32_t aphase = 0;
+            for (int st = cluster_id; st < num_super; st += num_clusters) {
+                mbar_wait_cluster(&tmem_empty_bar[as], aphase ^ 1);
+                tcgen05_fence_after();
+                const uint32_t d_tmem = tmem_base + (uint32_t)(as * BN);
+                for (int kb = 0; kb < p.k_blocks; ++kb) {
+                    mbar_wait_cluster(&full_bar[stage], phase);
+                    tcgen05_fence_after();
+                    const uint32_t a_addr = smem_u32(sA + stage * A_STAGE_BYTES);
+                    const uint32_t b_addr = smem_u32(sB + stage * Cfg2::B_HALF_BYTES);
+#pragma unroll
+                    for (int k = 0; k < BK / 16; ++k) {
+                        umma_bf16_ss_cg2(d_tmem, umma_desc_sw128(a_addr + k * 32), umma_desc_sw128(b_addr + k * 32), idesc,
+                                         (uint32_t)((kb | k) != 0));
+                    }
+                    umma_commit_mc_cg2(&empty_bar[stage], (uint16_t)0x3);  // frees the stage in both CTAs
+                    if (++stage == STAGES) {
+                        stage = 0;
+                        phase ^= 1;
+                    }
+                }
+                umma_commit_mc_cg2(&tmem_full_bar[as], (uint16_t)0x3);  // accumulator ready in both CTAs
+                as ^= 1;
+                if (as == 0) aphase ^= 1;
+            }
+        }
+    } else {
+        // ===== epilogue warps (both CTAs, each on its own 128 rows) =====
+        const int ew = warp - 2;
+        const int q = warp & 3;
+        const int half = ew >> 2;
+        float* myBias = sBias + ew * (Cfg::CHUNKS_PER_WARP * 32);
+        int as = 0;
+        uint32_t aphase = 0;
+        for (int st = cluster_id; st < num_super; st += num_clusters) {
+            const int m_blk = (st / p.n_tiles) * 2 + (int)cta_rank, n_blk = st % p.n_tiles;
+            const int n0 = n_blk * BN + half * (Cfg::CHUNKS_PER_WARP * 32);
+            for (int c = lane; c < Cfg::CHUNKS_PER_WARP * 32; c += 32)
+                myBias[c] = (p.bias != nullptr && n0 + c < p.N) ? p.bias[n0 + c] : 0.0f;
+            __syncwarp();
+            mbar_wait_cluster(&tmem_full_bar[as], aphase);
+            tcgen05_fence_after();
+            epilogue_tile<BN>(p, myBias, tmem_base, as, m_blk, n0, q, half, lane);
+            tcgen05_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster(mapa_u32(smem_u32(&tmem_empty_bar[as]), 0));
+            as ^= 1;
+            if (as == 0) aphase ^= 1;
+        }
+    }
+
+    tcgen05_fence_before();
+    cluster_sync_all();
+    if (warp == 1) {
+        tcgen05_fence_after();
+        tmem_dealloc_cg2<Cfg2::TMEM_COLS>(tmem_base);
+    }
+}
+
+template <int BN>
+static int launch_gemm_cg2(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, cudaStream_t stream) {
+    using Cfg2 = Gemm2Cfg<BN>;
+    GVL_CUDA(cudaFuncSetAttribute(gemm_bf16_cg2_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  Cfg2::SMEM_BYTES));
+    const int super_tiles = p.m_pairs * p.n_tiles;
+    const int max_clusters = sm_count() / 2;
+    const int clusters = super_tiles < max_clusters ? super_tiles : max_clusters;
+    ProfScope prof(GVL_K_GEMM, 2.0 * p.M * (double)p.N * p.K, stream);
+    gemm_bf16_cg2_kernel<BN><<<2 * clusters, kGemmThreads, Cfg2::SMEM_BYTES, stream>>>(tmA, tmB, p);
+    GVL_LAUNCH_CHECK("gemm_bf16_cg2_kernel");
+    return 0;
 }
 
 template <int BN>
@@ -329,6 +507,17 @@ extern "C" int gvl_gemm_bf16(const void* A, int lda, const void* W, int ldw, con
     if (rc) return rc;
 
     cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+    static const bool multicast_variant = [] {
+        const char* e = getenv("GVL_GEMM_MC");  // A/B switch: the 1-CTA-MMA + multicast kernel
+        return e && e[0] == '1';
+    }();
+    if (!multicast_variant) {
+        switch (bn) {
+            case 256: return launch_gemm_cg2<256>(tmA, tmB, p, s);
+            case 192: return launch_gemm_cg2<192>(tmA, tmB, p, s);
+            default: return launch_gemm_cg2<128>(tmA, tmB, p, s);
+        }
+    }
     switch (bn) {
         case 256: return launch_gemm<256>(tmA, tmB, p, s);
         case 192: return launch_gemm<192>(tmA, tmB, p, s);

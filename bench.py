@@ -205,7 +205,7 @@ def main_ours(args) -> None:
     if os.path.exists(tpath):
         with open(tpath) as f:
             traffic = json.load(f).get("dram_bytes_per_launch")
-    roofline = {"kernel": "gemm_bf16_tcgen05_kernel", "bound": "tensor", "achieved": round(gemm_tflops, 2),
+    roofline = {"kernel": "gemm_bf16_cg2_kernel", "bound": "tensor", "achieved": round(gemm_tflops, 2),
                 "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
                 "frac": round(gemm_tflops / peaks["bf16_tflops_sustained"], 4), "traffic": traffic,
                 "peak_source": f"{peaks['source']} (sustained; burst {peaks['bf16_tflops']})",

@@ -43,6 +43,7 @@ struct GemmParams {
     int M, N, K;
     int act;
     int m_pairs, n_tiles, k_blocks;
+    int debug;  // tuning experiments only (GVL_GEMM_DEBUG): bit 0 = stop issuing TMA loads once the ring was filled
 };
 
 template <int BN>
@@ -344,11 +345,17 @@ gemm_bf16_cg2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
                 const int m_blk = (st / p.n_tiles) * 2 + (int)cta_rank, n_blk = st % p.n_tiles;
                 for (int kb = 0; kb < p.k_blocks; ++kb) {
                     mbar_wait_cluster(&empty_bar[stage], phase ^ 1);
-                    if (cta_rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * Cfg2::STAGE_BYTES);
-                    const uint32_t fb = mapa_u32(smem_u32(&full_bar[stage]), 0);
-                    tma_load_2d_cg2(sA + stage * A_STAGE_BYTES, &tmA, fb, kb * BK, m_blk * BM);
-                    tma_load_2d_cg2(sB + stage * Cfg2::B_HALF_BYTES, &tmB, fb, kb * BK,
-                                    n_blk * BN + (int)cta_rank * (BN / 2));
+                    if ((p.debug & 1) && (phase || st != cluster_id)) {
+                        if (cta_rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 0);
+                    } else {
+                        if (cta_rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * Cfg2::STAGE_BYTES);
+                        const uint32_t fb = mapa_u32(smem_u32(&full_bar[stage]), 0);
+                        const bool same = (p.debug & 2) != 0;  // experiment: always the same (L2-resident) boxes
+                        tma_load_2d_cg2(sA + stage * A_STAGE_BYTES, &tmA, fb, same ? 0 : kb * BK,
+                                        same ? (int)cta_rank * BM : m_blk * BM);
+                        tma_load_2d_cg2(sB + stage * Cfg2::B_HALF_BYTES, &tmB, fb, same ? 0 : kb * BK,
+                                        (same ? 0 : n_blk * BN) + (int)cta_rank * (BN / 2));
+                    }
                     if (++stage == STAGES) {
                         stage = 0;
                         phase ^= 1;
@@ -483,8 +490,12 @@ extern "C" int gvl_gemm_bf16(const void* A, int lda, const void* W, int ldw, con
                   "gvl_gemm_bf16: bad residual ld/alignment");
     GVL_CHECK_ARG(act >= 0 && act <= 2, "gvl_gemm_bf16: bad act %d", act);
 
-    const int bn = pick_bn(N);
+    int bn = pick_bn(N);
+    static const int debug = [] { const char* e = getenv("GVL_GEMM_DEBUG"); return e ? atoi(e) : 0; }();
+    static const int force_bn = [] { const char* e = getenv("GVL_GEMM_BN"); return e ? atoi(e) : 0; }();
+    if (force_bn == 256 || force_bn == 192 || force_bn == 128) bn = force_bn;
     GemmParams p;
+    p.debug = debug;
     p.bias = bias;
     p.residual = reinterpret_cast<const __nv_bfloat16*>(residual);
     p.ldr = ldr;

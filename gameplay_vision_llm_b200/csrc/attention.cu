@@ -340,6 +340,8 @@ static int launch_attention(const void* qkv, void* out, int B, int T, int H, flo
 
 template <int HD>
 int launch_attention_tc(const void* qkv, void* out, int B, int T, int H, float scale, cudaStream_t s);  // attention_tc.cu
+template <int HD>
+int launch_attention_sdb(const void* qkv, void* out, int B, int T, int H, float scale, cudaStream_t s);  // attention_sdb.cu
 
 }  // namespace gvl
 
@@ -355,7 +357,15 @@ extern "C" int gvl_attention_bf16(const void* qkv, void* out, int B, int T, int 
         const char* e = getenv("GVL_ATTN_LEGACY");
         return e && e[0] == '1';
     }();
-    if (!legacy) {
+    // GVL_ATTN_TC1=1 selects the single-tile tcgen05 kernel (two CTAs per SM), also A/B only
+    static const bool single_tile = [] {
+        const char* e = getenv("GVL_ATTN_TC1");
+        return e && e[0] == '1';
+    }();
+    if (!legacy && !single_tile) {
+        if (hd == 72) return launch_attention_sdb<72>(qkv, out, B, T, H, scale, s);
+        if (hd == 64) return launch_attention_sdb<64>(qkv, out, B, T, H, scale, s);
+    } else if (!legacy) {
         if (hd == 72) return launch_attention_tc<72>(qkv, out, B, T, H, scale, s);
         if (hd == 64) return launch_attention_tc<64>(qkv, out, B, T, H, scale, s);
     } else {

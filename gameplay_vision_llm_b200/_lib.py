@@ -43,6 +43,13 @@ SIGNATURES = {
                                 POINTER(c_int), POINTER(c_int)]),
     "gvl_preprocess_u8": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_float_p, c_float_p, c_void_p,
                                   c_int, c_int, c_int, c_void_p]),
+    "gvl_preprocess_u8_crop": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
+                                       c_float_p, c_float_p, c_void_p, c_int, c_void_p]),
+    "gvl_patchify_tubelet_bf16": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
+    "gvl_mean_tokens_bf16": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_void_p]),
+    "gvl_videomae_workspace_bytes": (c_size_t, [POINTER(VitWeights), c_int]),
+    "gvl_videomae_forward": (c_int, [POINTER(VitWeights), c_void_p, c_int, c_void_p, c_size_t, c_void_p, c_int, c_void_p,
+                                     c_void_p]),
     "gvl_patchify_f32": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     "gvl_gemm_bf16": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_void_p, c_int,
                               c_int, c_int, c_int, c_int, c_int, c_void_p]),

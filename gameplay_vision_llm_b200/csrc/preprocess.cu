@@ -113,7 +113,7 @@ struct DevTables {
 };
 
 static std::mutex g_tab_mu;
-typedef std::tuple<int, int, int, int, int, int, int, int, int, int> TabKey;
+typedef std::tuple<int, int, int, int, int, int, int, int, int, int, int, int> TabKey;
 static std::map<TabKey, DevTables> g_tabs;
 
 template <typename T>
@@ -123,12 +123,14 @@ static int upload(const std::vector<T>& v, T** dptr) {
     return 0;
 }
 
+// eff_h x eff_w = region actually produced, starting at (cy0, cx0) of the resized image (crop window; the patch
+// layout drops the remainder rows / columns)
 static int get_tables(int H, int W, int eff_h, int eff_w, int out_h, int out_w, int resample, int TX, int TY,
-                      DevTables& out) {
+                      DevTables& out, int cy0 = 0, int cx0 = 0) {
     int dev = 0;
     GVL_CUDA(cudaGetDevice(&dev));
     std::lock_guard<std::mutex> lk(g_tab_mu);
-    TabKey key = std::make_tuple(dev, H, W, out_h, out_w, resample, TX, TY, eff_h, eff_w);
+    TabKey key = std::make_tuple(dev, H, W, out_h, out_w, resample, TX, TY, eff_h, eff_w, cy0, cx0);
     auto it = g_tabs.find(key);
     if (it != g_tabs.end()) {
         out = it->second;
@@ -146,17 +148,17 @@ static int get_tables(int H, int W, int eff_h, int eff_w, int out_h, int out_w, 
     d.v_prec = tv.precision;
     d.TX = TX;
     d.TY = TY;
-    for (int x0 = 0; x0 < eff_w; x0 += TX) {
-        const int x1 = std::min(x0 + TX, eff_w);
+    for (int x0 = cx0; x0 < cx0 + eff_w; x0 += TX) {
+        const int x1 = std::min(x0 + TX, cx0 + eff_w);
         const int c_lo = th.xmin[x0], c_hi = th.xmin[x1 - 1] + th.xsize[x1 - 1];
         const int a_lo = (3 * c_lo) & ~15, a_hi = (3 * c_hi + 15) & ~15;
         d.max_seg_bytes = std::max(d.max_seg_bytes, a_hi - a_lo);
         d.nch_max = std::max(d.nch_max, ((c_hi + 15) >> 4) - (c_lo >> 4));
     }
-    for (int i = 0; i < eff_w; ++i) d.max_hsize = std::max(d.max_hsize, (int)th.xsize[i]);
-    for (int i = 0; i < eff_h; ++i) d.max_vsize = std::max(d.max_vsize, (int)tv.xsize[i]);
-    for (int y0 = 0; y0 < eff_h; y0 += TY) {
-        const int y1 = std::min(y0 + TY, eff_h);
+    for (int i = cx0; i < cx0 + eff_w; ++i) d.max_hsize = std::max(d.max_hsize, (int)th.xsize[i]);
+    for (int i = cy0; i < cy0 + eff_h; ++i) d.max_vsize = std::max(d.max_vsize, (int)tv.xsize[i]);
+    for (int y0 = cy0; y0 < cy0 + eff_h; y0 += TY) {
+        const int y1 = std::min(y0 + TY, cy0 + eff_h);
         d.max_rows = std::max(d.max_rows, tv.xmin[y1 - 1] + tv.xsize[y1 - 1] - tv.xmin[y0]);
     }
     int rc = upload(th.xmin, &d.h_min) || upload(th.xsize, &d.h_size) || upload(th.w, &d.h_w) ||
@@ -185,14 +187,14 @@ struct PlanarTables {
     uint32_t *hq = nullptr, *vq = nullptr;
     int vq_stride = 0;
 };
-static std::map<std::tuple<int, int, int, int, int, int, int, int, int, int, int>, PlanarTables> g_ptabs;
+static std::map<std::tuple<int, int, int, int, int, int, int, int, int, int>, PlanarTables> g_ptabs;
 
-static int get_planar_tables(int H, int W, int eff_h, int eff_w, int out_h, int out_w, int resample, int TY, int nw,
-                             int nwv, PlanarTables& out) {
+static int get_planar_tables(int H, int W, int out_h, int out_w, int resample, int TY, int cy0, int nw, int nwv,
+                             PlanarTables& out) {
     int dev = 0;
     GVL_CUDA(cudaGetDevice(&dev));
     std::lock_guard<std::mutex> lk(g_tab_mu);
-    auto key = std::make_tuple(dev, H, W, out_h, out_w, resample, TY, eff_h, eff_w, nw, nwv);
+    auto key = std::make_tuple(dev, H, W, out_h, out_w, resample, TY, cy0, nw, nwv);
     auto it = g_ptabs.find(key);
     if (it != g_ptabs.end()) {
         out = it->second;
@@ -202,8 +204,8 @@ static int get_planar_tables(int H, int W, int eff_h, int eff_w, int out_h, int 
     if (compute_axis_taps(W, out_w, resample, th) || compute_axis_taps(H, out_h, resample, tv)) return 1;
     PlanarTables t;
     const int hs = 4 * nw + 4;
-    std::vector<uint32_t> hq((size_t)eff_w * hs, 0u);
-    for (int x = 0; x < eff_w; ++x) {
+    std::vector<uint32_t> hq((size_t)out_w * hs, 0u);
+    for (int x = 0; x < out_w; ++x) {
         uint32_t* row = hq.data() + (size_t)x * hs;
         const int o = th.xmin[x] & 3;
         int first = 2 * nw, last = 0;
@@ -218,10 +220,10 @@ static int get_planar_tables(int H, int W, int eff_h, int eff_w, int out_h, int 
         row[4 * nw + 1] = (uint32_t)(th.xmin[x] & ~3);
     }
     t.vq_stride = (2 * nwv + 1 + 3) & ~3;
-    std::vector<uint32_t> vq((size_t)eff_h * t.vq_stride, 0u);
-    for (int y = 0; y < eff_h; ++y) {
+    std::vector<uint32_t> vq((size_t)out_h * t.vq_stride, 0u);
+    for (int y = cy0; y < out_h; ++y) {  // y tiles start at the crop origin
         uint32_t* row = vq.data() + (size_t)y * t.vq_stride;
-        const int rel = tv.xmin[y] - tv.xmin[(y / TY) * TY];
+        const int rel = tv.xmin[y] - tv.xmin[cy0 + ((y - cy0) / TY) * TY];
         for (int h = 0; h < 2 * nwv; ++h)
             row[h] = host_weight_pair(tv.w.data() + (size_t)y * tv.taps, tv.taps, h, rel & 3);
         row[2 * nwv] = (uint32_t)(rel >> 2);
@@ -446,7 +448,8 @@ constexpr int PL_HALF = PL_THREADS / 2;
 struct PlanarParams {
     const uint8_t* frames;
     int B, H, W;
-    int out_h, out_w, eff_h, eff_w;
+    int out_h, out_w, eff_h, eff_w;  // out_* = dims of the written image (the crop window), eff_* = produced region
+    int cy0, cx0;                    // origin of the produced region inside the resized image
     const int32_t *h_min, *h_size, *v_min, *v_size;
     const int16_t *h_w, *v_w;
     int h_taps, v_taps, h_prec, v_prec;
@@ -536,8 +539,8 @@ preprocess_planar_kernel(const PlanarParams p) {
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int b = blockIdx.z;
-    const int x0 = blockIdx.x * p.TX, x1 = min(x0 + p.TX, p.eff_w);
-    const int y0 = blockIdx.y * p.TY, y1 = min(y0 + p.TY, p.eff_h);
+    const int x0 = p.cx0 + blockIdx.x * p.TX, x1 = min(x0 + p.TX, p.cx0 + p.eff_w);
+    const int y0 = p.cy0 + blockIdx.y * p.TY, y1 = min(y0 + p.TY, p.cy0 + p.eff_h);
     const int ntx = x1 - x0, nty = y1 - y0;
     const int r_lo = p.v_min[y0];
     const int r_hi = p.v_min[y1 - 1] + p.v_size[y1 - 1];
@@ -767,7 +770,7 @@ preprocess_planar_kernel(const PlanarParams p) {
         __syncthreads();
         // copy-out: contiguous segments
         if (patch_layout) {
-            const size_t prow = ((size_t)b * p.gh + (y0 + band0) / p.patch) * p.gw + x0 / p.patch;
+            const size_t prow = ((size_t)b * p.gh + (y0 - p.cy0 + band0) / p.patch) * p.gw + (x0 - p.cx0) / p.patch;
             uint4* gdst = reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(p.out) + prow * p.ld * 2);
             const int n16 = (ntx / p.patch) * p.ld * 2 / 16;
             for (int i = tid; i < n16; i += PL_THREADS) gdst[i] = reinterpret_cast<const uint4*>(sOut)[i];
@@ -776,7 +779,7 @@ preprocess_planar_kernel(const PlanarParams p) {
             for (int s = warp; s < 3 * nb; s += PL_THREADS / 32) {
                 const int c = s / nb, yl = s - c * nb;
                 uint8_t* gdst = reinterpret_cast<uint8_t*>(p.out) +
-                                ((((size_t)b * 3 + c) * p.out_h + y0 + band0 + yl) * p.out_w + x0) * esize;
+                                ((((size_t)b * 3 + c) * p.out_h + (y0 - p.cy0) + band0 + yl) * p.out_w + (x0 - p.cx0)) * esize;
                 const uint8_t* ssrc = sOut + (size_t)((c * p.VB + yl) * p.TX) * esize;
                 if (((reinterpret_cast<uintptr_t>(gdst) | (uintptr_t)seg_bytes | reinterpret_cast<uintptr_t>(ssrc)) & 15) == 0) {
                     for (int i = lane; i < (seg_bytes >> 4); i += 32)
@@ -817,13 +820,18 @@ static int get_lut(const float* sub, const float* div, float** out) {
 }
 
 // returns -1 when the geometry is outside the planar kernel's limits (caller falls back to v1)
+// (cy0, cx0, crop_h, crop_w): window of the resized out_h x out_w image that is written (CHW layouts); the whole
+// image when crop_h == 0.
 static int launch_planar(const uint8_t* frames, int B, int H, int W, int out_h, int out_w, int resample,
                          const float* h_sub, const float* h_div, void* out, int layout, int patch, int ld,
-                         cudaStream_t s) {
+                         cudaStream_t s, int cy0 = 0, int cx0 = 0, int crop_h = 0, int crop_w = 0) {
     PlanarParams p;
     memset(&p, 0, sizeof(p));
-    p.eff_h = out_h;
-    p.eff_w = out_w;
+    if (crop_h == 0) crop_h = out_h, crop_w = out_w;
+    p.eff_h = crop_h;
+    p.eff_w = crop_w;
+    p.cy0 = cy0;
+    p.cx0 = cx0;
     int TX = 128, VB = 8, ty_unit = 8, ty_mult = 4;
     const int esize = layout == GVL_LAYOUT_U8_CHW ? 1 : (layout == GVL_LAYOUT_F32_CHW ? 4 : 2);
     if (layout == GVL_LAYOUT_BF16_PATCH) {
@@ -842,7 +850,7 @@ static int launch_planar(const uint8_t* frames, int B, int H, int W, int out_h, 
     int TY = 0, pw = 0, g_max = 0, stage_bytes = 0;
     for (; ty_mult >= 1; --ty_mult) {
         TY = ty_unit * ty_mult;
-        int rc = get_tables(H, W, p.eff_h, p.eff_w, out_h, out_w, resample, TX, TY, tb);
+        int rc = get_tables(H, W, p.eff_h, p.eff_w, out_h, out_w, resample, TX, TY, tb, cy0, cx0);
         if (rc) return rc;
         nw = tb.max_hsize + 3 <= 16 ? 4 : (tb.max_hsize + 3 <= 24 ? 6 : (tb.max_hsize + 3 <= 32 ? 8 : 0));
         nwv = tb.max_vsize + 3 <= 12 ? 3 : (tb.max_vsize + 3 <= 16 ? 4 : (tb.max_vsize + 3 <= 32 ? 8 : 0));
@@ -864,7 +872,7 @@ static int launch_planar(const uint8_t* frames, int B, int H, int W, int out_h, 
     int rc = get_lut(h_sub, h_div, &lut);
     if (rc) return rc;
     PlanarTables pt;
-    rc = get_planar_tables(H, W, p.eff_h, p.eff_w, out_h, out_w, resample, TY, nw, nwv, pt);
+    rc = get_planar_tables(H, W, out_h, out_w, resample, TY, cy0, nw, nwv, pt);
     if (rc) return rc;
     p.hq = pt.hq;
     p.vq = pt.vq;
@@ -873,8 +881,8 @@ static int launch_planar(const uint8_t* frames, int B, int H, int W, int out_h, 
     p.B = B;
     p.H = H;
     p.W = W;
-    p.out_h = out_h;
-    p.out_w = out_w;
+    p.out_h = crop_h;
+    p.out_w = crop_w;
     p.h_min = tb.h_min;
     p.h_size = tb.h_size;
     p.v_min = tb.v_min;
@@ -899,7 +907,7 @@ static int launch_planar(const uint8_t* frames, int B, int H, int W, int out_h, 
     p.fast_rows = (W % 16 == 0 && (uintptr_t)frames % 16 == 0) ? 1 : 0;
     dim3 grid((p.eff_w + TX - 1) / TX, (p.eff_h + TY - 1) / TY, B);
     const double out_bytes = layout == GVL_LAYOUT_BF16_PATCH ? (double)p.gh * p.gw * 3 * patch * patch * 2
-                                                              : (double)3 * out_h * out_w * esize;
+                                                              : (double)3 * crop_h * crop_w * esize;
     ProfScope prof(GVL_K_PREPROCESS, (double)B * ((double)H * W * 3 + out_bytes), s);
     auto launch = [&](auto kernel) -> int {
         GVL_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -967,6 +975,76 @@ extern "C" int gvl_patchify_f32(const float* pixel_values, int B, int H, int W, 
         pixel_values, B, H, W, patch, ld, gh, gw, reinterpret_cast<__nv_bfloat16*>(out));
     GVL_LAUNCH_CHECK("patchify_f32_kernel");
     return 0;
+}
+
+// bf16 pixel_values [clips*frames, 3, H, W] (frame-major inside a clip) -> bf16 tubelet im2col rows for the
+// Conv3d(kernel = stride = (tubelet, patch, patch)) patch embedding: row = ((clip*(frames/tubelet) + t/tubelet)*gh +
+// py)*gw + px, col = c*tubelet*p*p + (t % tubelet)*p*p + ky*p + kx.  One thread moves 8 consecutive kx (16 bytes).
+namespace gvl {
+__global__ void __launch_bounds__(256)
+patchify_tubelet_kernel(const __nv_bfloat16* __restrict__ pv, int nframes_total, int frames, int H, int W, int patch,
+                        int tubelet, __nv_bfloat16* __restrict__ out) {
+    const int gh = H / patch, gw = W / patch, PP = patch * patch, K = 3 * tubelet * PP;
+    const int kchunks = patch >> 3;  // 16-byte chunks per patch row
+    const size_t total = (size_t)nframes_total * 3 * gh * patch * gw * kchunks;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        size_t r = i;
+        const int kc = (int)(r % kchunks); r /= kchunks;
+        const int px = (int)(r % gw); r /= gw;
+        const int ky = (int)(r % patch); r /= patch;
+        const int py = (int)(r % gh); r /= gh;
+        const int c = (int)(r % 3); r /= 3;
+        const int f = (int)r;  // global frame index
+        const int clip = f / frames, t = f - clip * frames;
+        const uint4 v = *reinterpret_cast<const uint4*>(pv + (((size_t)f * 3 + c) * H + py * patch + ky) * W + px * patch + kc * 8);
+        const size_t row = (((size_t)clip * (frames / tubelet) + t / tubelet) * gh + py) * gw + px;
+        *reinterpret_cast<uint4*>(out + row * K + (size_t)c * tubelet * PP + (t % tubelet) * PP + ky * patch + kc * 8) = v;
+    }
+}
+}  // namespace gvl
+
+extern "C" int gvl_patchify_tubelet_bf16(const void* pixel_values, int clips, int frames, int H, int W, int patch,
+                                         int tubelet, void* out, void* stream) {
+    using namespace gvl;
+    GVL_CHECK_ARG(pixel_values && out, "gvl_patchify_tubelet_bf16: null pointer");
+    GVL_CHECK_ARG(clips > 0 && frames > 0 && tubelet > 0 && frames % tubelet == 0 && patch % 8 == 0 && H % patch == 0 &&
+                      W % patch == 0 && W % 8 == 0,
+                  "gvl_patchify_tubelet_bf16: bad shape clips=%d frames=%d H=%d W=%d patch=%d tubelet=%d", clips, frames, H,
+                  W, patch, tubelet);
+    GVL_CHECK_ARG((uintptr_t)pixel_values % 16 == 0 && (uintptr_t)out % 16 == 0,
+                  "gvl_patchify_tubelet_bf16: pointers must be 16-byte aligned");
+    const size_t total = (size_t)clips * frames * 3 * H * (W / 8);
+    const int grid = (int)std::min<size_t>((total + 255) / 256, (size_t)sm_count() * 16);
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+    ProfScope prof(GVL_K_PATCHIFY, (double)clips * frames * 3 * H * W * 4, s);
+    patchify_tubelet_kernel<<<grid, 256, 0, s>>>(reinterpret_cast<const __nv_bfloat16*>(pixel_values), clips * frames,
+                                                 frames, H, W, patch, tubelet, reinterpret_cast<__nv_bfloat16*>(out));
+    GVL_LAUNCH_CHECK("patchify_tubelet_kernel");
+    return 0;
+}
+
+extern "C" int gvl_preprocess_u8_crop(const uint8_t* frames, int B, int H, int W, int out_h, int out_w, int crop_y0,
+                                      int crop_x0, int crop_h, int crop_w, int resample, const float* h_sub,
+                                      const float* h_div, void* out, int layout, void* stream) {
+    using namespace gvl;
+    GVL_CHECK_ARG(frames && out && h_sub && h_div, "gvl_preprocess_u8_crop: null pointer");
+    GVL_CHECK_ARG(B > 0 && B <= 65535 && H > 0 && W > 0 && out_h > 0 && out_w > 0, "gvl_preprocess_u8_crop: bad shape");
+    GVL_CHECK_ARG(layout >= GVL_LAYOUT_U8_CHW && layout <= GVL_LAYOUT_BF16_CHW,
+                  "gvl_preprocess_u8_crop: only the CHW layouts take a crop window (layout %d)", layout);
+    GVL_CHECK_ARG(H >= out_h && W >= out_w, "gvl_preprocess_u8_crop: only downscaling is supported (%dx%d -> %dx%d)", H,
+                  W, out_h, out_w);
+    GVL_CHECK_ARG(crop_y0 >= 0 && crop_x0 >= 0 && crop_h > 0 && crop_w > 0 && crop_y0 + crop_h <= out_h &&
+                      crop_x0 + crop_w <= out_w,
+                  "gvl_preprocess_u8_crop: crop window [%d,%d)+%dx%d outside the %dx%d resized image", crop_y0, crop_x0,
+                  crop_h, crop_w, out_h, out_w);
+    const int rc = launch_planar(frames, B, H, W, out_h, out_w, resample, h_sub, h_div, out, layout, 0, 0,
+                                 reinterpret_cast<cudaStream_t>(stream), crop_y0, crop_x0, crop_h, crop_w);
+    if (rc == -1) {
+        set_error("gvl_preprocess_u8_crop: resize geometry %dx%d -> %dx%d is outside the kernel's tap window", H, W, out_h,
+                  out_w);
+        return 1;
+    }
+    return rc;
 }
 
 extern "C" int gvl_resize_taps(int in_size, int out_size, int resample, int max_taps, int32_t* h_xmin, int32_t* h_xsize,

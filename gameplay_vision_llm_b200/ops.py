@@ -10,7 +10,7 @@ import numpy as np
 import torch
 
 from . import _lib
-from .weights import ProjectorPack, SiglipPack
+from .weights import ProjectorPack, SiglipPack, VideoMAEPack
 
 LAYOUT_U8_CHW, LAYOUT_F32_CHW, LAYOUT_BF16_CHW, LAYOUT_BF16_PATCH = 0, 1, 2, 3
 ACT_NONE, ACT_GELU_TANH, ACT_GELU_ERF = 0, 1, 2
@@ -78,6 +78,77 @@ def preprocess(frames: torch.Tensor, out_h: int = 384, out_w: int = 384, resampl
         frames.data_ptr(), B, H, W, out_h, out_w, resample, sub.ctypes.data_as(_lib.c_float_p),
         div.ctypes.data_as(_lib.c_float_p), out.data_ptr(), layout, patch, ld, _stream()), "gvl_preprocess_u8")
     return out
+
+
+def preprocess_crop(frames: torch.Tensor, out_h: int, out_w: int, crop_y0: int, crop_x0: int, crop_h: int, crop_w: int,
+                    resample: int = BILINEAR, image_mean=(0.5, 0.5, 0.5), image_std=(0.5, 0.5, 0.5),
+                    layout: int = LAYOUT_BF16_CHW, out: torch.Tensor | None = None) -> torch.Tensor:
+    """uint8 [B,H,W,3] frames -> the crop window of the resized (out_h x out_w) image, normalized, CHW."""
+    _need_cuda(frames)
+    if frames.dtype != torch.uint8 or frames.dim() != 4 or frames.shape[-1] != 3 or not frames.is_contiguous():
+        raise RuntimeError("frames must be a contiguous uint8 [B,H,W,3] tensor")
+    B, H, W, _ = frames.shape
+    dtype = {LAYOUT_U8_CHW: torch.uint8, LAYOUT_F32_CHW: torch.float32, LAYOUT_BF16_CHW: torch.bfloat16}[layout]
+    shape = (B, 3, crop_h, crop_w)
+    if out is None:
+        out = torch.empty(shape, dtype=dtype, device=frames.device)
+    elif tuple(out.shape) != shape or out.dtype != dtype or not out.is_contiguous():
+        raise RuntimeError(f"preprocess_crop: `out` must be contiguous {dtype} {shape}")
+    sub, div = fused_sub_div(image_mean, image_std)
+    _lib.check(_lib.lib().gvl_preprocess_u8_crop(
+        frames.data_ptr(), B, H, W, out_h, out_w, crop_y0, crop_x0, crop_h, crop_w, resample,
+        sub.ctypes.data_as(_lib.c_float_p), div.ctypes.data_as(_lib.c_float_p), out.data_ptr(), layout, _stream()),
+        "gvl_preprocess_u8_crop")
+    return out
+
+
+def patchify_tubelet(pixel_values: torch.Tensor, frames: int, patch: int = 16, tubelet: int = 2,
+                     out: torch.Tensor | None = None) -> torch.Tensor:
+    """bf16 pixel_values [clips*frames,3,H,W] -> bf16 tubelet rows [clips*(frames/tubelet)*gh*gw, 3*tubelet*p*p]."""
+    _need_cuda(pixel_values)
+    if pixel_values.dtype != torch.bfloat16 or pixel_values.dim() != 4 or pixel_values.shape[1] != 3 or \
+            not pixel_values.is_contiguous() or pixel_values.shape[0] % frames:
+        raise RuntimeError("patchify_tubelet: pixel_values must be contiguous bf16 [clips*frames,3,H,W]")
+    n, _, H, W = pixel_values.shape
+    clips = n // frames
+    shape = (clips * (frames // tubelet) * (H // patch) * (W // patch), 3 * tubelet * patch * patch)
+    if out is None:
+        out = torch.empty(shape, dtype=torch.bfloat16, device=pixel_values.device)
+    _lib.check(_lib.lib().gvl_patchify_tubelet_bf16(pixel_values.data_ptr(), clips, frames, H, W, patch, tubelet,
+                                                    out.data_ptr(), _stream()), "gvl_patchify_tubelet_bf16")
+    return out
+
+
+def mean_tokens(x: torch.Tensor, B: int, T: int, out_dtype: torch.dtype = torch.float32) -> torch.Tensor:
+    """bf16 [B*T, D] -> [B, D] mean over the T tokens of each item."""
+    _need_cuda(x)
+    if x.dtype != torch.bfloat16 or not x.is_contiguous() or x.shape[0] != B * T:
+        raise RuntimeError("mean_tokens: x must be contiguous bf16 [B*T, D]")
+    D = x.shape[1]
+    out = torch.empty((B, D), dtype=out_dtype, device=x.device)
+    _lib.check(_lib.lib().gvl_mean_tokens_bf16(x.data_ptr(), B, T, D, out.data_ptr(),
+                                               1 if out_dtype == torch.float32 else 0, _stream()), "gvl_mean_tokens_bf16")
+    return out
+
+
+def videomae_forward(pack: VideoMAEPack, patches: torch.Tensor, workspace: torch.Tensor | None = None,
+                     out_dtype: torch.dtype = torch.float32, return_tokens: bool = False):
+    """bf16 tubelet patches [B*T, patch_k] -> mean-pooled clip embeddings [B, D] (fp32 like the reference)."""
+    _need_cuda(patches)
+    spec = pack.spec
+    if patches.dtype != torch.bfloat16 or patches.shape[1] != spec.patch_ld or patches.shape[0] % spec.tokens:
+        raise RuntimeError("videomae_forward: patches must be bf16 [B*T, patch_k]")
+    B = patches.shape[0] // spec.tokens
+    need = pack.workspace_bytes(B)
+    if workspace is None:
+        workspace = torch.empty(need, dtype=torch.uint8, device=patches.device)
+    pooled = torch.empty((B, spec.hidden), dtype=out_dtype, device=patches.device)
+    tokens = torch.empty((B * spec.tokens, spec.hidden), dtype=torch.bfloat16, device=patches.device) if return_tokens else None
+    _lib.check(_lib.lib().gvl_videomae_forward(ctypes.byref(pack.struct), patches.data_ptr(), B, workspace.data_ptr(),
+                                               workspace.numel(), pooled.data_ptr(),
+                                               1 if out_dtype == torch.float32 else 0, _ptr(tokens), _stream()),
+               "gvl_videomae_forward")
+    return (pooled, tokens) if return_tokens else pooled
 
 
 def patchify(pixel_values: torch.Tensor, patch: int = 14, ld: int | None = None) -> torch.Tensor:

@@ -236,3 +236,164 @@ class ProjectorPack:
         self.w2 = sd["net.2.weight"].detach().to(torch.bfloat16).contiguous().to(dev)
         self.b2 = sd["net.2.bias"].detach().to(torch.float32).contiguous().to(dev)
         self.llm_dim, self.encoder_dim = self.w1.shape
+
+
+# ---------------------------------------------------------------------------------------------- VideoMAE
+@dataclass(frozen=True)
+class VideoMAESpec:
+    """`VideoMAEModel` geometry (HF: models/videomae/configuration_videomae.py).  The reference loads
+    `MCG-NJU/videomae-base` (scripts/extract_features.py:348-350)."""
+    hidden: int = 768
+    intermediate: int = 3072
+    layers: int = 12
+    heads: int = 12
+    image: int = 224
+    patch: int = 16
+    frames: int = 16
+    tubelet: int = 2
+    eps: float = 1e-12
+    act: str = "gelu"
+    final_norm: bool = True  # checkpoints with use_mean_pooling=False (MCG-NJU/videomae-base) carry `layernorm`
+
+    @property
+    def head_dim(self) -> int:
+        return self.hidden // self.heads
+
+    @property
+    def grid(self) -> int:
+        return self.image // self.patch
+
+    @property
+    def tokens(self) -> int:
+        return (self.frames // self.tubelet) * self.grid * self.grid
+
+    @property
+    def patch_k(self) -> int:
+        return 3 * self.tubelet * self.patch * self.patch
+
+    patch_ld = patch_k
+
+    @staticmethod
+    def base() -> "VideoMAESpec":
+        return VideoMAESpec()
+
+    @staticmethod
+    def tiny() -> "VideoMAESpec":
+        """Small encoder (head dim 64, ragged token count 2*3*3 = 18 per clip) for fast parity tests."""
+        return VideoMAESpec(hidden=128, intermediate=272, layers=2, heads=2, image=48, patch=16, frames=4)
+
+    def flops_per_clip(self, with_projector_llm: int | None = 4096) -> int:
+        T, D, I = self.tokens, self.hidden, self.intermediate
+        total = 2 * T * D * self.patch_k + self.layers * (2 * T * 3 * D * D + 2 * T * D * D + 4 * T * T * D + 4 * T * D * I)
+        if with_projector_llm:
+            total += 2 * D * with_projector_llm + 2 * with_projector_llm * with_projector_llm
+        return total
+
+
+def sinusoid_table(n_position: int, d_hid: int) -> torch.Tensor:
+    """The fixed position table of `VideoMAEEmbeddings` (HF: models/videomae/modeling_videomae.py:80-91), float64
+    math like the numpy original, returned as fp32 [n_position, d_hid]."""
+    pos = torch.arange(n_position, dtype=torch.float64)[:, None]
+    j = torch.arange(d_hid, dtype=torch.float64)[None, :]
+    angle = pos / torch.pow(torch.tensor(10000.0, dtype=torch.float64), 2.0 * torch.div(j, 2, rounding_mode="floor") / d_hid)
+    table = angle.clone()
+    table[:, 0::2] = torch.sin(angle[:, 0::2])
+    table[:, 1::2] = torch.cos(angle[:, 1::2])
+    return table.to(torch.float32)
+
+
+def synth_videomae_state_dict(spec: VideoMAESpec, seed: int = 2) -> dict[str, torch.Tensor]:
+    """Random encoder weights under the HF `VideoMAEModel` names; bf16-representable values (see module doc)."""
+    g = torch.Generator().manual_seed(int(seed))
+    D, I, P = spec.hidden, spec.intermediate, spec.patch
+    sd: dict[str, torch.Tensor] = {}
+
+    def normal(*shape, std):
+        return _bf16_round(torch.randn(*shape, generator=g) * std)
+
+    def layernorm(prefix):
+        sd[prefix + ".weight"] = _bf16_round(1.0 + 0.1 * torch.randn(D, generator=g))
+        sd[prefix + ".bias"] = normal(D, std=0.05)
+
+    sd["embeddings.patch_embeddings.projection.weight"] = normal(D, 3, spec.tubelet, P, P, std=1.0 / math.sqrt(spec.patch_k))
+    sd["embeddings.patch_embeddings.projection.bias"] = normal(D, std=0.02)
+    for i in range(spec.layers):
+        p = f"encoder.layer.{i}."
+        layernorm(p + "layernorm_before")
+        sd[p + "attention.attention.query.weight"] = normal(D, D, std=1.5 / math.sqrt(D))
+        sd[p + "attention.attention.key.weight"] = normal(D, D, std=1.5 / math.sqrt(D))
+        sd[p + "attention.attention.value.weight"] = normal(D, D, std=1.0 / math.sqrt(D))
+        sd[p + "attention.attention.q_bias"] = normal(D, std=0.02)
+        sd[p + "attention.attention.v_bias"] = normal(D, std=0.02)
+        sd[p + "attention.output.dense.weight"] = normal(D, D, std=1.0 / math.sqrt(D))
+        sd[p + "attention.output.dense.bias"] = normal(D, std=0.02)
+        layernorm(p + "layernorm_after")
+        sd[p + "intermediate.dense.weight"] = normal(I, D, std=1.0 / math.sqrt(D))
+        sd[p + "intermediate.dense.bias"] = normal(I, std=0.02)
+        sd[p + "output.dense.weight"] = normal(D, I, std=1.0 / math.sqrt(I))
+        sd[p + "output.dense.bias"] = normal(D, std=0.02)
+    if spec.final_norm:
+        layernorm("layernorm")
+    return sd
+
+
+class VideoMAEPack:
+    """Device-resident VideoMAE encoder weights in the `gvl_vit_weights` layout (include/gvl.h, K6b)."""
+
+    def __init__(self, sd: dict[str, torch.Tensor], spec: VideoMAESpec, device: torch.device | str):
+        self.spec = spec
+        self.device = torch.device(device)
+        self._keep: list[torch.Tensor] = []
+        D, I = spec.hidden, spec.intermediate
+        pre = "videomae." if any(k.startswith("videomae.") for k in sd) else ""
+
+        def get(name):
+            return sd[pre + name].detach().to(torch.float32)
+
+        def mat(t):
+            d = t.to(torch.bfloat16).contiguous().to(self.device)
+            self._keep.append(d)
+            return d
+
+        def vec(t):
+            d = t.to(torch.float32).contiguous().to(self.device)
+            self._keep.append(d)
+            return d
+
+        w = _lib.VitWeights()
+        w.D, w.I, w.H, w.hd, w.L, w.T = D, I, spec.heads, spec.head_dim, spec.layers, spec.tokens
+        w.patch_k, w.patch_ld = spec.patch_k, spec.patch_ld
+        w.eps = spec.eps
+        w.act = _ACT[spec.act]
+        # Conv3d weight (D, 3, tubelet, P, P) flattens to exactly the im2col column order c, kt, ky, kx
+        w.w_patch = mat(get("embeddings.patch_embeddings.projection.weight").reshape(D, spec.patch_k)).data_ptr()
+        w.b_patch = vec(get("embeddings.patch_embeddings.projection.bias")).data_ptr()
+        w.pos = mat(sinusoid_table(spec.tokens, D)).data_ptr()
+        self._layers = (_lib.VitLayer * spec.layers)()
+        for i in range(spec.layers):
+            p = f"encoder.layer.{i}."
+            a = p + "attention.attention."
+            ly = self._layers[i]
+            ly.ln1_g = vec(get(p + "layernorm_before.weight")).data_ptr()
+            ly.ln1_b = vec(get(p + "layernorm_before.bias")).data_ptr()
+            ly.w_qkv = mat(torch.cat([get(a + "query.weight"), get(a + "key.weight"), get(a + "value.weight")], 0)).data_ptr()
+            has_bias = (pre + a + "q_bias") in sd
+            qb = get(a + "q_bias") if has_bias else torch.zeros(D)
+            vb = get(a + "v_bias") if has_bias else torch.zeros(D)
+            ly.b_qkv = vec(torch.cat([qb, torch.zeros(D), vb], 0)).data_ptr()  # the key projection has no bias
+            ly.w_o = mat(get(p + "attention.output.dense.weight")).data_ptr()
+            ly.b_o = vec(get(p + "attention.output.dense.bias")).data_ptr()
+            ly.ln2_g = vec(get(p + "layernorm_after.weight")).data_ptr()
+            ly.ln2_b = vec(get(p + "layernorm_after.bias")).data_ptr()
+            ly.w_fc1 = mat(get(p + "intermediate.dense.weight")).data_ptr()
+            ly.b_fc1 = vec(get(p + "intermediate.dense.bias")).data_ptr()
+            ly.w_fc2 = mat(get(p + "output.dense.weight")).data_ptr()
+            ly.b_fc2 = vec(get(p + "output.dense.bias")).data_ptr()
+        w.layers = ctypes.cast(self._layers, ctypes.POINTER(_lib.VitLayer))
+        if (pre + "layernorm.weight") in sd:
+            w.post_g = vec(get("layernorm.weight")).data_ptr()
+            w.post_b = vec(get("layernorm.bias")).data_ptr()
+        self.struct = w
+
+    def workspace_bytes(self, batch: int) -> int:
+        return int(_lib.lib().gvl_videomae_workspace_bytes(ctypes.byref(self.struct), int(batch)))

@@ -101,6 +101,23 @@ GVL_API int gvl_preprocess_u8(const uint8_t* frames, int B, int H, int W, int ou
 GVL_API int gvl_patchify_f32(const float* pixel_values, int B, int H, int W, int patch, int ld, void* out,
                              void* stream);
 
+/* Same as gvl_preprocess_u8 for the CHW layouts, but only the window [crop_y0, crop_y0+crop_h) x [crop_x0,
+ * crop_x0+crop_w) of the resized out_h x out_w image is produced: out is [B,3,crop_h,crop_w].  Replaces
+ * `VideoMAEImageProcessor(pil_frames, return_tensors="pt")` (scripts/extract_features.py:345-375 ->
+ * HF:models/videomae/image_processing_videomae.py:35-105: shortest-edge-224 uint8 antialias resize, center crop
+ * 224, fused rescale+normalize). */
+GVL_API int gvl_preprocess_u8_crop(const uint8_t* frames, int B, int H, int W, int out_h, int out_w, int crop_y0,
+                           int crop_x0, int crop_h, int crop_w, int resample, const float* h_sub,
+                           const float* h_div, void* out, int layout, void* stream);
+
+/* pixel_values: bf16 [clips*frames, 3, H, W] (frames of a clip consecutive) -> bf16 tubelet im2col rows
+ * [clips*(frames/tubelet)*(H/p)*(W/p), 3*tubelet*p*p] for the Conv3d(kernel = stride = (tubelet,p,p)) patch
+ * embedding (HF:models/videomae/modeling_videomae.py:157-178: permute to (B,C,T,H,W), conv, flatten(2),
+ * transpose): row = ((clip*(frames/tubelet) + t/tubelet)*gh + py)*gw + px, col = c*tubelet*p*p + (t%tubelet)*p*p +
+ * ky*p + kx.  patch % 8 == 0. */
+GVL_API int gvl_patchify_tubelet_bf16(const void* pixel_values, int clips, int frames, int H, int W, int patch,
+                              int tubelet, void* out, void* stream);
+
 /* ---- K2: tcgen05 GEMM with fused epilogue ---------------------------------------------------- */
 /*
  * out[M,N] = act(A[M,K] . W[N,K]^T + bias[N]) + residual[(row % res_row_mod), N]
@@ -192,6 +209,22 @@ GVL_API size_t gvl_siglip_workspace_bytes(const gvl_vit_weights* w, int B);
  * 604-625). */
 GVL_API int gvl_siglip_forward(const gvl_vit_weights* w, const void* patches, int B, void* workspace,
                        size_t workspace_bytes, void* pooled, void* last_hidden, void* stream);
+
+/* ---- K6b: VideoMAE clip encoder ------------------------------------------------------------------- */
+/* out[b, :] = mean over the T tokens of x[b] (bf16 [B,T,D]); out bf16 or float [B,D].
+ * Replaces `outputs.last_hidden_state.mean(dim=1)` (scripts/extract_features.py:381). */
+GVL_API int gvl_mean_tokens_bf16(const void* x, int B, int T, int D, void* out, int out_f32, void* stream);
+
+/* The VideoMAE encoder takes the same weight pack as the SigLIP tower with: T = (frames/tubelet)*(H/p)*(W/p),
+ * patch_k = patch_ld = 3*tubelet*p*p, pos = the fixed sinusoid table (bf16 [T,D]), act = GVL_ACT_GELU_ERF,
+ * eps = 1e-12, b_qkv = cat(q_bias, 0, v_bias) (the key projection has no bias), post_g/post_b = the final
+ * LayerNorm or NULL when the checkpoint was trained with use_mean_pooling (no final norm); the MAP-head fields
+ * are unused.  patches: bf16 [B*T, patch_ld] (gvl_patchify_tubelet_bf16).  pooled: bf16 or float [B, D].
+ * last_hidden: optional bf16 [B*T, D].  Replaces `VideoMAEModel(**inputs).last_hidden_state.mean(dim=1)`
+ * (scripts/extract_features.py:377-381 -> HF:models/videomae/modeling_videomae.py:407-475). */
+GVL_API size_t gvl_videomae_workspace_bytes(const gvl_vit_weights* w, int B);
+GVL_API int gvl_videomae_forward(const gvl_vit_weights* w, const void* patches, int B, void* workspace,
+                         size_t workspace_bytes, void* pooled, int pooled_f32, void* last_hidden, void* stream);
 
 /* ---- K7: projector ------------------------------------------------------------------------------ */
 /* out = W2 . gelu_erf(W1 . x + b1) + b2.  Replaces MultiModalProjector.forward

@@ -1,0 +1,109 @@
+"""VideoMAE clip route (SURVEY.md §8f.1 / BASELINE.json configs[3]) through the C ABI against the oracle and the
+committed HF golden vectors: preprocessing bit-exact, embeddings within the stated bf16 tolerance."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from gameplay_vision_llm_b200 import ops, synth  # noqa: E402
+from gameplay_vision_llm_b200.videomae_encoder import VideoMAEClipEncoder  # noqa: E402
+from gameplay_vision_llm_b200.weights import (ProjectorPack, VideoMAEPack, VideoMAESpec,  # noqa: E402
+                                                synth_projector_state_dict, synth_videomae_state_dict)
+from oracle import siglip_ref, videomae_ref  # noqa: E402
+
+DEV = "cuda:0"
+
+
+def _cos(a, b):
+    return torch.nn.functional.cosine_similarity(a.double().cpu(), b.double().cpu(), dim=-1)
+
+
+@pytest.mark.parametrize("H,W,size", [(1080, 1920, 224), (123, 211, 48), (720, 1280, 224), (400, 300, 64)])
+def test_preprocess_crop_bit_exact(H, W, size):
+    frames = synth.noise_frames(3, H, W, seed=H)
+    pv = videomae_ref.pixel_values(frames.numpy(), size, size)
+    oh, ow, y0, x0 = videomae_ref.resize_geometry(H, W, size, size)
+    dev = frames.to(DEV)
+    got = ops.preprocess_crop(dev, oh, ow, y0, x0, size, size, layout=ops.LAYOUT_F32_CHW).cpu().numpy()
+    assert np.array_equal(got.view(np.uint32), pv.view(np.uint32)), "fp32 pixel_values differ"
+    got16 = ops.preprocess_crop(dev, oh, ow, y0, x0, size, size, layout=ops.LAYOUT_BF16_CHW).cpu()
+    assert torch.equal(got16.view(torch.int16), torch.from_numpy(pv).to(torch.bfloat16).view(torch.int16))
+    u8 = ops.preprocess_crop(dev, oh, ow, y0, x0, size, size, layout=ops.LAYOUT_U8_CHW).cpu().numpy()
+    assert np.array_equal(u8, np.rint(pv * 127.5 + 127.5).astype(np.uint8))
+
+
+def test_patchify_tubelet_bit_exact():
+    g = torch.Generator().manual_seed(0)
+    pv = torch.randn(2 * 4, 3, 48, 64, generator=g).to(torch.bfloat16)
+    want = videomae_ref.tubelet_patches(pv.float(), 4, 16, 2).reshape(-1, 3 * 2 * 256).to(torch.bfloat16)
+    got = ops.patchify_tubelet(pv.to(DEV), 4, 16, 2).cpu()
+    assert got.shape == want.shape and torch.equal(got.view(torch.int16), want.view(torch.int16))
+
+
+def test_mean_tokens():
+    g = torch.Generator().manual_seed(1)
+    x = torch.randn(3 * 1568, 768, generator=g).to(torch.bfloat16)
+    got = ops.mean_tokens(x.to(DEV), 3, 1568).cpu()
+    want = x.float().view(3, 1568, 768).mean(1)
+    assert (got - want).abs().max() < 1e-5
+
+
+def test_tiny_encoder_vs_oracle_and_golden(golden_dir):
+    gold = np.load(f"{golden_dir}/golden_videomae.npz")
+    spec = VideoMAESpec.tiny()
+    sd = synth_videomae_state_dict(spec, seed=2)
+    frames = synth.noise_frames(2 * spec.frames, 123, 211, seed=9)
+    seams = {}
+    pv = torch.from_numpy(videomae_ref.pixel_values(frames.numpy(), spec.image, spec.image))
+    want = videomae_ref.encoder_forward(sd, pv, spec.frames, spec.heads, spec.patch, spec.tubelet, spec.eps, seams=seams)
+    enc = VideoMAEClipEncoder(sd, spec, DEV)
+    dev_pv = enc.preprocess(frames.to(DEV))
+    patches = ops.patchify_tubelet(dev_pv, spec.frames, spec.patch, spec.tubelet)
+    pooled, tokens = ops.videomae_forward(enc.pack, patches, return_tokens=True)
+    torch.cuda.synchronize()
+    ctok = _cos(tokens.float().view(2, spec.tokens, -1), seams["last_hidden_state"])
+    print(f"tiny videomae: token cos min {ctok.min():.6f} pooled cos {_cos(pooled, want).tolist()}")
+    assert ctok.min() > 0.999 and _cos(pooled, want).min() > 0.999
+    assert _cos(pooled, torch.from_numpy(gold["tiny_pooled"])).min() > 0.999
+    assert (pooled.cpu() - torch.from_numpy(gold["tiny_pooled"])).abs().max() < 0.05
+
+
+def test_base_encoder_vs_hf_golden(golden_dir):
+    """VideoMAE-base geometry, one 16-frame 1080p clip (two scenes), synthetic weights seed 2, vs HF fp32."""
+    gold = np.load(f"{golden_dir}/golden_videomae.npz")
+    spec = VideoMAESpec.base()
+    sd = synth_videomae_state_dict(spec, seed=2)
+    enc = VideoMAEClipEncoder(sd, spec, DEV)
+    clip = torch.cat([synth.scene_frames(0, 8, device=DEV), synth.scene_frames(30, 8, device=DEV)], 0)
+    pooled = enc.encode_clips(clip)
+    pp = ProjectorPack(synth_projector_state_dict(spec.hidden, 4096, seed=3), DEV)
+    proj = ops.project(pp, pooled.to(torch.bfloat16))
+    torch.cuda.synchronize()
+    want, want_proj = torch.from_numpy(gold["base_pooled"]), torch.from_numpy(gold["base_projected"])
+    e = (pooled.cpu() - want).abs().max().item()
+    print(f"videomae-base: pooled cos {_cos(pooled, want).tolist()} max_abs {e:.4f}; projected cos "
+          f"{_cos(proj, want_proj).tolist()}")
+    assert _cos(pooled, want).min() >= 0.999 and _cos(proj, want_proj).min() >= 0.999
+    assert e < 0.1  # mean over 1568 tokens of |x| ~ 1 states: bf16 noise averages out, stated bound
+
+
+def test_run_mirrors_reference_clip_bookkeeping():
+    """`run_videomae_encoder` semantics (scripts/extract_features.py:355-390): non-overlapping clips, tail padded
+    with its last frame, start/end timestamps, one fp32 CPU embedding per clip."""
+    spec = VideoMAESpec.tiny()
+    sd = synth_videomae_state_dict(spec, seed=2)
+    enc = VideoMAEClipEncoder(sd, spec, DEV, clips_per_batch=2)
+    n = 3 * spec.frames + 1  # 13 frames -> 4 clips, the last one padded from a single frame
+    frames = synth.noise_frames(n, 90, 120, seed=4)
+    ts = [i / 2.0 for i in range(n)]
+    out = enc.run(frames, ts, projector=ProjectorPack(synth_projector_state_dict(spec.hidden, 256, seed=3), DEV))
+    assert out["num_input_frames"] == n and out["num_embeddings"] == 4 and out["embedding_dim"] == spec.hidden
+    last = out["embeddings"][-1]
+    assert last["start_time"] == ts[12] and last["end_time"] == ts[12] and last["source_frame_count"] == spec.frames
+    assert out["embeddings"][0]["start_time"] == 0.0 and out["embeddings"][0]["end_time"] == ts[3]
+    assert last["embedding"].dtype == torch.float32 and last["embedding"].device.type == "cpu"
+    assert last["projected"].shape == (256,)
+    # the padded clip equals a clip made of 4 copies of the last frame
+    rep = enc.encode_clips(frames[-1:].expand(spec.frames, -1, -1, -1).contiguous().to(DEV)).cpu()[0]
+    assert torch.allclose(rep, last["embedding"], atol=1e-6)

@@ -17,7 +17,8 @@ c_float_p = POINTER(c_float)
 
 class VitLayer(ctypes.Structure):
     _fields_ = [(n, c_void_p) for n in (
-        "ln1_g", "ln1_b", "w_qkv", "b_qkv", "w_o", "b_o", "ln2_g", "ln2_b", "w_fc1", "b_fc1", "w_fc2", "b_fc2")]
+        "ln1_g", "ln1_b", "w_qkv", "b_qkv", "w_o", "b_o", "ln2_g", "ln2_b", "w_fc1", "b_fc1", "w_fc2", "b_fc2",
+        "c1_qkv", "c1_fc1")]
 
 
 class VitWeights(ctypes.Structure):
@@ -27,8 +28,13 @@ class VitWeights(ctypes.Structure):
         + [("w_patch", c_void_p), ("b_patch", c_void_p), ("pos", c_void_p), ("layers", POINTER(VitLayer)),
            ("post_g", c_void_p), ("post_b", c_void_p), ("probe_q", c_void_p), ("w_kv", c_void_p), ("b_kv", c_void_p),
            ("w_ho", c_void_p), ("b_ho", c_void_p), ("hln_g", c_void_p), ("hln_b", c_void_p), ("w_hfc1", c_void_p),
-           ("b_hfc1", c_void_p), ("w_hfc2", c_void_p), ("b_hfc2", c_void_p)]
+           ("b_hfc1", c_void_p), ("w_hfc2", c_void_p), ("b_hfc2", c_void_p), ("fold_ln", c_int32), ("c1_kv", c_void_p)]
     )
+
+
+class GemmFusion(ctypes.Structure):
+    _fields_ = [("stats_out", c_void_p), ("ln_stats", c_void_p), ("ln_slots", c_int32), ("ln_dim", c_int32),
+                ("ln_c1", c_void_p), ("ln_eps", c_float)]
 
 
 # name -> (restype, argtypes); every symbol include/gvl.h declares
@@ -53,6 +59,9 @@ SIGNATURES = {
     "gvl_patchify_f32": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     "gvl_gemm_bf16": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_void_p, c_int,
                               c_int, c_int, c_int, c_int, c_int, c_void_p]),
+    "gvl_gemm_stats_slots": (c_int, [c_int]),
+    "gvl_gemm_bf16_fused": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_void_p, c_int,
+                                    c_int, c_int, c_int, c_int, c_int, POINTER(GemmFusion), c_void_p]),
     "gvl_layernorm_bf16": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_float,
                                    c_void_p]),
     "gvl_attention_bf16": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_float, c_void_p]),
@@ -82,7 +91,7 @@ def lib() -> ctypes.CDLL:
             fn = getattr(handle, name)
             fn.restype = res
             fn.argtypes = args
-        if handle.gvl_abi_version() != 1:
+        if handle.gvl_abi_version() != 2:
             raise RuntimeError("libgvl_sm100a.so ABI version mismatch; rebuild the extension")
         _LIB = handle
     return _LIB

@@ -44,6 +44,13 @@ struct GemmParams {
     int act;
     int m_pairs, n_tiles, k_blocks;
     int debug;  // tuning experiments only (GVL_GEMM_DEBUG): bit 0 = stop issuing TMA loads once the ring was filled
+    // LayerNorm fusion (gvl_gemm_fusion): producer side writes per-slab partial row sums of its bf16 outputs,
+    // consumer side normalises the rows of A algebraically in the epilogue
+    float* stats_out;       // [M, 2 * n_tiles, 2] or null
+    const float* ln_stats;  // [M, ln_slots, 2] or null
+    const float* ln_c1;     // [N]
+    int ln_slots;
+    float ln_inv_d, ln_eps;
 };
 
 template <int BN>
@@ -55,53 +62,103 @@ struct GemmCfg {
     static constexpr int TMEM_COLS = (2 * BN <= 256) ? 256 : 512;
     static constexpr int CHUNKS = BN / 32;               // 32-column epilogue chunks per tile
     static constexpr int CHUNKS_PER_WARP = CHUNKS / 2;   // two epilogue warps share a lane quadrant
-    static constexpr int BIAS_BYTES = kEpiWarps * CHUNKS_PER_WARP * 32 * 4;
+    static constexpr int BIAS_BYTES = 2 * kEpiWarps * CHUNKS_PER_WARP * 32 * 4;  // bias (or c2) and c1 per column
     static constexpr int BAR_BYTES = (2 * STAGES + 4) * 8 + 16;
     static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + BIAS_BYTES + BAR_BYTES + 1024 /*alignment slack*/;
 };
 
+struct Gemm2Stage {
+    static constexpr int TILE = 32 * 64;  // one staged 32-row x 32-column bf16 output tile
+};
+
+// Residual values of one 32-column chunk of this thread's output row (4 x 8 bf16).  Issued one chunk ahead of
+// their use — and, for the first chunk of a tile, before the wait on the accumulator — so that their L2 / HBM
+// latency never sits on the epilogue's critical path (the out-proj GEMM was epilogue-bound on exactly that).
+__device__ __forceinline__ void load_residual_chunk(const GemmParams& p, int row, int c0, uint4 (&rv)[4]) {
+    const bool row_ok = row < p.M;
+    const int rrow = p.res_row_mod > 0 ? (row % p.res_row_mod) : row;
+    const __nv_bfloat16* rp = p.residual + (size_t)rrow * p.ldr + c0;
+#pragma unroll
+    for (int g = 0; g < 4; ++g)
+        rv[g] = (p.residual != nullptr && row_ok && c0 + g * 8 < p.N) ? *reinterpret_cast<const uint4*>(rp + g * 8)
+                                                                      : make_uint4(0, 0, 0, 0);
+}
+
+// mean * rstd and rstd of one row of A from the producer's partial sums (fixed order: deterministic).  Called
+// before the wait on the accumulator so the loads stay off the epilogue's critical path.
+__device__ __forceinline__ void load_ln_row(const GemmParams& p, int row, float& ln_rstd, float& ln_mr) {
+    ln_rstd = 1.0f;
+    ln_mr = 0.0f;
+    if (p.ln_stats == nullptr || row >= p.M) return;
+    const float2* sp = reinterpret_cast<const float2*>(p.ln_stats) + (size_t)row * p.ln_slots;
+    float s1 = 0.f, s2 = 0.f;
+    for (int i = 0; i < p.ln_slots; ++i) {
+        const float2 t = sp[i];
+        s1 += t.x;
+        s2 += t.y;
+    }
+    const float mean = s1 * p.ln_inv_d;
+    const float var = fmaxf(s2 * p.ln_inv_d - mean * mean, 0.0f);
+    ln_rstd = rsqrtf(var + p.ln_eps);
+    ln_mr = mean * ln_rstd;
+}
+
 // Epilogue of one 128 x BN accumulator tile for one warp: TMEM lane quadrant q, column half `half`.
+// rv holds the residual of the first chunk (load_residual_chunk, issued by the caller before it waited for the tile).
 template <int BN>
 __device__ __forceinline__ void epilogue_tile(const GemmParams& p, const float* myBias, uint32_t tmem_base, int as,
-                                              int m_blk, int n0, int q, int half, int lane) {
+                                              int m_blk, int n0, int q, int half, int lane, uint4 (&rv)[4],
+                                              float ln_rstd, float ln_mr, const CUtensorMap* tmC = nullptr,
+                                              uint8_t* stage = nullptr, int* stage_parity = nullptr) {
     using Cfg = GemmCfg<BN>;
     const int row = m_blk * BM + q * 32 + lane;
     const bool row_ok = row < p.M;
-    const int rrow = p.res_row_mod > 0 ? (row % p.res_row_mod) : row;
     const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) +
                             (uint32_t)(as * BN + half * (Cfg::CHUNKS_PER_WARP * 32));
     const bool has_res = p.residual != nullptr;
+    // fused LayerNorm of the A rows: out = rstd * (acc - mean * c1[n]) + c2[n]  (c2 arrives through the bias slot)
+    const uint32_t bias_s = smem_u32(myBias);
+    const uint32_t c1_s = bias_s + kEpiWarps * Cfg::CHUNKS_PER_WARP * 32 * 4;
+    const bool ln = p.ln_stats != nullptr;
+    float st1 = 0.f, st2 = 0.f;  // partial row sums of this warp's bf16 outputs (stats_out)
 #pragma unroll 1
     for (int chunk = 0; chunk < Cfg::CHUNKS_PER_WARP; ++chunk) {
         const int c0 = n0 + chunk * 32;
         if (c0 >= p.N) break;  // warp-uniform
         uint32_t r[32];
         tmem_ld_32x32(t_addr + (uint32_t)(chunk * 32), r);
-        // residual loads are issued before waiting on TMEM so their latency overlaps it
-        uint4 rv[4];
-        if (has_res && row_ok) {
-            const __nv_bfloat16* rp = p.residual + (size_t)rrow * p.ldr + c0;
-#pragma unroll
-            for (int g = 0; g < 4; ++g)
-                rv[g] = (c0 + g * 8 < p.N) ? *reinterpret_cast<const uint4*>(rp + g * 8) : make_uint4(0, 0, 0, 0);
-        }
+        uint4 rn[4];  // next chunk's residual, in flight while this chunk is finished
+        if (has_res && chunk + 1 < Cfg::CHUNKS_PER_WARP) load_residual_chunk(p, row, c0 + 32, rn);
         tmem_ld_wait();
         if (row_ok) {
 #pragma unroll
             for (int g = 0; g < 4; ++g) {
                 const int col = c0 + g * 8;
                 if (col < p.N) {
-                    const float4 b0 = *reinterpret_cast<const float4*>(myBias + chunk * 32 + g * 8);
-                    const float4 b1 = *reinterpret_cast<const float4*>(myBias + chunk * 32 + g * 8 + 4);
+                    const float4 b0 = ld_shared_f4(bias_s + (chunk * 32 + g * 8) * 4);
+                    const float4 b1 = ld_shared_f4(bias_s + (chunk * 32 + g * 8 + 4) * 4);
                     float v[8];
-                    v[0] = __uint_as_float(r[g * 8 + 0]) + b0.x;
-                    v[1] = __uint_as_float(r[g * 8 + 1]) + b0.y;
-                    v[2] = __uint_as_float(r[g * 8 + 2]) + b0.z;
-                    v[3] = __uint_as_float(r[g * 8 + 3]) + b0.w;
-                    v[4] = __uint_as_float(r[g * 8 + 4]) + b1.x;
-                    v[5] = __uint_as_float(r[g * 8 + 5]) + b1.y;
-                    v[6] = __uint_as_float(r[g * 8 + 6]) + b1.z;
-                    v[7] = __uint_as_float(r[g * 8 + 7]) + b1.w;
+                    if (ln) {
+                        const float4 k0 = ld_shared_f4(c1_s + (chunk * 32 + g * 8) * 4);
+                        const float4 k1 = ld_shared_f4(c1_s + (chunk * 32 + g * 8 + 4) * 4);
+                        v[0] = fmaf(__uint_as_float(r[g * 8 + 0]), ln_rstd, fmaf(-ln_mr, k0.x, b0.x));
+                        v[1] = fmaf(__uint_as_float(r[g * 8 + 1]), ln_rstd, fmaf(-ln_mr, k0.y, b0.y));
+                        v[2] = fmaf(__uint_as_float(r[g * 8 + 2]), ln_rstd, fmaf(-ln_mr, k0.z, b0.z));
+                        v[3] = fmaf(__uint_as_float(r[g * 8 + 3]), ln_rstd, fmaf(-ln_mr, k0.w, b0.w));
+                        v[4] = fmaf(__uint_as_float(r[g * 8 + 4]), ln_rstd, fmaf(-ln_mr, k1.x, b1.x));
+                        v[5] = fmaf(__uint_as_float(r[g * 8 + 5]), ln_rstd, fmaf(-ln_mr, k1.y, b1.y));
+                        v[6] = fmaf(__uint_as_float(r[g * 8 + 6]), ln_rstd, fmaf(-ln_mr, k1.z, b1.z));
+                        v[7] = fmaf(__uint_as_float(r[g * 8 + 7]), ln_rstd, fmaf(-ln_mr, k1.w, b1.w));
+                    } else {
+                        v[0] = __uint_as_float(r[g * 8 + 0]) + b0.x;
+                        v[1] = __uint_as_float(r[g * 8 + 1]) + b0.y;
+                        v[2] = __uint_as_float(r[g * 8 + 2]) + b0.z;
+                        v[3] = __uint_as_float(r[g * 8 + 3]) + b0.w;
+                        v[4] = __uint_as_float(r[g * 8 + 4]) + b1.x;
+                        v[5] = __uint_as_float(r[g * 8 + 5]) + b1.y;
+                        v[6] = __uint_as_float(r[g * 8 + 6]) + b1.z;
+                        v[7] = __uint_as_float(r[g * 8 + 7]) + b1.w;
+                    }
                     if (p.act == GVL_ACT_GELU_TANH) {
 #pragma unroll
                         for (int j = 0; j < 8; ++j) v[j] = gelu_tanh_f(v[j]);
@@ -126,11 +183,46 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, const float* 
                         ov.y = pack_bf16x2(v[2], v[3]);
                         ov.z = pack_bf16x2(v[4], v[5]);
                         ov.w = pack_bf16x2(v[6], v[7]);
-                        *reinterpret_cast<uint4*>(o) = ov;
+                        if (tmC != nullptr)  // staging tile row = lane, 16-byte slot g, SWIZZLE_64B: slot ^= (row >> 1) & 3
+                            st_shared_v4(smem_u32(stage + *stage_parity * Gemm2Stage::TILE) + lane * 64 +
+                                             ((g ^ ((lane >> 1) & 3)) << 4),
+                                         ov);
+                        else
+                            *reinterpret_cast<uint4*>(o) = ov;
+                        if (p.stats_out != nullptr) {  // statistics of the values as stored (bf16-rounded)
+                            const uint32_t w4[4] = {ov.x, ov.y, ov.z, ov.w};
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) {
+                                const float a0 = bf16_lo(w4[e]), a1 = bf16_hi(w4[e]);
+                                st1 += a0 + a1;
+                                st2 = fmaf(a0, a0, fmaf(a1, a1, st2));
+                            }
+                        }
                     }
                 }
             }
         }
+        if (tmC != nullptr && !p.out_f32) {
+            // hand the staged 32 x 32 tile to the TMA engine (rows / columns beyond M / N are clipped) and make sure
+            // the tile written two chunks ago has been read before it is overwritten next time
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) {
+                tma_store_2d(tmC, stage + *stage_parity * Gemm2Stage::TILE, c0, m_blk * BM + q * 32);
+                tma_store_commit();
+                tma_store_wait_read<1>();
+            }
+            __syncwarp();
+            *stage_parity ^= 1;
+        }
+        if (has_res && chunk + 1 < Cfg::CHUNKS_PER_WARP) {
+#pragma unroll
+            for (int g = 0; g < 4; ++g) rv[g] = rn[g];
+        }
+    }
+    if (p.stats_out != nullptr && row_ok) {
+        const int slot = (n0 / BN) * 2 + half;
+        reinterpret_cast<float2*>(p.stats_out)[(size_t)row * (2 * p.n_tiles) + slot] = make_float2(st1, st2);
     }
 }
 
@@ -246,12 +338,19 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
         for (int st = cluster_id; st < num_super; st += num_clusters) {
             const int m_blk = (st / p.n_tiles) * 2 + (int)cta_rank, n_blk = st % p.n_tiles;
             const int n0 = n_blk * BN + half * (Cfg::CHUNKS_PER_WARP * 32);
-            for (int c = lane; c < Cfg::CHUNKS_PER_WARP * 32; c += 32)
+            for (int c = lane; c < Cfg::CHUNKS_PER_WARP * 32; c += 32) {
                 myBias[c] = (p.bias != nullptr && n0 + c < p.N) ? p.bias[n0 + c] : 0.0f;
+                if (p.ln_stats != nullptr)
+                    myBias[kEpiWarps * Cfg::CHUNKS_PER_WARP * 32 + c] = (n0 + c < p.N) ? p.ln_c1[n0 + c] : 0.0f;
+            }
             __syncwarp();
+            uint4 rv[4];
+            float ln_rstd, ln_mr;
+            load_residual_chunk(p, m_blk * BM + q * 32 + lane, n0, rv);
+            load_ln_row(p, m_blk * BM + q * 32 + lane, ln_rstd, ln_mr);
             mbar_wait(&tmem_full_bar[as], aphase);
             tcgen05_fence_after();
-            epilogue_tile<BN>(p, myBias, tmem_base, as, m_blk, n0, q, half, lane);
+            epilogue_tile<BN>(p, myBias, tmem_base, as, m_blk, n0, q, half, lane, rv, ln_rstd, ln_mr);
             tcgen05_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&tmem_empty_bar[as]);
@@ -283,16 +382,19 @@ template <int BN>
 struct Gemm2Cfg {
     static constexpr int B_HALF_BYTES = (BN / 2) * BK * 2;
     static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_HALF_BYTES;  // per CTA
-    static constexpr int STAGES = BN == 256 ? 6 : (BN == 192 ? 7 : 8);
+    static constexpr int STAGES = BN == 256 ? 5 : (BN == 192 ? 6 : 7);
     static constexpr int TMEM_COLS = (2 * BN <= 256) ? 256 : 512;
     static constexpr int BAR_BYTES = (2 * STAGES + 4) * 8 + 16;
-    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + GemmCfg<BN>::BIAS_BYTES + BAR_BYTES + 1024;
+    // bf16 outputs leave through per-warp staging tiles (32 rows x 64 B, SWIZZLE_64B, double-buffered) and TMA stores
+    static constexpr int OUT_TILE_BYTES = 32 * 64;
+    static constexpr int OUT_STAGE_BYTES = kEpiWarps * 2 * OUT_TILE_BYTES;
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + OUT_STAGE_BYTES + GemmCfg<BN>::BIAS_BYTES + BAR_BYTES + 1024;
 };
 
 template <int BN>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
 gemm_bf16_cg2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                     const GemmParams p) {
+                     const __grid_constant__ CUtensorMap tmC, const GemmParams p) {
     using Cfg = GemmCfg<BN>;
     using Cfg2 = Gemm2Cfg<BN>;
     constexpr int STAGES = Cfg2::STAGES;
@@ -301,8 +403,9 @@ gemm_bf16_cg2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* sA = smem;
     uint8_t* sB = smem + STAGES * A_STAGE_BYTES;
-    float* sBias = reinterpret_cast<float*>(smem + STAGES * Cfg2::STAGE_BYTES);
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg2::STAGE_BYTES + Cfg::BIAS_BYTES);
+    uint8_t* sOutStage = smem + STAGES * Cfg2::STAGE_BYTES;  // [epilogue warp][2][32 rows x 64 B], 1024-byte aligned
+    float* sBias = reinterpret_cast<float*>(sOutStage + Cfg2::OUT_STAGE_BYTES);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(sBias) + Cfg::BIAS_BYTES);
     uint64_t* full_bar = bars;                       // used in the leader only
     uint64_t* empty_bar = bars + STAGES;             // per CTA: "this stage may be overwritten"
     uint64_t* tmem_full_bar = bars + 2 * STAGES;     // per CTA: accumulator stage ready
@@ -316,6 +419,7 @@ gemm_bf16_cg2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmA);
         tma_prefetch_desc(&tmB);
+        tma_prefetch_desc(&tmC);
         for (int s = 0; s < STAGES; ++s) {
             mbar_init(&full_bar[s], 1);   // leader producer's arrive.expect_tx (+ tx bytes of both CTAs' loads)
             mbar_init(&empty_bar[s], 1);  // one multicast tcgen05.commit
@@ -402,23 +506,37 @@ gemm_bf16_cg2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         const int q = warp & 3;
         const int half = ew >> 2;
         float* myBias = sBias + ew * (Cfg::CHUNKS_PER_WARP * 32);
+        uint8_t* myStage = sOutStage + ew * (2 * Cfg2::OUT_TILE_BYTES);
+        const CUtensorMap* out_map = p.out_f32 ? nullptr : &tmC;  // fp32 outputs keep the direct stores
+        int stage_parity = 0;
         int as = 0;
         uint32_t aphase = 0;
         for (int st = cluster_id; st < num_super; st += num_clusters) {
             const int m_blk = (st / p.n_tiles) * 2 + (int)cta_rank, n_blk = st % p.n_tiles;
             const int n0 = n_blk * BN + half * (Cfg::CHUNKS_PER_WARP * 32);
-            for (int c = lane; c < Cfg::CHUNKS_PER_WARP * 32; c += 32)
+            for (int c = lane; c < Cfg::CHUNKS_PER_WARP * 32; c += 32) {
                 myBias[c] = (p.bias != nullptr && n0 + c < p.N) ? p.bias[n0 + c] : 0.0f;
+                if (p.ln_stats != nullptr)
+                    myBias[kEpiWarps * Cfg::CHUNKS_PER_WARP * 32 + c] = (n0 + c < p.N) ? p.ln_c1[n0 + c] : 0.0f;
+            }
             __syncwarp();
+            uint4 rv[4];
+            float ln_rstd, ln_mr;
+            load_residual_chunk(p, m_blk * BM + q * 32 + lane, n0, rv);
+            load_ln_row(p, m_blk * BM + q * 32 + lane, ln_rstd, ln_mr);
             mbar_wait_cluster(&tmem_full_bar[as], aphase);
             tcgen05_fence_after();
-            epilogue_tile<BN>(p, myBias, tmem_base, as, m_blk, n0, q, half, lane);
+            epilogue_tile<BN>(p, myBias, tmem_base, as, m_blk, n0, q, half, lane, rv, ln_rstd, ln_mr, out_map, myStage,
+                              &stage_parity);
             tcgen05_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive_cluster(mapa_u32(smem_u32(&tmem_empty_bar[as]), 0));
+            // the accumulator values are in registers (tcgen05.wait::ld): a relaxed arrive is enough, and unlike a
+            // release at cluster scope it does not wait for this warp's output stores to drain
+            if (lane == 0) mbar_arrive_cluster_relaxed(mapa_u32(smem_u32(&tmem_empty_bar[as]), 0));
             as ^= 1;
             if (as == 0) aphase ^= 1;
         }
+        if (lane == 0) tma_store_wait_all();  // staged tiles fully written out before the CTA's smem goes away
     }
 
     tcgen05_fence_before();
@@ -430,7 +548,8 @@ gemm_bf16_cg2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
 }
 
 template <int BN>
-static int launch_gemm_cg2(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, cudaStream_t stream) {
+static int launch_gemm_cg2(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const GemmParams& p,
+                           cudaStream_t stream) {
     using Cfg2 = Gemm2Cfg<BN>;
     GVL_CUDA(cudaFuncSetAttribute(gemm_bf16_cg2_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   Cfg2::SMEM_BYTES));
@@ -438,7 +557,7 @@ static int launch_gemm_cg2(const CUtensorMap& tmA, const CUtensorMap& tmB, const
     const int max_clusters = sm_count() / 2;
     const int clusters = super_tiles < max_clusters ? super_tiles : max_clusters;
     ProfScope prof(GVL_K_GEMM, 2.0 * p.M * (double)p.N * p.K, stream);
-    gemm_bf16_cg2_kernel<BN><<<2 * clusters, kGemmThreads, Cfg2::SMEM_BYTES, stream>>>(tmA, tmB, p);
+    gemm_bf16_cg2_kernel<BN><<<2 * clusters, kGemmThreads, Cfg2::SMEM_BYTES, stream>>>(tmA, tmB, tmC, p);
     GVL_LAUNCH_CHECK("gemm_bf16_cg2_kernel");
     return 0;
 }
@@ -475,9 +594,21 @@ static int pick_bn(int N) {
 
 }  // namespace gvl
 
+extern "C" int gvl_gemm_stats_slots(int N) {
+    const int bn = gvl::pick_bn(N);
+    return 2 * ((N + bn - 1) / bn);
+}
+
 extern "C" int gvl_gemm_bf16(const void* A, int lda, const void* W, int ldw, const float* bias, const void* residual,
                              int ldr, int res_row_mod, void* out, int ldo, int out_f32, int M, int N, int K, int act,
                              void* stream) {
+    return gvl_gemm_bf16_fused(A, lda, W, ldw, bias, residual, ldr, res_row_mod, out, ldo, out_f32, M, N, K, act, nullptr,
+                               stream);
+}
+
+extern "C" int gvl_gemm_bf16_fused(const void* A, int lda, const void* W, int ldw, const float* bias,
+                                   const void* residual, int ldr, int res_row_mod, void* out, int ldo, int out_f32, int M,
+                                   int N, int K, int act, const gvl_gemm_fusion* fusion, void* stream) {
     using namespace gvl;
     GVL_CHECK_ARG(A && W && out, "gvl_gemm_bf16: null pointer");
     GVL_CHECK_ARG(M > 0 && N > 0 && K > 0, "gvl_gemm_bf16: bad shape M=%d N=%d K=%d", M, N, K);
@@ -493,9 +624,25 @@ extern "C" int gvl_gemm_bf16(const void* A, int lda, const void* W, int ldw, con
     int bn = pick_bn(N);
     static const int debug = [] { const char* e = getenv("GVL_GEMM_DEBUG"); return e ? atoi(e) : 0; }();
     static const int force_bn = [] { const char* e = getenv("GVL_GEMM_BN"); return e ? atoi(e) : 0; }();
-    if (force_bn == 256 || force_bn == 192 || force_bn == 128) bn = force_bn;
+    if ((force_bn == 256 || force_bn == 192 || force_bn == 128) && fusion == nullptr) bn = force_bn;
     GemmParams p;
     p.debug = debug;
+    p.stats_out = nullptr;
+    p.ln_stats = nullptr;
+    p.ln_c1 = nullptr;
+    p.ln_slots = 0;
+    p.ln_inv_d = p.ln_eps = 0.f;
+    if (fusion != nullptr) {
+        GVL_CHECK_ARG(fusion->stats_out == nullptr || !out_f32, "gvl_gemm_bf16_fused: row statistics need a bf16 output");
+        GVL_CHECK_ARG(fusion->ln_stats == nullptr || (fusion->ln_c1 && fusion->ln_slots > 0 && fusion->ln_dim > 0),
+                      "gvl_gemm_bf16_fused: incomplete LayerNorm fusion arguments");
+        p.stats_out = fusion->stats_out;
+        p.ln_stats = fusion->ln_stats;
+        p.ln_c1 = fusion->ln_c1;
+        p.ln_slots = fusion->ln_slots;
+        p.ln_inv_d = fusion->ln_dim > 0 ? 1.0f / (float)fusion->ln_dim : 0.f;
+        p.ln_eps = fusion->ln_eps;
+    }
     p.bias = bias;
     p.residual = reinterpret_cast<const __nv_bfloat16*>(residual);
     p.ldr = ldr;
@@ -523,10 +670,19 @@ extern "C" int gvl_gemm_bf16(const void* A, int lda, const void* W, int ldw, con
         return e && e[0] == '1';
     }();
     if (!multicast_variant) {
+        // output map for the epilogue's TMA stores: 32 x 32 bf16 boxes, SWIZZLE_64B staging tiles
+        CUtensorMap tmC = tmA;  // placeholder for fp32 outputs (never dereferenced)
+        if (!out_f32) {
+            const uint64_t cdims[2] = {(uint64_t)N, (uint64_t)M};
+            const uint64_t cstr[1] = {(uint64_t)ldo * 2};
+            const uint32_t cbox[2] = {32, 32};
+            rc = make_tmap_nd_bf16(&tmC, out, 2, cdims, cstr, cbox, 64);
+            if (rc) return rc;
+        }
         switch (bn) {
-            case 256: return launch_gemm_cg2<256>(tmA, tmB, p, s);
-            case 192: return launch_gemm_cg2<192>(tmA, tmB, p, s);
-            default: return launch_gemm_cg2<128>(tmA, tmB, p, s);
+            case 256: return launch_gemm_cg2<256>(tmA, tmB, tmC, p, s);
+            case 192: return launch_gemm_cg2<192>(tmA, tmB, tmC, p, s);
+            default: return launch_gemm_cg2<128>(tmA, tmB, tmC, p, s);
         }
     }
     switch (bn) {

@@ -20,6 +20,7 @@ struct Workspace {
 
 struct VitBuffers {
     void *x, *xn, *qkv, *attn, *h, *pa, *hx, *hxn, *hh;
+    float *stats_a, *stats_b;  // LayerNorm-fusion partial row sums ([M, slots, 2] each)
 };
 
 static size_t carve(const gvl_vit_weights* w, int B, uint8_t* base, VitBuffers& vb) {
@@ -34,6 +35,9 @@ static size_t carve(const gvl_vit_weights* w, int B, uint8_t* base, VitBuffers& 
     vb.hx = ws.take((size_t)B * D * 2);
     vb.hxn = ws.take((size_t)B * D * 2);
     vb.hh = ws.take((size_t)B * I * 2);
+    const size_t slots = (size_t)gvl_gemm_stats_slots((int)D);
+    vb.stats_a = reinterpret_cast<float*>(ws.take(M * slots * 2 * sizeof(float)));
+    vb.stats_b = reinterpret_cast<float*>(ws.take(M * slots * 2 * sizeof(float)));
     return ws.off + 256;
 }
 
@@ -66,26 +70,56 @@ extern "C" int gvl_siglip_forward(const gvl_vit_weights* w, const void* patches,
     const int M = B * T;
     const float scale = 1.0f / sqrtf((float)hd);
 
-    // embeddings: conv-as-GEMM + bias + learned position embedding (row % T)
-    GVL_TRY(gvl_gemm_bf16(patches, w->patch_ld, w->w_patch, w->patch_ld, w->b_patch, w->pos, D, T, vb.x, D, 0, M, D,
-                          w->patch_ld, GVL_ACT_NONE, stream));
-    for (int l = 0; l < w->L; ++l) {
-        const gvl_vit_layer& ly = w->layers[l];
-        GVL_TRY(gvl_layernorm_bf16(vb.x, D, ly.ln1_g, ly.ln1_b, vb.xn, D, M, D, w->eps, stream));
-        GVL_TRY(gvl_gemm_bf16(vb.xn, D, ly.w_qkv, D, ly.b_qkv, nullptr, 0, 0, vb.qkv, 3 * D, 0, M, 3 * D, D,
-                              GVL_ACT_NONE, stream));
-        GVL_TRY(gvl_attention_bf16(vb.qkv, vb.attn, B, T, H, hd, scale, stream));
-        GVL_TRY(gvl_gemm_bf16(vb.attn, D, ly.w_o, D, ly.b_o, vb.x, D, 0, vb.x, D, 0, M, D, D, GVL_ACT_NONE, stream));
-        GVL_TRY(gvl_layernorm_bf16(vb.x, D, ly.ln2_g, ly.ln2_b, vb.xn, D, M, D, w->eps, stream));
-        GVL_TRY(gvl_gemm_bf16(vb.xn, D, ly.w_fc1, D, ly.b_fc1, nullptr, 0, 0, vb.h, I, 0, M, I, D, w->act, stream));
-        GVL_TRY(gvl_gemm_bf16(vb.h, I, ly.w_fc2, I, ly.b_fc2, vb.x, D, 0, vb.x, D, 0, M, D, I, GVL_ACT_NONE, stream));
-    }
-    void* tokens = last_hidden ? last_hidden : vb.xn;
-    GVL_TRY(gvl_layernorm_bf16(vb.x, D, w->post_g, w->post_b, tokens, D, M, D, w->eps, stream));
+    if (w->fold_ln) {
+        // LayerNorm folded into the GEMMs (gvl_gemm_fusion): the GEMMs that write the residual stream x also write
+        // its partial row sums; the GEMMs that consume LayerNorm(x) read x and normalise in their epilogue.
+        GVL_CHECK_ARG(w->c1_kv != nullptr, "gvl_siglip_forward: fold_ln pack without c1 vectors");
+        const int slots = gvl_gemm_stats_slots(D);
+        gvl_gemm_fusion prod_a = {vb.stats_a, nullptr, 0, 0, nullptr, 0.f};
+        gvl_gemm_fusion prod_b = {vb.stats_b, nullptr, 0, 0, nullptr, 0.f};
+        GVL_TRY(gvl_gemm_bf16_fused(patches, w->patch_ld, w->w_patch, w->patch_ld, w->b_patch, w->pos, D, T, vb.x, D, 0, M,
+                                    D, w->patch_ld, GVL_ACT_NONE, &prod_a, stream));
+        for (int l = 0; l < w->L; ++l) {
+            const gvl_vit_layer& ly = w->layers[l];
+            gvl_gemm_fusion ln1 = {nullptr, vb.stats_a, slots, D, ly.c1_qkv, w->eps};
+            gvl_gemm_fusion ln2 = {nullptr, vb.stats_b, slots, D, ly.c1_fc1, w->eps};
+            GVL_TRY(gvl_gemm_bf16_fused(vb.x, D, ly.w_qkv, D, ly.b_qkv, nullptr, 0, 0, vb.qkv, 3 * D, 0, M, 3 * D, D,
+                                        GVL_ACT_NONE, &ln1, stream));
+            GVL_TRY(gvl_attention_bf16(vb.qkv, vb.attn, B, T, H, hd, scale, stream));
+            GVL_TRY(gvl_gemm_bf16_fused(vb.attn, D, ly.w_o, D, ly.b_o, vb.x, D, 0, vb.x, D, 0, M, D, D, GVL_ACT_NONE,
+                                        &prod_b, stream));
+            GVL_TRY(gvl_gemm_bf16_fused(vb.x, D, ly.w_fc1, D, ly.b_fc1, nullptr, 0, 0, vb.h, I, 0, M, I, D, w->act, &ln2,
+                                        stream));
+            GVL_TRY(gvl_gemm_bf16_fused(vb.h, I, ly.w_fc2, I, ly.b_fc2, vb.x, D, 0, vb.x, D, 0, M, D, I, GVL_ACT_NONE,
+                                        &prod_a, stream));
+        }
+        if (last_hidden)  // only materialised when the caller asks for the post-layernorm tokens
+            GVL_TRY(gvl_layernorm_bf16(vb.x, D, w->post_g, w->post_b, last_hidden, D, M, D, w->eps, stream));
+        gvl_gemm_fusion lnp = {nullptr, vb.stats_a, slots, D, w->c1_kv, w->eps};
+        GVL_TRY(gvl_gemm_bf16_fused(vb.x, D, w->w_kv, D, w->b_kv, nullptr, 0, 0, vb.qkv, 2 * D, 0, M, 2 * D, D,
+                                    GVL_ACT_NONE, &lnp, stream));
+    } else {
+        // embeddings: conv-as-GEMM + bias + learned position embedding (row % T)
+        GVL_TRY(gvl_gemm_bf16(patches, w->patch_ld, w->w_patch, w->patch_ld, w->b_patch, w->pos, D, T, vb.x, D, 0, M, D,
+                              w->patch_ld, GVL_ACT_NONE, stream));
+        for (int l = 0; l < w->L; ++l) {
+            const gvl_vit_layer& ly = w->layers[l];
+            GVL_TRY(gvl_layernorm_bf16(vb.x, D, ly.ln1_g, ly.ln1_b, vb.xn, D, M, D, w->eps, stream));
+            GVL_TRY(gvl_gemm_bf16(vb.xn, D, ly.w_qkv, D, ly.b_qkv, nullptr, 0, 0, vb.qkv, 3 * D, 0, M, 3 * D, D,
+                                  GVL_ACT_NONE, stream));
+            GVL_TRY(gvl_attention_bf16(vb.qkv, vb.attn, B, T, H, hd, scale, stream));
+            GVL_TRY(gvl_gemm_bf16(vb.attn, D, ly.w_o, D, ly.b_o, vb.x, D, 0, vb.x, D, 0, M, D, D, GVL_ACT_NONE, stream));
+            GVL_TRY(gvl_layernorm_bf16(vb.x, D, ly.ln2_g, ly.ln2_b, vb.xn, D, M, D, w->eps, stream));
+            GVL_TRY(gvl_gemm_bf16(vb.xn, D, ly.w_fc1, D, ly.b_fc1, nullptr, 0, 0, vb.h, I, 0, M, I, D, w->act, stream));
+            GVL_TRY(gvl_gemm_bf16(vb.h, I, ly.w_fc2, I, ly.b_fc2, vb.x, D, 0, vb.x, D, 0, M, D, I, GVL_ACT_NONE, stream));
+        }
+        void* tokens = last_hidden ? last_hidden : vb.xn;
+        GVL_TRY(gvl_layernorm_bf16(vb.x, D, w->post_g, w->post_b, tokens, D, M, D, w->eps, stream));
 
-    // MAP head: K/V projections of all tokens, probe attention, out-proj, LN, MLP with residual
-    GVL_TRY(gvl_gemm_bf16(tokens, D, w->w_kv, D, w->b_kv, nullptr, 0, 0, vb.qkv, 2 * D, 0, M, 2 * D, D, GVL_ACT_NONE,
-                          stream));
+        // MAP head: K/V projections of all tokens, probe attention, out-proj, LN, MLP with residual
+        GVL_TRY(gvl_gemm_bf16(tokens, D, w->w_kv, D, w->b_kv, nullptr, 0, 0, vb.qkv, 2 * D, 0, M, 2 * D, D, GVL_ACT_NONE,
+                              stream));
+    }
     GVL_TRY(gvl_probe_attention_bf16(w->probe_q, vb.qkv, vb.pa, B, T, H, hd, stream));
     GVL_TRY(gvl_gemm_bf16(vb.pa, D, w->w_ho, D, w->b_ho, nullptr, 0, 0, vb.hx, D, 0, B, D, D, GVL_ACT_NONE, stream));
     GVL_TRY(gvl_layernorm_bf16(vb.hx, D, w->hln_g, w->hln_b, vb.hxn, D, B, D, w->eps, stream));

@@ -165,10 +165,19 @@ def patchify(pixel_values: torch.Tensor, patch: int = 14, ld: int | None = None)
     return out
 
 
+def gemm_stats_slots(N: int) -> int:
+    """Slabs per row a GEMM with N output columns writes into `stats_out` (host only)."""
+    return int(_lib.lib().gvl_gemm_stats_slots(int(N)))
+
+
 def gemm(a: torch.Tensor, w: torch.Tensor, bias: torch.Tensor | None = None, residual: torch.Tensor | None = None,
          res_row_mod: int = 0, act: int = ACT_NONE, out: torch.Tensor | None = None,
-         out_dtype: torch.dtype = torch.bfloat16) -> torch.Tensor:
-    """act(a @ w.T + bias) + residual; a [M,K] bf16, w [N,K] bf16, bias fp32 [N], residual bf16."""
+         out_dtype: torch.dtype = torch.bfloat16, stats_out: torch.Tensor | None = None,
+         ln_stats: torch.Tensor | None = None, ln_c1: torch.Tensor | None = None, ln_dim: int = 0,
+         ln_eps: float = 0.0) -> torch.Tensor:
+    """act(a @ w.T + bias) + residual; a [M,K] bf16, w [N,K] bf16, bias fp32 [N], residual bf16.
+    stats_out fp32 [M, gemm_stats_slots(N), 2]: also write the partial (sum, sum of squares) of every stored row.
+    ln_stats (+ ln_c1 fp32 [N], ln_dim, ln_eps): normalise the rows of `a` in the epilogue (see gvl_gemm_fusion)."""
     _need_cuda(a, w, bias, residual, out)
     M, K = a.shape
     N, K2 = w.shape
@@ -187,9 +196,20 @@ def gemm(a: torch.Tensor, w: torch.Tensor, bias: torch.Tensor | None = None, res
         if residual.dtype != torch.bfloat16 or residual.stride(1) != 1:
             raise RuntimeError("gemm: residual must be bf16, row-major")
         ldr = residual.stride(0)
-    _lib.check(_lib.lib().gvl_gemm_bf16(
+    fusion = None
+    if stats_out is not None or ln_stats is not None:
+        _need_cuda(stats_out, ln_stats, ln_c1)
+        fusion = _lib.GemmFusion()
+        fusion.stats_out = _ptr(stats_out)
+        fusion.ln_stats = _ptr(ln_stats)
+        fusion.ln_slots = 0 if ln_stats is None else int(ln_stats.shape[1])
+        fusion.ln_dim = int(ln_dim)
+        fusion.ln_c1 = _ptr(ln_c1)
+        fusion.ln_eps = float(ln_eps)
+    _lib.check(_lib.lib().gvl_gemm_bf16_fused(
         a.data_ptr(), a.stride(0), w.data_ptr(), w.stride(0), _ptr(bias), _ptr(residual), ldr, res_row_mod,
-        out.data_ptr(), out.stride(0), 1 if out.dtype == torch.float32 else 0, M, N, K, act, _stream()), "gvl_gemm_bf16")
+        out.data_ptr(), out.stride(0), 1 if out.dtype == torch.float32 else 0, M, N, K, act,
+        ctypes.byref(fusion) if fusion is not None else None, _stream()), "gvl_gemm_bf16_fused")
     return out
 
 

@@ -150,12 +150,24 @@ _ACT = {"gelu_pytorch_tanh": 1, "gelu": 2, "gelu_erf": 2, "none": 0}
 class SiglipPack:
     """Device-resident weights + the ctypes `gvl_vit_weights` struct pointing at them."""
 
-    def __init__(self, sd: dict[str, torch.Tensor], spec: SiglipVisionSpec, device: torch.device | str):
+    def __init__(self, sd: dict[str, torch.Tensor], spec: SiglipVisionSpec, device: torch.device | str,
+                 fold_ln: bool = False):
+        """fold_ln: fold every token-level LayerNorm into the Linear that consumes it (include/gvl.h,
+        `gvl_gemm_fusion`): W' = bf16(W * gamma), c1[n] = sum_k W'[n,k], c2 = bias + W @ beta.  The LayerNorm
+        kernels then disappear from the forward pass.  Off by default: measured on B200 the extra epilogue work
+        (+40 us per consumer GEMM) cancels the 44 us LayerNorm kernel it removes (profiles/README.md), so the
+        production path keeps the reference's op order."""
         self.spec = spec
         self.device = torch.device(device)
         self._keep: list[torch.Tensor] = []
         D, I, T = spec.hidden, spec.intermediate, spec.tokens
         vm = "vision_model." if any(k.startswith("vision_model.") for k in sd) else ""
+
+        def folded(weight: torch.Tensor, bias: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor):
+            wf = (weight.double() * gamma.double()[None, :]).to(torch.bfloat16)
+            c1 = wf.double().sum(dim=1).to(torch.float32)
+            c2 = (bias.double() + weight.double() @ beta.double()).to(torch.float32)
+            return wf, c1, c2
 
         def get(name):
             return sd[vm + name].detach().to(torch.float32)
@@ -188,14 +200,23 @@ class SiglipPack:
             ly = self._layers[i]
             ly.ln1_g = vec(get(p + "layer_norm1.weight")).data_ptr()
             ly.ln1_b = vec(get(p + "layer_norm1.bias")).data_ptr()
-            ly.w_qkv = mat(torch.cat([get(p + f"self_attn.{n}_proj.weight") for n in "qkv"], 0)).data_ptr()
-            ly.b_qkv = vec(torch.cat([get(p + f"self_attn.{n}_proj.bias") for n in "qkv"], 0)).data_ptr()
+            wqkv = torch.cat([get(p + f"self_attn.{n}_proj.weight") for n in "qkv"], 0)
+            bqkv = torch.cat([get(p + f"self_attn.{n}_proj.bias") for n in "qkv"], 0)
+            if fold_ln:
+                wqkv, c1, bqkv = folded(wqkv, bqkv, get(p + "layer_norm1.weight"), get(p + "layer_norm1.bias"))
+                ly.c1_qkv = vec(c1).data_ptr()
+            ly.w_qkv = mat(wqkv).data_ptr()
+            ly.b_qkv = vec(bqkv).data_ptr()
             ly.w_o = mat(get(p + "self_attn.out_proj.weight")).data_ptr()
             ly.b_o = vec(get(p + "self_attn.out_proj.bias")).data_ptr()
             ly.ln2_g = vec(get(p + "layer_norm2.weight")).data_ptr()
             ly.ln2_b = vec(get(p + "layer_norm2.bias")).data_ptr()
-            ly.w_fc1 = mat(get(p + "mlp.fc1.weight")).data_ptr()
-            ly.b_fc1 = vec(get(p + "mlp.fc1.bias")).data_ptr()
+            wfc1, bfc1 = get(p + "mlp.fc1.weight"), get(p + "mlp.fc1.bias")
+            if fold_ln:
+                wfc1, c1, bfc1 = folded(wfc1, bfc1, get(p + "layer_norm2.weight"), get(p + "layer_norm2.bias"))
+                ly.c1_fc1 = vec(c1).data_ptr()
+            ly.w_fc1 = mat(wfc1).data_ptr()
+            ly.b_fc1 = vec(bfc1).data_ptr()
             ly.w_fc2 = mat(get(p + "mlp.fc2.weight")).data_ptr()
             ly.b_fc2 = vec(get(p + "mlp.fc2.bias")).data_ptr()
         w.layers = ctypes.cast(self._layers, ctypes.POINTER(_lib.VitLayer))
@@ -207,8 +228,13 @@ class SiglipPack:
         probe = get("head.probe").reshape(D)
         q = (ipw[:D] @ probe + ipb[:D]) * (spec.head_dim ** -0.5)
         w.probe_q = vec(q).data_ptr()
-        w.w_kv = mat(ipw[D:]).data_ptr()
-        w.b_kv = vec(ipb[D:]).data_ptr()
+        wkv, bkv = ipw[D:], ipb[D:]
+        w.fold_ln = 1 if fold_ln else 0
+        if fold_ln:
+            wkv, c1, bkv = folded(wkv, bkv, get("post_layernorm.weight"), get("post_layernorm.bias"))
+            w.c1_kv = vec(c1).data_ptr()
+        w.w_kv = mat(wkv).data_ptr()
+        w.b_kv = vec(bkv).data_ptr()
         w.w_ho = mat(get("head.attention.out_proj.weight")).data_ptr()
         w.b_ho = vec(get("head.attention.out_proj.bias")).data_ptr()
         w.hln_g = vec(get("head.layernorm.weight")).data_ptr()

@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define GVL_ABI_VERSION 1
+#define GVL_ABI_VERSION 2
 
 #if defined(__GNUC__)
 #define GVL_API __attribute__((visibility("default")))
@@ -138,6 +138,28 @@ GVL_API int gvl_gemm_bf16(const void* A, int lda, const void* W, int ldw, const 
                   const void* residual, int ldr, int res_row_mod, void* out, int ldo, int out_f32,
                   int M, int N, int K, int act, void* stream);
 
+/* LayerNorm folded into the GEMMs on either side of it (used by gvl_siglip_forward when the weight pack says
+ * fold_ln): the GEMM that WRITES the residual stream also writes, per output row and per slab of columns (two slabs
+ * per N tile), the partial sums (sum x, sum x^2) of the bf16 values it stored; the GEMM that CONSUMES LayerNorm(x)
+ * reads x itself as A, uses weights pre-multiplied by gamma, and applies
+ *     out[m,n] = act( rstd[m] * (acc[m,n] - mean[m] * c1[n]) + c2[n] ),   c1[n] = sum_k W'[n,k],
+ *     c2[n] = bias[n] + sum_k beta[k] W[n,k]   (passed through `bias`),
+ * with mean / rstd from the partial sums added in a fixed order (deterministic; no atomics).  Algebraically
+ * identical to LayerNorm followed by the Linear (HF:models/siglip/modeling_siglip.py:340-361); it removes one
+ * read + write of the [M,D] activations per LayerNorm. */
+typedef struct gvl_gemm_fusion {
+    float* stats_out;      /* producer: float [M, gvl_gemm_stats_slots(N), 2], or NULL */
+    const float* ln_stats; /* consumer: statistics of the rows of A written by a producer GEMM, or NULL */
+    int32_t ln_slots;      /* slabs per row in ln_stats */
+    int32_t ln_dim;        /* number of columns the statistics cover (D) */
+    const float* ln_c1;    /* [N] */
+    float ln_eps;
+} gvl_gemm_fusion;
+GVL_API int gvl_gemm_stats_slots(int N); /* slabs per row a producer GEMM with N output columns writes. Host only. */
+GVL_API int gvl_gemm_bf16_fused(const void* A, int lda, const void* W, int ldw, const float* bias,
+                        const void* residual, int ldr, int res_row_mod, void* out, int ldo, int out_f32,
+                        int M, int N, int K, int act, const gvl_gemm_fusion* fusion, void* stream);
+
 /* ---- K3: LayerNorm -------------------------------------------------------------------------- */
 /* y = (x - mean) / sqrt(var + eps) * gamma + beta over the last dim, fp32 statistics.
  * Replaces nn.LayerNorm (HF:models/siglip/modeling_siglip.py:334-336,596,636). x,y bf16; D % 4 == 0. */
@@ -174,6 +196,9 @@ typedef struct gvl_vit_layer {
     const float* b_fc1;
     const void* w_fc2; /* bf16 [D, I] */
     const float* b_fc2;
+    /* fold_ln packs only: w_qkv / w_fc1 hold W * gamma (ln1 / ln2), b_qkv / b_fc1 hold c2, and these hold c1 */
+    const float* c1_qkv; /* [3D] */
+    const float* c1_fc1; /* [I] */
 } gvl_vit_layer;
 
 typedef struct gvl_vit_weights {
@@ -197,6 +222,11 @@ typedef struct gvl_vit_weights {
     const float* b_hfc1;
     const void* w_hfc2; /* bf16 [D, I] */
     const float* b_hfc2;
+    /* LayerNorm folding (gvl_gemm_fusion): when fold_ln != 0 the per-layer LayerNorms and post_layernorm are not run
+     * as kernels; w_kv / b_kv hold the folded MAP-head K/V projection and c1_kv its column sums.  ln*_g / ln*_b and
+     * post_g / post_b must still be valid (last_hidden output, VideoMAE final norm). */
+    int32_t fold_ln;
+    const float* c1_kv; /* [2D] */
 } gvl_vit_weights;
 
 /* Bytes of scratch gvl_siglip_forward needs for a batch of B images. Host only. */

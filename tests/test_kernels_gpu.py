@@ -83,6 +83,36 @@ def test_gemm_strided_views():
     assert rel < 6e-3
 
 
+def test_gemm_layernorm_fusion():
+    """Producer GEMM writes partial row sums of what it stored; consumer GEMM on raw x with gamma-folded weights
+    reproduces Linear(LayerNorm(x)) (include/gvl.h: gvl_gemm_fusion)."""
+    g = torch.Generator().manual_seed(11)
+    M, D, N2 = 1000, 1152, 4304
+    a = torch.randn(M, 592, generator=g).to(torch.bfloat16).to(DEV)
+    w0 = (torch.randn(D, 592, generator=g) / 24).to(torch.bfloat16).to(DEV)
+    res = (torch.randn(M, D, generator=g) * 3 + 0.7).to(torch.bfloat16).to(DEV)
+    slots = ops.gemm_stats_slots(D)
+    stats = torch.full((M, slots, 2), float("nan"), device=DEV)
+    x = ops.gemm(a, w0, None, residual=res, stats_out=stats)  # x = a @ w0.T + res, bf16, + statistics
+    torch.cuda.synchronize()
+    xs = x.float()
+    assert torch.allclose(stats[:, :, 0].sum(1), xs.sum(1), rtol=1e-5, atol=1e-2)
+    assert torch.allclose(stats[:, :, 1].sum(1), (xs * xs).sum(1), rtol=1e-5, atol=1e-2)
+    gamma = (1 + 0.1 * torch.randn(D, generator=g)).to(DEV)
+    beta = (0.05 * torch.randn(D, generator=g)).to(DEV)
+    w1 = (torch.randn(N2, D, generator=g) / 34).to(torch.bfloat16).to(DEV)
+    b1 = (0.02 * torch.randn(N2, generator=g)).to(DEV)
+    wf = (w1.double() * gamma.double()[None]).to(torch.bfloat16)
+    c1 = wf.double().sum(1).float()
+    c2 = (b1.double() + w1.double() @ beta.double()).float()
+    got = ops.gemm(x, wf, c2, act=1, ln_stats=stats, ln_c1=c1, ln_dim=D, ln_eps=1e-6)
+    torch.cuda.synchronize()
+    ref = siglip_ref.gelu_tanh(torch.nn.functional.layer_norm(xs, (D,), gamma, beta, 1e-6) @ w1.float().T + b1)
+    mx, rel, mean = _rel_err(got, ref)
+    print(f"gemm LN fusion: max_abs={mx:.3e} rel={rel:.3e} mean={mean:.3e}")
+    assert rel < 8e-3
+
+
 # ------------------------------------------------------------------------------------------- LayerNorm
 @pytest.mark.parametrize("rows,D", [(7, 1152), (1458, 1152), (33, 768), (5, 144), (9, 4096)])
 def test_layernorm(rows, D):

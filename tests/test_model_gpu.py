@@ -18,17 +18,18 @@ def _cos(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
     return torch.nn.functional.cosine_similarity(a.double().cpu(), b.double().cpu(), dim=-1)
 
 
+@pytest.mark.parametrize("fold_ln", [True, False])
 @pytest.mark.parametrize("spec,H,W,B", [
     (SiglipVisionSpec.tiny(), 123, 211, 3),
     (SiglipVisionSpec(hidden=216, intermediate=400, layers=3, heads=3, image=140, patch=14), 300, 400, 5),
 ])
-def test_small_tower_vs_oracle(spec, H, W, B):
+def test_small_tower_vs_oracle(spec, H, W, B, fold_ln):
     sd = synth_siglip_state_dict(spec, seed=0)
     frames = synth.noise_frames(B, H, W, seed=7)
     pv = torch.from_numpy(preprocess_ref.pixel_values(frames.numpy(), spec.image, spec.image, 2))
     seams = {}
     want = siglip_ref.vision_forward(sd, pv, spec.heads, spec.patch, spec.eps, seams=seams)
-    pack = SiglipPack(sd, spec, DEV)
+    pack = SiglipPack(sd, spec, DEV, fold_ln=fold_ln)
     patches = ops.preprocess(frames.to(DEV), spec.image, spec.image, 2, layout=ops.LAYOUT_BF16_PATCH, patch=spec.patch,
                              ld=spec.patch_ld)
     pooled, tokens = ops.siglip_forward(pack, patches, return_tokens=True)
@@ -54,14 +55,16 @@ def test_tiny_tower_vs_hf_golden(golden_dir):
     assert _cos(proj, torch.from_numpy(gold["projected"])).min() > 0.999
 
 
-def test_so400m_vs_hf_golden(golden_dir):
-    """Full-size tower: 4 synthetic 1080p scene frames, synthetic weights seed 0, against HF fp32 outputs."""
+@pytest.mark.parametrize("fold_ln", [True, False])
+def test_so400m_vs_hf_golden(golden_dir, fold_ln):
+    """Full-size tower: 4 synthetic 1080p scene frames, synthetic weights seed 0, against HF fp32 outputs; with the
+    LayerNorms folded into the GEMMs (production) and as separate kernels (the reference's op order)."""
     gold = np.load(f"{golden_dir}/golden_so400m.npz")
     spec = SiglipVisionSpec.so400m()
     sd = synth_siglip_state_dict(spec, seed=0)
     wsum = float(sum(v.double().sum() for v in sd.values()))
     assert abs(wsum - float(gold["weight_checksum"][0])) < 1e-6 * max(1.0, abs(wsum)), "synthetic weights drifted"
-    pack = SiglipPack(sd, spec, DEV)
+    pack = SiglipPack(sd, spec, DEV, fold_ln=fold_ln)
     del sd
     frames = torch.cat([synth.scene_frames(0, 2, device=DEV), synth.scene_frames(30, 2, device=DEV)], 0)
     patches = ops.preprocess(frames, 384, 384, 2, layout=ops.LAYOUT_BF16_PATCH, patch=14)
@@ -74,7 +77,7 @@ def test_so400m_vs_hf_golden(golden_dir):
     c_pool, c_proj = _cos(pooled.float(), want_pooled), _cos(proj32, want_proj)
     e_pool = (pooled.float().cpu() - want_pooled).abs().max().item()
     e_proj = (proj32.cpu() - want_proj).abs().max().item()
-    print(f"so400m: token0 cos {c_tok.tolist()} pooled cos {c_pool.tolist()} max_abs {e_pool:.4f}; "
+    print(f"so400m fold_ln={fold_ln}: token0 cos {c_tok.tolist()} pooled cos {c_pool.tolist()} max_abs {e_pool:.4f}; "
           f"projected cos {c_proj.tolist()} max_abs {e_proj:.4f}")
     assert c_pool.min() >= 0.999 and c_proj.min() >= 0.999
     assert e_pool < 0.35 and e_proj < 0.35  # |pooled| ~ N(0, 1.6): bf16 end-to-end noise, stated bound

@@ -50,6 +50,27 @@ def gemm_cases():
     print(f"gemm total per step ~ {tot:.2f} ms")
 
 
+def gemm_fused_cases():
+    """The LayerNorm-fusion variants at the layer shapes (producer = stats_out, consumer = ln_stats)."""
+    D = 1152
+    slots = ops.gemm_stats_slots(D)
+    stats = torch.zeros(M, slots, 2, device=DEV)
+    x = torch.randn(M, D, device=DEV).to(torch.bfloat16)
+    for name, n, k, act, mode in [("qkv+ln", 3456, D, 0, "c"), ("fc1+ln", 4304, D, 1, "c"), ("out+st", D, D, 0, "p"),
+                                  ("fc2+st", D, 4304, 0, "p")]:
+        a = torch.randn(M, k, device=DEV).to(torch.bfloat16)
+        w = (torch.randn(n, k, device=DEV) / math.sqrt(k)).to(torch.bfloat16)
+        bias = torch.randn(n, device=DEV)
+        out = torch.empty(M, n, device=DEV, dtype=torch.bfloat16) if mode == "c" else x
+        c1 = torch.randn(n, device=DEV)
+        if mode == "c":
+            fn = lambda: ops.gemm(a, w, bias, act=act, out=out, ln_stats=stats, ln_c1=c1, ln_dim=D, ln_eps=1e-6)  # noqa: E731
+        else:
+            fn = lambda: ops.gemm(a, w, bias, residual=x, out=x, stats_out=stats)  # noqa: E731
+        ms = timeit(fn)
+        print(f"gemm {name:7s} N={n} K={k}: {ms*1e3:8.1f} us  {2.0*M*n*k/ms/1e9:7.1f} TFLOP/s")
+
+
 def attn_case():
     B, T, H, hd = 64, 729, 16, 72
     qkv = torch.randn(B * T, 3 * H * hd, device=DEV).to(torch.bfloat16)
@@ -80,6 +101,8 @@ if __name__ == "__main__":
     what = sys.argv[1] if len(sys.argv) > 1 else "all"
     if what in ("gemm", "all"):
         gemm_cases()
+    if what in ("gemmf", "all"):
+        gemm_fused_cases()
     if what in ("attn", "all"):
         attn_case()
     if what in ("ln", "all"):

@@ -143,7 +143,7 @@ def main_ours(args) -> None:
     spec = SiglipVisionSpec.so400m()
     B, K, W = args.batch, args.steps, args.warmup
     pipe = EmbeddingPipeline(synth_siglip_state_dict(spec, seed=0), synth_projector_state_dict(spec.hidden, 4096, seed=1),
-                             spec, dev, batch=B)
+                             spec, dev, batch=B, fold_ln=not args.no_fold_ln)
 
     # this rank's chunk of the timeline, resident in HBM: K batches of B frames (22.7 GB at K=57, B=64)
     n_local = K * B
@@ -252,7 +252,8 @@ def main_ours(args) -> None:
             "config": {"workload": "1 h synthetic 1080p gameplay @1 fps (BASELINE.json configs[1]: 3600 frames, rounded up "
                                    "to 57 batches of 64) through SigLIP2-so400m-patch14-384 + ProjectorBank 1152->4096->4096",
                        "frames_per_gpu": n_local, "batch": B, "frame": [FRAME_H, FRAME_W, 3],
-                       "weights": "random init, seeds 0/1", "sharding": "contiguous timeline chunk per rank, "
+                       "weights": "random init, seeds 0/1", "layernorm": "separate kernels" if args.no_fold_ln else
+                       "folded into the consuming GEMM epilogues", "sharding": "contiguous timeline chunk per rank, "
                        "NCCL all-gather of the projected index inside the timed region" if world > 1 else "single GPU",
                        "l2": "inputs larger than L2 (398 MB of frames per step, never reused)"},
             "model_tflops_per_gpu": round(model_tflops, 1),
@@ -433,6 +434,8 @@ if __name__ == "__main__":
     ap.add_argument("--batch", type=int, default=64)
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-fold-ln", action="store_true",
+                    help="A/B: run the 56 LayerNorm kernels per batch instead of folding them into the GEMM epilogues")
     ap.add_argument("--workload", choices=["siglip", "videomae"], default="siglip",
                     help="siglip = the headline metric (default); videomae = BASELINE.json configs[3]")
     a = ap.parse_args()

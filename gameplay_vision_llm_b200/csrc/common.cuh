@@ -417,12 +417,17 @@ __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.
 
 // ---- small math ----
 __device__ __forceinline__ float gelu_tanh_f(float x) {
-    // 0.5 x (1 + tanh(sqrt(2/pi) (x + 0.044715 x^3)))  — torch GELU(approximate="tanh")
-    // evaluated as x * sigmoid(2u) = x / (1 + exp(-2u)): ex2 + rcp, ~1e-6 relative everywhere
-    // (tanh.approx's 2^-11 error is amplified where 1 + tanh is small).
-    const float k0 = 0.7978845608028654f, k1 = 0.044715f;
-    float u = k0 * (x + k1 * x * x * x);
-    return __fdividef(x, 1.0f + __expf(-2.0f * u));
+    // 0.5 x (1 + tanh(u)), u = sqrt(2/pi) (x + 0.044715 x^3)  — torch GELU(approximate="tanh") —
+    // evaluated as x * sigmoid(2u) = x / (1 + 2^(x (a + b x^2))) with the constants folded: 3 FMUL + FFMA + FADD +
+    // ex2 + rcp.  ~1e-6 relative everywhere (tanh.approx's 2^-11 error is amplified where 1 + tanh is small).
+    // Saturation is exact: 2^(+big) = inf -> rcp = 0 -> -0; 2^(-big) = 0 -> x.
+    const float a = -2.0f * 0.7978845608028654f * 1.4426950408889634f;
+    const float b = a * 0.044715f;
+    const float e = x * fmaf(x * x, b, a);
+    float t, r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(e));
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.0f + t));
+    return x * r;
 }
 __device__ __forceinline__ float gelu_erf_f(float x) { return 0.5f * x * (1.0f + erff(x * 0.7071067811865476f)); }
 

@@ -1,25 +1,32 @@
 // gemm.cu — K2: persistent, warp-specialised tcgen05 GEMM with a fused epilogue.
 //
-//   out[M,N] = act(A[M,K] . W[N,K]^T + bias) + residual
+//   out[M,N] = act(A[M,K] . W[N,K]^T + bias) + residual        (optionally with LayerNorm(A) folded in)
 //
 // Both operands are K-major bf16, so a [rows x 64] box lands in shared memory as rows of 128 bytes —
 // exactly one SWIZZLE_128B atom wide — and the same bytes are addressed by the UMMA shared-memory
 // descriptor.  The grid is one 2-CTA cluster per SM pair; a cluster loops over "super tiles" of
 // 256 x BN outputs (m-major order: clusters running at the same time share A panels, the whole weight
-// stays in the 126 MB L2).  Inside a cluster the two CTAs own the two 128-row halves and SHARE the
-// weight tile: each CTA fetches one half of the BN x 64 weight box and TMA-multicasts it into both
-// CTAs' shared memory, which cuts the L2->SM operand traffic per FLOP by a third (v1 of this kernel was
-// operand-feed bound: 15 TB/s of L2 reads at 64 % tensor-pipe utilisation, profiles/r01_v1_*).
+// stays in the 126 MB L2) and runs ONE tcgen05.mma.cta_group::2 (256 x BN x 16) per k-step: each CTA
+// stages only its own 128 A rows and HALF of the W tile (BN/2 rows), the hardware reads the other half
+// from the peer's shared memory.  Per CTA and k-block that is 16 KB + BN*64 B of shared-memory traffic
+// instead of 16 KB + BN*128 B, which takes the kernel off the operand-feed limit (v1, one CTA per tile:
+// 15 TB/s of L2 reads at 64 % tensor-pipe utilisation, profiles/r01_v1_*).
 //
-//   warp 0     TMA producer: own A box 128x64 + half W box (BN/2)x64 multicast to the pair, expect_tx
-//   warp 1     tcgen05.mma issuer (one elected lane): 4 x (128 x BN x 16) per stage into TMEM;
-//              tcgen05.commit (multicast) releases the stage in BOTH CTAs / publishes the accumulator
-//   warps 2-9  epilogue, two warps per TMEM lane quadrant (each takes half of the columns):
-//              tcgen05.ld 32 lanes x 32 columns -> bias, GELU, residual -> bf16/fp32 stores
+//   warp 0       TMA producer (both CTAs): own A box 128x64 + own half W box (BN/2)x64; completion on the
+//                LEADER's full barrier
+//   warp 1       tcgen05.mma issuer (leader CTA, one elected lane); tcgen05.commit multicasts to both CTAs'
+//                empty / tmem_full barriers
+//   warps 2..    epilogue, BN/16 warps = BN/64 per TMEM lane quadrant, 64 columns (two 32-column chunks) each:
+//                tcgen05.ld 32 lanes x 32 columns -> bias / LayerNorm fold / GELU / residual -> bf16 into a
+//                swizzled staging tile -> TMA bulk store (fp32 outputs: direct stores)
 //
 // The accumulator is double-buffered in TMEM (2 x BN columns), so the epilogue of tile i overlaps the
-// MMAs of tile i+1.  Ragged M / N / K edges are handled by TMA (out-of-bounds reads are zero, including
-// the phantom second half of an odd last super tile) and by row / column guards on the stores.
+// MMAs of tile i+1.  The epilogue is a single-warp-latency-bound instruction stream (ncu: ~5.5 cycles per
+// issued instruction per warp), so (a) it runs on 4 warps per scheduler and (b) the hot flag combinations
+// are compiled as separate instantiations (EF_* below) so that no per-element branch survives; any other
+// combination takes the generic instantiation with run-time flags.  Ragged M / N / K edges are handled by
+// TMA (out-of-bounds reads are zero, including the phantom second half of an odd last super tile, and
+// out-of-bounds parts of stored boxes are clipped) and by row / column guards on the direct stores.
 #include "common.cuh"
 
 #include <cstdlib>
@@ -28,9 +35,11 @@ namespace gvl {
 
 constexpr int BM = 128;
 constexpr int BK = 64;
-constexpr int kEpiWarps = 8;
-constexpr int kGemmThreads = 64 + kEpiWarps * 32;
 constexpr int A_STAGE_BYTES = BM * BK * 2;
+constexpr int kMaxLnSlotPairs = 10;  // LayerNorm-fusion consumers read at most 20 partial-sum slots per row
+
+// epilogue flavour, compile-time unless EF_ANY is set
+enum : uint32_t { EF_ACT = 3u, EF_RES = 4u, EF_LN = 8u, EF_STATS = 16u, EF_F32 = 32u, EF_ANY = 64u };
 
 struct GemmParams {
     const float* bias;
@@ -43,10 +52,12 @@ struct GemmParams {
     int M, N, K;
     int act;
     int m_pairs, n_tiles, k_blocks;
-    int debug;  // tuning experiments only (GVL_GEMM_DEBUG): bit 0 = stop issuing TMA loads once the ring was filled
+    int debug;  // tuning experiments only (GVL_GEMM_DEBUG): 1 = stop issuing TMA loads once the ring was filled,
+                // 2 = always load the same boxes, 8 = skip the output stores
     // LayerNorm fusion (gvl_gemm_fusion): producer side writes per-slab partial row sums of its bf16 outputs,
     // consumer side normalises the rows of A algebraically in the epilogue
-    float* stats_out;       // [M, 2 * n_tiles, 2] or null
+    float* stats_out;       // [M, stats_slots, 2] or null
+    int stats_slots;
     const float* ln_stats;  // [M, ln_slots, 2] or null
     const float* ln_c1;     // [N]
     int ln_slots;
@@ -55,33 +66,31 @@ struct GemmParams {
 
 template <int BN>
 struct GemmCfg {
-    static constexpr int B_STAGE_BYTES = BN * BK * 2;
-    static constexpr int B_HALF_BYTES = B_STAGE_BYTES / 2;
-    static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
-    static constexpr int STAGES = BN == 256 ? 4 : (BN == 192 ? 5 : 6);
+    static constexpr int EPI_WARPS = BN / 16;          // BN/64 per TMEM lane quadrant
+    static constexpr int THREADS = 64 + EPI_WARPS * 32;
+    static constexpr int COLS_PER_WARP = 64;           // two 32-column chunks
+    static constexpr int B_HALF_BYTES = (BN / 2) * BK * 2;
+    static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_HALF_BYTES;  // per CTA
+    static constexpr int STAGES = BN == 256 ? 5 : (BN == 192 ? 6 : 7);
     static constexpr int TMEM_COLS = (2 * BN <= 256) ? 256 : 512;
-    static constexpr int CHUNKS = BN / 32;               // 32-column epilogue chunks per tile
-    static constexpr int CHUNKS_PER_WARP = CHUNKS / 2;   // two epilogue warps share a lane quadrant
-    static constexpr int BIAS_BYTES = 2 * kEpiWarps * CHUNKS_PER_WARP * 32 * 4;  // bias (or c2) and c1 per column
     static constexpr int BAR_BYTES = (2 * STAGES + 4) * 8 + 16;
-    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + BIAS_BYTES + BAR_BYTES + 1024 /*alignment slack*/;
-};
-
-struct Gemm2Stage {
-    static constexpr int TILE = 32 * 64;  // one staged 32-row x 32-column bf16 output tile
+    // bf16 outputs leave through per-warp staging tiles (32 rows x 64 B, SWIZZLE_64B) and TMA stores
+    static constexpr int OUT_TILE_BYTES = 32 * 64;
+    static constexpr int OUT_STAGE_BYTES = EPI_WARPS * OUT_TILE_BYTES;
+    static constexpr int BIAS_BYTES = 2 * EPI_WARPS * COLS_PER_WARP * 4;  // bias (or c2) and c1, private per warp
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + OUT_STAGE_BYTES + BIAS_BYTES + BAR_BYTES + 1024;
 };
 
 // Residual values of one 32-column chunk of this thread's output row (4 x 8 bf16).  Issued one chunk ahead of
 // their use — and, for the first chunk of a tile, before the wait on the accumulator — so that their L2 / HBM
-// latency never sits on the epilogue's critical path (the out-proj GEMM was epilogue-bound on exactly that).
+// latency never sits on the epilogue's critical path.
 __device__ __forceinline__ void load_residual_chunk(const GemmParams& p, int row, int c0, uint4 (&rv)[4]) {
     const bool row_ok = row < p.M;
     const int rrow = p.res_row_mod > 0 ? (row % p.res_row_mod) : row;
     const __nv_bfloat16* rp = p.residual + (size_t)rrow * p.ldr + c0;
 #pragma unroll
     for (int g = 0; g < 4; ++g)
-        rv[g] = (p.residual != nullptr && row_ok && c0 + g * 8 < p.N) ? *reinterpret_cast<const uint4*>(rp + g * 8)
-                                                                      : make_uint4(0, 0, 0, 0);
+        rv[g] = (row_ok && c0 + g * 8 < p.N) ? *reinterpret_cast<const uint4*>(rp + g * 8) : make_uint4(0, 0, 0, 0);
 }
 
 // mean * rstd and rstd of one row of A from the producer's partial sums (fixed order: deterministic).  Called
@@ -89,13 +98,20 @@ __device__ __forceinline__ void load_residual_chunk(const GemmParams& p, int row
 __device__ __forceinline__ void load_ln_row(const GemmParams& p, int row, float& ln_rstd, float& ln_mr) {
     ln_rstd = 1.0f;
     ln_mr = 0.0f;
-    if (p.ln_stats == nullptr || row >= p.M) return;
-    const float2* sp = reinterpret_cast<const float2*>(p.ln_stats) + (size_t)row * p.ln_slots;
+    if (row >= p.M) return;
+    // slots come in pairs: 16-byte loads, all issued before the first use so the row costs one L2 round trip
+    const float4* sp = reinterpret_cast<const float4*>(p.ln_stats + (size_t)row * p.ln_slots * 2);
+    const int pairs = p.ln_slots >> 1;
+    float4 t[kMaxLnSlotPairs];
+#pragma unroll
+    for (int i = 0; i < kMaxLnSlotPairs; ++i) t[i] = i < pairs ? sp[i] : make_float4(0.f, 0.f, 0.f, 0.f);
     float s1 = 0.f, s2 = 0.f;
-    for (int i = 0; i < p.ln_slots; ++i) {
-        const float2 t = sp[i];
-        s1 += t.x;
-        s2 += t.y;
+#pragma unroll
+    for (int i = 0; i < kMaxLnSlotPairs; ++i) {
+        s1 += t[i].x;
+        s2 += t[i].y;
+        s1 += t[i].z;
+        s2 += t[i].w;
     }
     const float mean = s1 * p.ln_inv_d;
     const float var = fmaxf(s2 * p.ln_inv_d - mean * mean, 0.0f);
@@ -103,308 +119,135 @@ __device__ __forceinline__ void load_ln_row(const GemmParams& p, int row, float&
     ln_mr = mean * ln_rstd;
 }
 
-// Epilogue of one 128 x BN accumulator tile for one warp: TMEM lane quadrant q, column half `half`.
-// rv holds the residual of the first chunk (load_residual_chunk, issued by the caller before it waited for the tile).
-template <int BN>
-__device__ __forceinline__ void epilogue_tile(const GemmParams& p, const float* myBias, uint32_t tmem_base, int as,
-                                              int m_blk, int n0, int q, int half, int lane, uint4 (&rv)[4],
-                                              float ln_rstd, float ln_mr, const CUtensorMap* tmC = nullptr,
-                                              uint8_t* stage = nullptr, int* stage_parity = nullptr) {
+// Epilogue of one warp's 32 rows x 64 columns of a 128 x BN accumulator tile: TMEM lane quadrant q, columns
+// n0 .. n0+63 of the output (t_addr points at the first of them).  rv holds the residual of the first chunk.
+template <int BN, uint32_t EF>
+__device__ __forceinline__ void epilogue_tile(const GemmParams& p, const float* myBias, uint32_t t_addr, int row0, int n0,
+                                              int lane, uint4 (&rv)[4], float ln_rstd, float ln_mr,
+                                              const CUtensorMap* tmC, uint8_t* stage, bool& store_pending) {
     using Cfg = GemmCfg<BN>;
-    const int row = m_blk * BM + q * 32 + lane;
+    constexpr bool ANY = (EF & EF_ANY) != 0;
+    const int act = ANY ? p.act : (int)(EF & EF_ACT);
+    const bool has_res = ANY ? p.residual != nullptr : (EF & EF_RES) != 0;
+    const bool ln = ANY ? p.ln_stats != nullptr : (EF & EF_LN) != 0;
+    const bool stats = ANY ? p.stats_out != nullptr : (EF & EF_STATS) != 0;
+    const bool f32 = ANY ? p.out_f32 != 0 : (EF & EF_F32) != 0;
+    const int row = row0 + lane;
     const bool row_ok = row < p.M;
-    const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) +
-                            (uint32_t)(as * BN + half * (Cfg::CHUNKS_PER_WARP * 32));
-    const bool has_res = p.residual != nullptr;
     // fused LayerNorm of the A rows: out = rstd * (acc - mean * c1[n]) + c2[n]  (c2 arrives through the bias slot)
     const uint32_t bias_s = smem_u32(myBias);
-    const uint32_t c1_s = bias_s + kEpiWarps * Cfg::CHUNKS_PER_WARP * 32 * 4;
-    const bool ln = p.ln_stats != nullptr;
+    const uint32_t c1_s = bias_s + Cfg::EPI_WARPS * Cfg::COLS_PER_WARP * 4;
+    const uint32_t stage_s = smem_u32(stage);
     float st1 = 0.f, st2 = 0.f;  // partial row sums of this warp's bf16 outputs (stats_out)
 #pragma unroll 1
-    for (int chunk = 0; chunk < Cfg::CHUNKS_PER_WARP; ++chunk) {
+    for (int chunk = 0; chunk < Cfg::COLS_PER_WARP / 32; ++chunk) {
         const int c0 = n0 + chunk * 32;
         if (c0 >= p.N) break;  // warp-uniform
         uint32_t r[32];
         tmem_ld_32x32(t_addr + (uint32_t)(chunk * 32), r);
         uint4 rn[4];  // next chunk's residual, in flight while this chunk is finished
-        if (has_res && chunk + 1 < Cfg::CHUNKS_PER_WARP) load_residual_chunk(p, row, c0 + 32, rn);
+        if (has_res && chunk + 1 < Cfg::COLS_PER_WARP / 32) load_residual_chunk(p, row, c0 + 32, rn);
+        if (!f32 && store_pending) {  // the staging tile is reused: the previous store must have read it
+            if (lane == 0) tma_store_wait_read<0>();
+            __syncwarp();
+        }
         tmem_ld_wait();
-        if (row_ok) {
 #pragma unroll
-            for (int g = 0; g < 4; ++g) {
-                const int col = c0 + g * 8;
-                if (col < p.N) {
-                    const float4 b0 = ld_shared_f4(bias_s + (chunk * 32 + g * 8) * 4);
-                    const float4 b1 = ld_shared_f4(bias_s + (chunk * 32 + g * 8 + 4) * 4);
-                    float v[8];
-                    if (ln) {
-                        const float4 k0 = ld_shared_f4(c1_s + (chunk * 32 + g * 8) * 4);
-                        const float4 k1 = ld_shared_f4(c1_s + (chunk * 32 + g * 8 + 4) * 4);
-                        v[0] = fmaf(__uint_as_float(r[g * 8 + 0]), ln_rstd, fmaf(-ln_mr, k0.x, b0.x));
-                        v[1] = fmaf(__uint_as_float(r[g * 8 + 1]), ln_rstd, fmaf(-ln_mr, k0.y, b0.y));
-                        v[2] = fmaf(__uint_as_float(r[g * 8 + 2]), ln_rstd, fmaf(-ln_mr, k0.z, b0.z));
-                        v[3] = fmaf(__uint_as_float(r[g * 8 + 3]), ln_rstd, fmaf(-ln_mr, k0.w, b0.w));
-                        v[4] = fmaf(__uint_as_float(r[g * 8 + 4]), ln_rstd, fmaf(-ln_mr, k1.x, b1.x));
-                        v[5] = fmaf(__uint_as_float(r[g * 8 + 5]), ln_rstd, fmaf(-ln_mr, k1.y, b1.y));
-                        v[6] = fmaf(__uint_as_float(r[g * 8 + 6]), ln_rstd, fmaf(-ln_mr, k1.z, b1.z));
-                        v[7] = fmaf(__uint_as_float(r[g * 8 + 7]), ln_rstd, fmaf(-ln_mr, k1.w, b1.w));
-                    } else {
-                        v[0] = __uint_as_float(r[g * 8 + 0]) + b0.x;
-                        v[1] = __uint_as_float(r[g * 8 + 1]) + b0.y;
-                        v[2] = __uint_as_float(r[g * 8 + 2]) + b0.z;
-                        v[3] = __uint_as_float(r[g * 8 + 3]) + b0.w;
-                        v[4] = __uint_as_float(r[g * 8 + 4]) + b1.x;
-                        v[5] = __uint_as_float(r[g * 8 + 5]) + b1.y;
-                        v[6] = __uint_as_float(r[g * 8 + 6]) + b1.z;
-                        v[7] = __uint_as_float(r[g * 8 + 7]) + b1.w;
-                    }
-                    if (p.act == GVL_ACT_GELU_TANH) {
+        for (int g = 0; g < 4; ++g) {
+            const int col = c0 + g * 8;
+            const float4 b0 = ld_shared_f4(bias_s + (chunk * 32 + g * 8) * 4);
+            const float4 b1 = ld_shared_f4(bias_s + (chunk * 32 + g * 8 + 4) * 4);
+            const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+            float v[8];
+            if (ln) {
+                const float4 k0 = ld_shared_f4(c1_s + (chunk * 32 + g * 8) * 4);
+                const float4 k1 = ld_shared_f4(c1_s + (chunk * 32 + g * 8 + 4) * 4);
+                const float kk[8] = {k0.x, k0.y, k0.z, k0.w, k1.x, k1.y, k1.z, k1.w};
 #pragma unroll
-                        for (int j = 0; j < 8; ++j) v[j] = gelu_tanh_f(v[j]);
-                    } else if (p.act == GVL_ACT_GELU_ERF) {
+                for (int j = 0; j < 8; ++j) v[j] = fmaf(__uint_as_float(r[g * 8 + j]), ln_rstd, fmaf(-ln_mr, kk[j], bb[j]));
+            } else {
 #pragma unroll
-                        for (int j = 0; j < 8; ++j) v[j] = gelu_erf_f(v[j]);
-                    }
-                    if (has_res) {
-                        v[0] += bf16_lo(rv[g].x); v[1] += bf16_hi(rv[g].x);
-                        v[2] += bf16_lo(rv[g].y); v[3] += bf16_hi(rv[g].y);
-                        v[4] += bf16_lo(rv[g].z); v[5] += bf16_hi(rv[g].z);
-                        v[6] += bf16_lo(rv[g].w); v[7] += bf16_hi(rv[g].w);
-                    }
-                    if (p.out_f32) {
-                        float* o = reinterpret_cast<float*>(p.out) + (size_t)row * p.ldo + col;
-                        *reinterpret_cast<float4*>(o) = make_float4(v[0], v[1], v[2], v[3]);
-                        *reinterpret_cast<float4*>(o + 4) = make_float4(v[4], v[5], v[6], v[7]);
-                    } else {
-                        __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + (size_t)row * p.ldo + col;
-                        uint4 ov;
-                        ov.x = pack_bf16x2(v[0], v[1]);
-                        ov.y = pack_bf16x2(v[2], v[3]);
-                        ov.z = pack_bf16x2(v[4], v[5]);
-                        ov.w = pack_bf16x2(v[6], v[7]);
-                        if (tmC != nullptr)  // staging tile row = lane, 16-byte slot g, SWIZZLE_64B: slot ^= (row >> 1) & 3
-                            st_shared_v4(smem_u32(stage + *stage_parity * Gemm2Stage::TILE) + lane * 64 +
-                                             ((g ^ ((lane >> 1) & 3)) << 4),
-                                         ov);
-                        else
-                            *reinterpret_cast<uint4*>(o) = ov;
-                        if (p.stats_out != nullptr) {  // statistics of the values as stored (bf16-rounded)
-                            const uint32_t w4[4] = {ov.x, ov.y, ov.z, ov.w};
+                for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(r[g * 8 + j]) + bb[j];
+            }
+            if (act == GVL_ACT_GELU_TANH) {
 #pragma unroll
-                            for (int e = 0; e < 4; ++e) {
-                                const float a0 = bf16_lo(w4[e]), a1 = bf16_hi(w4[e]);
-                                st1 += a0 + a1;
-                                st2 = fmaf(a0, a0, fmaf(a1, a1, st2));
-                            }
-                        }
+                for (int j = 0; j < 8; ++j) v[j] = gelu_tanh_f(v[j]);
+            } else if (act == GVL_ACT_GELU_ERF) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) v[j] = gelu_erf_f(v[j]);
+            }
+            if (has_res) {
+                v[0] += bf16_lo(rv[g].x); v[1] += bf16_hi(rv[g].x);
+                v[2] += bf16_lo(rv[g].y); v[3] += bf16_hi(rv[g].y);
+                v[4] += bf16_lo(rv[g].z); v[5] += bf16_hi(rv[g].z);
+                v[6] += bf16_lo(rv[g].w); v[7] += bf16_hi(rv[g].w);
+            }
+            if (f32) {
+                if (row_ok && col < p.N) {
+                    float* o = reinterpret_cast<float*>(p.out) + (size_t)row * p.ldo + col;
+                    *reinterpret_cast<float4*>(o) = make_float4(v[0], v[1], v[2], v[3]);
+                    *reinterpret_cast<float4*>(o + 4) = make_float4(v[4], v[5], v[6], v[7]);
+                }
+            } else {
+                uint4 ov;
+                ov.x = pack_bf16x2(v[0], v[1]);
+                ov.y = pack_bf16x2(v[2], v[3]);
+                ov.z = pack_bf16x2(v[4], v[5]);
+                ov.w = pack_bf16x2(v[6], v[7]);
+                // staging tile row = lane, 16-byte slot g, SWIZZLE_64B: slot ^= (row >> 1) & 3.  Rows / columns beyond
+                // M / N are staged too (finite garbage) and clipped by the TMA store.
+                st_shared_v4(stage_s + lane * 64 + ((g ^ ((lane >> 1) & 3)) << 4), ov);
+                if (stats && col < p.N) {  // statistics of the values as stored (bf16-rounded)
+                    const uint32_t w4[4] = {ov.x, ov.y, ov.z, ov.w};
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        const float a0 = bf16_lo(w4[e]), a1 = bf16_hi(w4[e]);
+                        st1 += a0 + a1;
+                        st2 = fmaf(a0, a0, fmaf(a1, a1, st2));
                     }
                 }
             }
         }
-        if (tmC != nullptr && !p.out_f32) {
-            // hand the staged 32 x 32 tile to the TMA engine (rows / columns beyond M / N are clipped) and make sure
-            // the tile written two chunks ago has been read before it is overwritten next time
+        if (!f32) {
+            // hand the staged 32 x 32 tile to the TMA engine
             fence_proxy_async_smem();
             __syncwarp();
-            if (lane == 0) {
-                tma_store_2d(tmC, stage + *stage_parity * Gemm2Stage::TILE, c0, m_blk * BM + q * 32);
+            if (lane == 0 && !(p.debug & 8)) {
+                tma_store_2d(tmC, stage, c0, row0);
                 tma_store_commit();
-                tma_store_wait_read<1>();
             }
-            __syncwarp();
-            *stage_parity ^= 1;
+            store_pending = true;
         }
-        if (has_res && chunk + 1 < Cfg::CHUNKS_PER_WARP) {
+        if (has_res && chunk + 1 < Cfg::COLS_PER_WARP / 32) {
 #pragma unroll
             for (int g = 0; g < 4; ++g) rv[g] = rn[g];
         }
     }
-    if (p.stats_out != nullptr && row_ok) {
-        const int slot = (n0 / BN) * 2 + half;
-        reinterpret_cast<float2*>(p.stats_out)[(size_t)row * (2 * p.n_tiles) + slot] = make_float2(st1, st2);
+    if (stats && row_ok) {  // column groups entirely beyond N write zeros: every slot of the row is defined
+        const int slot = n0 / Cfg::COLS_PER_WARP, real = (BN / Cfg::COLS_PER_WARP) * p.n_tiles;
+        float2* so = reinterpret_cast<float2*>(p.stats_out) + (size_t)row * p.stats_slots;
+        so[slot] = make_float2(st1, st2);
+        // the slot count is padded to an even number for the consumer's 16-byte loads
+        if ((real & 1) && slot == real - 1) so[real] = make_float2(0.f, 0.f);
     }
 }
 
-template <int BN>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
-gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                         const GemmParams p) {
-    using Cfg = GemmCfg<BN>;
-    constexpr int STAGES = Cfg::STAGES;
-
-    extern __shared__ uint8_t smem_raw[];
-    // the dynamic smem window starts at the same CTA-relative offset in both CTAs of the cluster, so the
-    // aligned carve-up below is identical in both (required by the multicast writes / remote arrives)
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    uint8_t* sA = smem;
-    uint8_t* sB = smem + STAGES * A_STAGE_BYTES;
-    float* sBias = reinterpret_cast<float*>(smem + STAGES * Cfg::STAGE_BYTES);
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES + Cfg::BIAS_BYTES);
-    uint64_t* full_bar = bars;
-    uint64_t* empty_bar = bars + STAGES;
-    uint64_t* tmem_full_bar = bars + 2 * STAGES;
-    uint64_t* tmem_empty_bar = bars + 2 * STAGES + 2;
-    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
-
-    const int warp = threadIdx.x >> 5;
-    const int lane = threadIdx.x & 31;
-    const uint32_t cta_rank = cluster_ctarank();
-
-    if (warp == 0 && lane == 0) {
-        tma_prefetch_desc(&tmA);
-        tma_prefetch_desc(&tmB);
-        for (int s = 0; s < STAGES; ++s) {
-            mbar_init(&full_bar[s], 1);   // own producer's arrive.expect_tx (+ tx bytes from both CTAs' TMA)
-            mbar_init(&empty_bar[s], 2);  // one tcgen05.commit from each CTA of the pair
-        }
-        for (int s = 0; s < 2; ++s) {
-            mbar_init(&tmem_full_bar[s], 1);
-            mbar_init(&tmem_empty_bar[s], kEpiWarps);
-        }
-        fence_barrier_init();
-    }
-    if (warp == 1) tmem_alloc<Cfg::TMEM_COLS>(tmem_ptr_smem);
-    tcgen05_fence_before();
-    cluster_sync_all();  // barriers of both CTAs initialised before any multicast / remote arrive
-    tcgen05_fence_after();
-    const uint32_t tmem_base = *tmem_ptr_smem;
-
-    const int num_super = p.m_pairs * p.n_tiles;
-    const int cluster_id = blockIdx.x >> 1;
-    const int num_clusters = gridDim.x >> 1;
-
-    if (warp == 0) {
-        // ===== TMA producer =====
-        if (elect_one()) {
-            int stage = 0;
-            uint32_t phase = 0;
-            for (int st = cluster_id; st < num_super; st += num_clusters) {
-                const int m_blk = (st / p.n_tiles) * 2 + (int)cta_rank, n_blk = st % p.n_tiles;
-                for (int kb = 0; kb < p.k_blocks; ++kb) {
-                    mbar_wait(&empty_bar[stage], phase ^ 1);  // both CTAs are done reading this stage
-                    mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
-                    tma_load_2d(sA + stage * A_STAGE_BYTES, &tmA, &full_bar[stage], kb * BK, m_blk * BM);
-                    tma_load_2d_mc(sB + stage * Cfg::B_STAGE_BYTES + cta_rank * Cfg::B_HALF_BYTES, &tmB, &full_bar[stage],
-                                   kb * BK, n_blk * BN + (int)cta_rank * (BN / 2), (uint16_t)0x3);
-                    if (++stage == STAGES) {
-                        stage = 0;
-                        phase ^= 1;
-                    }
-                }
-            }
-        }
-    } else if (warp == 1) {
-        // ===== MMA issuer =====
-        if (elect_one()) {
-            constexpr uint32_t idesc = umma_idesc_bf16(BM, BN);
-            int stage = 0;
-            uint32_t phase = 0;
-            int as = 0;
-            uint32_t aphase = 0;
-            for (int st = cluster_id; st < num_super; st += num_clusters) {
-                mbar_wait(&tmem_empty_bar[as], aphase ^ 1);
-                tcgen05_fence_after();
-                const uint32_t d_tmem = tmem_base + (uint32_t)(as * BN);
-                for (int kb = 0; kb < p.k_blocks; ++kb) {
-                    mbar_wait(&full_bar[stage], phase);
-                    tcgen05_fence_after();
-                    const uint32_t a_addr = smem_u32(sA + stage * A_STAGE_BYTES);
-                    const uint32_t b_addr = smem_u32(sB + stage * Cfg::B_STAGE_BYTES);
-#pragma unroll
-                    for (int k = 0; k < BK / 16; ++k) {
-                        umma_bf16_ss(d_tmem, umma_desc_sw128(a_addr + k * 32), umma_desc_sw128(b_addr + k * 32), idesc,
-                                     (uint32_t)((kb | k) != 0));
-                    }
-                    umma_commit_mc(&empty_bar[stage], (uint16_t)0x3);  // frees the stage in both CTAs
-                    if (++stage == STAGES) {
-                        stage = 0;
-                        phase ^= 1;
-                    }
-                }
-                umma_commit(&tmem_full_bar[as]);
-                as ^= 1;
-                if (as == 0) aphase ^= 1;
-            }
-        }
-    } else {
-        // ===== epilogue warps =====
-        const int ew = warp - 2;
-        const int q = warp & 3;   // TMEM lane quadrant this warp may read
-        const int half = ew >> 2; // which half of the tile's column chunks
-        float* myBias = sBias + ew * (Cfg::CHUNKS_PER_WARP * 32);
-        int as = 0;
-        uint32_t aphase = 0;
-        for (int st = cluster_id; st < num_super; st += num_clusters) {
-            const int m_blk = (st / p.n_tiles) * 2 + (int)cta_rank, n_blk = st % p.n_tiles;
-            const int n0 = n_blk * BN + half * (Cfg::CHUNKS_PER_WARP * 32);
-            for (int c = lane; c < Cfg::CHUNKS_PER_WARP * 32; c += 32) {
-                myBias[c] = (p.bias != nullptr && n0 + c < p.N) ? p.bias[n0 + c] : 0.0f;
-                if (p.ln_stats != nullptr)
-                    myBias[kEpiWarps * Cfg::CHUNKS_PER_WARP * 32 + c] = (n0 + c < p.N) ? p.ln_c1[n0 + c] : 0.0f;
-            }
-            __syncwarp();
-            uint4 rv[4];
-            float ln_rstd, ln_mr;
-            load_residual_chunk(p, m_blk * BM + q * 32 + lane, n0, rv);
-            load_ln_row(p, m_blk * BM + q * 32 + lane, ln_rstd, ln_mr);
-            mbar_wait(&tmem_full_bar[as], aphase);
-            tcgen05_fence_after();
-            epilogue_tile<BN>(p, myBias, tmem_base, as, m_blk, n0, q, half, lane, rv, ln_rstd, ln_mr);
-            tcgen05_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&tmem_empty_bar[as]);
-            as ^= 1;
-            if (as == 0) aphase ^= 1;
-        }
-    }
-
-    // no CTA may exit while its peer can still multicast into its smem or arrive on its barriers
-    tcgen05_fence_before();
-    cluster_sync_all();
-    if (warp == 1) {
-        tcgen05_fence_after();
-        tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
-    }
-}
-
-// ---- CTA-pair kernel (cta_group::2): one MMA = 256 x BN x 16 over both CTAs' tensor cores ------------------------
-//
-// Same roles and pipelines as above, but the pair now runs ONE tcgen05.mma.cta_group::2 per k-step: each CTA
-// stages only its own 128 A rows and HALF of the W tile (BN/2 rows), the hardware reads the other half from the
-// peer's shared memory.  Per CTA and k-block that is 16 KB + BN*64 B of shared-memory writes and reads instead of
-// 16 KB + BN*128 B, which takes the kernel off the operand-feed limit (SS-mode at 128x256 reads 96 B/clk of the
-// 128 B/clk the SM has) and frees room for a 6-8 stage ring.
-//   - full barriers live in the leader CTA (cluster rank 0): both CTAs' TMA loads complete_tx on them
-//   - the leader's MMA thread issues for the pair; tcgen05.commit multicasts to both CTAs' empty / tmem_full barriers
-//   - both CTAs' epilogue warps arrive on the leader's tmem_empty barrier (remote arrive from the peer)
-template <int BN>
-struct Gemm2Cfg {
-    static constexpr int B_HALF_BYTES = (BN / 2) * BK * 2;
-    static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_HALF_BYTES;  // per CTA
-    static constexpr int STAGES = BN == 256 ? 5 : (BN == 192 ? 6 : 7);
-    static constexpr int TMEM_COLS = (2 * BN <= 256) ? 256 : 512;
-    static constexpr int BAR_BYTES = (2 * STAGES + 4) * 8 + 16;
-    // bf16 outputs leave through per-warp staging tiles (32 rows x 64 B, SWIZZLE_64B, double-buffered) and TMA stores
-    static constexpr int OUT_TILE_BYTES = 32 * 64;
-    static constexpr int OUT_STAGE_BYTES = kEpiWarps * 2 * OUT_TILE_BYTES;
-    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + OUT_STAGE_BYTES + GemmCfg<BN>::BIAS_BYTES + BAR_BYTES + 1024;
-};
-
-template <int BN>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
+template <int BN, uint32_t EF>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GemmCfg<BN>::THREADS, 1)
 gemm_bf16_cg2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                      const __grid_constant__ CUtensorMap tmC, const GemmParams p) {
     using Cfg = GemmCfg<BN>;
-    using Cfg2 = Gemm2Cfg<BN>;
-    constexpr int STAGES = Cfg2::STAGES;
+    constexpr int STAGES = Cfg::STAGES;
+    constexpr bool ANY = (EF & EF_ANY) != 0;
 
     extern __shared__ uint8_t smem_raw[];
+    // the dynamic smem window starts at the same CTA-relative offset in both CTAs of the cluster, so the
+    // aligned carve-up below is identical in both (required by the peer's smem reads / remote arrives)
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* sA = smem;
     uint8_t* sB = smem + STAGES * A_STAGE_BYTES;
-    uint8_t* sOutStage = smem + STAGES * Cfg2::STAGE_BYTES;  // [epilogue warp][2][32 rows x 64 B], 1024-byte aligned
-    float* sBias = reinterpret_cast<float*>(sOutStage + Cfg2::OUT_STAGE_BYTES);
+    uint8_t* sOutStage = smem + STAGES * Cfg::STAGE_BYTES;  // [epilogue warp][32 rows x 64 B], 1024-byte aligned
+    float* sBias = reinterpret_cast<float*>(sOutStage + Cfg::OUT_STAGE_BYTES);
     uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(sBias) + Cfg::BIAS_BYTES);
     uint64_t* full_bar = bars;                       // used in the leader only
     uint64_t* empty_bar = bars + STAGES;             // per CTA: "this stage may be overwritten"
@@ -426,13 +269,13 @@ gemm_bf16_cg2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         }
         for (int s = 0; s < 2; ++s) {
             mbar_init(&tmem_full_bar[s], 1);
-            mbar_init(&tmem_empty_bar[s], 2 * kEpiWarps);
+            mbar_init(&tmem_empty_bar[s], 2 * Cfg::EPI_WARPS);
         }
         fence_barrier_init();
     }
-    if (warp == 1) tmem_alloc_cg2<Cfg2::TMEM_COLS>(tmem_ptr_smem);
+    if (warp == 1) tmem_alloc_cg2<Cfg::TMEM_COLS>(tmem_ptr_smem);
     tcgen05_fence_before();
-    cluster_sync_all();
+    cluster_sync_all();  // barriers of both CTAs initialised before any remote arrive
     tcgen05_fence_after();
     const uint32_t tmem_base = *tmem_ptr_smem;
 
@@ -452,12 +295,12 @@ gemm_bf16_cg2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
                     if ((p.debug & 1) && (phase || st != cluster_id)) {
                         if (cta_rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 0);
                     } else {
-                        if (cta_rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * Cfg2::STAGE_BYTES);
+                        if (cta_rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * Cfg::STAGE_BYTES);
                         const uint32_t fb = mapa_u32(smem_u32(&full_bar[stage]), 0);
                         const bool same = (p.debug & 2) != 0;  // experiment: always the same (L2-resident) boxes
                         tma_load_2d_cg2(sA + stage * A_STAGE_BYTES, &tmA, fb, same ? 0 : kb * BK,
                                         same ? (int)cta_rank * BM : m_blk * BM);
-                        tma_load_2d_cg2(sB + stage * Cfg2::B_HALF_BYTES, &tmB, fb, same ? 0 : kb * BK,
+                        tma_load_2d_cg2(sB + stage * Cfg::B_HALF_BYTES, &tmB, fb, same ? 0 : kb * BK,
                                         (same ? 0 : n_blk * BN) + (int)cta_rank * (BN / 2));
                     }
                     if (++stage == STAGES) {
@@ -483,7 +326,7 @@ gemm_bf16_cg2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
                     mbar_wait_cluster(&full_bar[stage], phase);
                     tcgen05_fence_after();
                     const uint32_t a_addr = smem_u32(sA + stage * A_STAGE_BYTES);
-                    const uint32_t b_addr = smem_u32(sB + stage * Cfg2::B_HALF_BYTES);
+                    const uint32_t b_addr = smem_u32(sB + stage * Cfg::B_HALF_BYTES);
 #pragma unroll
                     for (int k = 0; k < BK / 16; ++k) {
                         umma_bf16_ss_cg2(d_tmem, umma_desc_sw128(a_addr + k * 32), umma_desc_sw128(b_addr + k * 32), idesc,
@@ -503,31 +346,32 @@ gemm_bf16_cg2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     } else {
         // ===== epilogue warps (both CTAs, each on its own 128 rows) =====
         const int ew = warp - 2;
-        const int q = warp & 3;
-        const int half = ew >> 2;
-        float* myBias = sBias + ew * (Cfg::CHUNKS_PER_WARP * 32);
-        uint8_t* myStage = sOutStage + ew * (2 * Cfg2::OUT_TILE_BYTES);
-        const CUtensorMap* out_map = p.out_f32 ? nullptr : &tmC;  // fp32 outputs keep the direct stores
-        int stage_parity = 0;
+        const int q = warp & 3;     // TMEM lane quadrant this warp may read
+        const int cgp = ew >> 2;    // which 64-column group of the tile
+        const bool has_res = ANY ? p.residual != nullptr : (EF & EF_RES) != 0;
+        const bool ln = ANY ? p.ln_stats != nullptr : (EF & EF_LN) != 0;
+        float* myBias = sBias + ew * Cfg::COLS_PER_WARP;
+        uint8_t* myStage = sOutStage + ew * Cfg::OUT_TILE_BYTES;
+        bool store_pending = false;
         int as = 0;
         uint32_t aphase = 0;
         for (int st = cluster_id; st < num_super; st += num_clusters) {
             const int m_blk = (st / p.n_tiles) * 2 + (int)cta_rank, n_blk = st % p.n_tiles;
-            const int n0 = n_blk * BN + half * (Cfg::CHUNKS_PER_WARP * 32);
-            for (int c = lane; c < Cfg::CHUNKS_PER_WARP * 32; c += 32) {
+            const int n0 = n_blk * BN + cgp * Cfg::COLS_PER_WARP;
+            const int row0 = m_blk * BM + q * 32;
+            for (int c = lane; c < Cfg::COLS_PER_WARP; c += 32) {
                 myBias[c] = (p.bias != nullptr && n0 + c < p.N) ? p.bias[n0 + c] : 0.0f;
-                if (p.ln_stats != nullptr)
-                    myBias[kEpiWarps * Cfg::CHUNKS_PER_WARP * 32 + c] = (n0 + c < p.N) ? p.ln_c1[n0 + c] : 0.0f;
+                if (ln) myBias[Cfg::EPI_WARPS * Cfg::COLS_PER_WARP + c] = (n0 + c < p.N) ? p.ln_c1[n0 + c] : 0.0f;
             }
             __syncwarp();
             uint4 rv[4];
-            float ln_rstd, ln_mr;
-            load_residual_chunk(p, m_blk * BM + q * 32 + lane, n0, rv);
-            load_ln_row(p, m_blk * BM + q * 32 + lane, ln_rstd, ln_mr);
+            float ln_rstd = 1.0f, ln_mr = 0.0f;
+            if (has_res) load_residual_chunk(p, row0 + lane, n0, rv);
+            if (ln) load_ln_row(p, row0 + lane, ln_rstd, ln_mr);
             mbar_wait_cluster(&tmem_full_bar[as], aphase);
             tcgen05_fence_after();
-            epilogue_tile<BN>(p, myBias, tmem_base, as, m_blk, n0, q, half, lane, rv, ln_rstd, ln_mr, out_map, myStage,
-                              &stage_parity);
+            const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BN + cgp * Cfg::COLS_PER_WARP);
+            epilogue_tile<BN, EF>(p, myBias, t_addr, row0, n0, lane, rv, ln_rstd, ln_mr, &tmC, myStage, store_pending);
             tcgen05_fence_before();
             __syncwarp();
             // the accumulator values are in registers (tcgen05.wait::ld): a relaxed arrive is enough, and unlike a
@@ -539,41 +383,45 @@ gemm_bf16_cg2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         if (lane == 0) tma_store_wait_all();  // staged tiles fully written out before the CTA's smem goes away
     }
 
+    // no CTA may exit while its peer can still read its smem or arrive on its barriers
     tcgen05_fence_before();
     cluster_sync_all();
     if (warp == 1) {
         tcgen05_fence_after();
-        tmem_dealloc_cg2<Cfg2::TMEM_COLS>(tmem_base);
+        tmem_dealloc_cg2<Cfg::TMEM_COLS>(tmem_base);
     }
 }
 
-template <int BN>
-static int launch_gemm_cg2(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const GemmParams& p,
-                           cudaStream_t stream) {
-    using Cfg2 = Gemm2Cfg<BN>;
-    GVL_CUDA(cudaFuncSetAttribute(gemm_bf16_cg2_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  Cfg2::SMEM_BYTES));
-    const int super_tiles = p.m_pairs * p.n_tiles;
-    const int max_clusters = sm_count() / 2;
-    const int clusters = super_tiles < max_clusters ? super_tiles : max_clusters;
-    ProfScope prof(GVL_K_GEMM, 2.0 * p.M * (double)p.N * p.K, stream);
-    gemm_bf16_cg2_kernel<BN><<<2 * clusters, kGemmThreads, Cfg2::SMEM_BYTES, stream>>>(tmA, tmB, tmC, p);
-    GVL_LAUNCH_CHECK("gemm_bf16_cg2_kernel");
-    return 0;
-}
-
-template <int BN>
-static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, cudaStream_t stream) {
+template <int BN, uint32_t EF>
+static int launch_gemm_ef(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const GemmParams& p,
+                          cudaStream_t stream) {
     using Cfg = GemmCfg<BN>;
-    GVL_CUDA(cudaFuncSetAttribute(gemm_bf16_tcgen05_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    static_assert(Cfg::SMEM_BYTES <= 227 * 1024, "GEMM shared memory budget");
+    GVL_CUDA(cudaFuncSetAttribute(gemm_bf16_cg2_kernel<BN, EF>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   Cfg::SMEM_BYTES));
     const int super_tiles = p.m_pairs * p.n_tiles;
     const int max_clusters = sm_count() / 2;
     const int clusters = super_tiles < max_clusters ? super_tiles : max_clusters;
     ProfScope prof(GVL_K_GEMM, 2.0 * p.M * (double)p.N * p.K, stream);
-    gemm_bf16_tcgen05_kernel<BN><<<2 * clusters, kGemmThreads, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, p);
-    GVL_LAUNCH_CHECK("gemm_bf16_tcgen05_kernel");
+    gemm_bf16_cg2_kernel<BN, EF><<<2 * clusters, Cfg::THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, tmC, p);
+    GVL_LAUNCH_CHECK("gemm_bf16_cg2_kernel");
     return 0;
+}
+
+// the flag combinations of the tower's hot GEMMs get their own instantiation; everything else is generic
+template <int BN>
+static int launch_gemm_bn(uint32_t ef, const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC,
+                          const GemmParams& p, cudaStream_t stream) {
+    switch (ef) {
+        case 0u: return launch_gemm_ef<BN, 0u>(tmA, tmB, tmC, p, stream);                                  // qkv, kv
+        case GVL_ACT_GELU_TANH: return launch_gemm_ef<BN, GVL_ACT_GELU_TANH>(tmA, tmB, tmC, p, stream);    // fc1
+        case EF_RES: return launch_gemm_ef<BN, EF_RES>(tmA, tmB, tmC, p, stream);                          // out, fc2, patch
+        case EF_RES | EF_STATS: return launch_gemm_ef<BN, EF_RES | EF_STATS>(tmA, tmB, tmC, p, stream);    // fold_ln producers
+        case EF_LN: return launch_gemm_ef<BN, EF_LN>(tmA, tmB, tmC, p, stream);                            // fold_ln qkv, kv
+        case EF_LN | GVL_ACT_GELU_TANH:
+            return launch_gemm_ef<BN, EF_LN | GVL_ACT_GELU_TANH>(tmA, tmB, tmC, p, stream);                // fold_ln fc1
+        default: return launch_gemm_ef<BN, EF_ANY>(tmA, tmB, tmC, p, stream);
+    }
 }
 
 static int pick_bn(int N) {
@@ -595,8 +443,10 @@ static int pick_bn(int N) {
 }  // namespace gvl
 
 extern "C" int gvl_gemm_stats_slots(int N) {
+    // one slot per epilogue warp column group (64 columns), padded to an even count
     const int bn = gvl::pick_bn(N);
-    return 2 * ((N + bn - 1) / bn);
+    const int slots = (bn / 64) * ((N + bn - 1) / bn);
+    return (slots + 1) & ~1;
 }
 
 extern "C" int gvl_gemm_bf16(const void* A, int lda, const void* W, int ldw, const float* bias, const void* residual,
@@ -628,6 +478,7 @@ extern "C" int gvl_gemm_bf16_fused(const void* A, int lda, const void* W, int ld
     GemmParams p;
     p.debug = debug;
     p.stats_out = nullptr;
+    p.stats_slots = gvl_gemm_stats_slots(N);
     p.ln_stats = nullptr;
     p.ln_c1 = nullptr;
     p.ln_slots = 0;
@@ -636,6 +487,10 @@ extern "C" int gvl_gemm_bf16_fused(const void* A, int lda, const void* W, int ld
         GVL_CHECK_ARG(fusion->stats_out == nullptr || !out_f32, "gvl_gemm_bf16_fused: row statistics need a bf16 output");
         GVL_CHECK_ARG(fusion->ln_stats == nullptr || (fusion->ln_c1 && fusion->ln_slots > 0 && fusion->ln_dim > 0),
                       "gvl_gemm_bf16_fused: incomplete LayerNorm fusion arguments");
+        GVL_CHECK_ARG(fusion->ln_stats == nullptr ||
+                          (fusion->ln_slots % 2 == 0 && fusion->ln_slots <= 2 * kMaxLnSlotPairs &&
+                           (uintptr_t)fusion->ln_stats % 16 == 0),
+                      "gvl_gemm_bf16_fused: ln_slots must be even and <= %d, ln_stats 16-byte aligned", 2 * kMaxLnSlotPairs);
         p.stats_out = fusion->stats_out;
         p.ln_stats = fusion->ln_stats;
         p.ln_c1 = fusion->ln_c1;
@@ -665,29 +520,20 @@ extern "C" int gvl_gemm_bf16_fused(const void* A, int lda, const void* W, int ld
     if (rc) return rc;
 
     cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
-    static const bool multicast_variant = [] {
-        const char* e = getenv("GVL_GEMM_MC");  // A/B switch: the 1-CTA-MMA + multicast kernel
-        return e && e[0] == '1';
-    }();
-    if (!multicast_variant) {
-        // output map for the epilogue's TMA stores: 32 x 32 bf16 boxes, SWIZZLE_64B staging tiles
-        CUtensorMap tmC = tmA;  // placeholder for fp32 outputs (never dereferenced)
-        if (!out_f32) {
-            const uint64_t cdims[2] = {(uint64_t)N, (uint64_t)M};
-            const uint64_t cstr[1] = {(uint64_t)ldo * 2};
-            const uint32_t cbox[2] = {32, 32};
-            rc = make_tmap_nd_bf16(&tmC, out, 2, cdims, cstr, cbox, 64);
-            if (rc) return rc;
-        }
-        switch (bn) {
-            case 256: return launch_gemm_cg2<256>(tmA, tmB, tmC, p, s);
-            case 192: return launch_gemm_cg2<192>(tmA, tmB, tmC, p, s);
-            default: return launch_gemm_cg2<128>(tmA, tmB, tmC, p, s);
-        }
+    // output map for the epilogue's TMA stores: 32 x 32 bf16 boxes, SWIZZLE_64B staging tiles
+    CUtensorMap tmC = tmA;  // placeholder for fp32 outputs (never dereferenced)
+    if (!out_f32) {
+        const uint64_t cdims[2] = {(uint64_t)N, (uint64_t)M};
+        const uint64_t cstr[1] = {(uint64_t)ldo * 2};
+        const uint32_t cbox[2] = {32, 32};
+        rc = make_tmap_nd_bf16(&tmC, out, 2, cdims, cstr, cbox, 64);
+        if (rc) return rc;
     }
+    const uint32_t ef = (uint32_t)act | (residual ? EF_RES : 0u) | (p.ln_stats ? EF_LN : 0u) |
+                        (p.stats_out ? EF_STATS : 0u) | (out_f32 ? EF_F32 : 0u);
     switch (bn) {
-        case 256: return launch_gemm<256>(tmA, tmB, p, s);
-        case 192: return launch_gemm<192>(tmA, tmB, p, s);
-        default: return launch_gemm<128>(tmA, tmB, p, s);
+        case 256: return launch_gemm_bn<256>(ef, tmA, tmB, tmC, p, s);
+        case 192: return launch_gemm_bn<192>(ef, tmA, tmB, tmC, p, s);
+        default: return launch_gemm_bn<128>(ef, tmA, tmB, tmC, p, s);
     }
 }

@@ -30,7 +30,9 @@ def shard_range(n_items: int, rank: int, world: int, align: int = 1) -> tuple[in
 class EmbeddingPipeline:
     def __init__(self, siglip_sd: dict, projector_sd: dict, spec: SiglipVisionSpec | None = None,
                  device: str | torch.device = "cuda:0", batch: int = 64, resample: int = ops.BILINEAR,
-                 image_mean=(0.5, 0.5, 0.5), image_std=(0.5, 0.5, 0.5)):
+                 image_mean=(0.5, 0.5, 0.5), image_std=(0.5, 0.5, 0.5), fold_ln: bool = True):
+        """fold_ln: run the tower with every token-level LayerNorm folded into the GEMM that consumes it
+        (weights.SiglipPack); the 56 LayerNorm launches per batch disappear.  False keeps the reference's op order."""
         self.spec = spec or SiglipVisionSpec.so400m()
         self.device = torch.device(device)
         if self.device.type != "cuda":
@@ -39,7 +41,7 @@ class EmbeddingPipeline:
         self.resample = resample
         self.image_mean, self.image_std = tuple(image_mean), tuple(image_std)
         with torch.cuda.device(self.device):
-            self.pack = SiglipPack(siglip_sd, self.spec, self.device)
+            self.pack = SiglipPack(siglip_sd, self.spec, self.device, fold_ln=fold_ln)
             self.proj = ProjectorPack(projector_sd, self.device)
             s = self.spec
             self.workspace = torch.empty(self.pack.workspace_bytes(self.batch), dtype=torch.uint8, device=self.device)

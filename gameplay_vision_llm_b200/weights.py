@@ -154,9 +154,9 @@ class SiglipPack:
                  fold_ln: bool = False):
         """fold_ln: fold every token-level LayerNorm into the Linear that consumes it (include/gvl.h,
         `gvl_gemm_fusion`): W' = bf16(W * gamma), c1[n] = sum_k W'[n,k], c2 = bias + W @ beta.  The LayerNorm
-        kernels then disappear from the forward pass.  Off by default: measured on B200 the extra epilogue work
-        (+40 us per consumer GEMM) cancels the 44 us LayerNorm kernel it removes (profiles/README.md), so the
-        production path keeps the reference's op order."""
+        kernels then disappear from the forward pass.  Measured on B200 (profiles/README.md): the folded epilogues cost
+        +18 us (qkv), +20 us (fc1), +6 / +9 us (the two producers) per layer against 2 x 44 us of LayerNorm kernels.
+        EmbeddingPipeline turns it on; the default here keeps the reference's op order."""
         self.spec = spec
         self.device = torch.device(device)
         self._keep: list[torch.Tensor] = []

@@ -50,6 +50,21 @@ def gemm_cases():
     print(f"gemm total per step ~ {tot:.2f} ms")
 
 
+def gemm_probe_cases():
+    """Epilogue-cost probes: the same shapes with / without activation and residual (run under GVL_GEMM_BN=192/128
+    for the tile-width variants; the environment knob is read once per process)."""
+    for name, n, k, act, res in [("fc1", 4304, 1152, 1, 0), ("fc1-noact", 4304, 1152, 0, 0), ("out", 1152, 1152, 0, 1),
+                                 ("out-nores", 1152, 1152, 0, 0), ("fc2", 1152, 4304, 0, 1), ("fc2-nores", 1152, 4304, 0, 0),
+                                 ("qkv", 3456, 1152, 0, 0), ("qkv-f32out", 3456, 1152, 0, -1)]:
+        a = torch.randn(M, k, device=DEV).to(torch.bfloat16)
+        w = (torch.randn(n, k, device=DEV) / math.sqrt(k)).to(torch.bfloat16)
+        bias = torch.randn(n, device=DEV)
+        out = torch.empty(M, n, device=DEV, dtype=torch.float32 if res < 0 else torch.bfloat16)
+        ms = timeit(lambda: ops.gemm(a, w, bias, out if res == 1 else None, act=act, out=out))
+        print(f"gemm {name:10s} N={n} K={k} BN={os.environ.get('GVL_GEMM_BN', 'auto')}: {ms*1e3:8.1f} us  "
+              f"{2.0*M*n*k/ms/1e9:7.1f} TFLOP/s")
+
+
 def gemm_fused_cases():
     """The LayerNorm-fusion variants at the layer shapes (producer = stats_out, consumer = ln_stats)."""
     D = 1152
@@ -101,6 +116,8 @@ if __name__ == "__main__":
     what = sys.argv[1] if len(sys.argv) > 1 else "all"
     if what in ("gemm", "all"):
         gemm_cases()
+    if what == "gemmx":
+        gemm_probe_cases()
     if what in ("gemmf", "all"):
         gemm_fused_cases()
     if what in ("attn", "all"):

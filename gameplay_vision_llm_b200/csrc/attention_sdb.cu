@@ -232,12 +232,16 @@ attention_sdb_kernel(const __grid_constant__ CUtensorMap tmq64, const __grid_con
                             for (int i = 0; i < 32; ++i)
                                 if (c * 32 + i >= valid) s[c][i] = 0xff800000u;  // -inf
                     }
-                    float mx = -INFINITY;
+                    // four independent max chains (one chain of 32 dependent FMNMX3 is ~130 cycles of pure latency)
+                    float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
 #pragma unroll
-                    for (int c = 0; c < 2; ++c)
-#pragma unroll
-                        for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(s[c][i]));
-                    const float mt = mx * scale_log2;
+                    for (int i = 0; i < 8; ++i) {
+                        mx0 = fmaxf(mx0, fmaxf(__uint_as_float(s[0][4 * i]), __uint_as_float(s[0][4 * i + 1])));
+                        mx1 = fmaxf(mx1, fmaxf(__uint_as_float(s[0][4 * i + 2]), __uint_as_float(s[0][4 * i + 3])));
+                        mx2 = fmaxf(mx2, fmaxf(__uint_as_float(s[1][4 * i]), __uint_as_float(s[1][4 * i + 1])));
+                        mx3 = fmaxf(mx3, fmaxf(__uint_as_float(s[1][4 * i + 2]), __uint_as_float(s[1][4 * i + 3])));
+                    }
+                    const float mt = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)) * scale_log2;
                     float factor = 1.0f;
                     bool need = false;
                     if (j == 0) {

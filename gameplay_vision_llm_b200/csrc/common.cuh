@@ -134,9 +134,12 @@ static __device__ __noinline__ void mbar_timeout_trap() {
 }
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     if (mbar_try_wait(bar, parity)) return;
+    // try_wait suspends the thread in hardware for a bounded time, so a failed probe is rare; the clock is only
+    // consulted every 4096 probes to keep the waiting warps (TMA / MMA issuers) off the issue ports
     const uint64_t t0 = global_timer_ns();
+    uint32_t probes = 0;
     while (!mbar_try_wait(bar, parity)) {
-        if (global_timer_ns() - t0 > 4000000000ull) mbar_timeout_trap();
+        if ((++probes & 0xfffu) == 0 && global_timer_ns() - t0 > 4000000000ull) mbar_timeout_trap();
     }
 }
 
@@ -320,8 +323,9 @@ __device__ __forceinline__ bool mbar_try_wait_cluster(uint64_t* bar, uint32_t pa
 __device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
     if (mbar_try_wait_cluster(bar, parity)) return;
     const uint64_t t0 = global_timer_ns();
+    uint32_t probes = 0;
     while (!mbar_try_wait_cluster(bar, parity)) {
-        if (global_timer_ns() - t0 > 4000000000ull) mbar_timeout_trap();
+        if ((++probes & 0xfffu) == 0 && global_timer_ns() - t0 > 4000000000ull) mbar_timeout_trap();
     }
 }
 

@@ -74,6 +74,10 @@ SIGNATURES = {
                             c_int, c_void_p]),
     "gvl_topk_cosine": (c_int, [c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_float, c_void_p, c_void_p, c_void_p,
                                 c_void_p]),
+    "gvl_topk_scratch_floats": (c_size_t, [c_int, c_int]),
+    "gvl_topk_cosine_ex": (c_int, [c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_float, c_void_p, c_void_p, c_int,
+                                   c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "gvl_row_inv_norm": (c_int, [c_void_p, c_int, c_int, c_float, c_void_p, c_void_p]),
 }
 
 _LIB = None
@@ -92,7 +96,7 @@ def lib() -> ctypes.CDLL:
             fn = getattr(handle, name)
             fn.restype = res
             fn.argtypes = args
-        if handle.gvl_abi_version() != 2:
+        if handle.gvl_abi_version() != 3:
             raise RuntimeError("libgvl_sm100a.so ABI version mismatch; rebuild the extension")
         _LIB = handle
     return _LIB

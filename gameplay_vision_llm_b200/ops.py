@@ -291,16 +291,49 @@ def project(pp: ProjectorPack, x: torch.Tensor, out_dtype: torch.dtype = torch.f
     return out
 
 
-def topk_cosine(index: torch.Tensor, queries: torch.Tensor, k: int, eps: float = 1e-12):
-    """index bf16 [N,D], queries bf16 [Q,D] -> (scores fp32 [Q,k], idx int32 [Q,k]), score desc / idx asc."""
-    _need_cuda(index, queries)
+TOPK_AUTO, TOPK_SCAN, TOPK_TENSOR = 0, 1, 2
+
+
+def row_inv_norm(rows: torch.Tensor, eps: float = 1e-12, out: torch.Tensor | None = None) -> torch.Tensor:
+    """1 / max(|row|, eps) of bf16 rows [N,D] -> fp32 [N] (cache it next to an index that does not change)."""
+    _need_cuda(rows, out)
+    if rows.dtype != torch.bfloat16 or not rows.is_contiguous():
+        raise RuntimeError("row_inv_norm: rows must be contiguous bf16")
+    N, D = rows.shape
+    if out is None:
+        out = torch.empty((N,), dtype=torch.float32, device=rows.device)
+    _lib.check(_lib.lib().gvl_row_inv_norm(rows.data_ptr(), N, D, float(eps), out.data_ptr(), _stream()),
+               "gvl_row_inv_norm")
+    return out
+
+
+def topk_cosine(index: torch.Tensor, queries: torch.Tensor, k: int, eps: float = 1e-12,
+                row_lo: torch.Tensor | None = None, row_hi: torch.Tensor | None = None,
+                span: tuple[int, int] | None = None, mode: int = TOPK_AUTO, inv_norm: torch.Tensor | None = None):
+    """index bf16 [N,D], queries bf16 [Q,D] -> (scores fp32 [Q,k], idx int32 [Q,k]), score desc / idx asc.
+    row_lo / row_hi (int32 [Q], device): query q only ranks rows [row_lo[q], row_hi[q]); `span` = (min lo, max hi),
+    the only rows that are scored (computed here from the tensors if omitted — one host sync).  Slots beyond the
+    number of eligible rows hold idx -1 / score -inf.  inv_norm: cached `row_inv_norm(index)` (TENSOR path)."""
+    _need_cuda(index, queries, row_lo, row_hi, inv_norm)
     if index.dtype != torch.bfloat16 or queries.dtype != torch.bfloat16 or not index.is_contiguous() or not queries.is_contiguous():
         raise RuntimeError("topk_cosine: index and queries must be contiguous bf16")
     N, D = index.shape
     Q = queries.shape[0]
-    scratch = torch.empty((Q, N), dtype=torch.float32, device=index.device)
+    if (row_lo is None) != (row_hi is None):
+        raise RuntimeError("topk_cosine: row_lo and row_hi come together")
+    lo_hi = (0, N)
+    if row_lo is not None:
+        if row_lo.dtype != torch.int32 or row_hi.dtype != torch.int32 or row_lo.numel() != Q or row_hi.numel() != Q:
+            raise RuntimeError("topk_cosine: row_lo / row_hi must be int32 [Q]")
+        lo_hi = span if span is not None else (max(0, int(row_lo.min())), min(N, int(row_hi.max())))
+        lo_hi = (lo_hi[0], max(lo_hi[0], lo_hi[1]))
+    if inv_norm is not None and (inv_norm.dtype != torch.float32 or inv_norm.numel() < N):
+        raise RuntimeError("topk_cosine: inv_norm must be fp32 [N]")
+    scratch = torch.empty((int(_lib.lib().gvl_topk_scratch_floats(N, Q)),), dtype=torch.float32, device=index.device)
     scores = torch.empty((Q, k), dtype=torch.float32, device=index.device)
     idx = torch.empty((Q, k), dtype=torch.int32, device=index.device)
-    _lib.check(_lib.lib().gvl_topk_cosine(index.data_ptr(), N, D, queries.data_ptr(), Q, k, float(eps), scratch.data_ptr(),
-                                          scores.data_ptr(), idx.data_ptr(), _stream()), "gvl_topk_cosine")
+    _lib.check(_lib.lib().gvl_topk_cosine_ex(
+        index.data_ptr(), N, D, queries.data_ptr(), Q, k, float(eps), _ptr(row_lo), _ptr(row_hi), int(lo_hi[0]),
+        int(lo_hi[1]), int(mode), _ptr(inv_norm), scratch.data_ptr(), scores.data_ptr(), idx.data_ptr(), _stream()),
+        "gvl_topk_cosine_ex")
     return scores, idx

@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define GVL_ABI_VERSION 2
+#define GVL_ABI_VERSION 3
 
 #if defined(__GNUC__)
 #define GVL_API __attribute__((visibility("default")))
@@ -270,10 +270,30 @@ GVL_API int gvl_project(const void* x, int M, int enc_dim, int llm_dim, const vo
  * (src/agent_core/qwen_reasoning_core.py:1492-1528: cos_sim + argsort(descending)[:k]) and
  * SigLIPSemanticEncoder.find_similar_regions (src/perception/siglip_semantic_encoder.py:616-638:
  * stable sort => ties keep the lower index first).
- * index: bf16 [N, D] (ld = D); queries: bf16 [Q, D]; scratch: float [Q*N];
- * out_scores: float [Q,k]; out_idx: int32 [Q,k]; k <= 64; D % 8 == 0. */
+ * index: bf16 [N, D] (ld = D); queries: bf16 [Q, D]; scratch: float [gvl_topk_scratch_floats(N, Q)], 16-byte aligned;
+ * out_scores: float [Q,k]; out_idx: int32 [Q,k] (-1 / -inf when fewer than k rows are eligible); k <= 64; D % 8 == 0. */
 GVL_API int gvl_topk_cosine(const void* index, int N, int D, const void* queries, int Q, int k, float eps,
                     float* scratch, float* out_scores, int32_t* out_idx, void* stream);
+GVL_API size_t gvl_topk_scratch_floats(int N, int Q); /* Host only. */
+
+/* Scoring path: SCAN = CUDA-core fp32 scan, the index is read once per 8 queries (any Q, lowest latency for one
+ * query); TENSOR = one skinny tcgen05 GEMM scores = Q . E^T (fp32 out) that reads the index once for the whole query
+ * batch, then a scale pass with 1/|q| and 1/|e_n|; AUTO = TENSOR for Q >= 16 over >= 4096 rows. */
+enum { GVL_TOPK_AUTO = 0, GVL_TOPK_SCAN = 1, GVL_TOPK_TENSOR = 2 };
+
+/* gvl_topk_cosine restricted, per query, to the rows [row_lo[q], row_hi[q]) of the index.  The timeline index is in
+ * timestamp order, so this is the reference's "events within +-window seconds of t" filter
+ * (scripts/realtime_inference.py:988-998 `abs(e["timestamp"] - timestamp) < window`;
+ * src/agent_core/qwen_reasoning_core.py:1462-1490 retrieve_by_timestamp, start <= ts <= end) fused with the ranking
+ * of retrieve_by_semantic: rows outside a query's range are neither scored nor ranked.
+ * row_lo / row_hi: device int32 [Q], both NULL = whole index; [span_lo, span_hi) = union of the ranges (host-known:
+ * only these rows are scored).  inv_norm: optional device float [N] holding 1/max(|e_n|, eps) (gvl_row_inv_norm), so
+ * repeated searches over an unchanged index skip the norm pass of the TENSOR path; NULL = computed into scratch. */
+GVL_API int gvl_topk_cosine_ex(const void* index, int N, int D, const void* queries, int Q, int k, float eps,
+                       const int32_t* row_lo, const int32_t* row_hi, int span_lo, int span_hi, int mode,
+                       const float* inv_norm, float* scratch, float* out_scores, int32_t* out_idx, void* stream);
+/* inv_norm[n] = 1 / max(|rows[n]|, eps), rows bf16 [N, D]. */
+GVL_API int gvl_row_inv_norm(const void* rows, int N, int D, float eps, float* inv_norm, void* stream);
 
 #ifdef __cplusplus
 }

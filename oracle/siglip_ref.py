@@ -134,3 +134,47 @@ def cosine_topk(index: np.ndarray, queries: np.ndarray, k: int, eps: float = 1e-
         if N > kk:
             margins[i] = s[i, order[kk - 1]] - s[i, order[kk]]
     return top, idx, margins
+
+
+def window_rows(timestamps: np.ndarray, center: float, window: float, inclusive: bool):
+    """Rows of a timestamp-ordered timeline inside the reference's time filters, as a [lo, hi) range.
+
+    inclusive=False: `abs(ts - center) < window` (scripts/realtime_inference.py:994-998);
+    inclusive=True:  `center - window <= ts <= center + window` (src/agent_core/qwen_reasoning_core.py:1482-1490,
+    and TimelineIndexer.query_range `start <= ts <= end`, src/fusion_indexing/timeline_indexer.py:588-614).
+    Restated literally (a Python scan), not with searchsorted."""
+    ts = np.asarray(timestamps, np.float64)
+    if inclusive:
+        sel = [i for i, t in enumerate(ts) if center - window <= t <= center + window]
+    else:
+        sel = [i for i, t in enumerate(ts) if abs(t - center) < window]
+    if not sel:
+        return 0, 0
+    assert sel == list(range(sel[0], sel[-1] + 1)), "timestamps must be sorted"
+    return sel[0], sel[-1] + 1
+
+
+def cosine_topk_windowed(index: np.ndarray, queries: np.ndarray, k: int, row_lo, row_hi, eps: float = 1e-12):
+    """cosine_topk restricted per query to rows [row_lo[q], row_hi[q]); missing slots are idx -1 / score -inf."""
+    Q = np.asarray(queries).shape[0]
+    top = np.full((Q, k), -np.inf)
+    idx = np.full((Q, k), -1, np.int64)
+    for q in range(Q):
+        lo, hi = int(row_lo[q]), int(row_hi[q])
+        if hi <= lo:
+            continue
+        s, i, _ = cosine_topk(np.asarray(index)[lo:hi], np.asarray(queries)[q:q + 1], k, eps)
+        top[q, : s.shape[1]] = s[0]
+        idx[q, : i.shape[1]] = i[0] + lo
+    return top, idx
+
+
+def hybrid_merge(time_rows: list, semantic_rows: list) -> list:
+    """TimelineRetriever.hybrid_retrieve's merge (src/agent_core/qwen_reasoning_core.py:1548-1561): the time-window
+    events in timeline order, then the semantic hits that are not already present, in rank order."""
+    out = list(time_rows)
+    seen = set(out)
+    for r in semantic_rows:
+        if r not in seen:
+            out.append(r)
+    return out

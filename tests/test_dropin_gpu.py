@@ -102,3 +102,16 @@ def test_pipeline_stream_equals_resident_and_index_search():
     assert hits[0][0] == 3.0  # frame 6 at 2 fps
     sel, emb = idx.window(2.0, window_sec=1.0)
     assert sel.tolist() == [3, 4, 5] and emb.shape == (3, 512)
+    sel, emb = idx.window(None)          # realtime_inference.py:1000: no timestamp -> the first 20 rows
+    assert sel.tolist() == list(range(10))
+    # retrieval service: time window fused with the ranking, and hybrid_retrieve's merge order
+    e64, ts = resident.float().cpu().numpy(), idx.timestamps
+    q = resident[6:7]
+    lo, hi = siglip_ref.window_rows(ts, 2.0, 1.0, True)            # rows 2..6 (inclusive bounds)
+    assert idx.retrieve_by_timestamp(2.0, 1.0) == list(range(lo, hi)) == [2, 3, 4, 5, 6]
+    _, want_i = siglip_ref.cosine_topk_windowed(e64, q.float().cpu().numpy(), 3, [lo], [hi])
+    _, got_i = idx.search(q, top_k=3, windows=[(2.0, 1.0)], inclusive=True)
+    assert got_i[0].tolist() == want_i[0].tolist() and got_i[0, 0].item() == 6
+    _, sem5 = siglip_ref.cosine_topk(e64, q.float().cpu().numpy(), 5)[:2]
+    assert idx.hybrid_retrieve(q, timestamp=0.5, window=0.5) == siglip_ref.hybrid_merge([0, 1, 2], sem5[0].tolist())
+    assert idx.hybrid_retrieve(q) == siglip_ref.cosine_topk(e64, q.float().cpu().numpy(), 10)[1][0].tolist()

@@ -121,3 +121,40 @@ def test_embeddings_pt_and_npz_layouts(tmp_path):
                                 frame_indices=np.arange(4))
     z = np.load(os.path.join(d, "siglip.npz"))
     assert z["embeddings"].shape == (4, 1152) and z["embeddings"].dtype == np.float32
+
+
+def test_timeline_window_range_matches_reference_filters():
+    """window_range (binary search) == the reference's literal list filters (oracle.window_rows), including
+    timestamps that sit exactly on t +- w and windows that fall off either end of the timeline."""
+    from gameplay_vision_llm_b200.timeline import TimelineEmbeddingIndex
+    from oracle import siglip_ref
+    rng = np.random.default_rng(7)
+    for fps in (1.0, 2.0, 29.97):
+        ts = np.arange(400, dtype=np.float64) / fps
+        idx = TimelineEmbeddingIndex(400, 8, device="cpu", timestamps=ts)
+        cases = [(0.0, 30.0), (ts[-1], 30.0), (ts[100], 0.0), (ts[100], 1.0 / fps), (ts[57] + 0.25 / fps, 2.5 / fps),
+                 (-100.0, 10.0), (1e6, 10.0), (ts[200], 1e9)]
+        cases += [(float(rng.uniform(-5, ts[-1] + 5)), float(rng.uniform(0, 40))) for _ in range(40)]
+        for t, w in cases:
+            for inclusive in (False, True):
+                assert idx.window_range(t, w, inclusive) == siglip_ref.window_rows(ts, t, w, inclusive), (fps, t, w, inclusive)
+    # irregular (but sorted) timestamps with duplicates
+    ts = np.sort(np.round(rng.uniform(0, 50, 300), 1))
+    idx = TimelineEmbeddingIndex(300, 8, device="cpu", timestamps=ts)
+    for t in (0.0, 10.0, 10.05, 25.3, 50.0):
+        for w in (0.0, 0.1, 0.3, 5.0):
+            for inclusive in (False, True):
+                assert idx.window_range(t, w, inclusive) == siglip_ref.window_rows(ts, t, w, inclusive)
+
+
+def test_oracle_windowed_topk_and_hybrid_merge():
+    from oracle import siglip_ref
+    rng = np.random.default_rng(3)
+    e = rng.standard_normal((50, 16))
+    q = rng.standard_normal((3, 16))
+    s, i = siglip_ref.cosine_topk_windowed(e, q, 4, [0, 10, 20], [50, 12, 20])
+    full = siglip_ref.cosine_topk(e, q[:1], 4)
+    assert np.array_equal(i[0], full[1][0]) and np.allclose(s[0], full[0][0])
+    assert set(i[1][:2]) == {10, 11} and list(i[1][2:]) == [-1, -1] and np.isinf(s[1][2:]).all()
+    assert list(i[2]) == [-1] * 4
+    assert siglip_ref.hybrid_merge([4, 5, 6], [9, 5, 2]) == [4, 5, 6, 9, 2]

@@ -22,6 +22,32 @@ namespace gvl {
 
 constexpr int TOPK_QB = 8;        // queries per scan pass
 constexpr int TOPK_THREADS = 256;
+constexpr int TOPK_CAND = 512;    // candidates per query the tensor path re-scores exactly
+constexpr float TOPK_MARGIN = 6e-5f;  // > 2 x the tensor path's score error (measured 9e-6 at D = 4096)
+
+// The per-lane arithmetic of one 8-element chunk, shared by the scan and the rescoring kernel so that both
+// produce bit-identical scores for the same (row, query) pair.
+__device__ __forceinline__ void tk_unpack8(const uint4& u, float (&e)[8]) {
+    e[0] = bf16_lo(u.x); e[1] = bf16_hi(u.x); e[2] = bf16_lo(u.y); e[3] = bf16_hi(u.y);
+    e[4] = bf16_lo(u.z); e[5] = bf16_hi(u.z); e[6] = bf16_lo(u.w); e[7] = bf16_hi(u.w);
+}
+__device__ __forceinline__ float tk_sq8(float acc, const float (&e)[8]) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc = fmaf(e[j], e[j], acc);
+    return acc;
+}
+__device__ __forceinline__ float tk_dot8(float acc, const float (&e)[8], const uint4& v) {
+    float q[8];
+    tk_unpack8(v, q);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc = fmaf(e[j], q[j], acc);
+    return acc;
+}
+__device__ __forceinline__ float tk_warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
 
 __global__ void __launch_bounds__(TOPK_THREADS)
 cos_scores_kernel(const __nv_bfloat16* __restrict__ index, int r0, int r1, int D,
@@ -38,14 +64,11 @@ cos_scores_kernel(const __nv_bfloat16* __restrict__ index, int r0, int r1, int D
     if (warp < nq) {
         float acc = 0.f;
         for (int c = lane; c < chunks; c += 32) {
-            const uint4 u = sQ[warp * chunks + c];
-            const float f[8] = {bf16_lo(u.x), bf16_hi(u.x), bf16_lo(u.y), bf16_hi(u.y),
-                                bf16_lo(u.z), bf16_hi(u.z), bf16_lo(u.w), bf16_hi(u.w)};
-#pragma unroll
-            for (int j = 0; j < 8; ++j) acc += f[j] * f[j];
+            float f[8];
+            tk_unpack8(sQ[warp * chunks + c], f);
+            acc = tk_sq8(acc, f);
         }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+        acc = tk_warp_sum(acc);
         if (lane == 0) sQn[warp] = 1.0f / fmaxf(sqrtf(acc), eps);
     }
     __syncthreads();
@@ -57,30 +80,31 @@ cos_scores_kernel(const __nv_bfloat16* __restrict__ index, int r0, int r1, int D
 #pragma unroll
         for (int q = 0; q < TOPK_QB; ++q) dot[q] = 0.f;
         float nrm = 0.f;
-        for (int c = lane; c < chunks; c += 32) {
-            const uint4 u = __ldg(er + c);
-            const float e[8] = {bf16_lo(u.x), bf16_hi(u.x), bf16_lo(u.y), bf16_hi(u.y),
-                                bf16_lo(u.z), bf16_hi(u.z), bf16_lo(u.w), bf16_hi(u.w)};
+        // four 16-byte loads in flight per lane (the arithmetic below consumes them in the same order as a plain loop)
+        for (int c0 = lane; c0 < chunks; c0 += 128) {
+            uint4 u[4];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) nrm += e[j] * e[j];
+            for (int i = 0; i < 4; ++i)
+                u[i] = (c0 + 32 * i < chunks) ? __ldg(er + c0 + 32 * i) : make_uint4(0, 0, 0, 0);
 #pragma unroll
-            for (int q = 0; q < TOPK_QB; ++q) {
-                if (q < nq) {
-                    const uint4 v = sQ[q * chunks + c];
-                    dot[q] += e[0] * bf16_lo(v.x) + e[1] * bf16_hi(v.x) + e[2] * bf16_lo(v.y) + e[3] * bf16_hi(v.y) +
-                              e[4] * bf16_lo(v.z) + e[5] * bf16_hi(v.z) + e[6] * bf16_lo(v.w) + e[7] * bf16_hi(v.w);
+            for (int i = 0; i < 4; ++i) {
+                const int c = c0 + 32 * i;
+                if (c < chunks) {
+                    float e[8];
+                    tk_unpack8(u[i], e);
+                    nrm = tk_sq8(nrm, e);
+#pragma unroll
+                    for (int q = 0; q < TOPK_QB; ++q)
+                        if (q < nq) dot[q] = tk_dot8(dot[q], e, sQ[q * chunks + c]);
                 }
             }
         }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) nrm += __shfl_xor_sync(0xffffffffu, nrm, o);
+        nrm = tk_warp_sum(nrm);
         const float inv_e = 1.0f / fmaxf(sqrtf(nrm), eps);
 #pragma unroll
         for (int q = 0; q < TOPK_QB; ++q) {
             if (q < nq) {
-                float d = dot[q];
-#pragma unroll
-                for (int o = 16; o > 0; o >>= 1) d += __shfl_xor_sync(0xffffffffu, d, o);
+                const float d = tk_warp_sum(dot[q]);
                 if (lane == 0) scores[(size_t)q * ld + row] = d * sQn[q] * inv_e;
             }
         }
@@ -92,61 +116,219 @@ __device__ __forceinline__ bool tk_better(float sa, int ia, float sb, int ib) {
     return sa > sb || (sa == sb && ia < ib);
 }
 
-__global__ void __launch_bounds__(TOPK_THREADS)
-topk_select_kernel(const float* __restrict__ scores, int N, size_t ld, int k, const int32_t* __restrict__ row_lo,
-                   const int32_t* __restrict__ row_hi, float* __restrict__ out_scores, int32_t* __restrict__ out_idx) {
-    __shared__ float s_s[TOPK_THREADS / 32];
-    __shared__ int s_i[TOPK_THREADS / 32];
-    __shared__ float s_best_s;
-    __shared__ int s_best_i;
+// One round-based arg-max selection step shared by the kernels below: the block agrees on the best (score, index)
+// among the per-thread bests under (score desc, index asc).
+struct TkBlockBest {
+    float ws[TOPK_THREADS / 32];
+    int wi[TOPK_THREADS / 32];
+    float best_s;
+    int best_i;
+};
+__device__ __forceinline__ void tk_block_argmax(TkBlockBest& sh, float bs, int bi, float& out_s, int& out_i) {
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const float* sc = scores + (size_t)blockIdx.x * ld;
-    const int lo = row_lo ? max(0, row_lo[blockIdx.x]) : 0;
-    const int hi = row_hi ? min(N, row_hi[blockIdx.x]) : N;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const float os = __shfl_xor_sync(0xffffffffu, bs, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+        if (tk_better(os, oi, bs, bi)) {
+            bs = os;
+            bi = oi;
+        }
+    }
+    if (lane == 0) {
+        sh.ws[warp] = bs;
+        sh.wi[warp] = bi;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        float fs = sh.ws[0];
+        int fi = sh.wi[0];
+        for (int w = 1; w < TOPK_THREADS / 32; ++w)
+            if (tk_better(sh.ws[w], sh.wi[w], fs, fi)) {
+                fs = sh.ws[w];
+                fi = sh.wi[w];
+            }
+        sh.best_s = fs;
+        sh.best_i = fi;
+    }
+    __syncthreads();
+    out_s = sh.best_s;
+    out_i = sh.best_i;
+}
+
+// Selection, stage 1: the scored span is cut into gridDim.x segments; block (segment, query) stages its piece of the
+// query's score row in shared memory and selects the segment's k best by k rounds of a block-wide arg-max over the
+// elements that come after the previous winner in the total order — no mutation, no sort network, deterministic.
+// (One block per query over the whole row — the first version — left 128 blocks crawling over 72 000 scores 16 times:
+// 0.9 ms of the 1.1 ms retrieval.)
+constexpr int TOPK_SEG = 4096;      // scores per segment (16 KB of shared memory)
+constexpr int TOPK_MAX_SEGS = 64;
+
+__global__ void __launch_bounds__(TOPK_THREADS)
+topk_select_seg_kernel(const float* __restrict__ scores, int N, size_t ld, int k, int span_lo, int seg_len,
+                       const int32_t* __restrict__ row_lo, const int32_t* __restrict__ row_hi,
+                       float* __restrict__ cand_s, int32_t* __restrict__ cand_i) {
+    extern __shared__ float tk_seg[];  // [seg_len] when it fits, else unused
+    __shared__ TkBlockBest sh;
+    const int tid = threadIdx.x;
+    const int qi = blockIdx.y, seg = blockIdx.x;
+    const float* sc = scores + (size_t)qi * ld;
+    const int qlo = row_lo ? max(0, row_lo[qi]) : 0;
+    const int qhi = row_hi ? min(N, row_hi[qi]) : N;
+    const int lo = max(qlo, span_lo + seg * seg_len);
+    const int hi = min(qhi, span_lo + (seg + 1) * seg_len);
+    const bool staged = seg_len <= TOPK_SEG;
+    if (staged)
+        for (int t = lo + tid; t < hi; t += TOPK_THREADS) tk_seg[t - lo] = sc[t];
+    __syncthreads();
+    float* os = cand_s + ((size_t)qi * gridDim.x + seg) * k;
+    int32_t* oi = cand_i + ((size_t)qi * gridDim.x + seg) * k;
     float prev_s = INFINITY;
     int prev_i = -1;
     for (int r = 0; r < k; ++r) {
         float bs = -INFINITY;
         int bi = 0x7fffffff;
         for (int t = lo + tid; t < hi; t += TOPK_THREADS) {
-            const float v = sc[t];
-            // eligible = strictly after the previous winner in the total order
+            const float v = staged ? tk_seg[t - lo] : sc[t];
+            // eligible = strictly after the previous winner in the total order (NaN never is)
             const bool elig = (r == 0) ? (v == v) : (v < prev_s || (v == prev_s && t > prev_i));
             if (elig && tk_better(v, t, bs, bi)) {
                 bs = v;
                 bi = t;
             }
         }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            const float os = __shfl_xor_sync(0xffffffffu, bs, o);
-            const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-            if (tk_better(os, oi, bs, bi)) {
-                bs = os;
-                bi = oi;
+        tk_block_argmax(sh, bs, bi, prev_s, prev_i);
+        if (tid == 0) {
+            os[r] = prev_i == 0x7fffffff ? -INFINITY : prev_s;
+            oi[r] = prev_i == 0x7fffffff ? -1 : prev_i;
+        }
+        if (prev_i == 0x7fffffff) {  // segment exhausted: the remaining slots are empty
+            for (int r2 = r + 1 + tid; r2 < k; r2 += TOPK_THREADS) {
+                os[r2] = -INFINITY;
+                oi[r2] = -1;
+            }
+            break;
+        }
+    }
+}
+
+// Selection, stage 2: the k best of the segs x k segment winners of one query.
+__global__ void __launch_bounds__(TOPK_THREADS)
+topk_merge_kernel(const float* __restrict__ cand_s, const int32_t* __restrict__ cand_i, int segs, int k,
+                  float* __restrict__ out_scores, int32_t* __restrict__ out_idx) {
+    __shared__ TkBlockBest sh;
+    const int tid = threadIdx.x, qi = blockIdx.x;
+    const float* cs = cand_s + (size_t)qi * segs * k;
+    const int32_t* ci = cand_i + (size_t)qi * segs * k;
+    const int n = segs * k;
+    float prev_s = INFINITY;
+    int prev_i = -1;
+    for (int r = 0; r < k; ++r) {
+        float bs = -INFINITY;
+        int bi = 0x7fffffff;
+        for (int j = tid; j < n; j += TOPK_THREADS) {
+            const int t = ci[j];
+            const float v = cs[j];
+            const bool elig = t >= 0 && ((r == 0) || (v < prev_s || (v == prev_s && t > prev_i)));
+            if (elig && tk_better(v, t, bs, bi)) {
+                bs = v;
+                bi = t;
             }
         }
-        if (lane == 0) {
-            s_s[warp] = bs;
-            s_i[warp] = bi;
-        }
-        __syncthreads();
+        tk_block_argmax(sh, bs, bi, prev_s, prev_i);
         if (tid == 0) {
-            float fs = s_s[0];
-            int fi = s_i[0];
-            for (int w = 1; w < TOPK_THREADS / 32; ++w)
-                if (tk_better(s_s[w], s_i[w], fs, fi)) {
-                    fs = s_s[w];
-                    fi = s_i[w];
-                }
-            s_best_s = fs;
-            s_best_i = fi;
-            out_scores[(size_t)blockIdx.x * k + r] = fi == 0x7fffffff ? -INFINITY : fs;
-            out_idx[(size_t)blockIdx.x * k + r] = fi == 0x7fffffff ? -1 : fi;
+            out_scores[(size_t)qi * k + r] = prev_i == 0x7fffffff ? -INFINITY : prev_s;
+            out_idx[(size_t)qi * k + r] = prev_i == 0x7fffffff ? -1 : prev_i;
         }
-        __syncthreads();
-        prev_s = s_best_s;
-        prev_i = s_best_i;
+    }
+}
+
+// Tensor path, second stage.  The GEMM scores carry tcgen05's accumulation rounding (~1e-5), enough to swap
+// near-equal neighbours.  Every row whose approximate score is within TOPK_MARGIN of the provisional k-th best is
+// re-scored with the scan kernel's exact arithmetic (tk_* helpers: bit-identical scores) and the final k are
+// selected among those candidates — the result equals the scan path's, at the cost of <= TOPK_CAND rows per
+// query.  More than TOPK_CAND candidates (hundreds of near-duplicates): the provisional result is kept and
+// *overflow is incremented.
+__global__ void __launch_bounds__(TOPK_THREADS)
+topk_rescore_kernel(const __nv_bfloat16* __restrict__ index, int N, int D, const __nv_bfloat16* __restrict__ queries,
+                    float eps, const float* __restrict__ scores, size_t ld, int k, const int32_t* __restrict__ row_lo,
+                    const int32_t* __restrict__ row_hi, float* __restrict__ out_scores, int32_t* __restrict__ out_idx,
+                    int* __restrict__ overflow) {
+    __shared__ int s_cand[TOPK_CAND];
+    __shared__ float s_exact[TOPK_CAND];
+    __shared__ int s_n;
+    __shared__ float s_qn;
+    __shared__ TkBlockBest sh;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int qi = blockIdx.x;
+    const float* sc = scores + (size_t)qi * ld;
+    const int lo = row_lo ? max(0, row_lo[qi]) : 0;
+    const int hi = row_hi ? min(N, row_hi[qi]) : N;
+    const float kth = out_scores[(size_t)qi * k + (k - 1)];  // -inf when fewer than k rows are eligible
+    const float thr = kth - TOPK_MARGIN;
+    if (tid == 0) s_n = 0;
+    __syncthreads();
+    for (int t = lo + tid; t < hi; t += TOPK_THREADS) {
+        const float v = sc[t];
+        if (v >= thr) {  // NaN scores never qualify, as in the select kernel
+            const int slot = atomicAdd(&s_n, 1);
+            if (slot < TOPK_CAND) s_cand[slot] = t;
+        }
+    }
+    __syncthreads();
+    const int n = s_n;
+    if (n > TOPK_CAND) {
+        if (tid == 0 && overflow) atomicAdd(overflow, 1);
+        return;  // provisional (tensor-score) result stays
+    }
+    // exact scores: one warp per candidate, the query streamed from global (L2-resident)
+    const int chunks = D >> 3;
+    const uint4* qr = reinterpret_cast<const uint4*>(queries + (size_t)qi * D);
+    if (warp == 0) {
+        float acc = 0.f;
+        for (int c = lane; c < chunks; c += 32) {
+            float f[8];
+            tk_unpack8(__ldg(qr + c), f);
+            acc = tk_sq8(acc, f);
+        }
+        acc = tk_warp_sum(acc);
+        if (lane == 0) s_qn = 1.0f / fmaxf(sqrtf(acc), eps);
+    }
+    __syncthreads();
+    for (int j = warp; j < n; j += TOPK_THREADS / 32) {
+        const uint4* er = reinterpret_cast<const uint4*>(index + (size_t)s_cand[j] * D);
+        float dot = 0.f, nrm = 0.f;
+        for (int c = lane; c < chunks; c += 32) {
+            float e[8];
+            tk_unpack8(__ldg(er + c), e);
+            nrm = tk_sq8(nrm, e);
+            dot = tk_dot8(dot, e, __ldg(qr + c));
+        }
+        nrm = tk_warp_sum(nrm);
+        dot = tk_warp_sum(dot);
+        if (lane == 0) s_exact[j] = dot * s_qn * (1.0f / fmaxf(sqrtf(nrm), eps));
+    }
+    __syncthreads();
+    // final selection among the candidates: k rounds of arg-max under (score desc, index asc)
+    float prev_s = INFINITY;
+    int prev_i = -1;
+    for (int r = 0; r < k; ++r) {
+        float bs = -INFINITY;
+        int bi = 0x7fffffff;
+        for (int j = tid; j < n; j += TOPK_THREADS) {
+            const float v = s_exact[j];
+            const int t = s_cand[j];
+            const bool elig = (r == 0) ? (v == v) : (v < prev_s || (v == prev_s && t > prev_i));
+            if (elig && tk_better(v, t, bs, bi)) {
+                bs = v;
+                bi = t;
+            }
+        }
+        tk_block_argmax(sh, bs, bi, prev_s, prev_i);
+        if (tid == 0) {
+            out_scores[(size_t)qi * k + r] = prev_i == 0x7fffffff ? -INFINITY : prev_s;
+            out_idx[(size_t)qi * k + r] = prev_i == 0x7fffffff ? -1 : prev_i;
+        }
     }
 }
 
@@ -160,14 +342,11 @@ row_inv_norm_kernel(const __nv_bfloat16* __restrict__ x, int rows, int D, float 
         const uint4* er = reinterpret_cast<const uint4*>(x + (size_t)row * D);
         float nrm = 0.f;
         for (int c = lane; c < chunks; c += 32) {
-            const uint4 u = __ldg(er + c);
-            const float e[8] = {bf16_lo(u.x), bf16_hi(u.x), bf16_lo(u.y), bf16_hi(u.y),
-                                bf16_lo(u.z), bf16_hi(u.z), bf16_lo(u.w), bf16_hi(u.w)};
-#pragma unroll
-            for (int j = 0; j < 8; ++j) nrm += e[j] * e[j];
+            float e[8];
+            tk_unpack8(__ldg(er + c), e);
+            nrm = tk_sq8(nrm, e);
         }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) nrm += __shfl_xor_sync(0xffffffffu, nrm, o);
+        nrm = tk_warp_sum(nrm);
         if (lane == 0) inv[row] = 1.0f / fmaxf(sqrtf(nrm), eps);
     }
 }
@@ -191,10 +370,16 @@ scale_scores_kernel(float* __restrict__ scores, size_t ld, int n_cols, const flo
 
 }  // namespace gvl
 
+// scratch layout (floats): [Q][ld] scores | [ld] 1/|e_n| | [Q up to 4] 1/|q| | 4: overflow counter |
+//                          [Q][TOPK_MAX_SEGS][64] segment-winner scores | same, int32 indices
+static size_t topk_cand_offset(int N, int Q) {
+    const size_t ld = ((size_t)N + 3) & ~(size_t)3;
+    return (size_t)Q * ld + ld + (((size_t)Q + 3) & ~(size_t)3) + 4;
+}
+
 extern "C" size_t gvl_topk_scratch_floats(int N, int Q) {
     if (N <= 0 || Q <= 0) return 0;
-    const size_t ld = ((size_t)N + 3) & ~(size_t)3;
-    return (size_t)Q * ld + ld /* 1/|e_n| */ + (((size_t)Q + 3) & ~(size_t)3) /* 1/|q| */;
+    return topk_cand_offset(N, Q) + 2 * (size_t)Q * gvl::TOPK_MAX_SEGS * 64;
 }
 
 extern "C" int gvl_row_inv_norm(const void* rows, int N, int D, float eps, float* inv_norm, void* stream) {
@@ -230,15 +415,19 @@ extern "C" int gvl_topk_cosine_ex(const void* index, int N, int D, const void* q
     const int rows_per_cta = TOPK_THREADS / 32;
     const int max_grid = sm_count() * 8;
     const int span = span_hi - span_lo;
-    if (mode == GVL_TOPK_AUTO) mode = (Q >= 16 && span >= 4096) ? GVL_TOPK_TENSOR : GVL_TOPK_SCAN;
+    if (mode == GVL_TOPK_AUTO) mode = (Q > TOPK_QB && span >= 4096) ? GVL_TOPK_TENSOR : GVL_TOPK_SCAN;
 
     int scan_lo = span_lo, scan_hi = span_hi;  // rows scored by the CUDA-core scan
+    bool tensor_scored = false;
+    int* overflow = nullptr;
     if (mode == GVL_TOPK_TENSOR && span > 0) {
         // GEMM over rows [g0, g1): g0 rounded down to the GEMM's N granularity (8 rows; the extra rows are harmless),
         // g1 rounded down — the <= 7 rows left over go through the scan kernel
         const int g0 = span_lo & ~7, g1 = g0 + ((span_hi - g0) & ~7);
         float* inv_e = scratch + (size_t)Q * ld;
         float* inv_q = inv_e + ld;
+        overflow = reinterpret_cast<int*>(inv_q + (((size_t)Q + 3) & ~(size_t)3));
+        GVL_CUDA(cudaMemsetAsync(overflow, 0, sizeof(int), s));
         if (g1 > g0) {
             if (inv_norm == nullptr) {
                 int rc = gvl_row_inv_norm(reinterpret_cast<const __nv_bfloat16*>(index) + (size_t)g0 * D, g1 - g0, D, eps,
@@ -255,6 +444,7 @@ extern "C" int gvl_topk_cosine_ex(const void* index, int N, int D, const void* q
             scale_scores_kernel<<<grid, TOPK_THREADS, 0, s>>>(scratch + g0, ld, g1 - g0, inv_q,
                                                               (inv_norm ? inv_norm : inv_e) + g0);
             GVL_LAUNCH_CHECK("scale_scores_kernel");
+            tensor_scored = true;
         }
         scan_lo = g1;
     }
@@ -272,9 +462,30 @@ extern "C" int gvl_topk_cosine_ex(const void* index, int N, int D, const void* q
             GVL_LAUNCH_CHECK("cos_scores_kernel");
         }
     }
-    ProfScope prof(GVL_K_TOPK_SELECT, (double)Q * span * 4 * k, s);
-    topk_select_kernel<<<Q, TOPK_THREADS, 0, s>>>(scratch, N, ld, k, row_lo, row_hi, out_scores, out_idx);
-    GVL_LAUNCH_CHECK("topk_select_kernel");
+    {
+        // two-stage selection: segment winners (grid = segments x queries), then their merge
+        int segs = (span + TOPK_SEG - 1) / TOPK_SEG;
+        segs = segs < 1 ? 1 : (segs > TOPK_MAX_SEGS ? TOPK_MAX_SEGS : segs);
+        int seg_len = ((span + segs - 1) / segs + 3) & ~3;
+        if (seg_len < 4) seg_len = 4;
+        float* cand_s = scratch + topk_cand_offset(N, Q);
+        int32_t* cand_i = reinterpret_cast<int32_t*>(cand_s + (size_t)Q * TOPK_MAX_SEGS * 64);
+        const size_t seg_smem = seg_len <= TOPK_SEG ? (size_t)seg_len * sizeof(float) : 0;
+        ProfScope prof(GVL_K_TOPK_SELECT, (double)Q * span * 4, s);
+        topk_select_seg_kernel<<<dim3((unsigned)segs, (unsigned)Q), TOPK_THREADS, seg_smem, s>>>(
+            scratch, N, ld, k, span_lo, seg_len, row_lo, row_hi, cand_s, cand_i);
+        GVL_LAUNCH_CHECK("topk_select_seg_kernel");
+        topk_merge_kernel<<<Q, TOPK_THREADS, 0, s>>>(cand_s, cand_i, segs, k, out_scores, out_idx);
+        GVL_LAUNCH_CHECK("topk_merge_kernel");
+    }
+    if (tensor_scored) {
+        // exact fp32 re-scoring of the near-top candidates: the final result is the scan path's
+        ProfScope prof(GVL_K_TOPK_SELECT, (double)Q * span * 4, s);
+        topk_rescore_kernel<<<Q, TOPK_THREADS, 0, s>>>(reinterpret_cast<const __nv_bfloat16*>(index), N, D,
+                                                       reinterpret_cast<const __nv_bfloat16*>(queries), eps, scratch, ld, k,
+                                                       row_lo, row_hi, out_scores, out_idx, overflow);
+        GVL_LAUNCH_CHECK("topk_rescore_kernel");
+    }
     return 0;
 }
 

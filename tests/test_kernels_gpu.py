@@ -306,8 +306,8 @@ def test_topk_windowed_matches_oracle(mode, N):
 
 
 def test_topk_tensor_path_equals_scan_path_72k():
-    """configs[4] size: the tensor-core scoring path (one skinny GEMM for all 128 queries) and the CUDA-core scan give
-    the same top-16 rows; prints the time of both."""
+    """configs[4] size: the tensor-core scoring path (one skinny GEMM for all 128 queries + exact re-scoring of the
+    near-top candidates) and the CUDA-core scan give bit-identical top-16 rows and scores; prints the time of both."""
     N, D, Q, k = 72000, 4096, 128, 16
     g = torch.Generator(device=DEV).manual_seed(5)
     centers = torch.randn(N // 60, D, device=DEV, generator=g)
@@ -331,7 +331,5 @@ def test_topk_tensor_path_equals_scan_path_72k():
     s0, i0 = res["scan"]
     for name in ("tensor", "tensor+cached norms"):
         s1, i1 = res[name]
-        # tcgen05 accumulates K = 4096 in fp32 with its own rounding: a systematic ~8e-6 offset against the warp
-        # reduction, the same for every row, well inside the 2e-5 the float64 oracle test allows
-        assert (s0 - s1).abs().max().item() < 2e-5
-        assert (i0 != i1).sum().item() <= 4  # rows may only swap between scores equal to accumulation accuracy
+        # the tensor path re-scores its near-top candidates with the scan path's arithmetic: identical results
+        assert torch.equal(i0, i1) and torch.equal(s0, s1)

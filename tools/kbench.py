@@ -112,6 +112,24 @@ def pre_case():
         print(f"preprocess 64x1080p rs={rs}: {ms*1e3:.1f} us  {gb:.0f} GB/s ({gb/6552.6*100:.1f}% of measured HBM peak)")
 
 
+def topk_case():
+    """configs[4] retrieval: top-16 of 128 queries over a 72 000 x 4096 bf16 index, per-kernel-family breakdown."""
+    from gameplay_vision_llm_b200 import _lib
+    N, D, Q, k = 72000, 4096, 128, 16
+    index = torch.randn(N, D, device=DEV).to(torch.bfloat16)
+    queries = torch.randn(Q, D, device=DEV).to(torch.bfloat16)
+    inv = ops.row_inv_norm(index)
+    for name, mode, kw in (("scan", ops.TOPK_SCAN, {}), ("tensor", ops.TOPK_TENSOR, {}),
+                           ("tensor+cached", ops.TOPK_TENSOR, {"inv_norm": inv})):
+        ms = timeit(lambda: ops.topk_cosine(index, queries, k, mode=mode, **kw), reps=5, warm=2)
+        _lib.prof_enable(True)
+        ops.topk_cosine(index, queries, k, mode=mode, **kw)
+        torch.cuda.synchronize()
+        _lib.prof_enable(False)
+        parts = ", ".join(f"{f} {v['ms']*1e3:.0f} us x{v['launches']}" for f, v in _lib.prof_summary().items())
+        print(f"topk {name:14s}: {ms*1e3:8.1f} us  ({N*D*2/ms/1e6:.0f} GB/s of index)  [{parts}]")
+
+
 if __name__ == "__main__":
     what = sys.argv[1] if len(sys.argv) > 1 else "all"
     if what in ("gemm", "all"):
@@ -126,3 +144,5 @@ if __name__ == "__main__":
         ln_case()
     if what in ("pre", "all"):
         pre_case()
+    if what in ("topk", "all"):
+        topk_case()

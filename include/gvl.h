@@ -281,7 +281,7 @@ GVL_API size_t gvl_topk_scratch_floats(int N, int Q); /* Host only. */
  * batch, a scale pass with 1/|q| and 1/|e_n|, and an exact second stage: every row within 6e-5 of the provisional
  * k-th score is re-scored with SCAN's fp32 arithmetic and the final k are chosen among those, so both paths return
  * identical indices and scores (more than 512 such candidates for one query: its provisional result is kept and the
- * int at scratch[gvl_topk_scratch_floats - 4] counts the queries this happened to).  AUTO = TENSOR for Q > 8 (more than one
+ * int at float offset Q*ld + ld + roundup4(Q) of scratch, ld = roundup4(N), counts the queries this happened to).  AUTO = TENSOR for Q > 8 (more than one
  * scan pass) over >= 4096 rows. */
 enum { GVL_TOPK_AUTO = 0, GVL_TOPK_SCAN = 1, GVL_TOPK_TENSOR = 2 };
 

@@ -342,6 +342,8 @@ template <int HD>
 int launch_attention_tc(const void* qkv, void* out, int B, int T, int H, float scale, cudaStream_t s);  // attention_tc.cu
 template <int HD>
 int launch_attention_sdb(const void* qkv, void* out, int B, int T, int H, float scale, cudaStream_t s);  // attention_sdb.cu
+template <int HD>
+int launch_attention_split(const void* qkv, void* out, int B, int T, int H, float scale, cudaStream_t s);  // attention_split.cu
 
 }  // namespace gvl
 
@@ -362,7 +364,15 @@ extern "C" int gvl_attention_bf16(const void* qkv, void* out, int B, int T, int 
         const char* e = getenv("GVL_ATTN_TC1");
         return e && e[0] == '1';
     }();
-    if (!legacy && !single_tile) {
+    // GVL_ATTN_SPLIT=1 selects the split-row softmax variant (two threads per query row)
+    static const bool split_rows = [] {
+        const char* e = getenv("GVL_ATTN_SPLIT");
+        return e && e[0] == '1';
+    }();
+    if (!legacy && !single_tile && split_rows) {
+        if (hd == 72) return launch_attention_split<72>(qkv, out, B, T, H, scale, s);
+        if (hd == 64) return launch_attention_split<64>(qkv, out, B, T, H, scale, s);
+    } else if (!legacy && !single_tile) {
         if (hd == 72) return launch_attention_sdb<72>(qkv, out, B, T, H, scale, s);
         if (hd == 64) return launch_attention_sdb<64>(qkv, out, B, T, H, scale, s);
     } else if (!legacy) {

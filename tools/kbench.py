@@ -86,12 +86,37 @@ def gemm_fused_cases():
         print(f"gemm {name:7s} N={n} K={k}: {ms*1e3:8.1f} us  {2.0*M*n*k/ms/1e9:7.1f} TFLOP/s")
 
 
+def sm_clock_during(fn, reps):
+    """median SM clock (MHz) and power (W) sampled through NVML while fn runs reps times back to back"""
+    import threading
+    import pynvml
+    pynvml.nvmlInit()
+    hdl = pynvml.nvmlDeviceGetHandleByIndex(0)
+    clk, pwr, stop = [], [], threading.Event()
+
+    def poll():
+        while not stop.is_set():
+            clk.append(pynvml.nvmlDeviceGetClockInfo(hdl, pynvml.NVML_CLOCK_SM))
+            pwr.append(pynvml.nvmlDeviceGetPowerUsage(hdl) / 1e3)
+            stop.wait(0.002)
+
+    th = threading.Thread(target=poll)
+    th.start()
+    ms = timeit(fn, reps=reps, warm=3)
+    stop.set()
+    th.join()
+    clk.sort()
+    return ms, clk[len(clk) // 2], max(pwr)
+
+
 def attn_case():
     B, T, H, hd = 64, 729, 16, 72
     qkv = torch.randn(B * T, 3 * H * hd, device=DEV).to(torch.bfloat16)
     out = torch.empty(B * T, H * hd, device=DEV, dtype=torch.bfloat16)
     ms = timeit(lambda: ops.attention(qkv, B, T, H, hd, out=out))
     print(f"attention B={B} T={T}: {ms*1e3:.1f} us  {4.0*B*H*T*T*hd/ms/1e9:.1f} TFLOP/s  (x27/step = {ms*27:.2f} ms)")
+    ms, mhz, watts = sm_clock_during(lambda: ops.attention(qkv, B, T, H, hd, out=out), reps=600)
+    print(f"attention sustained (600 launches): {ms*1e3:.1f} us at a median {mhz} MHz SM clock, peak {watts:.0f} W")
 
 
 def ln_case():
@@ -110,6 +135,26 @@ def pre_case():
         ms = timeit(lambda: ops.preprocess(frames, 384, 384, rs, out=out))
         gb = 64 * (1080 * 1920 * 3 + 729 * 588 * 2) / ms / 1e6
         print(f"preprocess 64x1080p rs={rs}: {ms*1e3:.1f} us  {gb:.0f} GB/s ({gb/6552.6*100:.1f}% of measured HBM peak)")
+
+
+def sustained_cases():
+    """Ours vs cuBLAS (torch.matmul, no epilogue) on the tower's GEMM shapes, each run back to back for ~1.5 s so the
+    power governor settles (MEASURED_PEAKS.json's 'sustained' figure is the same procedure on 8192^3)."""
+    for name, n, k, act, res in [("qkv", 3456, 1152, 0, 0), ("fc1", 4304, 1152, 1, 0), ("fc2", 1152, 4304, 0, 1),
+                                 ("out", 1152, 1152, 0, 1), ("sq8192", 8192, 8192, 0, 0)]:
+        m = 8192 if name == "sq8192" else M
+        a = torch.randn(m, k, device=DEV).to(torch.bfloat16)
+        w = (torch.randn(n, k, device=DEV) / math.sqrt(k)).to(torch.bfloat16)
+        bias = torch.randn(n, device=DEV)
+        out = torch.empty(m, n, device=DEV, dtype=torch.bfloat16)
+        wt = w.t()
+        flops = 2.0 * m * n * k
+        probe = timeit(lambda: ops.gemm(a, w, bias, out if res else None, act=act, out=out), reps=5)
+        reps = max(50, int(1500 / probe))
+        ms, mhz, watts = sm_clock_during(lambda: ops.gemm(a, w, bias, out if res else None, act=act, out=out), reps)
+        ms2, mhz2, watts2 = sm_clock_during(lambda: torch.matmul(a, wt, out=out), reps)
+        print(f"sustained {name:7s} M={m} N={n} K={k}: ours {flops/ms/1e9:7.1f} TFLOP/s @ {mhz} MHz {watts:.0f} W | "
+              f"cuBLAS (no bias/act/residual) {flops/ms2/1e9:7.1f} TFLOP/s @ {mhz2} MHz {watts2:.0f} W")
 
 
 def topk_case():
@@ -144,5 +189,7 @@ if __name__ == "__main__":
         ln_case()
     if what in ("pre", "all"):
         pre_case()
+    if what == "sustained":
+        sustained_cases()
     if what in ("topk", "all"):
         topk_case()

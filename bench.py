@@ -241,6 +241,13 @@ def main_ours(args) -> None:
         dist.all_reduce(ms_e2e, op=dist.ReduceOp.MAX)
     e2e_value = total_frames / (float(ms_e2e.item()) * 1e-3)
 
+    # ---- side measurement (not part of value / e2e): configs[4] retrieval over a 72 000-row timeline index ----
+    retrieval = None
+    if rank == 0 and world == 1 and not args.no_retrieval:
+        del frames, ring
+        torch.cuda.empty_cache()
+        retrieval = retrieval_probe(dev)
+
     if rank == 0:
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
@@ -266,9 +273,48 @@ def main_ours(args) -> None:
         if cpu is not None:
             line["cpu_baseline"] = {"value": cpu["frames_per_s"], "unit": "frames/s", "cores": cpu["cores"],
                                     "kind": cpu["kind"], "sample": cpu["sample"]}
+        if retrieval is not None:
+            line["retrieval"] = retrieval
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def retrieval_probe(dev, n_index: int = 72000, dim: int = 4096, n_queries: int = 128, k: int = 16) -> dict:
+    """BASELINE.json configs[4] retrieval step on one GPU: cosine top-16 of 128 queries over a (72 000, 4096) bf16
+    timeline index (10 h at 2 fps) through TimelineEmbeddingIndex.search — the tensor-core scoring path with exact
+    re-scoring.  Random clustered rows (the index content does not change the work).  HBM roofline: the index read once."""
+    import torch
+
+    from gameplay_vision_llm_b200.timeline import TimelineEmbeddingIndex
+
+    peaks = load_peaks()
+    idx = TimelineEmbeddingIndex(n_index, dim, fps=2.0, device=dev)
+    g = torch.Generator(device=dev).manual_seed(5)
+    centers = torch.randn(n_index // 60, dim, device=dev, generator=g)
+    rows = idx.local_rows()
+    for i0 in range(0, n_index, 6000):
+        c = centers[i0 // 60:(i0 + 6000) // 60].repeat_interleave(60, 0)
+        rows[i0:i0 + 6000] = (c + 0.35 * torch.randn(c.shape, device=dev, generator=g)).to(torch.bfloat16)
+    queries = (centers[torch.randint(0, n_index // 60, (n_queries,), device=dev, generator=g)]
+               + 0.35 * torch.randn(n_queries, dim, device=dev, generator=g)).to(torch.bfloat16)
+    del centers
+    idx.search(queries, top_k=k)  # warm-up: also fills the cached 1/|e_n|
+    idx.search(queries, top_k=k)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    reps = 10
+    e0.record()
+    for _ in range(reps):
+        idx.search(queries, top_k=k)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / reps
+    nbytes = n_index * dim * 2
+    return {"workload": f"cosine top-{k} of {n_queries} queries over a ({n_index}, {dim}) bf16 timeline index",
+            "ms_per_query_batch": round(ms, 4), "queries_per_s": round(n_queries / (ms * 1e-3), 1),
+            "index_gbs": round(nbytes / (ms * 1e-3) / 1e9, 1), "hbm_frac": round(nbytes / (ms * 1e-3) / 1e9 / peaks["hbm_gbs"], 4),
+            "path": "tcgen05 GEMM scores + segmented select + exact fp32 re-score (bit-identical to the scan path)"}
 
 
 # ------------------------------------------------------------------------------ VideoMAE workload (configs[3])
@@ -434,6 +480,7 @@ if __name__ == "__main__":
     ap.add_argument("--batch", type=int, default=64)
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-retrieval", action="store_true", help="skip the configs[4] retrieval side measurement")
     ap.add_argument("--no-fold-ln", action="store_true",
                     help="A/B: run the 56 LayerNorm kernels per batch instead of folding them into the GEMM epilogues")
     ap.add_argument("--workload", choices=["siglip", "videomae"], default="siglip",

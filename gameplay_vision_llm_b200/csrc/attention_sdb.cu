@@ -56,17 +56,28 @@ struct SdbCfg {
     static constexpr int SMEM_BYTES = NT * Q_BYTES + 2 * STAGES * KV_BYTES + 256 /*barriers*/ + 1024 /*alignment*/;
 };
 
+// Two non-negative fp32 probabilities -> packed bf16x2, rounded to nearest (ties up) with integer adds + one byte
+// permute.  F2FP.BF16.PACK_AB executes on the XU pipe — the same quarter-rate pipe as MUFU.EX2, which ncu shows is
+// this kernel's busiest unit (60 %) — so packing on the ALU pipe takes a third of the XU work away.
+__device__ __forceinline__ uint32_t sdb_pack_bf16x2(float lo, float hi) {
+    return __byte_perm(__float_as_uint(lo) + 0x8000u, __float_as_uint(hi) + 0x8000u, 0x7632);
+}
 __device__ __forceinline__ float sdb_ex2(float x) {
     float y;
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
     return y;
 }
 
+// Timeline instrumentation (tools/attn_trace.py): when `trace` is set, the CTA (1, 3, 17) records SM-clock stamps per
+// key block: softmax warp 0 / lane 0 -> slots 0-5, the MMA thread -> slots 8-11, the TMA thread -> slot 12.
+#define SDB_TRACE(jj, slot) \
+    do { if (trace != nullptr && traced) trace[(jj) * 16 + (slot)] = clock64(); } while (0)
+
 template <int HD, int NT>
 __global__ void __launch_bounds__(SdbCfg<HD, NT>::THREADS, NT == 2 ? 1 : 2)
 attention_sdb_kernel(const __grid_constant__ CUtensorMap tmq64, const __grid_constant__ CUtensorMap tmq16,
                      const __grid_constant__ CUtensorMap tmk64, const __grid_constant__ CUtensorMap tmk16,
-                     __nv_bfloat16* __restrict__ out, int T, int H, float scale_log2) {
+                     __nv_bfloat16* __restrict__ out, int T, int H, float scale_log2, int dbg, long long* __restrict__ trace) {
     using Cfg = SdbCfg<HD, NT>;
     constexpr int SDB_STAGES = Cfg::STAGES;
     constexpr int W_TMA = 4 * NT, W_MMA = 4 * NT + 1;  // warp roles: [0, 4 NT) softmax, then TMA, then NT MMA warps
@@ -90,6 +101,7 @@ attention_sdb_kernel(const __grid_constant__ CUtensorMap tmq64, const __grid_con
     const int q0 = blockIdx.x * (NT * SDB_BQ);
     const int h = blockIdx.y, b = blockIdx.z;
     const int nblk = (T + SDB_BKV - 1) / SDB_BKV;
+    const bool traced = blockIdx.x == 1 && blockIdx.y == 3 && blockIdx.z == 17 && (threadIdx.x & 31) == 0;
     const int ntile = (NT == 2 && q0 + SDB_BQ < T) ? 2 : 1;  // the second tile may lie entirely beyond the sequence
 
     if (warp == W_TMA && lane == 0) {
@@ -133,6 +145,7 @@ attention_sdb_kernel(const __grid_constant__ CUtensorMap tmq64, const __grid_con
             uint32_t ph = 0;
             for (int j = 0; j < nblk; ++j) {
                 mbar_wait(&kv_empty[st], ph ^ 1);
+                SDB_TRACE(j, 12);
                 mbar_arrive_expect_tx(&kv_full[st], 2 * Cfg::KV_BYTES);
                 uint8_t* k = sK + st * Cfg::KV_BYTES;
                 uint8_t* v = sV + st * Cfg::KV_BYTES;
@@ -167,7 +180,7 @@ attention_sdb_kernel(const __grid_constant__ CUtensorMap tmq64, const __grid_con
                 for (int k = 0; k < 4; ++k)
                     umma_bf16_ss(tS, umma_desc_sw128(q_addr + k * 32), umma_desc_sw128(k_addr + k * 32), idescS,
                                  (uint32_t)(k > 0));
-                if (Cfg::TAIL)
+                if (Cfg::TAIL && !(dbg & 2))
                     umma_bf16_ss(tS, umma_desc(q_addr + Cfg::Q_P0, 0, 256, 6), umma_desc(k_addr + Cfg::KV_P0, 0, 256, 6),
                                  idescS, 1u);
                 umma_commit(&s_full[t * 2 + (j & 1)]);
@@ -182,12 +195,14 @@ attention_sdb_kernel(const __grid_constant__ CUtensorMap tmq64, const __grid_con
                 const uint32_t v_addr = smem_u32(sV + st * Cfg::KV_BYTES);
                 // O_t += P_t(j) V(j): k runs over the keys of this block, 16 per MMA; P is read from TMEM
                 const uint32_t tP = tmem_base + (uint32_t)(t * 128 + (j & 1) * 64);
+                SDB_TRACE(j, 8);
                 mbar_wait(&p_full[t * 2 + (j & 1)], (uint32_t)(j >> 1) & 1u);
+                SDB_TRACE(j, 9);
                 tcgen05_fence_after();
                 for (int kk = 0; kk < ksteps; ++kk) {
                     const uint32_t acc = (uint32_t)((j | kk) != 0);
                     umma_bf16_ts(tO, tP + (uint32_t)(kk * 8), umma_desc(v_addr + kk * 2048, 0, 1024, 2), idescV64, acc);
-                    if (Cfg::TAIL)
+                    if (Cfg::TAIL && !(dbg & 1))
                         umma_bf16_ts(tO + 64, tP + (uint32_t)(kk * 8),
                                      umma_desc(v_addr + Cfg::KV_P0 + kk * 512, 0, 256, 6), idescV16, acc);
                 }
@@ -195,7 +210,9 @@ attention_sdb_kernel(const __grid_constant__ CUtensorMap tmq64, const __grid_con
                 umma_commit(&pv_done[t]);
                 if (j == nblk - 1) umma_commit(&o_done[t]);
                 // S_t(j+2) reuses the buffer of P_t(j): queued behind PV_t(j), in-order execution protects it
+                SDB_TRACE(j, 10);
                 if (j + 2 < nblk) issue_s(j + 2);
+                SDB_TRACE(j, 11);
             }
         }
     } else {
@@ -210,7 +227,9 @@ attention_sdb_kernel(const __grid_constant__ CUtensorMap tmq64, const __grid_con
             const bool rows_live = q0 + t * SDB_BQ + q * 32 < T;  // warp-uniform: at least one of the 32 rows exists
             auto load_s = [&](int j, uint32_t (&s)[2][32]) {     // wait for S_t(j), start its TMEM -> register loads
                 const uint32_t tS = tmem_base + (uint32_t)(t * 128 + (j & 1) * 64) + lane_off;
+                if (warp == 0) SDB_TRACE(j, 0);
                 mbar_wait(&s_full[t * 2 + (j & 1)], (uint32_t)(j >> 1) & 1u);
+                if (warp == 0) SDB_TRACE(j, 1);
                 tcgen05_fence_after();
 #pragma unroll
                 for (int c = 0; c < 2; ++c) tmem_ld_32x32(tS + (uint32_t)(c * 32), s[c]);
@@ -223,6 +242,7 @@ attention_sdb_kernel(const __grid_constant__ CUtensorMap tmq64, const __grid_con
                 uint32_t s[2][32];
                 load_s(j, s);
                 tmem_ld_wait();
+                if (warp == 0) SDB_TRACE(j, 2);
                 if (rows_live) {
                     const int valid = min(SDB_BKV, T - j * SDB_BKV);
                     if (valid < SDB_BKV) {
@@ -264,12 +284,13 @@ attention_sdb_kernel(const __grid_constant__ CUtensorMap tmq64, const __grid_con
                                 const float p1 = sdb_ex2(fmaf(__uint_as_float(s[c][2 * i + 1]), scale_log2, nm));
                                 rs0 += p0;
                                 rs1 += p1;
-                                pk[i] = pack_bf16x2(p0, p1);
+                                pk[i] = sdb_pack_bf16x2(p0, p1);
                             }
                             tmem_st_32x16(tS + (uint32_t)(c * 16), pk);
                         }
                     }
                     l += rs0 + rs1;
+                    if (warp == 0) SDB_TRACE(j, 3);
                     if (__any_sync(0xffffffffu, need)) {
                         // rare: the running max grew by more than the threshold -> rescale this warp's O rows once
                         // PV_t(j-1) has completed (S_t(j) complete implies PV_t(j-2) complete: parity unambiguous)
@@ -294,12 +315,14 @@ attention_sdb_kernel(const __grid_constant__ CUtensorMap tmq64, const __grid_con
                         }
                     }
                     tmem_st_wait();
+                    if (warp == 0) SDB_TRACE(j, 4);
                 }
                 // (a warp whose rows all lie beyond the sequence only keeps the barrier protocol going: its P rows
                 // are garbage, they feed O rows that are never stored)
                 tcgen05_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&p_full[t * 2 + buf]);
+                if (warp == 0) SDB_TRACE(j, 5);
             }
             // ---- finalise: O / l -> bf16 -> global ----
             mbar_wait(&o_done[t], 0);
@@ -348,6 +371,8 @@ attention_sdb_kernel(const __grid_constant__ CUtensorMap tmq64, const __grid_con
     }
 }
 
+long long* g_attn_trace = nullptr;  // set by gvl_debug_set_attn_trace (tuning aid)
+
 template <int HD, int NT>
 static int launch_attention_sdb_nt(const void* qkv, void* out, int B, int T, int H, float scale, cudaStream_t s) {
     using Cfg = SdbCfg<HD, NT>;
@@ -367,10 +392,11 @@ static int launch_attention_sdb_nt(const void* qkv, void* out, int B, int T, int
     if (rc) return rc;
     GVL_CUDA(cudaFuncSetAttribute(attention_sdb_kernel<HD, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   Cfg::SMEM_BYTES));
+    static const int dbg = [] { const char* e = getenv("GVL_ATTN_DEBUG"); return e ? atoi(e) : 0; }();  // timing experiments
     dim3 grid((T + NT * SDB_BQ - 1) / (NT * SDB_BQ), H, B);
     ProfScope prof(GVL_K_ATTENTION, 4.0 * B * (double)H * T * (double)T * HD, s);
     attention_sdb_kernel<HD, NT><<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, s>>>(
-        tq64, tq16, tk64, tk16, reinterpret_cast<__nv_bfloat16*>(out), T, H, scale * 1.4426950408889634f);
+        tq64, tq16, tk64, tk16, reinterpret_cast<__nv_bfloat16*>(out), T, H, scale * 1.4426950408889634f, dbg, g_attn_trace);
     GVL_LAUNCH_CHECK("attention_sdb_kernel");
     return 0;
 }
@@ -389,3 +415,9 @@ template int launch_attention_sdb<72>(const void*, void*, int, int, int, float, 
 template int launch_attention_sdb<64>(const void*, void*, int, int, int, float, cudaStream_t);
 
 }  // namespace gvl
+
+// Tuning aid, not part of the product ABI surface in include/gvl.h: device buffer of >= 16 x 16 int64 that receives
+// the timeline stamps of one CTA (see SDB_TRACE); NULL turns tracing off.
+extern "C" __attribute__((visibility("default"))) void gvl_debug_set_attn_trace(void* device_buffer) {
+    gvl::g_attn_trace = reinterpret_cast<long long*>(device_buffer);
+}

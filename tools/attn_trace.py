@@ -1,0 +1,34 @@
+#!/usr/bin/env python
+"""Timeline of one attention CTA (SM-clock stamps written by attention_sdb.cu when a trace buffer is set).
+python tools/attn_trace.py  -> per key block: softmax warp 0 phases, MMA thread phases, TMA refill time (cycles)."""
+import ctypes
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from gameplay_vision_llm_b200 import _lib, ops  # noqa: E402
+
+B, T, H, hd = 64, 729, 16, 72
+qkv = torch.randn(B * T, 3 * H * hd, device="cuda").to(torch.bfloat16)
+out = torch.empty(B * T, H * hd, device="cuda", dtype=torch.bfloat16)
+trace = torch.zeros(16 * 16, dtype=torch.int64, device="cuda")
+for _ in range(3):
+    ops.attention(qkv, B, T, H, hd, out=out)
+torch.cuda.synchronize()
+lib = _lib.lib()
+lib.gvl_debug_set_attn_trace.argtypes = [ctypes.c_void_p]
+lib.gvl_debug_set_attn_trace(trace.data_ptr())
+ops.attention(qkv, B, T, H, hd, out=out)
+torch.cuda.synchronize()
+lib.gvl_debug_set_attn_trace(None)
+t = trace.cpu().view(16, 16).numpy()
+t0 = t[0, 0]
+print("block | softmax: wait_S  ld  max+exp  st_wait  arrive | next-block gap || MMA: idle->p_full  issue_PV  issue_S(j+2) || TMA kv_empty at")
+for j in range(12):
+    r = t[j]
+    nxt = t[j + 1, 0] - r[5] if j + 1 < 12 else 0
+    print(f"{j:5d} | start {r[0]-t0:7d}: {r[1]-r[0]:6d} {r[2]-r[1]:5d} {r[3]-r[2]:7d} {r[4]-r[3]:7d} {r[5]-r[4]:6d} | {nxt:5d} || "
+          f"wait from {r[8]-t0:7d}: {r[9]-r[8]:6d} {r[10]-r[9]:6d} {r[11]-r[10]:6d} || {r[12]-t0:7d}")
+print("block period (softmax warp 0):", [int(t[j + 1, 0] - t[j, 0]) for j in range(11)])

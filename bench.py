@@ -95,6 +95,10 @@ def cpu_reference(n_frames: int, batch: int = 8, warmup_batches: int = 1) -> dic
     return hf_baseline.run(n_frames=n_frames, batch=batch, warmup_batches=warmup_batches, frame_hw=(FRAME_H, FRAME_W))
 
 
+WORKLOAD = ("1 h synthetic 1080p gameplay @1 fps (BASELINE.json configs[1]: 3600 frames, rounded up to 57 batches of 64) "
+            "through SigLIP2-so400m-patch14-384 + ProjectorBank 1152->4096->4096")
+
+
 def main_reference(args) -> None:
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -105,9 +109,10 @@ def main_reference(args) -> None:
         "impl": "reference", "metric": "frames/s SigLIP2+ProjectorBank", "value": res["frames_per_s"], "unit": "frames/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": res["seconds"] / (n / 8) * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "fp32", "data": "synthetic",
-        "config": {"workload": "SigLIP2-so400m-patch14-384 + ProjectorBank 1152->4096, synthetic 1080p frames, fp32 on "
-                               "host CPU, batch 8 (BASELINE.json configs[0] procedure), bounded sample",
-                   "frames": n, "batch": 8},
+        "config": {"workload": WORKLOAD, "frame": [FRAME_H, FRAME_W, 3],
+                   "sample": "bounded sample of the workload: one step = one batch of 8 frames on the host CPU in fp32, all "
+                             "host threads (BASELINE.json configs[0] procedure: HF SiglipImageProcessor + SiglipVisionModel "
+                             "+ projector)", "frames": n, "batch": 8},
         "cpu_baseline": {"value": res["frames_per_s"], "unit": "frames/s", "cores": res["cores"], "kind": res["kind"],
                          "sample": res["sample"]},
         "e2e": {"value": res["frames_per_s"], "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -256,8 +261,7 @@ def main_ours(args) -> None:
             "metric": "frames/s SigLIP2+ProjectorBank", "value": round(value, 2), "unit": "frames/s", "n_gpus": world,
             "steps": K, "warmup": W, "ms_per_step": round(ms / K, 3), "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": "1 h synthetic 1080p gameplay @1 fps (BASELINE.json configs[1]: 3600 frames, rounded up "
-                                   "to 57 batches of 64) through SigLIP2-so400m-patch14-384 + ProjectorBank 1152->4096->4096",
+            "config": {"workload": WORKLOAD,
                        "frames_per_gpu": n_local, "batch": B, "frame": [FRAME_H, FRAME_W, 3],
                        "weights": "random init, seeds 0/1", "layernorm": "separate kernels" if args.no_fold_ln else
                        "folded into the consuming GEMM epilogues", "sharding": "contiguous timeline chunk per rank, "

@@ -87,6 +87,7 @@ class EmbeddingPipeline:
         caller synchronises (e.g. `torch.cuda.current_stream().synchronize()`).
         """
         compute = torch.cuda.current_stream(self.device)
+        recycle = getattr(host_batches, "recycle", None)  # e.g. frame_ingest.FrameFeed: pinned ring buffers
         if not hasattr(self, "_copy_stream"):
             self._copy_stream = torch.cuda.Stream(self.device)
             self._dev_frames = [None, None]
@@ -107,6 +108,10 @@ class EmbeddingPipeline:
                     self._copy_stream.wait_stream(compute)
                 buf[:b].copy_(hb, non_blocking=True)
                 self._copied[slot].record(self._copy_stream)
+                if recycle is not None:  # the source may reuse the host buffer once this copy has run
+                    done_ev = torch.cuda.Event()
+                    done_ev.record(self._copy_stream)
+                    recycle(hb, done_ev)
             compute.wait_event(self._copied[slot])
             _, proj = self.embed(buf[:b], out_index=index[done:done + b])
             self._consumed[slot].record(compute)
@@ -114,6 +119,23 @@ class EmbeddingPipeline:
                 host_out[done:done + b].copy_(proj, non_blocking=True)
             done += b
         return done
+
+
+    # ---- a video file: decode -> pinned ring -> device, overlapped -------------------------------------
+    def embed_video(self, video_path: str, fps: float = 1.0, index: torch.Tensor | None = None,
+                    host_out: torch.Tensor | None = None):
+        """Replaces `extract_frames` + `run_siglip_encoder` (scripts/extract_features.py:230-264, 590-607) for one
+        video: frames are sampled with the reference's rule (every int(video_fps / fps)-th frame, timestamp =
+        idx / video_fps), decoded on a background thread into pinned batches and embedded while the next batch
+        decodes.  Returns (timestamps float64 [n], projected index bf16 [n, llm] on the device)."""
+        from .frame_ingest import FrameFeed
+        feed = FrameFeed(video_path, fps=fps, batch=self.batch, auto_release=False)
+        n_plan = len(feed.timestamps)
+        if index is None:
+            index = torch.empty((n_plan, self.llm_dim), dtype=torch.bfloat16, device=self.device)
+        n = self.embed_stream(feed, index, host_out)
+        torch.cuda.current_stream(self.device).synchronize()
+        return feed.timestamps[:n], index[:n]
 
 
 def pinned_batches(frames: np.ndarray | torch.Tensor, batch: int) -> Iterator[torch.Tensor]:

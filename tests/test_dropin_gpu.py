@@ -115,3 +115,25 @@ def test_pipeline_stream_equals_resident_and_index_search():
     _, sem5 = siglip_ref.cosine_topk(e64, q.float().cpu().numpy(), 5)[:2]
     assert idx.hybrid_retrieve(q, timestamp=0.5, window=0.5) == siglip_ref.hybrid_merge([0, 1, 2], sem5[0].tolist())
     assert idx.hybrid_retrieve(q) == siglip_ref.cosine_topk(e64, q.float().cpu().numpy(), 10)[1][0].tolist()
+
+
+def test_embed_video_matches_embedding_the_decoded_frames(tmp_path):
+    """video file -> sampled frames (reference rule) -> pinned ring -> device, overlapped; the result must
+    equal embedding the same decoded frames from a resident tensor, with the reference's timestamps."""
+    cv2 = pytest.importorskip("cv2")
+    from gameplay_vision_llm_b200 import frame_ingest as fi
+    path = str(tmp_path / "clip.avi")
+    w = cv2.VideoWriter(path, cv2.VideoWriter_fourcc(*"MJPG"), 30.0, (320, 180))
+    frames = synth.scene_frames_np(0, 50, 180, 320, frames_per_scene=10)
+    for f in frames:
+        w.write(cv2.cvtColor(f, cv2.COLOR_RGB2BGR))
+    w.release()
+    sd = synth_siglip_state_dict(SPEC, seed=0)
+    psd = synth_projector_state_dict(SPEC.hidden, 512, seed=1)
+    pipe = EmbeddingPipeline(sd, psd, SPEC, DEV, batch=4)
+    ts, index = pipe.embed_video(path, fps=5.0)          # every 6th frame: 0, 6, ..., 48 -> 9 frames, batches 4 + 4 + 1
+    assert ts.tolist() == [i / 30.0 for i in range(0, 50, 6)] and index.shape == (9, 512)
+    decoded = np.stack([f for _, f in fi.extract_frames(path, fps=5.0, as_pil=False)])
+    want = pipe.embed_resident(torch.from_numpy(decoded).to(DEV))
+    torch.cuda.synchronize()
+    assert torch.equal(index, want)

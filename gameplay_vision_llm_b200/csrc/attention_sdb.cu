@@ -1,31 +1,32 @@
-// attention_sdb.cu — K4, production variant: fused non-causal self-attention on tcgen05, two query tiles per CTA,
-// each with its score tile DOUBLE-BUFFERED in tensor memory.
+// attention_sdb.cu — K4, production variant: fused non-causal self-attention on tcgen05 with the score tile
+// DOUBLE-BUFFERED in tensor memory.
 //
-// For head dims this small the kernel is bound by the MUFU (exp2) pipe, not by the tensor cores: the B200 SM
-// retires 16 exp2 per clock, and a softmax-like instruction mix only gets there with two independent warps per
-// scheduler (tools/scratch/mufu_bench.cu: 9.5 exp/clk/SM with one warp per scheduler, 14.9 with two).  So the
-// design goal is that the softmax warps never wait and never run in lockstep:
+// Production configuration (NT = 1): one CTA = one 128-row query tile of one (image, head), 6 warps, two CTAs per SM
+// (2 x (2 x 64 S + 80 O + 16 L) TMEM columns).  NT = 2 (two tiles per CTA, one CTA per SM, K/V stages shared) and
+// NT = 3 (three tiles, S single-buffered) are selectable with GVL_ATTN_NT for A/B runs; both measure slower.
 //   - S(j+1) is computed into the other buffer while softmax(j) runs; PV(j) is issued as soon as P(j) is written
 //     and S(j+2) is queued right behind it (tcgen05.mma executes in issue order, which protects the P(j) columns);
-//   - a CTA owns 256 query rows of one (image, head) as two independent 128-row tiles, so each scheduler holds
-//     two softmax warps (one per tile) whose load / max / store phases overlap the other's exp phase;
-//   - keys are processed in blocks of 64 so that 2 tiles x 2 buffers x 64 score columns + 2 x 80 output columns
-//     fit the 512 TMEM columns; both tiles share every K/V stage.
-// The single-buffer kernel (attention_tc.cu, S -> softmax -> PV -> S serialised because P overwrites S) is kept
-// for A/B runs (GVL_ATTN_TC1=1).
+//   - keys are processed in blocks of 64;
+//   - the softmax inner loop is FFMA2 (two scores per instruction), MUFU.EX2 and F2FP only: the row sums are
+//     accumulated by the tensor cores (L += P . 1 with a constant tile of ones), so l is the sum of exactly the bf16
+//     P values the PV MMAs consume.
+// What bounds it (tools/attn_trace.py): a softmax warp alone issues one MUFU every ~13.5 cycles,
+// two per scheduler ~8.6; with ~400 cycles of fixed per-block hand-shake (mbarrier round trip, tcgen05.ld / st waits)
+// and a 6400-cycle CTA start-up the exp pipe is ~60 % busy.  Neither fewer softmax instructions, nor fewer MMAs, nor
+// more softmax warps per scheduler (NT = 3, split rows) moved the 282 us per layer.
+// The single-buffer kernel (attention_tc.cu, 128-key blocks) is kept for A/B runs (GVL_ATTN_TC1=1).
 //
-//   warps 0-3   softmax of tile 0, warps 4-7 softmax of tile 1: one thread = one query row x 64 keys; tcgen05.ld
-//               the S row, running max with lazy rescaling of O (only when the max grows by more than 2^8),
-//               p = exp2(s*c - m), fp32 row sum, P packed to bf16 pairs and written over the first 32 columns of
-//               the S buffer (the thread's own row, already in registers) with tcgen05.st.
-//   warp 8      TMA producer: Q tiles once, then K/V blocks of 64 keys through a 6-stage ring.  Head dim 72 is
-//               fetched as a 64-wide SWIZZLE_128B panel plus a 16-wide SWIZZLE_32B panel whose upper 8 columns are
-//               out of bounds (zero) — the k-padding 72 -> 80 costs no memory.
-//   warps 9,10  MMA issuers, one per tile (a single issuer would make each tile wait for the other's P):
-//               S = Q K^T (SS, both K-major), O += P V with P read from TMEM (TS form) and V as an MN-major
-//               shared-memory operand (64-wide and 16-wide N panels).
+//   warps [0, 4 NT)  softmax, four warps per tile: one thread = one query row x 64 keys; tcgen05.ld the S row,
+//               running max with lazy rescaling of O and L (only when the max grows by more than 2^8),
+//               p = exp2(s*c - m), P packed to bf16 pairs and written over the first 32 columns of the S buffer
+//               (the thread's own row, already in registers) with tcgen05.st.
+//   next warp   TMA producer: Q tiles once, then K/V blocks of 64 keys through a ring.  Head dim 72 is fetched as a
+//               64-wide SWIZZLE_128B panel plus a 16-wide SWIZZLE_32B panel whose upper 8 columns are out of bounds
+//               (zero) — the k-padding 72 -> 80 costs no memory.
+//   NT warps    MMA issuers, one per tile: S = Q K^T (SS, both K-major), O += P V and L += P 1 with P read from TMEM
+//               (TS form) and V as an MN-major shared-memory operand (64-wide and 16-wide N panels).
 //
-// TMEM columns: tile t, buffer u: S/P at [128 t + 64 u, +64); O_t at [256 + 80 t, +80).
+// TMEM columns: tile t, buffer u: S/P at [S_COLS t + 64 u, +64); O_t at [O_COL + DPAD t, +DPAD); L_t at [L_COL + 16 t, +16).
 #include "common.cuh"
 
 #include <cstdlib>
@@ -41,10 +42,13 @@ constexpr float SDB_RESCALE_THRESHOLD = 8.0f;  // log2 units
 
 template <int HD, int NT>
 struct SdbCfg {
+    static constexpr int NBUF = NT == 3 ? 1 : 2;             // S buffers per tile (NT = 3: single, P overwrites S)
     static constexpr int THREADS = (4 * NT + 1 + NT) * 32;  // 4 softmax warps per tile, TMA warp, one MMA warp per tile
-    static constexpr int TMEM_COLS = NT == 2 ? 512 : 256;
+    static constexpr int TMEM_COLS = NT >= 2 ? 512 : 256;
     static constexpr int STAGES = NT == 2 ? 6 : 4;
-    static constexpr int O_COL = NT * 128;                   // first output-accumulator column
+    static constexpr int S_COLS = NBUF * 64;                 // score columns per tile
+    static constexpr int O_COL = NT * S_COLS;                // first output-accumulator column
+    static constexpr int L_COL = O_COL + NT * (HD > 64 ? 80 : 64);  // row-sum accumulators, 16 columns per tile
     static constexpr bool TAIL = HD > 64;  // second, 16-wide panel for d in [64, 80)
     static constexpr int DPAD = TAIL ? 80 : 64;
     static constexpr int Q_P0 = 128 * 128;             // 128 rows x 64 bf16, SWIZZLE_128B
@@ -53,14 +57,21 @@ struct SdbCfg {
     static constexpr int KV_P0 = SDB_BKV * 128;
     static constexpr int KV_P1 = TAIL ? SDB_BKV * 32 : 0;
     static constexpr int KV_BYTES = KV_P0 + KV_P1;     // one K or V block
-    static constexpr int SMEM_BYTES = NT * Q_BYTES + 2 * STAGES * KV_BYTES + 256 /*barriers*/ + 1024 /*alignment*/;
+    static constexpr int ONES_BYTES = 512;             // 16 keys x 16 columns of bf16 1.0
+    static constexpr int SMEM_BYTES = NT * Q_BYTES + 2 * STAGES * KV_BYTES + ONES_BYTES + 256 /*barriers*/ + 1024 /*alignment*/;
 };
 
-// Two non-negative fp32 probabilities -> packed bf16x2, rounded to nearest (ties up) with integer adds + one byte
-// permute.  F2FP.BF16.PACK_AB executes on the XU pipe — the same quarter-rate pipe as MUFU.EX2, which ncu shows is
-// this kernel's busiest unit (60 %) — so packing on the ALU pipe takes a third of the XU work away.
-__device__ __forceinline__ uint32_t sdb_pack_bf16x2(float lo, float hi) {
-    return __byte_perm(__float_as_uint(lo) + 0x8000u, __float_as_uint(hi) + 0x8000u, 0x7632);
+// (s0, s1) * c + nm for two scores in one FFMA2 (fma.rn.f32x2, sm_100).  cc / nn = the constants packed twice.
+__device__ __forceinline__ uint64_t sdb_pack2(float lo, float hi) {
+    uint64_t d;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(d) : "f"(lo), "f"(hi));
+    return d;
+}
+__device__ __forceinline__ void sdb_scale2(uint32_t s0, uint32_t s1, uint64_t cc, uint64_t nn, float& x0, float& x1) {
+    uint64_t a, d;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(a) : "r"(s0), "r"(s1));
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(cc), "l"(nn));
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(x0), "=f"(x1) : "l"(d));
 }
 __device__ __forceinline__ float sdb_ex2(float x) {
     float y;
@@ -70,11 +81,17 @@ __device__ __forceinline__ float sdb_ex2(float x) {
 
 // Timeline instrumentation (tools/attn_trace.py): when `trace` is set, the CTA (1, 3, 17) records SM-clock stamps per
 // key block: softmax warp 0 / lane 0 -> slots 0-5, the MMA thread -> slots 8-11, the TMA thread -> slot 12.
+// (compiled in only with -DGVL_ATTN_TRACE: the stamps cost 10 % of the kernel — its softmax warps are bound by their
+// own instruction stream, every extra instruction per key block shows)
+#ifdef GVL_ATTN_TRACE
 #define SDB_TRACE(jj, slot) \
     do { if (trace != nullptr && traced) trace[(jj) * 16 + (slot)] = clock64(); } while (0)
+#else
+#define SDB_TRACE(jj, slot) do { } while (0)
+#endif
 
 template <int HD, int NT>
-__global__ void __launch_bounds__(SdbCfg<HD, NT>::THREADS, NT == 2 ? 1 : 2)
+__global__ void __launch_bounds__(SdbCfg<HD, NT>::THREADS, NT >= 2 ? 1 : 2)
 attention_sdb_kernel(const __grid_constant__ CUtensorMap tmq64, const __grid_constant__ CUtensorMap tmq16,
                      const __grid_constant__ CUtensorMap tmk64, const __grid_constant__ CUtensorMap tmk16,
                      __nv_bfloat16* __restrict__ out, int T, int H, float scale_log2, int dbg, long long* __restrict__ trace) {
@@ -86,23 +103,28 @@ attention_sdb_kernel(const __grid_constant__ CUtensorMap tmq64, const __grid_con
     uint8_t* sQ = smem;                                  // [tile][P0 | P1]
     uint8_t* sK = smem + NT * Cfg::Q_BYTES;              // [stage][P0 | P1]
     uint8_t* sV = sK + SDB_STAGES * Cfg::KV_BYTES;       // [stage][P0 | P1]
-    uint64_t* bars = reinterpret_cast<uint64_t*>(sV + SDB_STAGES * Cfg::KV_BYTES);
+    uint8_t* sOnes = sV + SDB_STAGES * Cfg::KV_BYTES;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sOnes + Cfg::ONES_BYTES);
     uint64_t* q_full = bars;                      // [1]
     uint64_t* kv_full = bars + 1;                 // [STAGES]
     uint64_t* kv_empty = kv_full + SDB_STAGES;    // [STAGES]
     uint64_t* s_full = kv_empty + SDB_STAGES;     // [tile][buffer]  S_t(j) complete in buffer j & 1
-    uint64_t* p_full = s_full + 4;                // [tile][buffer]  P_t(j) written (4 warps)
-    uint64_t* pv_done = p_full + 4;               // [tile]  PV_t(j) complete, one phase per block (rare rescale path
+    uint64_t* p_full = s_full + 2 * NT;           // [tile][buffer]  P_t(j) written (4 warps)
+    uint64_t* pv_done = p_full + 2 * NT;          // [tile]  PV_t(j) complete, one phase per block (rare rescale path
                                                   //         only: a parity wait is valid at most one phase behind)
-    uint64_t* o_done = pv_done + 2;               // [tile]  last PV_t complete
-    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(o_done + 2);
+    uint64_t* o_done = pv_done + NT;              // [tile]  last PV_t complete
+    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(o_done + NT);
+    constexpr int NBUF = Cfg::NBUF;
+    // buffer and mbarrier phase parity of key block j (double-buffered: two blocks per phase pair)
+    auto sbuf = [](int j) { return NBUF == 2 ? (j & 1) : 0; };
+    auto spar = [](int j) { return (uint32_t)(NBUF == 2 ? (j >> 1) : j) & 1u; };
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int q0 = blockIdx.x * (NT * SDB_BQ);
     const int h = blockIdx.y, b = blockIdx.z;
     const int nblk = (T + SDB_BKV - 1) / SDB_BKV;
     const bool traced = blockIdx.x == 1 && blockIdx.y == 3 && blockIdx.z == 17 && (threadIdx.x & 31) == 0;
-    const int ntile = (NT == 2 && q0 + SDB_BQ < T) ? 2 : 1;  // the second tile may lie entirely beyond the sequence
+    const int ntile = min(NT, (T - q0 + SDB_BQ - 1) / SDB_BQ);  // trailing tiles may lie entirely beyond the sequence
 
     if (warp == W_TMA && lane == 0) {
         tma_prefetch_desc(&tmq64);
@@ -116,15 +138,19 @@ attention_sdb_kernel(const __grid_constant__ CUtensorMap tmq64, const __grid_con
             mbar_init(&kv_full[s], 1);
             mbar_init(&kv_empty[s], ntile);  // one tcgen05.commit per tile's MMA warp
         }
-        for (int i = 0; i < 4; ++i) {
+        for (int i = 0; i < 2 * NT; ++i) {
             mbar_init(&s_full[i], 1);
             mbar_init(&p_full[i], 4);
         }
-        for (int t = 0; t < 2; ++t) {
+        for (int t = 0; t < NT; ++t) {
             mbar_init(&pv_done[t], 1);
             mbar_init(&o_done[t], 1);
         }
         fence_barrier_init();
+    }
+    if (warp == 0) {
+        for (int i = lane; i < Cfg::ONES_BYTES / 4; i += 32) reinterpret_cast<uint32_t*>(sOnes)[i] = 0x3F803F80u;
+        fence_proxy_async_smem();  // read by tcgen05.mma (async proxy)
     }
     if (warp == W_MMA) tmem_alloc<Cfg::TMEM_COLS>(tmem_ptr_smem);
     tcgen05_fence_before();
@@ -170,12 +196,14 @@ attention_sdb_kernel(const __grid_constant__ CUtensorMap tmq64, const __grid_con
             constexpr uint32_t idescV16 = umma_idesc_bf16_major(128, 16, 0, 1);
             const uint32_t q_addr = smem_u32(sQ + t * Cfg::Q_BYTES);
             const uint32_t tO = tmem_base + Cfg::O_COL + (uint32_t)(t * Cfg::DPAD);
+            const uint32_t tL = tmem_base + Cfg::L_COL + (uint32_t)(t * 16);
+            const uint32_t ones_addr = smem_u32(sOnes);
             auto issue_s = [&](int j) {  // S_t(j) -> buffer j & 1; K(j) sits in stage j % STAGES
                 const int st = j % SDB_STAGES;
                 mbar_wait(&kv_full[st], (uint32_t)(j / SDB_STAGES) & 1u);
                 tcgen05_fence_after();
                 const uint32_t k_addr = smem_u32(sK + st * Cfg::KV_BYTES);
-                const uint32_t tS = tmem_base + (uint32_t)(t * 128 + (j & 1) * 64);
+                const uint32_t tS = tmem_base + (uint32_t)(t * Cfg::S_COLS + sbuf(j) * 64);
 #pragma unroll
                 for (int k = 0; k < 4; ++k)
                     umma_bf16_ss(tS, umma_desc_sw128(q_addr + k * 32), umma_desc_sw128(k_addr + k * 32), idescS,
@@ -183,20 +211,20 @@ attention_sdb_kernel(const __grid_constant__ CUtensorMap tmq64, const __grid_con
                 if (Cfg::TAIL && !(dbg & 2))
                     umma_bf16_ss(tS, umma_desc(q_addr + Cfg::Q_P0, 0, 256, 6), umma_desc(k_addr + Cfg::KV_P0, 0, 256, 6),
                                  idescS, 1u);
-                umma_commit(&s_full[t * 2 + (j & 1)]);
+                umma_commit(&s_full[t * 2 + sbuf(j)]);
             };
             mbar_wait(q_full, 0);
             issue_s(0);
-            if (nblk > 1) issue_s(1);
+            if (NBUF == 2 && nblk > 1) issue_s(1);
             for (int j = 0; j < nblk; ++j) {
                 const int st = j % SDB_STAGES;
                 const int valid = min(SDB_BKV, T - j * SDB_BKV);
                 const int ksteps = (valid + 15) >> 4;
                 const uint32_t v_addr = smem_u32(sV + st * Cfg::KV_BYTES);
                 // O_t += P_t(j) V(j): k runs over the keys of this block, 16 per MMA; P is read from TMEM
-                const uint32_t tP = tmem_base + (uint32_t)(t * 128 + (j & 1) * 64);
+                const uint32_t tP = tmem_base + (uint32_t)(t * Cfg::S_COLS + sbuf(j) * 64);
                 SDB_TRACE(j, 8);
-                mbar_wait(&p_full[t * 2 + (j & 1)], (uint32_t)(j >> 1) & 1u);
+                mbar_wait(&p_full[t * 2 + sbuf(j)], spar(j));
                 SDB_TRACE(j, 9);
                 tcgen05_fence_after();
                 for (int kk = 0; kk < ksteps; ++kk) {
@@ -205,13 +233,16 @@ attention_sdb_kernel(const __grid_constant__ CUtensorMap tmq64, const __grid_con
                     if (Cfg::TAIL && !(dbg & 1))
                         umma_bf16_ts(tO + 64, tP + (uint32_t)(kk * 8),
                                      umma_desc(v_addr + Cfg::KV_P0 + kk * 512, 0, 256, 6), idescV16, acc);
+                    // row sums on the tensor cores: L += P . 1 (a constant 16 x 16 tile of ones, any layout): the tensor
+                    // pipe has slack, and l is then the sum of exactly the bf16 P values the PV MMAs consumed
+                    umma_bf16_ts(tL, tP + (uint32_t)(kk * 8), umma_desc(ones_addr, 0, 256, 6), idescV16, acc);
                 }
                 umma_commit(&kv_empty[st]);  // this tile is done with K(j) (read by S_t(j), issued earlier) and V(j)
                 umma_commit(&pv_done[t]);
                 if (j == nblk - 1) umma_commit(&o_done[t]);
                 // S_t(j+2) reuses the buffer of P_t(j): queued behind PV_t(j), in-order execution protects it
                 SDB_TRACE(j, 10);
-                if (j + 2 < nblk) issue_s(j + 2);
+                if (j + NBUF < nblk) issue_s(j + NBUF);  // the next S into the buffer PV_t(j) has just been queued to read
                 SDB_TRACE(j, 11);
             }
         }
@@ -222,13 +253,14 @@ attention_sdb_kernel(const __grid_constant__ CUtensorMap tmq64, const __grid_con
             const int q = warp & 3;  // TMEM lane quadrant this warp may access
             const uint32_t lane_off = (uint32_t)(q * 32) << 16;
             const uint32_t tO = tmem_base + Cfg::O_COL + (uint32_t)(t * Cfg::DPAD) + lane_off;
+            const uint32_t tL = tmem_base + Cfg::L_COL + (uint32_t)(t * 16) + lane_off;
             const int row = q0 + t * SDB_BQ + q * 32 + lane;
             float m_used = -INFINITY, l = 0.f;
             const bool rows_live = q0 + t * SDB_BQ + q * 32 < T;  // warp-uniform: at least one of the 32 rows exists
             auto load_s = [&](int j, uint32_t (&s)[2][32]) {     // wait for S_t(j), start its TMEM -> register loads
-                const uint32_t tS = tmem_base + (uint32_t)(t * 128 + (j & 1) * 64) + lane_off;
+                const uint32_t tS = tmem_base + (uint32_t)(t * Cfg::S_COLS + sbuf(j) * 64) + lane_off;
                 if (warp == 0) SDB_TRACE(j, 0);
-                mbar_wait(&s_full[t * 2 + (j & 1)], (uint32_t)(j >> 1) & 1u);
+                mbar_wait(&s_full[t * 2 + sbuf(j)], spar(j));
                 if (warp == 0) SDB_TRACE(j, 1);
                 tcgen05_fence_after();
 #pragma unroll
@@ -237,8 +269,8 @@ attention_sdb_kernel(const __grid_constant__ CUtensorMap tmq64, const __grid_con
             // (prefetching S_t(j+1) into a second register buffer while block j is exponentiated was tried: 168
             // registers do not hold both rows, ptxas spills one and the kernel gets 2x slower)
             for (int j = 0; j < nblk; ++j) {
-                const int buf = j & 1;
-                const uint32_t tS = tmem_base + (uint32_t)(t * 128 + buf * 64) + lane_off;
+                const int buf = sbuf(j);
+                const uint32_t tS = tmem_base + (uint32_t)(t * Cfg::S_COLS + buf * 64) + lane_off;
                 uint32_t s[2][32];
                 load_s(j, s);
                 tmem_ld_wait();
@@ -270,26 +302,24 @@ attention_sdb_kernel(const __grid_constant__ CUtensorMap tmq64, const __grid_con
                         need = true;
                         factor = sdb_ex2(m_used - mt);
                         m_used = mt;
-                        l *= factor;
                     }
                     const float nm = -m_used;
-                    float rs0 = 0.f, rs1 = 0.f;
+                    const uint64_t cc = sdb_pack2(scale_log2, scale_log2), nn = sdb_pack2(nm, nm);
 #pragma unroll
                     for (int c = 0; c < 2; ++c) {
                         if (c * 32 < valid) {  // warp-uniform: chunks without a single key are never read by PV
                             uint32_t pk[16];
 #pragma unroll
                             for (int i = 0; i < 16; ++i) {
-                                const float p0 = sdb_ex2(fmaf(__uint_as_float(s[c][2 * i]), scale_log2, nm));
-                                const float p1 = sdb_ex2(fmaf(__uint_as_float(s[c][2 * i + 1]), scale_log2, nm));
-                                rs0 += p0;
-                                rs1 += p1;
-                                pk[i] = sdb_pack_bf16x2(p0, p1);
+                                float x0, x1;
+                                sdb_scale2(s[c][2 * i], s[c][2 * i + 1], cc, nn, x0, x1);
+                                const float p0 = sdb_ex2(x0);
+                                const float p1 = sdb_ex2(x1);
+                                pk[i] = pack_bf16x2(p0, p1);
                             }
                             tmem_st_32x16(tS + (uint32_t)(c * 16), pk);
                         }
                     }
-                    l += rs0 + rs1;
                     if (warp == 0) SDB_TRACE(j, 3);
                     if (__any_sync(0xffffffffu, need)) {
                         // rare: the running max grew by more than the threshold -> rescale this warp's O rows once
@@ -313,6 +343,14 @@ attention_sdb_kernel(const __grid_constant__ CUtensorMap tmq64, const __grid_con
                             for (int i = 0; i < 16; ++i) o2[i] = __float_as_uint(__uint_as_float(o2[i]) * factor);
                             tmem_st_32x16(tO + 64, o2);
                         }
+                        {  // the row-sum accumulator scales with O
+                            uint32_t o2[16];
+                            tmem_ld_32x16(tL, o2);
+                            tmem_ld_wait();
+#pragma unroll
+                            for (int i = 0; i < 16; ++i) o2[i] = __float_as_uint(__uint_as_float(o2[i]) * factor);
+                            tmem_st_32x16(tL, o2);
+                        }
                     }
                     tmem_st_wait();
                     if (warp == 0) SDB_TRACE(j, 4);
@@ -327,6 +365,12 @@ attention_sdb_kernel(const __grid_constant__ CUtensorMap tmq64, const __grid_con
             // ---- finalise: O / l -> bf16 -> global ----
             mbar_wait(&o_done[t], 0);
             tcgen05_fence_after();
+            {  // the row sum: any column of the L accumulator (sum of the bf16 P the PV MMAs consumed)
+                uint32_t o2[16];
+                tmem_ld_32x16(tL, o2);
+                tmem_ld_wait();
+                l = __uint_as_float(o2[0]);
+            }
             const float inv = 1.0f / l;
             const int D = H * HD;
             __nv_bfloat16* orow = out + ((size_t)b * T + row) * D + (size_t)h * HD;
@@ -404,9 +448,10 @@ static int launch_attention_sdb_nt(const void* qkv, void* out, int B, int T, int
 template <int HD>
 int launch_attention_sdb(const void* qkv, void* out, int B, int T, int H, float scale, cudaStream_t s) {
     static const int nt = [] {
-        const char* e = getenv("GVL_ATTN_NT");  // tuning switch: query tiles per CTA
-        return (e && e[0] == '2') ? 2 : 1;
+        const char* e = getenv("GVL_ATTN_NT");  // tuning switch: query tiles per CTA (3 = single-buffered S, one CTA per SM)
+        return (e && (e[0] == '2' || e[0] == '3')) ? e[0] - '0' : 1;
     }();
+    if (nt == 3) return launch_attention_sdb_nt<HD, 3>(qkv, out, B, T, H, scale, s);
     return nt == 2 ? launch_attention_sdb_nt<HD, 2>(qkv, out, B, T, H, scale, s)
                    : launch_attention_sdb_nt<HD, 1>(qkv, out, B, T, H, scale, s);
 }

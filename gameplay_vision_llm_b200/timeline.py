@@ -77,6 +77,13 @@ class TimelineEmbeddingIndex:
         in the window hold index -1."""
         if not self.gathered:
             raise RuntimeError("index is sharded: call all_gather() first")
+        if self.n == 0 or queries.numel() == 0:
+            # an empty timeline (or no query) has no neighbours: the reference returns [] here
+            # (src/agent_core/qwen_reasoning_core.py:1508-1511), no device call is made
+            nq = 0 if queries.numel() == 0 else queries.reshape(-1, self.dim).shape[0]
+            return (torch.full((nq, top_k), float("-inf"), dtype=torch.float32, device=self.device),
+                    torch.full((nq, top_k), -1, dtype=torch.int32, device=self.device))
+        top_k = min(int(top_k), self.n)
         q = queries.to(self.device).to(torch.bfloat16).reshape(-1, self.dim).contiguous()
         if self._inv_norm is None:  # cached: the index does not change after the gather
             self._inv_norm = ops.row_inv_norm(self.index(), eps)
@@ -94,7 +101,7 @@ class TimelineEmbeddingIndex:
     def retrieve_by_semantic(self, query_embedding: torch.Tensor, top_k: int = 10) -> list[tuple[float, float]]:
         """[(timestamp, score)] best first — the embedding-index analogue of `TimelineRetriever.retrieve_by_semantic`
         (src/agent_core/qwen_reasoning_core.py:1492-1528, default semantic_top_k = 10, :655)."""
-        scores, idx = self.search(query_embedding.reshape(1, -1), min(top_k, self.n))
+        scores, idx = self.search(query_embedding.reshape(1, -1), top_k)
         return [(float(self.timestamps[i]), float(s)) for s, i in zip(scores[0].tolist(), idx[0].tolist()) if i >= 0]
 
     def retrieve_by_timestamp(self, timestamp: float, window: float = 30.0) -> list[int]:
@@ -111,10 +118,10 @@ class TimelineEmbeddingIndex:
         order followed by the semantic top-5 over the WHOLE timeline that are not among them; without one, the semantic
         top-k (default 10)."""
         if timestamp is None:
-            _, idx = self.search(query_embedding.reshape(1, -1), min(semantic_top_k, self.n))
+            _, idx = self.search(query_embedding.reshape(1, -1), semantic_top_k)
             return [i for i in idx[0].tolist() if i >= 0]
         rows = self.retrieve_by_timestamp(timestamp, window)
-        _, idx = self.search(query_embedding.reshape(1, -1), min(context_top_k, self.n))
+        _, idx = self.search(query_embedding.reshape(1, -1), context_top_k)
         seen = set(rows)
         for i in idx[0].tolist():
             if i >= 0 and i not in seen:

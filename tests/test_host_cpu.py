@@ -158,3 +158,20 @@ def test_oracle_windowed_topk_and_hybrid_merge():
     assert set(i[1][:2]) == {10, 11} and list(i[1][2:]) == [-1, -1] and np.isinf(s[1][2:]).all()
     assert list(i[2]) == [-1] * 4
     assert siglip_ref.hybrid_merge([4, 5, 6], [9, 5, 2]) == [4, 5, 6, 9, 2]
+
+
+def test_empty_timeline_and_empty_query_return_nothing_like_the_reference():
+    """TimelineRetriever.retrieve_by_semantic returns [] without embeddings (qwen_reasoning_core.py:1508-1511); the
+    index does the same without touching the device."""
+    from gameplay_vision_llm_b200.timeline import TimelineEmbeddingIndex
+    idx = TimelineEmbeddingIndex(0, 16, device="cpu")
+    q = torch.randn(1, 16)
+    assert idx.retrieve_by_semantic(q[0]) == [] and idx.retrieve_by_timestamp(3.0) == []
+    assert idx.hybrid_retrieve(q) == [] and idx.hybrid_retrieve(q, timestamp=1.0) == []
+    s, i = idx.search(q, top_k=4)
+    assert s.shape == (1, 4) and i.tolist() == [[-1] * 4]
+    sel, emb = idx.window(5.0)
+    assert sel.size == 0 and emb.shape == (0, 16)
+    idx2 = TimelineEmbeddingIndex(5, 16, device="cpu")
+    s, i = idx2.search(torch.empty(0, 16), top_k=3)
+    assert s.shape == (0, 3) and i.shape == (0, 3)

@@ -415,6 +415,7 @@ static int launch_gemm_bn(uint32_t ef, const CUtensorMap& tmA, const CUtensorMap
     switch (ef) {
         case 0u: return launch_gemm_ef<BN, 0u>(tmA, tmB, tmC, p, stream);                                  // qkv, kv
         case GVL_ACT_GELU_TANH: return launch_gemm_ef<BN, GVL_ACT_GELU_TANH>(tmA, tmB, tmC, p, stream);    // fc1
+        case GVL_ACT_GELU_ERF: return launch_gemm_ef<BN, GVL_ACT_GELU_ERF>(tmA, tmB, tmC, p, stream);      // VideoMAE fc1
         case EF_RES: return launch_gemm_ef<BN, EF_RES>(tmA, tmB, tmC, p, stream);                          // out, fc2, patch
         case EF_RES | EF_STATS: return launch_gemm_ef<BN, EF_RES | EF_STATS>(tmA, tmB, tmC, p, stream);    // fold_ln producers
         case EF_LN: return launch_gemm_ef<BN, EF_LN>(tmA, tmB, tmC, p, stream);                            // fold_ln qkv, kv

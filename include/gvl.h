@@ -139,8 +139,8 @@ GVL_API int gvl_gemm_bf16(const void* A, int lda, const void* W, int ldw, const 
                   int M, int N, int K, int act, void* stream);
 
 /* LayerNorm folded into the GEMMs on either side of it (used by gvl_siglip_forward when the weight pack says
- * fold_ln): the GEMM that WRITES the residual stream also writes, per output row and per slab of columns (two slabs
- * per N tile), the partial sums (sum x, sum x^2) of the bf16 values it stored; the GEMM that CONSUMES LayerNorm(x)
+ * fold_ln): the GEMM that WRITES the residual stream also writes, per output row and per slab of 64 columns (padded
+ * to an even slab count, at most 20), the partial sums (sum x, sum x^2) of the bf16 values it stored; the GEMM that CONSUMES LayerNorm(x)
  * reads x itself as A, uses weights pre-multiplied by gamma, and applies
  *     out[m,n] = act( rstd[m] * (acc[m,n] - mean[m] * c1[n]) + c2[n] ),   c1[n] = sum_k W'[n,k],
  *     c2[n] = bias[n] + sum_k beta[k] W[n,k]   (passed through `bias`),
@@ -150,7 +150,7 @@ GVL_API int gvl_gemm_bf16(const void* A, int lda, const void* W, int ldw, const 
 typedef struct gvl_gemm_fusion {
     float* stats_out;      /* producer: float [M, gvl_gemm_stats_slots(N), 2], or NULL */
     const float* ln_stats; /* consumer: statistics of the rows of A written by a producer GEMM, or NULL */
-    int32_t ln_slots;      /* slabs per row in ln_stats */
+    int32_t ln_slots;      /* slabs per row in ln_stats: even, <= 20; ln_stats 16-byte aligned */
     int32_t ln_dim;        /* number of columns the statistics cover (D) */
     const float* ln_c1;    /* [N] */
     float ln_eps;

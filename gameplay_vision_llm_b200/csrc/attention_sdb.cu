@@ -120,6 +120,7 @@ attention_sdb_kernel(const __grid_constant__ CUtensorMap tmq64, const __grid_con
     auto spar = [](int j) { return (uint32_t)(NBUF == 2 ? (j >> 1) : j) & 1u; };
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    pdl_trigger();
     const int q0 = blockIdx.x * (NT * SDB_BQ);
     const int h = blockIdx.y, b = blockIdx.z;
     const int nblk = (T + SDB_BKV - 1) / SDB_BKV;
@@ -157,6 +158,7 @@ attention_sdb_kernel(const __grid_constant__ CUtensorMap tmq64, const __grid_con
     __syncthreads();
     tcgen05_fence_after();
     const uint32_t tmem_base = *tmem_ptr_smem;
+    pdl_wait();  // the QKV GEMM's output is visible from here on
 
     if (warp == W_TMA) {
         // ===== TMA producer =====
@@ -439,8 +441,8 @@ static int launch_attention_sdb_nt(const void* qkv, void* out, int B, int T, int
     static const int dbg = [] { const char* e = getenv("GVL_ATTN_DEBUG"); return e ? atoi(e) : 0; }();  // timing experiments
     dim3 grid((T + NT * SDB_BQ - 1) / (NT * SDB_BQ), H, B);
     ProfScope prof(GVL_K_ATTENTION, 4.0 * B * (double)H * T * (double)T * HD, s);
-    attention_sdb_kernel<HD, NT><<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, s>>>(
-        tq64, tq16, tk64, tk16, reinterpret_cast<__nv_bfloat16*>(out), T, H, scale * 1.4426950408889634f, dbg, g_attn_trace);
+    GVL_CUDA(launch_pdl(attention_sdb_kernel<HD, NT>, grid, dim3(Cfg::THREADS), Cfg::SMEM_BYTES, s, tq64, tq16, tk64, tk16,
+                        reinterpret_cast<__nv_bfloat16*>(out), T, H, scale * 1.4426950408889634f, dbg, g_attn_trace));
     GVL_LAUNCH_CHECK("attention_sdb_kernel");
     return 0;
 }

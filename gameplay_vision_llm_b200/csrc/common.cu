@@ -2,6 +2,8 @@
 // device checks and the TMA descriptor helper.
 #include "common.cuh"
 
+#include <cstdlib>
+
 #include <mutex>
 #include <vector>
 
@@ -15,6 +17,14 @@ void set_error(const char* fmt, ...) {
     va_start(ap, fmt);
     vsnprintf(t_err, sizeof(t_err), fmt, ap);
     va_end(ap);
+}
+
+bool pdl_enabled() {
+    static const bool on = [] {
+        const char* e = getenv("GVL_PDL");
+        return !(e && e[0] == '0');
+    }();
+    return on;
 }
 
 int sm_count() {

@@ -51,6 +51,24 @@ inline void count_launch(int n = 1) { g_launches.fetch_add((unsigned long long)n
     } while (0)
 
 int sm_count();  // SMs of the current device (cached)
+bool pdl_enabled();  // GVL_PDL=0 turns programmatic dependent launch off (A/B runs)
+
+// kernel<<<grid, block, smem, stream>>>(args...) with the programmatic-stream-serialization attribute
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                              Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
 
 // Optional per-launch timing (gvl_prof_enable): CUDA events recorded on the launch stream around every
 // kernel, summed per kernel family by gvl_prof_summary.  `work` = algorithmic FLOPs or bytes of the launch.
@@ -145,6 +163,15 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         if ((++probes & 0xfffu) == 0 && global_timer_ns() - t0 > 4000000000ull) mbar_timeout_trap();
     }
 }
+
+// ---- programmatic dependent launch (PDL) ----
+// A kernel launched with launch_pdl() may have its CTAs scheduled while the previous kernel of the stream is still
+// draining: barrier initialisation, TMEM allocation and descriptor prefetch then overlap that kernel's tail.
+// pdl_wait() blocks until the previous kernel has completed and its writes are visible — every thread executes it
+// before its first global-memory access.  pdl_trigger() (first statement of a kernel) lets the NEXT kernel's CTAs be
+// scheduled as soon as this kernel's CTAs leave an SM.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
 // ---- TMA ----
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* m) {

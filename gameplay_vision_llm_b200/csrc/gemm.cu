@@ -258,6 +258,7 @@ gemm_bf16_cg2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
     const uint32_t cta_rank = cluster_ctarank();
+    pdl_trigger();  // the next kernel's CTAs may take this SM as soon as this CTA leaves it
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmA);
@@ -278,6 +279,7 @@ gemm_bf16_cg2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     cluster_sync_all();  // barriers of both CTAs initialised before any remote arrive
     tcgen05_fence_after();
     const uint32_t tmem_base = *tmem_ptr_smem;
+    pdl_wait();  // everything above overlapped the previous kernel's tail; its outputs are visible from here on
 
     const int num_super = p.m_pairs * p.n_tiles;
     const int cluster_id = blockIdx.x >> 1;
@@ -403,7 +405,8 @@ static int launch_gemm_ef(const CUtensorMap& tmA, const CUtensorMap& tmB, const 
     const int max_clusters = sm_count() / 2;
     const int clusters = super_tiles < max_clusters ? super_tiles : max_clusters;
     ProfScope prof(GVL_K_GEMM, 2.0 * p.M * (double)p.N * p.K, stream);
-    gemm_bf16_cg2_kernel<BN, EF><<<2 * clusters, Cfg::THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, tmC, p);
+    GVL_CUDA(launch_pdl(gemm_bf16_cg2_kernel<BN, EF>, dim3(2 * clusters), dim3(Cfg::THREADS), Cfg::SMEM_BYTES, stream, tmA,
+                        tmB, tmC, p));
     GVL_LAUNCH_CHECK("gemm_bf16_cg2_kernel");
     return 0;
 }

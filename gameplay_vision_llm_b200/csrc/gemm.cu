@@ -39,7 +39,8 @@ constexpr int A_STAGE_BYTES = BM * BK * 2;
 constexpr int kMaxLnSlotPairs = 10;  // LayerNorm-fusion consumers read at most 20 partial-sum slots per row
 
 // epilogue flavour, compile-time unless EF_ANY is set
-enum : uint32_t { EF_ACT = 3u, EF_RES = 4u, EF_LN = 8u, EF_STATS = 16u, EF_F32 = 32u, EF_ANY = 64u };
+enum : uint32_t { EF_ACT = 3u, EF_RES = 4u, EF_LN = 8u, EF_STATS = 16u, EF_F32 = 32u, EF_ANY = 64u,
+                  EF_TMARES = 128u /* residual tile fetched by TMA into the staging tile (compile-time flavours only) */ };
 
 struct GemmParams {
     const float* bias;
@@ -73,7 +74,7 @@ struct GemmCfg {
     static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_HALF_BYTES;  // per CTA
     static constexpr int STAGES = BN == 256 ? 5 : (BN == 192 ? 6 : 7);
     static constexpr int TMEM_COLS = (2 * BN <= 256) ? 256 : 512;
-    static constexpr int BAR_BYTES = (2 * STAGES + 4) * 8 + 16;
+    static constexpr int BAR_BYTES = (2 * STAGES + 4 + EPI_WARPS) * 8 + 16;  // + one residual-tile barrier per epilogue warp
     // bf16 outputs leave through per-warp staging tiles (32 rows x 64 B, SWIZZLE_64B) and TMA stores
     static constexpr int OUT_TILE_BYTES = 32 * 64;
     static constexpr int OUT_STAGE_BYTES = EPI_WARPS * OUT_TILE_BYTES;
@@ -124,9 +125,14 @@ __device__ __forceinline__ void load_ln_row(const GemmParams& p, int row, float&
 template <int BN, uint32_t EF>
 __device__ __forceinline__ void epilogue_tile(const GemmParams& p, const float* myBias, uint32_t t_addr, int row0, int n0,
                                               int lane, uint4 (&rv)[4], float ln_rstd, float ln_mr,
-                                              const CUtensorMap* tmC, uint8_t* stage, bool& store_pending) {
+                                              const CUtensorMap* tmC, uint8_t* stage, bool& store_pending,
+                                              const CUtensorMap* tmR, uint64_t* res_bar, uint32_t& res_phase) {
     using Cfg = GemmCfg<BN>;
     constexpr bool ANY = (EF & EF_ANY) != 0;
+    // residual through TMA: the 32 x 32 residual tile lands in this warp's staging tile (same SWIZZLE_64B layout the
+    // store uses), every thread adds its own 16-byte slots and writes the result back in place — full 64-byte row
+    // segments from L2 instead of 32 scattered 16-byte loads per warp instruction, and no residual registers
+    constexpr bool TMARES = !ANY && (EF & EF_TMARES) != 0;
     const int act = ANY ? p.act : (int)(EF & EF_ACT);
     const bool has_res = ANY ? p.residual != nullptr : (EF & EF_RES) != 0;
     const bool ln = ANY ? p.ln_stats != nullptr : (EF & EF_LN) != 0;
@@ -146,12 +152,23 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, const float* 
         uint32_t r[32];
         tmem_ld_32x32(t_addr + (uint32_t)(chunk * 32), r);
         uint4 rn[4];  // next chunk's residual, in flight while this chunk is finished
-        if (has_res && chunk + 1 < Cfg::COLS_PER_WARP / 32) load_residual_chunk(p, row, c0 + 32, rn);
+        if (!TMARES && has_res && chunk + 1 < Cfg::COLS_PER_WARP / 32) load_residual_chunk(p, row, c0 + 32, rn);
         if (!f32 && store_pending) {  // the staging tile is reused: the previous store must have read it
             if (lane == 0) tma_store_wait_read<0>();
             __syncwarp();
         }
+        if (TMARES) {
+            if (lane == 0) {
+                mbar_arrive_expect_tx(res_bar, 32 * 64);
+                tma_load_2d(stage, tmR, res_bar, c0, row0);
+            }
+            __syncwarp();
+        }
         tmem_ld_wait();
+        if (TMARES) {
+            mbar_wait(res_bar, res_phase);
+            res_phase ^= 1u;
+        }
 #pragma unroll
         for (int g = 0; g < 4; ++g) {
             const int col = c0 + g * 8;
@@ -176,7 +193,16 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, const float* 
 #pragma unroll
                 for (int j = 0; j < 8; ++j) v[j] = gelu_erf_f(v[j]);
             }
-            if (has_res) {
+            if (TMARES) {
+                const float4 rf = ld_shared_f4(stage_s + lane * 64 + ((g ^ ((lane >> 1) & 3)) << 4));
+                const uint32_t rw[4] = {__float_as_uint(rf.x), __float_as_uint(rf.y), __float_as_uint(rf.z),
+                                        __float_as_uint(rf.w)};
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    v[2 * e] += bf16_lo(rw[e]);
+                    v[2 * e + 1] += bf16_hi(rw[e]);
+                }
+            } else if (has_res) {
                 v[0] += bf16_lo(rv[g].x); v[1] += bf16_hi(rv[g].x);
                 v[2] += bf16_lo(rv[g].y); v[3] += bf16_hi(rv[g].y);
                 v[4] += bf16_lo(rv[g].z); v[5] += bf16_hi(rv[g].z);
@@ -218,7 +244,7 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, const float* 
             }
             store_pending = true;
         }
-        if (has_res && chunk + 1 < Cfg::COLS_PER_WARP / 32) {
+        if (!TMARES && has_res && chunk + 1 < Cfg::COLS_PER_WARP / 32) {
 #pragma unroll
             for (int g = 0; g < 4; ++g) rv[g] = rn[g];
         }
@@ -235,10 +261,12 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, const float* 
 template <int BN, uint32_t EF>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GemmCfg<BN>::THREADS, 1)
 gemm_bf16_cg2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                     const __grid_constant__ CUtensorMap tmC, const GemmParams p) {
+                     const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmR,
+                     const GemmParams p) {
     using Cfg = GemmCfg<BN>;
     constexpr int STAGES = Cfg::STAGES;
     constexpr bool ANY = (EF & EF_ANY) != 0;
+    constexpr bool TMARES = !ANY && (EF & EF_TMARES) != 0;
 
     extern __shared__ uint8_t smem_raw[];
     // the dynamic smem window starts at the same CTA-relative offset in both CTAs of the cluster, so the
@@ -253,7 +281,8 @@ gemm_bf16_cg2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     uint64_t* empty_bar = bars + STAGES;             // per CTA: "this stage may be overwritten"
     uint64_t* tmem_full_bar = bars + 2 * STAGES;     // per CTA: accumulator stage ready
     uint64_t* tmem_empty_bar = bars + 2 * STAGES + 2;  // leader only: both CTAs' epilogues drained the stage
-    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+    uint64_t* res_bar = bars + 2 * STAGES + 4;       // per epilogue warp: residual tile landed (EF_TMARES)
+    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4 + Cfg::EPI_WARPS);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -272,6 +301,8 @@ gemm_bf16_cg2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
             mbar_init(&tmem_full_bar[s], 1);
             mbar_init(&tmem_empty_bar[s], 2 * Cfg::EPI_WARPS);
         }
+        for (int w = 0; w < Cfg::EPI_WARPS; ++w) mbar_init(&res_bar[w], 1);
+        if (TMARES) tma_prefetch_desc(&tmR);
         fence_barrier_init();
     }
     if (warp == 1) tmem_alloc_cg2<Cfg::TMEM_COLS>(tmem_ptr_smem);
@@ -355,6 +386,7 @@ gemm_bf16_cg2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         float* myBias = sBias + ew * Cfg::COLS_PER_WARP;
         uint8_t* myStage = sOutStage + ew * Cfg::OUT_TILE_BYTES;
         bool store_pending = false;
+        uint32_t res_phase = 0;
         int as = 0;
         uint32_t aphase = 0;
         for (int st = cluster_id; st < num_super; st += num_clusters) {
@@ -368,12 +400,13 @@ gemm_bf16_cg2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
             __syncwarp();
             uint4 rv[4];
             float ln_rstd = 1.0f, ln_mr = 0.0f;
-            if (has_res) load_residual_chunk(p, row0 + lane, n0, rv);
+            if (has_res && !TMARES) load_residual_chunk(p, row0 + lane, n0, rv);
             if (ln) load_ln_row(p, row0 + lane, ln_rstd, ln_mr);
             mbar_wait_cluster(&tmem_full_bar[as], aphase);
             tcgen05_fence_after();
             const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BN + cgp * Cfg::COLS_PER_WARP);
-            epilogue_tile<BN, EF>(p, myBias, t_addr, row0, n0, lane, rv, ln_rstd, ln_mr, &tmC, myStage, store_pending);
+            epilogue_tile<BN, EF>(p, myBias, t_addr, row0, n0, lane, rv, ln_rstd, ln_mr, &tmC, myStage, store_pending, &tmR,
+                                  &res_bar[ew], res_phase);
             tcgen05_fence_before();
             __syncwarp();
             // the accumulator values are in registers (tcgen05.wait::ld): a relaxed arrive is enough, and unlike a
@@ -395,8 +428,8 @@ gemm_bf16_cg2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
 }
 
 template <int BN, uint32_t EF>
-static int launch_gemm_ef(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const GemmParams& p,
-                          cudaStream_t stream) {
+static int launch_gemm_ef(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const CUtensorMap& tmR,
+                          const GemmParams& p, cudaStream_t stream) {
     using Cfg = GemmCfg<BN>;
     static_assert(Cfg::SMEM_BYTES <= 227 * 1024, "GEMM shared memory budget");
     GVL_CUDA(cudaFuncSetAttribute(gemm_bf16_cg2_kernel<BN, EF>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -406,7 +439,7 @@ static int launch_gemm_ef(const CUtensorMap& tmA, const CUtensorMap& tmB, const 
     const int clusters = super_tiles < max_clusters ? super_tiles : max_clusters;
     ProfScope prof(GVL_K_GEMM, 2.0 * p.M * (double)p.N * p.K, stream);
     GVL_CUDA(launch_pdl(gemm_bf16_cg2_kernel<BN, EF>, dim3(2 * clusters), dim3(Cfg::THREADS), Cfg::SMEM_BYTES, stream, tmA,
-                        tmB, tmC, p));
+                        tmB, tmC, tmR, p));
     GVL_LAUNCH_CHECK("gemm_bf16_cg2_kernel");
     return 0;
 }
@@ -414,17 +447,20 @@ static int launch_gemm_ef(const CUtensorMap& tmA, const CUtensorMap& tmB, const 
 // the flag combinations of the tower's hot GEMMs get their own instantiation; everything else is generic
 template <int BN>
 static int launch_gemm_bn(uint32_t ef, const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC,
-                          const GemmParams& p, cudaStream_t stream) {
+                          const CUtensorMap& tmR, const GemmParams& p, cudaStream_t stream) {
     switch (ef) {
-        case 0u: return launch_gemm_ef<BN, 0u>(tmA, tmB, tmC, p, stream);                                  // qkv, kv
-        case GVL_ACT_GELU_TANH: return launch_gemm_ef<BN, GVL_ACT_GELU_TANH>(tmA, tmB, tmC, p, stream);    // fc1
-        case GVL_ACT_GELU_ERF: return launch_gemm_ef<BN, GVL_ACT_GELU_ERF>(tmA, tmB, tmC, p, stream);      // VideoMAE fc1
-        case EF_RES: return launch_gemm_ef<BN, EF_RES>(tmA, tmB, tmC, p, stream);                          // out, fc2, patch
-        case EF_RES | EF_STATS: return launch_gemm_ef<BN, EF_RES | EF_STATS>(tmA, tmB, tmC, p, stream);    // fold_ln producers
-        case EF_LN: return launch_gemm_ef<BN, EF_LN>(tmA, tmB, tmC, p, stream);                            // fold_ln qkv, kv
+        case 0u: return launch_gemm_ef<BN, 0u>(tmA, tmB, tmC, tmR, p, stream);                                  // qkv, kv
+        case GVL_ACT_GELU_TANH: return launch_gemm_ef<BN, GVL_ACT_GELU_TANH>(tmA, tmB, tmC, tmR, p, stream);    // fc1
+        case GVL_ACT_GELU_ERF: return launch_gemm_ef<BN, GVL_ACT_GELU_ERF>(tmA, tmB, tmC, tmR, p, stream);      // VideoMAE fc1
+        case EF_RES: return launch_gemm_ef<BN, EF_RES>(tmA, tmB, tmC, tmR, p, stream);                          // out, fc2, patch
+        case EF_RES | EF_STATS: return launch_gemm_ef<BN, EF_RES | EF_STATS>(tmA, tmB, tmC, tmR, p, stream);    // fold_ln producers
+        case EF_RES | EF_TMARES: return launch_gemm_ef<BN, EF_RES | EF_TMARES>(tmA, tmB, tmC, tmR, p, stream);
+        case EF_RES | EF_STATS | EF_TMARES:
+            return launch_gemm_ef<BN, EF_RES | EF_STATS | EF_TMARES>(tmA, tmB, tmC, tmR, p, stream);
+        case EF_LN: return launch_gemm_ef<BN, EF_LN>(tmA, tmB, tmC, tmR, p, stream);                            // fold_ln qkv, kv
         case EF_LN | GVL_ACT_GELU_TANH:
-            return launch_gemm_ef<BN, EF_LN | GVL_ACT_GELU_TANH>(tmA, tmB, tmC, p, stream);                // fold_ln fc1
-        default: return launch_gemm_ef<BN, EF_ANY>(tmA, tmB, tmC, p, stream);
+            return launch_gemm_ef<BN, EF_LN | GVL_ACT_GELU_TANH>(tmA, tmB, tmC, tmR, p, stream);                // fold_ln fc1
+        default: return launch_gemm_ef<BN, EF_ANY>(tmA, tmB, tmC, tmR, p, stream);
     }
 }
 
@@ -533,11 +569,23 @@ extern "C" int gvl_gemm_bf16_fused(const void* A, int lda, const void* W, int ld
         rc = make_tmap_nd_bf16(&tmC, out, 2, cdims, cstr, cbox, 64);
         if (rc) return rc;
     }
-    const uint32_t ef = (uint32_t)act | (residual ? EF_RES : 0u) | (p.ln_stats ? EF_LN : 0u) |
-                        (p.stats_out ? EF_STATS : 0u) | (out_f32 ? EF_F32 : 0u);
+    uint32_t ef = (uint32_t)act | (residual ? EF_RES : 0u) | (p.ln_stats ? EF_LN : 0u) |
+                  (p.stats_out ? EF_STATS : 0u) | (out_f32 ? EF_F32 : 0u);
+    // residual tile through TMA (GVL_GEMM_TMARES=0 turns it off for A/B runs): plain row-for-row bf16 residuals of the
+    // two hot flavours only; out-proj 111 -> 103 us, fc2 350 -> 343 us
+    static const bool tma_res = [] { const char* e = getenv("GVL_GEMM_TMARES"); return !(e && e[0] == '0'); }();
+    CUtensorMap tmR = tmC;
+    if (tma_res && residual && res_row_mod == 0 && !out_f32 && (ef == EF_RES || ef == (EF_RES | EF_STATS))) {
+        const uint64_t rdims[2] = {(uint64_t)N, (uint64_t)M};
+        const uint64_t rstr[1] = {(uint64_t)ldr * 2};
+        const uint32_t rbox[2] = {32, 32};
+        rc = make_tmap_nd_bf16(&tmR, residual, 2, rdims, rstr, rbox, 64);
+        if (rc) return rc;
+        ef |= EF_TMARES;
+    }
     switch (bn) {
-        case 256: return launch_gemm_bn<256>(ef, tmA, tmB, tmC, p, s);
-        case 192: return launch_gemm_bn<192>(ef, tmA, tmB, tmC, p, s);
-        default: return launch_gemm_bn<128>(ef, tmA, tmB, tmC, p, s);
+        case 256: return launch_gemm_bn<256>(ef, tmA, tmB, tmC, tmR, p, s);
+        case 192: return launch_gemm_bn<192>(ef, tmA, tmB, tmC, tmR, p, s);
+        default: return launch_gemm_bn<128>(ef, tmA, tmB, tmC, tmR, p, s);
     }
 }

@@ -61,6 +61,7 @@ SIGNATURES = {
     "gvl_gemm_bf16": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_void_p, c_int,
                               c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "gvl_gemm_stats_slots": (c_int, [c_int]),
+    "gvl_ln_finalize": (c_int, [c_void_p, c_int, c_int, c_int, c_float, c_void_p, c_void_p]),
     "gvl_gemm_bf16_fused": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_void_p, c_int,
                                     c_int, c_int, c_int, c_int, c_int, POINTER(GemmFusion), c_void_p]),
     "gvl_layernorm_bf16": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_float,
@@ -96,7 +97,7 @@ def lib() -> ctypes.CDLL:
             fn = getattr(handle, name)
             fn.restype = res
             fn.argtypes = args
-        if handle.gvl_abi_version() != 3:
+        if handle.gvl_abi_version() != 4:
             raise RuntimeError("libgvl_sm100a.so ABI version mismatch; rebuild the extension")
         _LIB = handle
     return _LIB

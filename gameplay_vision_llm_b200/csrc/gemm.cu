@@ -100,6 +100,12 @@ __device__ __forceinline__ void load_ln_row(const GemmParams& p, int row, float&
     ln_rstd = 1.0f;
     ln_mr = 0.0f;
     if (row >= p.M) return;
+    if (p.ln_slots == 0) {  // finalised by gvl_ln_finalize: (rstd, mean * rstd) per row
+        const float2 f = reinterpret_cast<const float2*>(p.ln_stats)[row];
+        ln_rstd = f.x;
+        ln_mr = f.y;
+        return;
+    }
     // slots come in pairs: 16-byte loads, all issued before the first use so the row costs one L2 round trip
     const float4* sp = reinterpret_cast<const float4*>(p.ln_stats + (size_t)row * p.ln_slots * 2);
     const int pairs = p.ln_slots >> 1;
@@ -525,11 +531,11 @@ extern "C" int gvl_gemm_bf16_fused(const void* A, int lda, const void* W, int ld
     p.ln_inv_d = p.ln_eps = 0.f;
     if (fusion != nullptr) {
         GVL_CHECK_ARG(fusion->stats_out == nullptr || !out_f32, "gvl_gemm_bf16_fused: row statistics need a bf16 output");
-        GVL_CHECK_ARG(fusion->ln_stats == nullptr || (fusion->ln_c1 && fusion->ln_slots > 0 && fusion->ln_dim > 0),
+        GVL_CHECK_ARG(fusion->ln_stats == nullptr || (fusion->ln_c1 && fusion->ln_slots >= 0 && fusion->ln_dim > 0),
                       "gvl_gemm_bf16_fused: incomplete LayerNorm fusion arguments");
         GVL_CHECK_ARG(fusion->ln_stats == nullptr ||
                           (fusion->ln_slots % 2 == 0 && fusion->ln_slots <= 2 * kMaxLnSlotPairs &&
-                           (uintptr_t)fusion->ln_stats % 16 == 0),
+                           (uintptr_t)fusion->ln_stats % (fusion->ln_slots ? 16 : 8) == 0),
                       "gvl_gemm_bf16_fused: ln_slots must be even and <= %d, ln_stats 16-byte aligned", 2 * kMaxLnSlotPairs);
         p.stats_out = fusion->stats_out;
         p.ln_stats = fusion->ln_stats;

@@ -73,6 +73,47 @@ layernorm_bf16_kernel(const __nv_bfloat16* __restrict__ x, int ldx, const float*
 
 }  // namespace gvl
 
+namespace gvl {
+
+// LayerNorm-fusion statistics, finalised once per row: the producer GEMM's per-slab partial sums (sum x, sum x^2) ->
+// (rstd, mean * rstd).  Same summation order as the consumer epilogue uses when it reads the slabs itself, so both
+// routes give identical bits; the consumer then needs ONE 8-byte load per row and tile instead of slots / 2 scattered
+// 16-byte loads.
+__global__ void __launch_bounds__(256)
+ln_finalize_kernel(const float* __restrict__ stats, int rows, int slots, float inv_d, float eps, float2* __restrict__ out) {
+    const int row = blockIdx.x * blockDim.x + threadIdx.x;
+    if (row >= rows) return;
+    const float4* sp = reinterpret_cast<const float4*>(stats + (size_t)row * slots * 2);
+    float s1 = 0.f, s2 = 0.f;
+    for (int i = 0; i < (slots >> 1); ++i) {
+        const float4 t = sp[i];
+        s1 += t.x;
+        s2 += t.y;
+        s1 += t.z;
+        s2 += t.w;
+    }
+    const float mean = s1 * inv_d;
+    const float var = fmaxf(s2 * inv_d - mean * mean, 0.0f);
+    const float rstd = rsqrtf(var + eps);
+    out[row] = make_float2(rstd, mean * rstd);
+}
+
+}  // namespace gvl
+
+extern "C" int gvl_ln_finalize(const float* stats, int rows, int slots, int dim, float eps, float* out, void* stream) {
+    using namespace gvl;
+    GVL_CHECK_ARG(stats && out, "gvl_ln_finalize: null pointer");
+    GVL_CHECK_ARG(rows > 0 && slots > 0 && slots % 2 == 0 && dim > 0, "gvl_ln_finalize: bad shape rows=%d slots=%d dim=%d",
+                  rows, slots, dim);
+    GVL_CHECK_ARG((uintptr_t)stats % 16 == 0 && (uintptr_t)out % 8 == 0, "gvl_ln_finalize: misaligned pointer");
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+    ProfScope prof(GVL_K_LAYERNORM, (double)rows * (slots * 8 + 8), s);
+    ln_finalize_kernel<<<(rows + 255) / 256, 256, 0, s>>>(stats, rows, slots, 1.0f / (float)dim, eps,
+                                                          reinterpret_cast<float2*>(out));
+    GVL_LAUNCH_CHECK("ln_finalize_kernel");
+    return 0;
+}
+
 extern "C" int gvl_layernorm_bf16(const void* x, int ldx, const float* gamma, const float* beta, void* y, int ldy,
                                   int rows, int D, float eps, void* stream) {
     using namespace gvl;

@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define GVL_ABI_VERSION 3
+#define GVL_ABI_VERSION 4
 
 #if defined(__GNUC__)
 #define GVL_API __attribute__((visibility("default")))
@@ -150,12 +150,16 @@ GVL_API int gvl_gemm_bf16(const void* A, int lda, const void* W, int ldw, const 
 typedef struct gvl_gemm_fusion {
     float* stats_out;      /* producer: float [M, gvl_gemm_stats_slots(N), 2], or NULL */
     const float* ln_stats; /* consumer: statistics of the rows of A written by a producer GEMM, or NULL */
-    int32_t ln_slots;      /* slabs per row in ln_stats: even, <= 20; ln_stats 16-byte aligned */
+    int32_t ln_slots;      /* slabs per row in ln_stats: even, <= 20; ln_stats 16-byte aligned.  0 = ln_stats is the
+                            * finalised float [M, 2] array (rstd, mean * rstd) written by gvl_ln_finalize */
     int32_t ln_dim;        /* number of columns the statistics cover (D) */
     const float* ln_c1;    /* [N] */
     float ln_eps;
 } gvl_gemm_fusion;
 GVL_API int gvl_gemm_stats_slots(int N); /* slabs per row a producer GEMM with N output columns writes. Host only. */
+/* out[m] = (rstd, mean * rstd) of row m from a producer's partial sums stats [rows, slots, 2] over `dim` columns; same
+ * summation order as the consumer epilogue, so both routes give identical bits. */
+GVL_API int gvl_ln_finalize(const float* stats, int rows, int slots, int dim, float eps, float* out, void* stream);
 GVL_API int gvl_gemm_bf16_fused(const void* A, int lda, const void* W, int ldw, const float* bias,
                         const void* residual, int ldr, int res_row_mod, void* out, int ldo, int out_f32,
                         int M, int N, int K, int act, const gvl_gemm_fusion* fusion, void* stream);

@@ -14,6 +14,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("GVL_LIB_PATH") or os.path.join(_HERE, "libgvl_sm100a.so")
 
 c_float_p = POINTER(c_float)
+ABI_VERSION = 5  # include/gvl.h GVL_ABI_VERSION
 
 
 class VitLayer(ctypes.Structure):
@@ -78,6 +79,8 @@ SIGNATURES = {
     "gvl_topk_scratch_floats": (c_size_t, [c_int, c_int]),
     "gvl_topk_cosine_ex": (c_int, [c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_float, c_void_p, c_void_p, c_int,
                                    c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "gvl_topk_cosine_f32": (c_int, [c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_float, c_void_p, c_void_p, c_void_p,
+                                    c_void_p]),
     "gvl_row_inv_norm": (c_int, [c_void_p, c_int, c_int, c_float, c_void_p, c_void_p]),
 }
 
@@ -97,7 +100,7 @@ def lib() -> ctypes.CDLL:
             fn = getattr(handle, name)
             fn.restype = res
             fn.argtypes = args
-        if handle.gvl_abi_version() != 4:
+        if handle.gvl_abi_version() != ABI_VERSION:
             raise RuntimeError("libgvl_sm100a.so ABI version mismatch; rebuild the extension")
         _LIB = handle
     return _LIB

@@ -14,7 +14,6 @@
 // two per scheduler ~8.6; with ~400 cycles of fixed per-block hand-shake (mbarrier round trip, tcgen05.ld / st waits)
 // and a 6400-cycle CTA start-up the exp pipe is ~60 % busy.  Neither fewer softmax instructions, nor fewer MMAs, nor
 // more softmax warps per scheduler (NT = 3, split rows) moved the 282 us per layer.
-// The single-buffer kernel (attention_tc.cu, 128-key blocks) is kept for A/B runs (GVL_ATTN_TC1=1).
 //
 //   warps [0, 4 NT)  softmax, four warps per tile: one thread = one query row x 64 keys; tcgen05.ld the S row,
 //               running max with lazy rescaling of O and L (only when the max grows by more than 2^8),

@@ -111,6 +111,60 @@ cos_scores_kernel(const __nv_bfloat16* __restrict__ index, int r0, int r1, int D
     }
 }
 
+// fp32 inputs (find_similar_regions / compute_similarity on fp32 embeddings, e.g. VideoMAE clip vectors or fp32
+// projections — the reference upcasts with .float(), src/perception/siglip_semantic_encoder.py:604-638): the same
+// warp-per-row scan with fp32 rows and queries, 4 queries per pass held in shared memory.
+constexpr int TOPK_QB_F32 = 4;
+
+__global__ void __launch_bounds__(TOPK_THREADS)
+cos_scores_f32_kernel(const float* __restrict__ index, int N, int D, const float* __restrict__ queries, int nq, float eps,
+                      float* __restrict__ scores /* [nq, ld] */, size_t ld) {
+    extern __shared__ __align__(16) uint8_t tk_smem[];
+    float4* sQ = reinterpret_cast<float4*>(tk_smem);                                       // [nq][D/4]
+    float* sQn = reinterpret_cast<float*>(tk_smem + (size_t)TOPK_QB_F32 * D * 4);          // [TOPK_QB_F32]
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int chunks = D >> 2;
+    for (int i = tid; i < nq * chunks; i += TOPK_THREADS) sQ[i] = reinterpret_cast<const float4*>(queries)[i];
+    __syncthreads();
+    if (warp < nq) {
+        float acc = 0.f;
+        for (int c = lane; c < chunks; c += 32) {
+            const float4 f = sQ[warp * chunks + c];
+            acc = fmaf(f.x, f.x, acc); acc = fmaf(f.y, f.y, acc); acc = fmaf(f.z, f.z, acc); acc = fmaf(f.w, f.w, acc);
+        }
+        acc = tk_warp_sum(acc);
+        if (lane == 0) sQn[warp] = 1.0f / fmaxf(sqrtf(acc), eps);
+    }
+    __syncthreads();
+    const int warps_total = gridDim.x * (TOPK_THREADS / 32);
+    for (int row = blockIdx.x * (TOPK_THREADS / 32) + warp; row < N; row += warps_total) {
+        const float4* er = reinterpret_cast<const float4*>(index + (size_t)row * D);
+        float dot[TOPK_QB_F32];
+#pragma unroll
+        for (int q = 0; q < TOPK_QB_F32; ++q) dot[q] = 0.f;
+        float nrm = 0.f;
+        for (int c = lane; c < chunks; c += 32) {
+            const float4 e = __ldg(er + c);
+            nrm = fmaf(e.x, e.x, nrm); nrm = fmaf(e.y, e.y, nrm); nrm = fmaf(e.z, e.z, nrm); nrm = fmaf(e.w, e.w, nrm);
+#pragma unroll
+            for (int q = 0; q < TOPK_QB_F32; ++q)
+                if (q < nq) {
+                    const float4 v = sQ[q * chunks + c];
+                    dot[q] = fmaf(e.x, v.x, dot[q]); dot[q] = fmaf(e.y, v.y, dot[q]);
+                    dot[q] = fmaf(e.z, v.z, dot[q]); dot[q] = fmaf(e.w, v.w, dot[q]);
+                }
+        }
+        nrm = tk_warp_sum(nrm);
+        const float inv_e = 1.0f / fmaxf(sqrtf(nrm), eps);
+#pragma unroll
+        for (int q = 0; q < TOPK_QB_F32; ++q)
+            if (q < nq) {
+                const float d = tk_warp_sum(dot[q]);
+                if (lane == 0) scores[(size_t)q * ld + row] = d * sQn[q] * inv_e;
+            }
+    }
+}
+
 // (score, idx) a "better" than b under (score desc, idx asc)
 __device__ __forceinline__ bool tk_better(float sa, int ia, float sb, int ib) {
     return sa > sb || (sa == sb && ia < ib);
@@ -377,6 +431,27 @@ static size_t topk_cand_offset(int N, int Q) {
     return (size_t)Q * ld + ld + (((size_t)Q + 3) & ~(size_t)3) + 4;
 }
 
+// two-stage selection over scratch[Q][ld] scores: segment winners (grid = segments x queries), then their merge
+static int topk_select(float* scratch, int N, int Q, int k, int span_lo, int span, const int32_t* row_lo,
+                       const int32_t* row_hi, float* out_scores, int32_t* out_idx, cudaStream_t s) {
+    using namespace gvl;
+    const size_t ld = ((size_t)N + 3) & ~(size_t)3;
+    int segs = (span + TOPK_SEG - 1) / TOPK_SEG;
+    segs = segs < 1 ? 1 : (segs > TOPK_MAX_SEGS ? TOPK_MAX_SEGS : segs);
+    int seg_len = ((span + segs - 1) / segs + 3) & ~3;
+    if (seg_len < 4) seg_len = 4;
+    float* cand_s = scratch + topk_cand_offset(N, Q);
+    int32_t* cand_i = reinterpret_cast<int32_t*>(cand_s + (size_t)Q * TOPK_MAX_SEGS * 64);
+    const size_t seg_smem = seg_len <= TOPK_SEG ? (size_t)seg_len * sizeof(float) : 0;
+    ProfScope prof(GVL_K_TOPK_SELECT, (double)Q * span * 4, s);
+    topk_select_seg_kernel<<<dim3((unsigned)segs, (unsigned)Q), TOPK_THREADS, seg_smem, s>>>(
+        scratch, N, ld, k, span_lo, seg_len, row_lo, row_hi, cand_s, cand_i);
+    GVL_LAUNCH_CHECK("topk_select_seg_kernel");
+    topk_merge_kernel<<<Q, TOPK_THREADS, 0, s>>>(cand_s, cand_i, segs, k, out_scores, out_idx);
+    GVL_LAUNCH_CHECK("topk_merge_kernel");
+    return 0;
+}
+
 extern "C" size_t gvl_topk_scratch_floats(int N, int Q) {
     if (N <= 0 || Q <= 0) return 0;
     return topk_cand_offset(N, Q) + 2 * (size_t)Q * gvl::TOPK_MAX_SEGS * 64;
@@ -463,20 +538,8 @@ extern "C" int gvl_topk_cosine_ex(const void* index, int N, int D, const void* q
         }
     }
     {
-        // two-stage selection: segment winners (grid = segments x queries), then their merge
-        int segs = (span + TOPK_SEG - 1) / TOPK_SEG;
-        segs = segs < 1 ? 1 : (segs > TOPK_MAX_SEGS ? TOPK_MAX_SEGS : segs);
-        int seg_len = ((span + segs - 1) / segs + 3) & ~3;
-        if (seg_len < 4) seg_len = 4;
-        float* cand_s = scratch + topk_cand_offset(N, Q);
-        int32_t* cand_i = reinterpret_cast<int32_t*>(cand_s + (size_t)Q * TOPK_MAX_SEGS * 64);
-        const size_t seg_smem = seg_len <= TOPK_SEG ? (size_t)seg_len * sizeof(float) : 0;
-        ProfScope prof(GVL_K_TOPK_SELECT, (double)Q * span * 4, s);
-        topk_select_seg_kernel<<<dim3((unsigned)segs, (unsigned)Q), TOPK_THREADS, seg_smem, s>>>(
-            scratch, N, ld, k, span_lo, seg_len, row_lo, row_hi, cand_s, cand_i);
-        GVL_LAUNCH_CHECK("topk_select_seg_kernel");
-        topk_merge_kernel<<<Q, TOPK_THREADS, 0, s>>>(cand_s, cand_i, segs, k, out_scores, out_idx);
-        GVL_LAUNCH_CHECK("topk_merge_kernel");
+        int rc = topk_select(scratch, N, Q, k, span_lo, span, row_lo, row_hi, out_scores, out_idx, s);
+        if (rc) return rc;
     }
     if (tensor_scored) {
         // exact fp32 re-scoring of the near-top candidates: the final result is the scan path's
@@ -494,4 +557,28 @@ extern "C" int gvl_topk_cosine(const void* index, int N, int D, const void* quer
     // scratch: gvl_topk_scratch_floats(N, Q) floats
     return gvl_topk_cosine_ex(index, N, D, queries, Q, k, eps, nullptr, nullptr, 0, N, GVL_TOPK_AUTO, nullptr, scratch,
                               out_scores, out_idx, stream);
+}
+
+extern "C" int gvl_topk_cosine_f32(const float* index, int N, int D, const float* queries, int Q, int k, float eps,
+                                   float* scratch, float* out_scores, int32_t* out_idx, void* stream) {
+    using namespace gvl;
+    GVL_CHECK_ARG(index && queries && scratch && out_scores && out_idx, "gvl_topk_cosine_f32: null pointer");
+    GVL_CHECK_ARG(N > 0 && Q > 0 && D > 0 && D % 4 == 0 && D <= 8192, "gvl_topk_cosine_f32: bad shape N=%d Q=%d D=%d", N, Q, D);
+    GVL_CHECK_ARG(k > 0 && k <= 64, "gvl_topk_cosine_f32: k=%d out of range [1,64]", k);
+    GVL_CHECK_ARG((uintptr_t)index % 16 == 0 && (uintptr_t)queries % 16 == 0 && (uintptr_t)scratch % 16 == 0,
+                  "gvl_topk_cosine_f32: misaligned pointer");
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+    const size_t ld = ((size_t)N + 3) & ~(size_t)3;
+    const size_t smem = (size_t)TOPK_QB_F32 * D * 4 + TOPK_QB_F32 * sizeof(float);
+    GVL_CUDA(cudaFuncSetAttribute(cos_scores_f32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int grid = (N + TOPK_THREADS / 32 - 1) / (TOPK_THREADS / 32);
+    if (grid > sm_count() * 4) grid = sm_count() * 4;
+    for (int q0 = 0; q0 < Q; q0 += TOPK_QB_F32) {
+        const int nq = Q - q0 < TOPK_QB_F32 ? Q - q0 : TOPK_QB_F32;
+        ProfScope prof(GVL_K_TOPK_SCORES, (double)N * D * 4, s);
+        cos_scores_f32_kernel<<<grid, TOPK_THREADS, smem, s>>>(index, N, D, queries + (size_t)q0 * D, nq, eps,
+                                                               scratch + (size_t)q0 * ld, ld);
+        GVL_LAUNCH_CHECK("cos_scores_f32_kernel");
+    }
+    return topk_select(scratch, N, Q, k, 0, N, nullptr, nullptr, out_scores, out_idx, s);
 }

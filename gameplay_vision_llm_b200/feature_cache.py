@@ -129,23 +129,105 @@ def write_embeddings_pt(path: str, siglip_records: Sequence[dict], videomae_reco
     return data
 
 
-def write_perception_npz(cache_dir: str, video_path: str, siglip: Optional[torch.Tensor] = None,
-                         videomae: Optional[torch.Tensor] = None, frame_indices: Optional[np.ndarray] = None,
-                         timestamps: Optional[np.ndarray] = None) -> str:
-    """`PerceptionCache` directory (benchmarks/perception_cache.py:11-24, 203-283): `{md5(path:size:mtime)[:16]}/`
-    with `siglip.npz` / `videomae.npz` (key `embeddings`, fp32 — numpy has no bf16), `frames.npz`, `metadata.json`."""
-    st = os.stat(video_path)
-    vid = hashlib.md5(f"{video_path}:{st.st_size}:{st.st_mtime}".encode()).hexdigest()[:16]
-    d = Path(cache_dir) / vid
+PERCEPTION_CACHE_VERSION = "1.0.0"  # benchmarks/perception_cache.py:42
+
+
+def perception_video_hash(video_path: str) -> str:
+    """`PerceptionCache.compute_video_hash` (benchmarks/perception_cache.py:166-181): md5 of `path:size:mtime`, or of
+    the bare path string when the file does not exist; first 16 hex digits."""
+    if not Path(video_path).exists():
+        return hashlib.md5(video_path.encode()).hexdigest()[:16]
+    st = Path(video_path).stat()
+    return hashlib.md5(f"{video_path}:{st.st_size}:{st.st_mtime}".encode()).hexdigest()[:16]
+
+
+def _np_embeddings(t) -> Optional[np.ndarray]:
+    """numpy has no bf16: device / bf16 rows are stored as fp32 (every bf16 value is exact in fp32)."""
+    if t is None:
+        return None
+    if torch.is_tensor(t):
+        t = t.detach().cpu()
+        return (t.float() if t.dtype in (torch.bfloat16, torch.float16) else t).numpy()
+    return np.asarray(t)
+
+
+def write_perception_npz(cache_dir: str, video_path: str, siglip=None, videomae=None,
+                         frame_indices: Optional[np.ndarray] = None, timestamps: Optional[np.ndarray] = None,
+                         video_duration_sec: float = 0.0, perception_config: Optional[dict] = None) -> str:
+    """What `PerceptionCache.save` leaves on disk for the embedding part of `CachedFeatures`
+    (benchmarks/perception_cache.py:203-283), so that the reference's own `PerceptionCache.load` (:285-372) reads it:
+
+      cache_dir/{hash}/metadata.json   the keys of `CachedFeatures.to_metadata()` (:99-116)
+      cache_dir/{hash}/frames.npz      `indices`, `timestamps`           (only with frame_indices, :232-237)
+      cache_dir/{hash}/siglip.npz      `embeddings` (N, 1152)
+      cache_dir/{hash}/videomae.npz    `embeddings` (N, 768)
+      cache_dir/index.json             {hash: metadata} — `load` returns None for a hash that is not listed (:297)
+    """
+    import time
+    vid = perception_video_hash(video_path)
+    root = Path(cache_dir)
+    d = root / vid
     d.mkdir(parents=True, exist_ok=True)
-    if siglip is not None:
-        np.savez_compressed(d / "siglip.npz", embeddings=siglip.detach().float().cpu().numpy())
-    if videomae is not None:
-        np.savez_compressed(d / "videomae.npz", embeddings=videomae.detach().float().cpu().numpy())
-    if frame_indices is not None or timestamps is not None:
-        np.savez_compressed(d / "frames.npz", indices=np.asarray(frame_indices if frame_indices is not None else []),
-                            timestamps=np.asarray(timestamps if timestamps is not None else []))
+    sig, vmae = _np_embeddings(siglip), _np_embeddings(videomae)
+    if timestamps is not None and frame_indices is None:
+        frame_indices = np.arange(len(timestamps), dtype=np.int64)
+    metadata = {
+        "video_hash": vid,
+        "video_path": video_path,
+        "video_duration_sec": float(video_duration_sec),
+        "cache_version": PERCEPTION_CACHE_VERSION,
+        "cached_at": time.strftime("%Y-%m-%dT%H:%M:%SZ"),
+        "perception_config": dict(perception_config or {}),
+        "has_siglip": sig is not None,
+        "has_videomae": vmae is not None,
+        "has_sam": False, "has_ocr": False, "has_audio": False, "has_timeline": False, "has_kb": False,
+        "num_frames": int(len(frame_indices)) if frame_indices is not None else 0,
+    }
     with open(d / "metadata.json", "w") as f:
-        json.dump({"video_path": video_path, "video_id": vid, "cache_version": "1.0.0",
-                   "num_frames": int(siglip.shape[0]) if siglip is not None else 0}, f)
+        json.dump(metadata, f, indent=2)
+    if frame_indices is not None:
+        np.savez_compressed(d / "frames.npz", indices=np.asarray(frame_indices),
+                            timestamps=np.asarray(timestamps if timestamps is not None else [], dtype=np.float64))
+    if sig is not None:
+        np.savez_compressed(d / "siglip.npz", embeddings=sig)
+    if vmae is not None:
+        np.savez_compressed(d / "videomae.npz", embeddings=vmae)
+    index_path = root / "index.json"
+    index: dict = {}
+    if index_path.exists():
+        try:
+            with open(index_path) as f:
+                index = json.load(f)
+        except Exception as exc:  # same tolerance as `_load_index` (:148-156)
+            logger.warning("Failed to load cache index: %s", exc)
+            index = {}
+    index[vid] = metadata
+    with open(index_path, "w") as f:
+        json.dump(index, f, indent=2)
     return str(d)
+
+
+def load_perception_npz(cache_dir: str, video_path: str) -> Optional[dict]:
+    """Reader twin of `PerceptionCache.load` for the embedding part (benchmarks/perception_cache.py:285-346):
+    None unless the hash is listed in index.json and its directory + metadata.json exist."""
+    root = Path(cache_dir)
+    vid = perception_video_hash(video_path)
+    try:
+        with open(root / "index.json") as f:
+            index = json.load(f)
+    except Exception:
+        return None
+    d = root / vid
+    if vid not in index or not (d / "metadata.json").exists():
+        return None
+    with open(d / "metadata.json") as f:
+        out = {"metadata": json.load(f), "frame_indices": None, "frame_timestamps": None, "siglip_embeddings": None,
+               "videomae_embeddings": None}
+    if (d / "frames.npz").exists():
+        z = np.load(d / "frames.npz")
+        out["frame_indices"], out["frame_timestamps"] = z["indices"], z["timestamps"]
+    if (d / "siglip.npz").exists():
+        out["siglip_embeddings"] = np.load(d / "siglip.npz")["embeddings"]
+    if (d / "videomae.npz").exists():
+        out["videomae_embeddings"] = np.load(d / "videomae.npz")["embeddings"]
+    return out

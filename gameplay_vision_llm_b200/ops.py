@@ -5,12 +5,13 @@ CUDA stream and raises RuntimeError on any failure (there is no eager/PyTorch fa
 from __future__ import annotations
 
 import ctypes
+import functools
 
 import numpy as np
 import torch
 
 from . import _lib
-from .weights import ProjectorPack, SiglipPack, VideoMAEPack
+from .weights import ProjectorPack, SiglipPack, VideoMAEPack, resolve_device  # noqa: F401
 
 LAYOUT_U8_CHW, LAYOUT_F32_CHW, LAYOUT_BF16_CHW, LAYOUT_BF16_PATCH = 0, 1, 2, 3
 ACT_NONE, ACT_GELU_TANH, ACT_GELU_ERF = 0, 1, 2
@@ -19,6 +20,29 @@ BILINEAR, BICUBIC = 2, 3
 
 def _stream() -> int:
     return int(torch.cuda.current_stream().cuda_stream)
+
+
+def _on_tensor_device(fn):
+    """Run `fn` with the device of its first CUDA tensor argument made current: the library launches on the current
+    device and `_stream()` reads that device's current stream, so a tensor on cuda:1 must never be launched from a
+    process whose current device is cuda:0.  All tensor arguments must live on that one device."""
+    @functools.wraps(fn)
+    def wrapper(*args, **kwargs):
+        dev = None
+        for a in list(args) + list(kwargs.values()):
+            if torch.is_tensor(a) and a.is_cuda:
+                if dev is None:
+                    dev = a.device
+                elif a.device != dev:
+                    raise RuntimeError(f"{fn.__name__}: tensors on different devices ({dev} and {a.device})")
+            elif isinstance(a, (SiglipPack, ProjectorPack, VideoMAEPack)) and dev is not None and \
+                    torch.device(a.device) != dev:
+                raise RuntimeError(f"{fn.__name__}: weights on {a.device}, tensors on {dev}")
+        if dev is None or dev.index == torch.cuda.current_device():
+            return fn(*args, **kwargs)
+        with torch.cuda.device(dev):
+            return fn(*args, **kwargs)
+    return wrapper
 
 
 def _need_cuda(*tensors: torch.Tensor) -> None:
@@ -52,6 +76,7 @@ def fused_sub_div(image_mean=(0.5, 0.5, 0.5), image_std=(0.5, 0.5, 0.5), rescale
     return sub, div
 
 
+@_on_tensor_device
 def preprocess(frames: torch.Tensor, out_h: int = 384, out_w: int = 384, resample: int = BILINEAR,
                image_mean=(0.5, 0.5, 0.5), image_std=(0.5, 0.5, 0.5), layout: int = LAYOUT_BF16_PATCH, patch: int = 14,
                ld: int | None = None, out: torch.Tensor | None = None) -> torch.Tensor:
@@ -80,6 +105,7 @@ def preprocess(frames: torch.Tensor, out_h: int = 384, out_w: int = 384, resampl
     return out
 
 
+@_on_tensor_device
 def preprocess_crop(frames: torch.Tensor, out_h: int, out_w: int, crop_y0: int, crop_x0: int, crop_h: int, crop_w: int,
                     resample: int = BILINEAR, image_mean=(0.5, 0.5, 0.5), image_std=(0.5, 0.5, 0.5),
                     layout: int = LAYOUT_BF16_CHW, out: torch.Tensor | None = None) -> torch.Tensor:
@@ -102,6 +128,7 @@ def preprocess_crop(frames: torch.Tensor, out_h: int, out_w: int, crop_y0: int, 
     return out
 
 
+@_on_tensor_device
 def patchify_tubelet(pixel_values: torch.Tensor, frames: int, patch: int = 16, tubelet: int = 2,
                      out: torch.Tensor | None = None) -> torch.Tensor:
     """bf16 pixel_values [clips*frames,3,H,W] -> bf16 tubelet rows [clips*(frames/tubelet)*gh*gw, 3*tubelet*p*p]."""
@@ -119,6 +146,7 @@ def patchify_tubelet(pixel_values: torch.Tensor, frames: int, patch: int = 16, t
     return out
 
 
+@_on_tensor_device
 def mean_tokens(x: torch.Tensor, B: int, T: int, out_dtype: torch.dtype = torch.float32) -> torch.Tensor:
     """bf16 [B*T, D] -> [B, D] mean over the T tokens of each item."""
     _need_cuda(x)
@@ -131,6 +159,7 @@ def mean_tokens(x: torch.Tensor, B: int, T: int, out_dtype: torch.dtype = torch.
     return out
 
 
+@_on_tensor_device
 def videomae_forward(pack: VideoMAEPack, patches: torch.Tensor, workspace: torch.Tensor | None = None,
                      out_dtype: torch.dtype = torch.float32, return_tokens: bool = False):
     """bf16 tubelet patches [B*T, patch_k] -> mean-pooled clip embeddings [B, D] (fp32 like the reference)."""
@@ -151,6 +180,7 @@ def videomae_forward(pack: VideoMAEPack, patches: torch.Tensor, workspace: torch
     return (pooled, tokens) if return_tokens else pooled
 
 
+@_on_tensor_device
 def patchify(pixel_values: torch.Tensor, patch: int = 14, ld: int | None = None) -> torch.Tensor:
     """fp32 pixel_values [B,3,H,W] -> bf16 patch rows [B*gh*gw, ld] (the get_image_features seam)."""
     _need_cuda(pixel_values)
@@ -170,6 +200,7 @@ def gemm_stats_slots(N: int) -> int:
     return int(_lib.lib().gvl_gemm_stats_slots(int(N)))
 
 
+@_on_tensor_device
 def gemm(a: torch.Tensor, w: torch.Tensor, bias: torch.Tensor | None = None, residual: torch.Tensor | None = None,
          res_row_mod: int = 0, act: int = ACT_NONE, out: torch.Tensor | None = None,
          out_dtype: torch.dtype = torch.bfloat16, stats_out: torch.Tensor | None = None,
@@ -213,6 +244,7 @@ def gemm(a: torch.Tensor, w: torch.Tensor, bias: torch.Tensor | None = None, res
     return out
 
 
+@_on_tensor_device
 def layernorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: float,
               out: torch.Tensor | None = None) -> torch.Tensor:
     _need_cuda(x, gamma, beta, out)
@@ -227,6 +259,7 @@ def layernorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: flo
     return out
 
 
+@_on_tensor_device
 def attention(qkv: torch.Tensor, B: int, T: int, H: int, hd: int, scale: float | None = None,
               out: torch.Tensor | None = None) -> torch.Tensor:
     """qkv bf16 [B*T, 3*H*hd] -> bf16 [B*T, H*hd]."""
@@ -241,6 +274,7 @@ def attention(qkv: torch.Tensor, B: int, T: int, H: int, hd: int, scale: float |
     return out
 
 
+@_on_tensor_device
 def probe_attention(q: torch.Tensor, kv: torch.Tensor, B: int, T: int, H: int, hd: int) -> torch.Tensor:
     """q fp32 [H*hd] (pre-scaled), kv bf16 [B*T, 2*H*hd] -> bf16 [B, H*hd]."""
     _need_cuda(q, kv)
@@ -252,6 +286,7 @@ def probe_attention(q: torch.Tensor, kv: torch.Tensor, B: int, T: int, H: int, h
     return out
 
 
+@_on_tensor_device
 def siglip_forward(pack: SiglipPack, patches: torch.Tensor, workspace: torch.Tensor | None = None,
                    return_tokens: bool = False):
     """bf16 patches [B*T, patch_ld] -> pooled bf16 [B, D] (and post-LN tokens [B*T, D] if asked)."""
@@ -271,6 +306,7 @@ def siglip_forward(pack: SiglipPack, patches: torch.Tensor, workspace: torch.Ten
     return (pooled, tokens) if return_tokens else pooled
 
 
+@_on_tensor_device
 def project(pp: ProjectorPack, x: torch.Tensor, out_dtype: torch.dtype = torch.float32,
             hidden: torch.Tensor | None = None, out: torch.Tensor | None = None) -> torch.Tensor:
     """MultiModalProjector: bf16 [M, enc] -> [M, llm] (fp32 like the reference, or bf16 for the index)."""
@@ -294,6 +330,7 @@ def project(pp: ProjectorPack, x: torch.Tensor, out_dtype: torch.dtype = torch.f
 TOPK_AUTO, TOPK_SCAN, TOPK_TENSOR = 0, 1, 2
 
 
+@_on_tensor_device
 def row_inv_norm(rows: torch.Tensor, eps: float = 1e-12, out: torch.Tensor | None = None) -> torch.Tensor:
     """1 / max(|row|, eps) of bf16 rows [N,D] -> fp32 [N] (cache it next to an index that does not change)."""
     _need_cuda(rows, out)
@@ -307,14 +344,28 @@ def row_inv_norm(rows: torch.Tensor, eps: float = 1e-12, out: torch.Tensor | Non
     return out
 
 
+@_on_tensor_device
 def topk_cosine(index: torch.Tensor, queries: torch.Tensor, k: int, eps: float = 1e-12,
                 row_lo: torch.Tensor | None = None, row_hi: torch.Tensor | None = None,
                 span: tuple[int, int] | None = None, mode: int = TOPK_AUTO, inv_norm: torch.Tensor | None = None):
-    """index bf16 [N,D], queries bf16 [Q,D] -> (scores fp32 [Q,k], idx int32 [Q,k]), score desc / idx asc.
+    """index bf16 [N,D], queries bf16 [Q,D] (or both fp32) -> (scores fp32 [Q,k], idx int32 [Q,k]), score desc / idx asc.
     row_lo / row_hi (int32 [Q], device): query q only ranks rows [row_lo[q], row_hi[q]); `span` = (min lo, max hi),
     the only rows that are scored (computed here from the tensors if omitted — one host sync).  Slots beyond the
     number of eligible rows hold idx -1 / score -inf.  inv_norm: cached `row_inv_norm(index)` (TENSOR path)."""
     _need_cuda(index, queries, row_lo, row_hi, inv_norm)
+    if index.dtype == torch.float32 and queries.dtype == torch.float32:
+        # fp32 rows stay fp32 (reference: `.float()` before F.cosine_similarity); scan path, whole index only
+        if row_lo is not None or not index.is_contiguous() or not queries.is_contiguous():
+            raise RuntimeError("topk_cosine: the fp32 path takes contiguous tensors and no row ranges")
+        N, D = index.shape
+        Q = queries.shape[0]
+        scratch = torch.empty((int(_lib.lib().gvl_topk_scratch_floats(N, Q)),), dtype=torch.float32, device=index.device)
+        scores = torch.empty((Q, k), dtype=torch.float32, device=index.device)
+        idx = torch.empty((Q, k), dtype=torch.int32, device=index.device)
+        _lib.check(_lib.lib().gvl_topk_cosine_f32(index.data_ptr(), N, D, queries.data_ptr(), Q, k, float(eps),
+                                                  scratch.data_ptr(), scores.data_ptr(), idx.data_ptr(), _stream()),
+                   "gvl_topk_cosine_f32")
+        return scores, idx
     if index.dtype != torch.bfloat16 or queries.dtype != torch.bfloat16 or not index.is_contiguous() or not queries.is_contiguous():
         raise RuntimeError("topk_cosine: index and queries must be contiguous bf16")
     N, D = index.shape

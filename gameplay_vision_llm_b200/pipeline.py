@@ -15,7 +15,7 @@ import numpy as np
 import torch
 
 from . import ops
-from .weights import ProjectorPack, SiglipPack, SiglipVisionSpec
+from .weights import ProjectorPack, SiglipPack, SiglipVisionSpec, resolve_device
 
 
 def shard_range(n_items: int, rank: int, world: int, align: int = 1) -> tuple[int, int]:
@@ -29,14 +29,12 @@ def shard_range(n_items: int, rank: int, world: int, align: int = 1) -> tuple[in
 
 class EmbeddingPipeline:
     def __init__(self, siglip_sd: dict, projector_sd: dict, spec: SiglipVisionSpec | None = None,
-                 device: str | torch.device = "cuda:0", batch: int = 64, resample: int = ops.BILINEAR,
+                 device: str | torch.device = "cuda", batch: int = 64, resample: int = ops.BILINEAR,
                  image_mean=(0.5, 0.5, 0.5), image_std=(0.5, 0.5, 0.5), fold_ln: bool = True):
         """fold_ln: run the tower with every token-level LayerNorm folded into the GEMM that consumes it
         (weights.SiglipPack); the 56 LayerNorm launches per batch disappear.  False keeps the reference's op order."""
         self.spec = spec or SiglipVisionSpec.so400m()
-        self.device = torch.device(device)
-        if self.device.type != "cuda":
-            raise RuntimeError("EmbeddingPipeline needs a CUDA device: this path has no CPU fallback")
+        self.device = resolve_device(device)  # raises off-CUDA: this path has no CPU fallback
         self.batch = int(batch)
         self.resample = resample
         self.image_mean, self.image_std = tuple(image_mean), tuple(image_std)
@@ -77,23 +75,31 @@ class EmbeddingPipeline:
 
     # ---- host frames streamed through pinned memory -----------------------------------------------
     def embed_stream(self, host_batches: Iterable[torch.Tensor], index: torch.Tensor,
-                     host_out: torch.Tensor | None = None) -> int:
+                     host_out: torch.Tensor | None = None, pooled_out: torch.Tensor | None = None,
+                     host_pooled: torch.Tensor | None = None) -> int:
         """The call a user makes with decoded frames in host memory.
 
         host_batches yields pinned uint8 [b,H,W,3] tensors (b <= batch) in timeline order; rows of `index`
-        (bf16 [>=N, llm], device) are filled in order; if `host_out` (pinned bf16 [>=N, llm]) is given, every
-        batch's result is also copied device->host asynchronously.  H2D copies run on a side stream and
-        overlap the previous batch's compute (two device frame buffers).  Returns the number of frames; the
-        caller synchronises (e.g. `torch.cuda.current_stream().synchronize()`).
+        (bf16 [>=N, llm], device) are filled in order.  `pooled_out` (bf16 [>=N, hidden], device) also keeps the
+        1152-d SigLIP vectors — what the reference caches (scripts/extract_features.py:597-603, 1447-1468) — so ONE
+        pass yields both the timeline index and the cache files.  `host_out` / `host_pooled` (pinned bf16 [>=N, llm] /
+        [>=N, hidden]) receive asynchronous device->host copies of each batch's rows.  H2D copies run on one side
+        stream and overlap the previous batch's compute (two device frame buffers); D2H copies run on a second side
+        stream behind an event, so neither direction ever sits on the compute stream.  Returns the number of frames;
+        the compute stream is made to wait for the last D2H, so the caller only synchronises its current stream.
         """
         compute = torch.cuda.current_stream(self.device)
         recycle = getattr(host_batches, "recycle", None)  # e.g. frame_ingest.FrameFeed: pinned ring buffers
         if not hasattr(self, "_copy_stream"):
             self._copy_stream = torch.cuda.Stream(self.device)
+            self._d2h_stream = torch.cuda.Stream(self.device)
             self._dev_frames = [None, None]
             self._copied = [torch.cuda.Event(), torch.cuda.Event()]
             self._consumed = [torch.cuda.Event(), torch.cuda.Event()]
+        if host_pooled is not None and pooled_out is None:
+            pooled_out = torch.empty((index.shape[0], self.spec.hidden), dtype=torch.bfloat16, device=self.device)
         done = 0
+        d2h_used = False
         for step, hb in enumerate(host_batches):
             slot = step & 1
             b = hb.shape[0]
@@ -113,29 +119,59 @@ class EmbeddingPipeline:
                     done_ev.record(self._copy_stream)
                     recycle(hb, done_ev)
             compute.wait_event(self._copied[slot])
-            _, proj = self.embed(buf[:b], out_index=index[done:done + b])
+            pooled, _ = self.embed(buf[:b], out_index=index[done:done + b])
+            if pooled_out is not None:  # `pooled` is a fresh allocation of the compute stream: park it before the D2H
+                pooled_out[done:done + b].copy_(pooled, non_blocking=True)
             self._consumed[slot].record(compute)
-            if host_out is not None:
-                host_out[done:done + b].copy_(proj, non_blocking=True)
+            if host_out is not None or host_pooled is not None:
+                d2h_used = True
+                with torch.cuda.stream(self._d2h_stream):
+                    self._d2h_stream.wait_event(self._consumed[slot])
+                    if host_out is not None:
+                        host_out[done:done + b].copy_(index[done:done + b], non_blocking=True)
+                    if host_pooled is not None:
+                        host_pooled[done:done + b].copy_(pooled_out[done:done + b], non_blocking=True)
             done += b
+        if d2h_used:
+            compute.wait_stream(self._d2h_stream)
         return done
-
 
     # ---- a video file: decode -> pinned ring -> device, overlapped -------------------------------------
     def embed_video(self, video_path: str, fps: float = 1.0, index: torch.Tensor | None = None,
-                    host_out: torch.Tensor | None = None):
+                    host_out: torch.Tensor | None = None, return_pooled: bool = False):
         """Replaces `extract_frames` + `run_siglip_encoder` (scripts/extract_features.py:230-264, 590-607) for one
         video: frames are sampled with the reference's rule (every int(video_fps / fps)-th frame, timestamp =
         idx / video_fps), decoded on a background thread into pinned batches and embedded while the next batch
-        decodes.  Returns (timestamps float64 [n], projected index bf16 [n, llm] on the device)."""
+        decodes.  Returns (timestamps float64 [n], projected index bf16 [n, llm] on the device) and, with
+        `return_pooled`, the 1152-d SigLIP rows bf16 [n, hidden] the reference's cache files hold."""
         from .frame_ingest import FrameFeed
         feed = FrameFeed(video_path, fps=fps, batch=self.batch, auto_release=False)
         n_plan = len(feed.timestamps)
         if index is None:
             index = torch.empty((n_plan, self.llm_dim), dtype=torch.bfloat16, device=self.device)
-        n = self.embed_stream(feed, index, host_out)
-        torch.cuda.current_stream(self.device).synchronize()
+        pooled = torch.empty((n_plan, self.spec.hidden), dtype=torch.bfloat16, device=self.device) if return_pooled else None
+        with torch.cuda.device(self.device):
+            n = self.embed_stream(feed, index, host_out, pooled_out=pooled)
+            torch.cuda.current_stream(self.device).synchronize()
+        if return_pooled:
+            return feed.timestamps[:n], index[:n], pooled[:n]
         return feed.timestamps[:n], index[:n]
+
+    def write_caches(self, video_path: str, out_dir: str, fps: float = 1.0, perception_cache_dir: str | None = None):
+        """One pass over a video -> the reference's cache files: `{stem}_embeddings.pt` (C1,
+        scripts/extract_features.py:1431-1468) and, if asked, the `PerceptionCache` directory (C3,
+        benchmarks/perception_cache.py:203-283).  Returns (timestamps, index, pooled)."""
+        import os
+
+        from . import feature_cache as fc
+        ts, index, pooled = self.embed_video(video_path, fps=fps, return_pooled=True)
+        stem = os.path.splitext(os.path.basename(video_path))[0]
+        os.makedirs(out_dir, exist_ok=True)
+        fc.write_embeddings_pt(os.path.join(out_dir, f"{stem}_embeddings.pt"), fc.siglip_embedding_records(ts, pooled))
+        if perception_cache_dir is not None:
+            fc.write_perception_npz(perception_cache_dir, video_path, siglip=pooled, timestamps=np.asarray(ts),
+                                    video_duration_sec=float(ts[-1]) if len(ts) else 0.0, perception_config={"fps": fps})
+        return ts, index, pooled
 
 
 def pinned_batches(frames: np.ndarray | torch.Tensor, batch: int) -> Iterator[torch.Tensor]:

@@ -67,6 +67,7 @@ class NaFlexConfig:
     image_std: tuple = (0.5, 0.5, 0.5)
     synthetic_seed: Optional[int] = None  # random-init weights in the HF layout (no network here)
     state_dict: Optional[dict] = None  # an already loaded HF state_dict (vision_model.* keys)
+    num_attention_heads: Optional[int] = None  # only needed for a bare state dict of an unpublished tower width
 
 
 class BatchFeature(dict):
@@ -175,6 +176,25 @@ def _load_state_dict(model_name: str) -> dict:
     return torch.load(path, map_location="cpu", weights_only=True)
 
 
+def _load_checkpoint_configs(model_name: str) -> tuple[Optional[dict], Optional[dict]]:
+    """(vision config, preprocessor config) from `config.json` / `preprocessor_config.json` beside a local
+    checkpoint — what `AutoModel` / `AutoProcessor.from_pretrained` would read (reference :184-204)."""
+    import json
+    d = model_name if os.path.isdir(model_name) else os.path.dirname(model_name)
+    out = []
+    for name in ("config.json", "preprocessor_config.json"):
+        f = os.path.join(d, name)
+        cfg = None
+        if d and os.path.isfile(f):
+            with open(f) as fh:
+                cfg = json.load(fh)
+        out.append(cfg)
+    vision = out[0]
+    if vision is not None and "vision_config" in vision:
+        vision = vision["vision_config"]
+    return vision, out[1]
+
+
 class SigLIPEncoder:
     """Lazy loader with the reference's attribute seam (`_model`, `_processor`, `_load_model`)."""
 
@@ -187,21 +207,30 @@ class SigLIPEncoder:
         if self._model is not None:
             return
         cfg = self.config
-        device = torch.device(cfg.device if cfg.device != "cuda" else "cuda:0")
-        if device.type != "cuda":
-            raise RuntimeError("SigLIPEncoder runs on a CUDA (sm_100a) device only; there is no CPU fallback")
+        device = ops.resolve_device(cfg.device)
+        vision_cfg = pre_cfg = None
         if cfg.state_dict is not None:
             sd = cfg.state_dict
         elif cfg.synthetic_seed is not None:
             sd = None
         else:
             sd = _load_state_dict(cfg.model_name)
-        spec = SiglipVisionSpec.so400m() if sd is None else spec_from_state_dict(sd, cfg.base_resolution)
+            vision_cfg, pre_cfg = _load_checkpoint_configs(cfg.model_name)
+        heads = cfg.num_attention_heads or (vision_cfg or {}).get("num_attention_heads")
+        spec = SiglipVisionSpec.so400m() if sd is None else spec_from_state_dict(
+            sd, cfg.base_resolution, heads=heads, eps=(vision_cfg or {}).get("layer_norm_eps"))
         if sd is None:
             sd = synth_siglip_state_dict(spec, cfg.synthetic_seed)
+        resample, mean, std = cfg.resample, cfg.image_mean, cfg.image_std
+        if pre_cfg is not None:  # the checkpoint's own preprocessing constants win over the dataclass defaults
+            resample = int(pre_cfg.get("resample", resample))
+            mean = tuple(pre_cfg.get("image_mean", mean))
+            std = tuple(pre_cfg.get("image_std", std))
+            self.config.resample, self.config.image_mean, self.config.image_std = resample, mean, std
         logger.info("Loading SigLIP encoder: %s (%d layers, hidden %d)", cfg.model_name, spec.layers, spec.hidden)
-        self._model = GvlSiglipModel(SiglipPack(sd, spec, device))
-        self._processor = GvlSiglipProcessor(spec.image, cfg.resample, cfg.image_mean, cfg.image_std, device)
+        with torch.cuda.device(device):
+            self._model = GvlSiglipModel(SiglipPack(sd, spec, device))
+        self._processor = GvlSiglipProcessor(spec.image, resample, mean, std, device)
 
     def forward(self, pixel_values: torch.Tensor):
         """(sequence_output, pooled_output) like the reference's `SigLIPEncoder.forward` (:246-289)."""
@@ -214,7 +243,16 @@ class SigLIPEncoder:
     __call__ = forward
 
 
-def spec_from_state_dict(sd: dict, image: int = 384) -> SiglipVisionSpec:
+# attention heads of the published SigLIP / SigLIP2 vision towers by width (a state dict does not carry the count)
+_KNOWN_HEADS = {768: 12, 1024: 16, 1152: 16}
+
+
+def spec_from_state_dict(sd: dict, image: int = 384, heads: Optional[int] = None,
+                         eps: Optional[float] = None) -> SiglipVisionSpec:
+    """Tower geometry from the HF tensor shapes.  The head count is not recoverable from shapes: it comes from the
+    checkpoint's config.json (`heads`), else from the table of published towers, else from the one supported head
+    dim (64 / 72) that divides the width; a width both divide (e.g. 576) raises — guessing would silently change the
+    arithmetic."""
     pre = "vision_model." if any(k.startswith("vision_model.") for k in sd) else ""
     w = sd[pre + "embeddings.patch_embedding.weight"]
     hidden, patch = w.shape[0], w.shape[-1]
@@ -222,10 +260,22 @@ def spec_from_state_dict(sd: dict, image: int = 384) -> SiglipVisionSpec:
     grid = int(round(tokens ** 0.5))
     layers = 1 + max(int(k[len(pre):].split(".")[2]) for k in sd if k.startswith(pre + "encoder.layers."))
     inter = sd[pre + "encoder.layers.0.mlp.fc1.weight"].shape[0]
-    # so400m: 1152 / 16 heads = 72; other SigLIP towers use head dim 64
-    heads = hidden // 72 if hidden % 72 == 0 else hidden // 64
+    if heads is None:
+        heads = _KNOWN_HEADS.get(hidden)
+    if heads is None:
+        # the attention kernel supports head dims 64 and 72 only: a width only one of them divides is unambiguous
+        fits = [hd for hd in (64, 72) if hidden % hd == 0]
+        if len(fits) == 1:
+            heads = hidden // fits[0]
+    if heads is None:
+        raise RuntimeError(f"cannot infer the attention head count of a {hidden}-wide tower from its state dict: pass "
+                           "NaFlexConfig.num_attention_heads or keep config.json beside the checkpoint")
+    if hidden % heads or hidden // heads not in (64, 72):
+        raise RuntimeError(f"head dim {hidden / heads:g} is not supported by the attention kernel (64 and 72 are)")
     img = image if image // patch == grid else grid * patch
-    return SiglipVisionSpec(hidden=hidden, intermediate=inter, layers=layers, heads=heads, image=img, patch=patch)
+    kw = {} if eps is None else {"eps": float(eps)}
+    return SiglipVisionSpec(hidden=hidden, intermediate=inter, layers=layers, heads=int(heads), image=img, patch=patch,
+                            **kw)
 
 
 class SigLIPSemanticEncoder:
@@ -273,9 +323,16 @@ class SigLIPSemanticEncoder:
             "scripts/extract_features.py and fails in the reference with the fixed 729-position checkpoint")
 
     # ---- similarity (reference :604-638) ------------------------------------------------------------
+    @staticmethod
+    def _sim_dtype(*tensors: torch.Tensor) -> torch.dtype:
+        """bf16 when every side already is bf16 (what encode_image returns: the cast to fp32 is exact either way),
+        fp32 otherwise — the reference computes on `.float()` copies, so wider inputs are never narrowed."""
+        return torch.bfloat16 if all(t.dtype == torch.bfloat16 for t in tensors) else torch.float32
+
     def compute_similarity(self, emb1: SemanticEmbedding, emb2: SemanticEmbedding) -> float:
-        e1 = emb1.embedding.to(self._sim_device(emb1.embedding)).to(torch.bfloat16).reshape(1, -1).contiguous()
-        e2 = emb2.embedding.to(e1.device).to(torch.bfloat16).reshape(1, -1).contiguous()
+        dt = self._sim_dtype(emb1.embedding, emb2.embedding)
+        e1 = emb1.embedding.to(self._sim_device(emb1.embedding)).to(dt).reshape(1, -1).contiguous()
+        e2 = emb2.embedding.to(e1.device).to(dt).reshape(1, -1).contiguous()
         scores, _ = ops.topk_cosine(e2, e1, 1, eps=1e-8)
         return float(scores.item())
 
@@ -285,26 +342,20 @@ class SigLIPSemanticEncoder:
         (the reference's stable `list.sort(reverse=True)`, :637)."""
         if not candidates:
             return []
-        dev = self._sim_device(query.embedding)
-        index = torch.stack([c.embedding.to(dev).to(torch.bfloat16).reshape(-1) for c in candidates]).contiguous()
-        q = query.embedding.to(dev).to(torch.bfloat16).reshape(1, -1).contiguous()
-        out = []
         k_total = min(top_k, len(candidates))
-        # the selection kernel returns up to 64 per call
-        scores, idx = ops.topk_cosine(index, q, min(k_total, 64), eps=1e-8)
-        for s, i in zip(scores[0].tolist(), idx[0].tolist()):
-            out.append((candidates[i], float(s)))
         if k_total > 64:
             raise RuntimeError("find_similar_regions: top_k > 64 is not supported by the selection kernel")
-        return out
+        dev = self._sim_device(query.embedding)
+        dt = self._sim_dtype(query.embedding, *(c.embedding for c in candidates))
+        index = torch.stack([c.embedding.to(dev).to(dt).reshape(-1) for c in candidates]).contiguous()
+        q = query.embedding.to(dev).to(dt).reshape(1, -1).contiguous()
+        scores, idx = ops.topk_cosine(index, q, k_total, eps=1e-8)
+        return [(candidates[i], float(s)) for s, i in zip(scores[0].tolist(), idx[0].tolist())]
 
     def _sim_device(self, t: torch.Tensor) -> torch.device:
         if t.is_cuda:
             return t.device
-        d = torch.device(self.config.device if self.config.device != "cuda" else "cuda:0")
-        if d.type != "cuda":
-            raise RuntimeError("similarity search runs on the GPU only (no CPU fallback)")
-        return d
+        return ops.resolve_device(self.config.device)
 
 
 def create_siglip_encoder(model_name: str = "google/siglip2-so400m-patch14-384", device: str = "cuda",

@@ -16,13 +16,16 @@ import torch
 
 from . import ops
 from .pipeline import shard_range
+from .weights import resolve_device
 
 
 class TimelineEmbeddingIndex:
-    def __init__(self, n_items: int, dim: int = 4096, fps: float = 1.0, device: str | torch.device = "cuda:0",
+    def __init__(self, n_items: int, dim: int = 4096, fps: float = 1.0, device: str | torch.device = "cuda",
                  rank: int = 0, world: int = 1, timestamps: Optional[np.ndarray] = None):
         self.n, self.dim, self.rank, self.world = int(n_items), int(dim), int(rank), int(world)
         self.device = torch.device(device)
+        if self.device.type == "cuda":  # a CPU index exists only to assemble shards in the gloo tests; search needs CUDA
+            self.device = resolve_device(self.device)
         self.per_rank = -(-self.n // self.world)
         self.lo, self.hi = shard_range(self.n, self.rank, self.world)
         # padded so every rank contributes per_rank rows to the gather
@@ -33,8 +36,14 @@ class TimelineEmbeddingIndex:
         self._inv_norm = None  # 1/|e_n| of the gathered index (cosine top-k, tensor path)
 
     def local_rows(self) -> torch.Tensor:
-        """This rank's slice of the index (rows [lo, hi)), to be filled by EmbeddingPipeline.embed(out_index=...)."""
+        """This rank's slice of the index (rows [lo, hi)), to be filled by EmbeddingPipeline.embed(out_index=...).
+        Handing out a writable view invalidates the cached 1/|e_n| (streaming use: rows appended between searches)."""
+        self._inv_norm = None
         return self.embeddings[self.lo:self.hi]
+
+    def mark_dirty(self) -> None:
+        """Call after writing rows through a view obtained earlier: the next search recomputes the cached norms."""
+        self._inv_norm = None
 
     def all_gather(self) -> torch.Tensor:
         """One in-place all-gather of the (per_rank, dim) bf16 shards; afterwards every rank holds rows [0, n)."""
@@ -47,6 +56,7 @@ class TimelineEmbeddingIndex:
         return self.embeddings[: self.n]
 
     def index(self) -> torch.Tensor:
+        """Rows [0, n) — a view; callers that WRITE through it must call mark_dirty() before the next search."""
         return self.embeddings[: self.n]
 
     # ---- time filters: the index is in timestamp order, so a window is a contiguous row range ----------------
@@ -77,6 +87,8 @@ class TimelineEmbeddingIndex:
         in the window hold index -1."""
         if not self.gathered:
             raise RuntimeError("index is sharded: call all_gather() first")
+        if not 1 <= int(top_k) <= 64:
+            raise RuntimeError(f"search: top_k={top_k} out of range [1, 64] (the selection kernel's limit)")
         if self.n == 0 or queries.numel() == 0:
             # an empty timeline (or no query) has no neighbours: the reference returns [] here
             # (src/agent_core/qwen_reasoning_core.py:1508-1511), no device call is made

@@ -2,8 +2,10 @@
 (scripts/extract_features.py:335-403; twin: scripts/realtime_inference.py:339-381).
 
 Same contract: frames are taken 16 at a time (non-overlapping, the tail clip padded by repeating its last
-frame), each clip goes through `VideoMAEImageProcessor` (shortest-edge-224 uint8 resize, center crop 224,
-(x/255 - 0.5)/0.5) and `VideoMAEModel`, the 1568 token states are averaged, and the result is a dict with one
+frame; the realtime twin takes windows of 16 with stride 8 and drops the tail), each clip goes through
+`VideoMAEImageProcessor` (shortest-edge-224 uint8 resize, center crop 224, (x/255 - mean)/std with the
+checkpoint's `preprocessor_config.json` constants — ImageNet mean / std for MCG-NJU/videomae-base; the class
+default 0.5 / 0.5 only applies to a config without values) and `VideoMAEModel`, the 1568 token states are averaged, and the result is a dict with one
 `{"start_time", "end_time", "embedding" (768,) fp32 on the CPU, "source_frame_count"}` entry per clip.  Here
 the frames are a uint8 `(N, H, W, 3)` tensor (host or device), clips are batched, and every step is a kernel of
 libgvl_sm100a.so: gvl_preprocess_u8_crop -> gvl_patchify_tubelet_bf16 -> gvl_videomae_forward (the SigLIP
@@ -14,8 +16,11 @@ from __future__ import annotations
 
 import torch
 
+import json
+import os
+
 from . import ops
-from .weights import ProjectorPack, VideoMAEPack, VideoMAESpec
+from .weights import ProjectorPack, VideoMAEPack, VideoMAESpec, resolve_device
 
 
 def resize_geometry(H: int, W: int, shortest_edge: int = 224, crop: int = 224):
@@ -27,16 +32,58 @@ def resize_geometry(H: int, W: int, shortest_edge: int = 224, crop: int = 224):
     return out_h, out_w, int(round((out_h - crop) / 2.0)), int(round((out_w - crop) / 2.0))
 
 
+# preprocessor_config.json of MCG-NJU/videomae-base (the checkpoint both reference routes load): ImageNet statistics
+IMAGENET_MEAN, IMAGENET_STD = (0.485, 0.456, 0.406), (0.229, 0.224, 0.225)
+
+
+def clip_windows(n_frames: int, clip: int = 16, stride: int | None = None, drop_tail: bool = False) -> list[tuple[int, int]]:
+    """[start, end) frame ranges of the clips of an n-frame video.
+
+    stride None / == clip, drop_tail False: `run_videomae_encoder` (scripts/extract_features.py:355-365) —
+    non-overlapping clips, the last one short (the caller pads it by repeating its last frame).
+    stride 8, drop_tail True: `extract_videomae_embeddings` (scripts/realtime_inference.py:352-355) —
+    `range(0, n - clip + 1, clip // 2)`, windows that do not fit are dropped."""
+    stride = clip if stride is None else int(stride)
+    if drop_tail:
+        return [(i, i + clip) for i in range(0, n_frames - clip + 1, stride)]
+    return [(i, min(i + clip, n_frames)) for i in range(0, n_frames, stride)]
+
+
 class VideoMAEClipEncoder:
     """Batched clip encoder over device-resident weights (an HF `VideoMAEModel.state_dict()` or synthetic)."""
 
+    @classmethod
+    def from_checkpoint(cls, path: str, device: str | torch.device = "cuda", **kwargs) -> "VideoMAEClipEncoder":
+        """A local HF checkpoint directory (`VideoMAEModel.from_pretrained` + `VideoMAEImageProcessor.from_pretrained`,
+        scripts/extract_features.py:348-350): weights from model.safetensors / pytorch_model.bin, geometry from
+        config.json, mean / std / resample from preprocessor_config.json."""
+        from .siglip_semantic_encoder import _load_state_dict
+        sd = _load_state_dict(path)
+        d = path if os.path.isdir(path) else os.path.dirname(path)
+        spec_kw, pre_kw = {}, {}
+        cfg_file, pre_file = os.path.join(d, "config.json"), os.path.join(d, "preprocessor_config.json")
+        if os.path.isfile(cfg_file):
+            with open(cfg_file) as f:
+                c = json.load(f)
+            names = {"hidden_size": "hidden", "intermediate_size": "intermediate", "num_hidden_layers": "layers",
+                     "num_attention_heads": "heads", "image_size": "image", "patch_size": "patch", "num_frames": "frames",
+                     "tubelet_size": "tubelet", "layer_norm_eps": "eps", "hidden_act": "act"}
+            spec_kw = {ours: c[theirs] for theirs, ours in names.items() if theirs in c}
+            if "use_mean_pooling" in c:
+                spec_kw["final_norm"] = not c["use_mean_pooling"]
+        if os.path.isfile(pre_file):
+            with open(pre_file) as f:
+                pc = json.load(f)
+            pre_kw = {ours: pc[theirs] for theirs, ours in (("image_mean", "image_mean"), ("image_std", "image_std"),
+                                                             ("resample", "resample")) if theirs in pc}
+        pre_kw.update(kwargs)
+        return cls(sd, VideoMAESpec(**spec_kw), device, **pre_kw)
+
     def __init__(self, state_dict: dict, spec: VideoMAESpec | None = None, device: str | torch.device = "cuda",
-                 image_mean=(0.5, 0.5, 0.5), image_std=(0.5, 0.5, 0.5), resample: int = ops.BILINEAR,
+                 image_mean=IMAGENET_MEAN, image_std=IMAGENET_STD, resample: int = ops.BILINEAR,
                  clips_per_batch: int = 32):
         self.spec = spec or VideoMAESpec.base()
-        self.device = torch.device(device)
-        if self.device.type != "cuda":
-            raise RuntimeError("VideoMAEClipEncoder runs on a CUDA device only (no CPU fallback)")
+        self.device = resolve_device(device)  # raises off-CUDA (no CPU fallback)
         self.pack = VideoMAEPack(state_dict, self.spec, self.device)
         self.image_mean, self.image_std, self.resample = tuple(image_mean), tuple(image_std), resample
         self.clips_per_batch = int(clips_per_batch)
@@ -91,3 +138,23 @@ class VideoMAEClipEncoder:
                 embeddings.append(item)
         return {"num_input_frames": n, "num_embeddings": len(embeddings), "embeddings": embeddings,
                 "embedding_dim": s.hidden}
+
+    def run_realtime(self, frames: torch.Tensor, timestamps) -> list[dict]:
+        """Mirror of `extract_videomae_embeddings(frames)` (scripts/realtime_inference.py:339-381): windows of 16
+        frames with stride 8, windows that do not fit are dropped, one `{"timestamp": ts of the window's middle frame,
+        "embedding": (768,) fp32 on the CPU}` per window.  Every frame is resized / normalized once although it
+        belongs to two windows; the windows are then gathered on the device."""
+        s = self.spec
+        n = int(frames.shape[0])
+        windows = clip_windows(n, s.frames, s.frames // 2, drop_tail=True)
+        out: list[dict] = []
+        for w0 in range(0, len(windows), self.clips_per_batch):
+            batch = windows[w0:w0 + self.clips_per_batch]
+            f0, f1 = batch[0][0], batch[-1][1]
+            pv = self.preprocess(frames[f0:f1].to(self.device, non_blocking=True).contiguous())
+            gather = torch.tensor([i - f0 for a, b in batch for i in range(a, b)], dtype=torch.long, device=self.device)
+            patches = ops.patchify_tubelet(pv.index_select(0, gather), s.frames, s.patch, s.tubelet)
+            emb = ops.videomae_forward(self.pack, patches, self._workspace(len(batch)), out_dtype=torch.float32).cpu()
+            for c, (a, _) in enumerate(batch):
+                out.append({"timestamp": float(timestamps[a + s.frames // 2]), "embedding": emb[c]})
+        return out

@@ -21,6 +21,15 @@ import torch
 from . import _lib
 
 
+def resolve_device(device) -> torch.device:
+    """'cuda' -> the process's CURRENT device (what the reference's `device="cuda"` means under torchrun with
+    `set_device(local_rank)`), 'cuda:N' -> itself; anything else raises (no CPU fallback)."""
+    d = torch.device(device)
+    if d.type != "cuda":
+        raise RuntimeError(f"this path runs on a CUDA (sm_100a) device only, got '{device}': there is no CPU fallback")
+    return d if d.index is not None else torch.device("cuda", torch.cuda.current_device())
+
+
 @dataclass(frozen=True)
 class SiglipVisionSpec:
     hidden: int = 1152
@@ -158,7 +167,7 @@ class SiglipPack:
         +18 us (qkv), +20 us (fc1), +6 / +9 us (the two producers) per layer against 2 x 44 us of LayerNorm kernels.
         EmbeddingPipeline turns it on; the default here keeps the reference's op order."""
         self.spec = spec
-        self.device = torch.device(device)
+        self.device = resolve_device(device)
         self._keep: list[torch.Tensor] = []
         D, I, T = spec.hidden, spec.intermediate, spec.tokens
         vm = "vision_model." if any(k.startswith("vision_model.") for k in sd) else ""
@@ -256,7 +265,7 @@ class ProjectorPack:
     """Device-resident bf16 projector (Linear - GELU(erf) - Linear) weights."""
 
     def __init__(self, sd: dict[str, torch.Tensor], device: torch.device | str):
-        dev = torch.device(device)
+        dev = self.device = resolve_device(device)
         self.w1 = sd["net.0.weight"].detach().to(torch.bfloat16).contiguous().to(dev)
         self.b1 = sd["net.0.bias"].detach().to(torch.float32).contiguous().to(dev)
         self.w2 = sd["net.2.weight"].detach().to(torch.bfloat16).contiguous().to(dev)
@@ -368,7 +377,7 @@ class VideoMAEPack:
 
     def __init__(self, sd: dict[str, torch.Tensor], spec: VideoMAESpec, device: torch.device | str):
         self.spec = spec
-        self.device = torch.device(device)
+        self.device = resolve_device(device)
         self._keep: list[torch.Tensor] = []
         D, I = spec.hidden, spec.intermediate
         pre = "videomae." if any(k.startswith("videomae.") for k in sd) else ""

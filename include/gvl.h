@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define GVL_ABI_VERSION 4
+#define GVL_ABI_VERSION 5
 
 #if defined(__GNUC__)
 #define GVL_API __attribute__((visibility("default")))
@@ -174,7 +174,7 @@ GVL_API int gvl_layernorm_bf16(const void* x, int ldx, const float* gamma, const
 /* qkv: bf16 [B*T, 3*H*hd] (q | k | v, head-major inside each third); out: bf16 [B*T, H*hd].
  * softmax(q k^T * scale) v, non-causal, no mask, fp32 softmax.
  * Replaces SiglipAttention's SDPA call (HF:models/siglip/modeling_siglip.py:293-306; eager
- * definition :229-249).  hd % 8 == 0, hd <= 80. */
+ * definition :229-249).  hd = 64 or 72 (the two instantiations; anything else returns an error). */
 GVL_API int gvl_attention_bf16(const void* qkv, void* out, int B, int T, int H, int hd, float scale,
                        void* stream);
 
@@ -300,6 +300,12 @@ enum { GVL_TOPK_AUTO = 0, GVL_TOPK_SCAN = 1, GVL_TOPK_TENSOR = 2 };
 GVL_API int gvl_topk_cosine_ex(const void* index, int N, int D, const void* queries, int Q, int k, float eps,
                        const int32_t* row_lo, const int32_t* row_hi, int span_lo, int span_hi, int mode,
                        const float* inv_norm, float* scratch, float* out_scores, int32_t* out_idx, void* stream);
+/* gvl_topk_cosine for fp32 rows and queries (index: float [N, D], queries: float [Q, D], D % 4 == 0, scan path only):
+ * SigLIPSemanticEncoder.compute_similarity / find_similar_regions upcast both sides with .float() before
+ * F.cosine_similarity (src/perception/siglip_semantic_encoder.py:604-638), so fp32 embeddings (VideoMAE clip vectors,
+ * fp32 projections) must not be ranked through a bf16 cast. */
+GVL_API int gvl_topk_cosine_f32(const float* index, int N, int D, const float* queries, int Q, int k, float eps,
+                        float* scratch, float* out_scores, int32_t* out_idx, void* stream);
 /* inv_norm[n] = 1 / max(|rows[n]|, eps), rows bf16 [N, D]. */
 GVL_API int gvl_row_inv_norm(const void* rows, int N, int D, float eps, float* inv_norm, void* stream);
 

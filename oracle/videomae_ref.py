@@ -4,7 +4,8 @@ CPU fp32 restatement of the reference's VideoMAE clip route (scripts/extract_fea
 `VideoMAEImageProcessor(pil_frames)` -> `VideoMAEModel(**inputs).last_hidden_state.mean(dim=1)`.
 The arithmetic lives in HuggingFace transformers (5.5.0 installed here and restated):
   models/videomae/image_processing_videomae.py:35-105  shortest-edge resize (uint8, antialias) -> center crop ->
-                                                        fused rescale + normalize (mean = std = 0.5)
+                                                        fused rescale + normalize (class default mean = std = 0.5;
+                                                        MCG-NJU/videomae-base's preprocessor_config.json: ImageNet)
   models/videomae/modeling_videomae.py:80-91            fixed sinusoid position table
   :120-178 tubelet Conv3d patch embedding   :209-268 self-attention (q_bias / v_bias, key without bias)
   :335-385 pre-LN encoder layer (exact-erf GELU, eps 1e-12)   :407-475 optional final LayerNorm.
@@ -30,9 +31,13 @@ def resize_geometry(H: int, W: int, shortest_edge: int = 224, crop: int = 224):
     return out_h, out_w, int(round((out_h - crop) / 2.0)), int(round((out_w - crop) / 2.0))
 
 
+IMAGENET_MEAN, IMAGENET_STD = (0.485, 0.456, 0.406), (0.229, 0.224, 0.225)
+
+
 def pixel_values(frames_hwc: np.ndarray, shortest_edge: int = 224, crop: int = 224, resample: int = 2,
-                 image_mean=(0.5, 0.5, 0.5), image_std=(0.5, 0.5, 0.5)) -> np.ndarray:
-    """uint8 [N,H,W,3] -> float32 [N,3,crop,crop] == VideoMAEImageProcessor(frames).pixel_values[0]."""
+                 image_mean=IMAGENET_MEAN, image_std=IMAGENET_STD) -> np.ndarray:
+    """uint8 [N,H,W,3] -> float32 [N,3,crop,crop] == VideoMAEImageProcessor(frames).pixel_values[0] with the
+    constants of MCG-NJU/videomae-base's preprocessor_config.json (pass 0.5 / 0.5 for the class defaults)."""
     _, H, W, _ = frames_hwc.shape
     out_h, out_w, y0, x0 = resize_geometry(H, W, shortest_edge, crop)
     u8 = preprocess_ref.resize_u8(frames_hwc, out_h, out_w, resample)[:, :, y0:y0 + crop, x0:x0 + crop]

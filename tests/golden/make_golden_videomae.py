@@ -31,9 +31,16 @@ def hf_model(spec, sd):
     return m.float()
 
 
-def hf_processor(size):
+IMAGENET_MEAN, IMAGENET_STD = [0.485, 0.456, 0.406], [0.229, 0.224, 0.225]
+
+
+def hf_processor(size, checkpoint_constants=True):
+    """checkpoint_constants: the values of MCG-NJU/videomae-base's preprocessor_config.json (ImageNet mean / std,
+    resample 2) — what `VideoMAEImageProcessor.from_pretrained` builds in the reference; False = the class defaults
+    (0.5 / 0.5), which only apply to a config that carries no values."""
     from transformers import VideoMAEImageProcessor
-    return VideoMAEImageProcessor(size={"shortest_edge": size}, crop_size={"height": size, "width": size})
+    kw = {"image_mean": IMAGENET_MEAN, "image_std": IMAGENET_STD} if checkpoint_constants else {}
+    return VideoMAEImageProcessor(size={"shortest_edge": size}, crop_size={"height": size, "width": size}, resample=2, **kw)
 
 
 def main():
@@ -42,11 +49,15 @@ def main():
     out = {}
     # ---- preprocessing: the class-default processor on 1080p frames (224 x 398 resize, crop columns [87, 311)) ----
     frames = np.concatenate([synth.scene_frames_np(0, 2), synth.noise_frames(2, seed=1001).numpy()], 0)
-    pv = hf_processor(224)([Image.fromarray(f) for f in frames], return_tensors="pt")["pixel_values"][0].numpy()
+    pv = hf_processor(224, False)([Image.fromarray(f) for f in frames], return_tensors="pt")["pixel_values"][0].numpy()
     u8 = np.rint(pv * 127.5 + 127.5).astype(np.uint8)
     assert np.array_equal(((u8.astype(np.float32) - 127.5) / 127.5).astype(np.float32), pv)
     out["pre1080_sha"] = np.frombuffer(bytes.fromhex(hashlib.sha256(u8.tobytes()).hexdigest()), np.uint8)
     out["pre1080_rows"] = u8[:, :, ::28, :].copy()
+    # the same frames with the checkpoint's constants: fp32 pixel_values, full-tensor hash + sampled rows
+    pv = hf_processor(224)([Image.fromarray(f) for f in frames], return_tensors="pt")["pixel_values"][0].numpy()
+    out["pre1080_imagenet_sha"] = np.frombuffer(bytes.fromhex(hashlib.sha256(np.ascontiguousarray(pv).tobytes()).hexdigest()), np.uint8)
+    out["pre1080_imagenet_rows"] = pv[:, :, ::28, :].copy()
 
     # ---- tiny encoder: every seam from HF, frames small enough for a pure-CPU run ----
     spec = VideoMAESpec.tiny()
@@ -58,6 +69,15 @@ def main():
     pv = torch.cat([pv, pv2], 0)  # [2 clips, frames, 3, S, S]
     with torch.no_grad():
         o = m(pixel_values=pv, output_hidden_states=True)
+    # the use_mean_pooling=True variant (fine-tuned checkpoints): VideoMAEModel has no final LayerNorm
+    import dataclasses
+    spec_nf = dataclasses.replace(spec, final_norm=False)
+    sd_nf = synth_videomae_state_dict(spec_nf, seed=2)
+    assert "layernorm.weight" in sd and "layernorm.weight" not in sd_nf
+    with torch.no_grad():
+        o_nf = hf_model(spec_nf, sd_nf)(pixel_values=pv)
+    out.update(tiny_nofinal_last_hidden_state=o_nf.last_hidden_state.numpy(),
+               tiny_nofinal_pooled=o_nf.last_hidden_state.mean(dim=1).numpy())
     out.update(tiny_pixel_values=pv.numpy(), tiny_embeddings=o.hidden_states[0].numpy(),
                tiny_layer0=o.hidden_states[1].numpy(), tiny_last_hidden_state=o.last_hidden_state.numpy(),
                tiny_pooled=o.last_hidden_state.mean(dim=1).numpy())

@@ -25,7 +25,7 @@ def test_header_symbols_exported_and_bound():
     for n in names:
         assert hasattr(handle, n), f"{n} declared in include/gvl.h but not exported"
         assert n in _lib.SIGNATURES, f"{n} has no ctypes signature"
-    assert handle.gvl_abi_version() == 4
+    assert handle.gvl_abi_version() == _lib.ABI_VERSION == int(re.search(r"#define GVL_ABI_VERSION (\d+)", open(os.path.join(ROOT, "include", "gvl.h")).read()).group(1))
     assert isinstance(_lib.launch_count(), int)
 
 

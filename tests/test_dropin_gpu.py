@@ -137,3 +137,88 @@ def test_embed_video_matches_embedding_the_decoded_frames(tmp_path):
     want = pipe.embed_resident(torch.from_numpy(decoded).to(DEV))
     torch.cuda.synchronize()
     assert torch.equal(index, want)
+
+
+def test_one_streaming_pass_yields_index_and_reference_cache_files(tmp_path):
+    """the reference caches the 1152-d SigLIP vector (scripts/extract_features.py:597-603,
+    1447-1468), not the projection — `embed_stream` hands both out in one pass (pooled rows via the D2H side stream),
+    and `write_caches` turns a video into `{stem}_embeddings.pt` + the PerceptionCache directory."""
+    cv2 = pytest.importorskip("cv2")
+    from gameplay_vision_llm_b200 import feature_cache as fc
+    sd = synth_siglip_state_dict(SPEC, seed=0)
+    psd = synth_projector_state_dict(SPEC.hidden, 512, seed=1)
+    pipe = EmbeddingPipeline(sd, psd, SPEC, DEV, batch=4)
+    frames = synth.scene_frames_np(0, 10, 180, 320, frames_per_scene=5)
+    dev_frames = torch.from_numpy(frames).to(DEV)
+    want_pooled = torch.cat([pipe.embed(dev_frames[i:i + 4])[0].clone() for i in range(0, 10, 4)])
+    want_index = pipe.embed_resident(dev_frames).clone()
+    index = torch.zeros((10, 512), dtype=torch.bfloat16, device=DEV)
+    pooled = torch.zeros((10, SPEC.hidden), dtype=torch.bfloat16, device=DEV)
+    host_idx = torch.zeros((10, 512), dtype=torch.bfloat16).pin_memory()
+    host_pooled = torch.zeros((10, SPEC.hidden), dtype=torch.bfloat16).pin_memory()
+    n = pipe.embed_stream(pinned_batches(frames, 4), index, host_idx, pooled_out=pooled, host_pooled=host_pooled)
+    torch.cuda.current_stream().synchronize()  # the compute stream waits for the D2H side stream
+    assert n == 10 and torch.equal(index, want_index) and torch.equal(pooled, want_pooled)
+    assert torch.equal(host_idx, want_index.cpu()) and torch.equal(host_pooled, want_pooled.cpu())
+    # host_pooled alone (no device buffer passed) works too
+    host_pooled2 = torch.zeros_like(host_pooled)
+    pipe.embed_stream(pinned_batches(frames, 4), index, host_pooled=host_pooled2)
+    torch.cuda.current_stream().synchronize()
+    assert torch.equal(host_pooled2, want_pooled.cpu())
+    # a video file -> cache files in the reference's layouts
+    path = str(tmp_path / "clip.avi")
+    w = cv2.VideoWriter(path, cv2.VideoWriter_fourcc(*"MJPG"), 30.0, (320, 180))
+    for f in synth.scene_frames_np(0, 20, 180, 320, frames_per_scene=10):
+        w.write(cv2.cvtColor(f, cv2.COLOR_RGB2BGR))
+    w.release()
+    ts, idx2, pooled2 = pipe.write_caches(path, str(tmp_path / "out"), fps=10.0, perception_cache_dir=str(tmp_path / "pc"))
+    assert len(ts) == 7 and idx2.shape == (7, 512) and pooled2.shape == (7, SPEC.hidden)
+    data = torch.load(tmp_path / "out" / "clip_embeddings.pt", weights_only=False)
+    assert [e["timestamp"] for e in data["siglip"]] == ts.tolist()
+    assert torch.equal(torch.stack([e["embedding"] for e in data["siglip"]]), pooled2.cpu())
+    back = fc.load_perception_npz(str(tmp_path / "pc"), path)
+    assert np.array_equal(back["siglip_embeddings"], pooled2.float().cpu().numpy())
+    assert back["metadata"]["has_siglip"] and back["metadata"]["num_frames"] == 7
+
+
+def test_timeline_norm_cache_follows_appended_rows():
+    """rows written through `local_rows()` after a first search must be ranked with fresh 1/|e| values
+    (the streaming / realtime use) — tensor path, 4096+ rows so that AUTO picks it."""
+    g = torch.Generator().manual_seed(2)
+    n, d = 4200, 256
+    rows = (torch.randn(n, d, generator=g) * torch.rand(n, 1, generator=g) * 4).to(torch.bfloat16).to(DEV)
+    idx = TimelineEmbeddingIndex(n, d, device=DEV)
+    idx.local_rows()[: n // 2].copy_(rows[: n // 2])  # second half still zero
+    q = rows[n // 2 + 5: n // 2 + 21]                  # 16 queries that are NOT indexed yet
+    _, first = idx.search(q, top_k=4, mode=ops.TOPK_TENSOR)
+    assert (first[:, 0].cpu() != torch.arange(n // 2 + 5, n // 2 + 21)).all()
+    idx.local_rows()[n // 2:].copy_(rows[n // 2:])    # append; local_rows() drops the cached norms
+    _, second = idx.search(q, top_k=4, mode=ops.TOPK_TENSOR)
+    _, want, _ = siglip_ref.cosine_topk(rows.float().cpu().numpy(), q.float().cpu().numpy(), 4)
+    assert np.array_equal(second.cpu().numpy(), want)
+    with pytest.raises(RuntimeError, match="top_k"):
+        idx.search(q, top_k=65)
+
+
+def test_ops_bind_to_the_tensors_device():
+    """a pipeline on cuda:1 must launch on cuda:1 even when the process's current device is cuda:0
+    (weights, streams and TMA descriptors all follow the tensors).  Needs two GPUs; on one GPU the same code path is
+    exercised with the current device == the tensors' device, and a cross-device call must raise, not fault."""
+    sd = synth_siglip_state_dict(SPEC, seed=0)
+    psd = synth_projector_state_dict(SPEC.hidden, 512, seed=1)
+    frames = synth.scene_frames_np(0, 3, 180, 320)
+    pipe0 = EmbeddingPipeline(sd, psd, SPEC, "cuda:0", batch=4)
+    want = pipe0.embed_resident(torch.from_numpy(frames).to("cuda:0")).cpu()
+    assert EmbeddingPipeline(sd, psd, SPEC, "cuda", batch=4).device == torch.device("cuda", torch.cuda.current_device())
+    if torch.cuda.device_count() < 2:
+        pytest.skip("one GPU visible: the cuda:1 half needs --gpus 2")
+    assert torch.cuda.current_device() == 0
+    pipe1 = EmbeddingPipeline(sd, psd, SPEC, "cuda:1", batch=4)
+    got = pipe1.embed_resident(torch.from_numpy(frames).to("cuda:1"))
+    torch.cuda.synchronize("cuda:1")
+    assert got.device == torch.device("cuda:1") and torch.equal(got.cpu(), want) and torch.cuda.current_device() == 0
+    idx = TimelineEmbeddingIndex(3, 512, device="cuda:1")
+    idx.local_rows().copy_(got)
+    assert idx.search(got[1:2], top_k=1)[1].item() == 1
+    with pytest.raises(RuntimeError, match="different devices|weights on"):
+        pipe1.embed(torch.from_numpy(frames).to("cuda:0"))

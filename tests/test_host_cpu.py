@@ -175,3 +175,61 @@ def test_empty_timeline_and_empty_query_return_nothing_like_the_reference():
     idx2 = TimelineEmbeddingIndex(5, 16, device="cpu")
     s, i = idx2.search(torch.empty(0, 16), top_k=3)
     assert s.shape == (0, 3) and i.shape == (0, 3)
+
+
+def test_checkpoint_loader_safetensors_bin_and_configs(tmp_path):
+    """`_load_state_dict` / `_load_checkpoint_configs` / `spec_from_state_dict` on files laid out like an HF
+    `SiglipModel` checkpoint: `vision_model.*` keys next to text-tower keys, config.json with a nested
+    `vision_config`, preprocessor_config.json (reference: AutoModel / AutoProcessor.from_pretrained, :184-204)."""
+    import json
+
+    from safetensors.torch import save_file
+
+    from gameplay_vision_llm_b200.siglip_semantic_encoder import (_load_checkpoint_configs, _load_state_dict,
+                                                                  spec_from_state_dict)
+    from gameplay_vision_llm_b200.weights import SiglipVisionSpec, synth_siglip_state_dict
+    spec = SiglipVisionSpec.tiny()
+    sd = synth_siglip_state_dict(spec, seed=0)
+    assert all(k.startswith("vision_model.") for k in sd)
+    full = dict(sd)
+    full.update({"text_model.embeddings.token_embedding.weight": torch.zeros(8, 4), "logit_scale": torch.zeros(1),
+                 "logit_bias": torch.zeros(1), "text_model.encoder.layers.0.mlp.fc1.weight": torch.zeros(4, 4)})
+    d = tmp_path / "ckpt"
+    d.mkdir()
+    save_file({k: v.contiguous() for k, v in full.items()}, str(d / "model.safetensors"))
+    json.dump({"model_type": "siglip", "vision_config": {"num_attention_heads": spec.heads, "layer_norm_eps": 1e-6,
+                                                        "hidden_size": spec.hidden}, "text_config": {}},
+              open(d / "config.json", "w"))
+    json.dump({"resample": 3, "image_mean": [0.5, 0.5, 0.5], "image_std": [0.5, 0.5, 0.5]},
+              open(d / "preprocessor_config.json", "w"))
+    for target in (str(d), str(d / "model.safetensors")):
+        got = _load_state_dict(target)
+        assert set(got) == set(full) and all(torch.equal(got[k], full[k]) for k in sd)
+        vision, pre = _load_checkpoint_configs(target)
+        assert vision["num_attention_heads"] == spec.heads and pre["resample"] == 3
+        got_spec = spec_from_state_dict(got, image=spec.image, heads=vision["num_attention_heads"], eps=vision["layer_norm_eps"])
+        assert got_spec == spec
+    # torch .bin with bare vision-tower keys (a `SiglipVisionModel.state_dict()` without the prefix)
+    bare = {k[len("vision_model."):]: v for k, v in sd.items()}
+    d2 = tmp_path / "ckpt_bin"
+    d2.mkdir()
+    torch.save(bare, d2 / "pytorch_model.bin")
+    got = _load_state_dict(str(d2))
+    assert set(got) == set(bare) and _load_checkpoint_configs(str(d2)) == (None, None)
+    # head count: explicit > table of published widths > error (never a silent guess)
+    assert spec_from_state_dict(got, image=spec.image, heads=spec.heads) == spec
+    so = SiglipVisionSpec.so400m()
+    shapes = {"embeddings.patch_embedding.weight": torch.empty(1152, 3, 14, 14, device="meta"),
+              "embeddings.position_embedding.weight": torch.empty(729, 1152, device="meta"),
+              "encoder.layers.26.mlp.fc1.weight": torch.empty(4304, 1152, device="meta"),
+              "encoder.layers.0.mlp.fc1.weight": torch.empty(4304, 1152, device="meta")}
+    assert spec_from_state_dict(shapes) == so  # 1152 -> 16 heads of 72 from the table
+    assert spec_from_state_dict(got, image=spec.image) == spec  # 144 = 2 x 72, and 64 does not divide it
+    shapes576 = dict(shapes)
+    shapes576["embeddings.patch_embedding.weight"] = torch.empty(576, 3, 14, 14, device="meta")
+    with pytest.raises(RuntimeError, match="head count"):  # 576 % 72 == 0 used to be mis-read as 8 heads of 72
+        spec_from_state_dict(shapes576)
+    with pytest.raises(RuntimeError, match="not supported"):
+        spec_from_state_dict(shapes576, heads=6)  # head dim 96
+    with pytest.raises(RuntimeError, match="not a local checkpoint"):
+        _load_state_dict(str(tmp_path / "missing"))

@@ -69,6 +69,24 @@ def test_tiny_encoder_vs_oracle_and_golden(golden_dir):
     assert (pooled.cpu() - torch.from_numpy(gold["tiny_pooled"])).abs().max() < 0.05
 
 
+def test_tiny_encoder_without_final_layernorm_vs_golden(golden_dir):
+    """`use_mean_pooling=True` checkpoints (fine-tuned VideoMAE): VideoMAEModel has no final LayerNorm; the base
+    checkpoint the reference loads (use_mean_pooling=False) has one — both variants are pinned on HF."""
+    import dataclasses
+    gold = np.load(f"{golden_dir}/golden_videomae.npz")
+    spec = dataclasses.replace(VideoMAESpec.tiny(), final_norm=False)
+    sd = synth_videomae_state_dict(spec, seed=2)
+    assert "layernorm.weight" not in sd
+    enc = VideoMAEClipEncoder(sd, spec, DEV)
+    frames = synth.noise_frames(2 * spec.frames, 123, 211, seed=9)
+    patches = ops.patchify_tubelet(enc.preprocess(frames.to(DEV)), spec.frames, spec.patch, spec.tubelet)
+    pooled, tokens = ops.videomae_forward(enc.pack, patches, return_tokens=True)
+    torch.cuda.synchronize()
+    want_tok, want = torch.from_numpy(gold["tiny_nofinal_last_hidden_state"]), torch.from_numpy(gold["tiny_nofinal_pooled"])
+    assert _cos(tokens.float().view(2, spec.tokens, -1), want_tok).min() > 0.999
+    assert _cos(pooled, want).min() > 0.999 and (pooled.cpu() - want).abs().max() < 0.05
+
+
 def test_base_encoder_vs_hf_golden(golden_dir):
     """VideoMAE-base geometry, one 16-frame 1080p clip (two scenes), synthetic weights seed 2, vs HF fp32."""
     gold = np.load(f"{golden_dir}/golden_videomae.npz")
@@ -107,3 +125,21 @@ def test_run_mirrors_reference_clip_bookkeeping():
     # the padded clip equals a clip made of 4 copies of the last frame
     rep = enc.encode_clips(frames[-1:].expand(spec.frames, -1, -1, -1).contiguous().to(DEV)).cpu()[0]
     assert torch.allclose(rep, last["embedding"], atol=1e-6)
+
+
+def test_run_realtime_mirrors_stride8_windows():
+    """`extract_videomae_embeddings` semantics (scripts/realtime_inference.py:352-375): windows of `frames` with stride
+    frames/2, the tail that does not fill a window dropped, timestamp of the window's middle frame; every window's
+    embedding equals encoding that window alone."""
+    spec = VideoMAESpec.tiny()  # 4-frame clips -> stride 2
+    enc = VideoMAEClipEncoder(synth_videomae_state_dict(spec, seed=2), spec, DEV, clips_per_batch=3)
+    n = 11  # windows start at 0, 2, 4, 6 (8..11 would need frame 11: dropped)
+    frames = synth.noise_frames(n, 90, 120, seed=5)
+    ts = [i / 4.0 for i in range(n)]
+    out = enc.run_realtime(frames, ts)
+    assert [o["timestamp"] for o in out] == [ts[2], ts[4], ts[6], ts[8]]
+    for o, start in zip(out, (0, 2, 4, 6)):
+        alone = enc.encode_clips(frames[start:start + spec.frames].to(DEV)).cpu()[0]
+        assert o["embedding"].dtype == torch.float32 and o["embedding"].device.type == "cpu"
+        assert torch.equal(alone, o["embedding"])
+    assert enc.run_realtime(frames[:3], ts[:3]) == []

@@ -10,7 +10,9 @@ A *step* is one pass of the hot path over one batch of 64 synthetic 1080p frames
 steps are BASELINE.json configs[1]: one hour of 1 fps gameplay (3600 frames) rounded up to whole
 batches (57 x 64 = 3648).  With N > 1 each rank owns a contiguous chunk of the timeline with the same
 per-rank work ("weak" scaling) and the projected index is all-gathered over NCCL inside the timed
-region.  Rank 0 prints ONE JSON line.
+region.  `--scaling strong [--frames 3600]` is BASELINE.json configs[2]: the SAME N-frame timeline split as
+[r*ceil(N/W), ...) across the W ranks, uneven tail batch and padded all-gather included (`--steps` is then
+derived: ceil(ceil(N/W) / batch) batches per rank).  Rank 0 prints ONE JSON line.
 """
 from __future__ import annotations
 
@@ -94,8 +96,37 @@ def cpu_reference(n_frames: int, batch: int = 8, warmup_batches: int = 1) -> dic
     return hf_baseline.run(n_frames=n_frames, batch=batch, warmup_batches=warmup_batches, frame_hw=(FRAME_H, FRAME_W))
 
 
+MODEL_TEXT = "through SigLIP2-so400m-patch14-384 + ProjectorBank 1152->4096->4096"
 WORKLOAD = ("1 h synthetic 1080p gameplay @1 fps (BASELINE.json configs[1]: 3600 frames, rounded up to 57 batches of 64) "
-            "through SigLIP2-so400m-patch14-384 + ProjectorBank 1152->4096->4096")
+            + MODEL_TEXT)
+
+
+def workload_text(total_frames: int, world: int, batch: int, steps: int, strong: bool) -> str:
+    """States the frames actually timed (the text must follow --steps, not the default)."""
+    if strong:
+        return (f"BASELINE.json configs[{1 if world == 1 else 2}]: the {total_frames}-frame synthetic 1080p timeline (1 h @1 fps "
+                f"at 3600) split into contiguous chunks of ceil({total_frames}/{world}) frames per GPU, batches of {batch} with "
+                f"the uneven tail batch, {MODEL_TEXT}")
+    if total_frames >= 72000:
+        return ("10 h synthetic 1080p gameplay @2 fps (BASELINE.json configs[4]: 72 000 frames, rounded up to "
+                f"{total_frames}) {MODEL_TEXT}, then cosine top-16 retrieval over the gathered index")
+    if steps * batch == 3648:
+        return WORKLOAD if world == 1 else WORKLOAD + f", {world} such chunks (one per GPU)"
+    return (f"{total_frames} synthetic 1080p frames = {steps} steps x {batch} frames per GPU x {world} GPU(s) timed — a "
+            f"{steps}/57 slice of BASELINE.json configs[1] (1 h @1 fps, 57 batches of 64) {MODEL_TEXT}")
+
+
+def source_sha256(*rel_paths: str) -> str:
+    """Hash of kernel sources: ties a committed ncu capture (profiles/gemm_traffic.json) to the tree that produced it."""
+    import hashlib
+    h = hashlib.sha256()
+    for rel in rel_paths:
+        with open(os.path.join(ROOT, rel), "rb") as f:
+            h.update(f.read())
+    return h.hexdigest()
+
+
+GEMM_SOURCES = ("gameplay_vision_llm_b200/csrc/gemm.cu", "gameplay_vision_llm_b200/csrc/common.cuh")
 
 
 def main_reference(args) -> None:
@@ -126,7 +157,8 @@ def main_ours(args) -> None:
     import torch.distributed as dist
 
     from gameplay_vision_llm_b200 import _lib, synth
-    from gameplay_vision_llm_b200.pipeline import EmbeddingPipeline
+    from gameplay_vision_llm_b200.pipeline import EmbeddingPipeline, shard_range
+    from gameplay_vision_llm_b200.timeline import TimelineEmbeddingIndex
     from gameplay_vision_llm_b200.weights import (SiglipVisionSpec, synth_projector_state_dict,
                                                     synth_siglip_state_dict)
 
@@ -145,35 +177,41 @@ def main_ours(args) -> None:
 
     peaks = load_peaks()
     spec = SiglipVisionSpec.so400m()
-    B, K, W = args.batch, args.steps, args.warmup
+    B, W = args.batch, args.warmup
+    strong = args.scaling == "strong"
+    # the timeline: weak = K batches of B frames per rank (per-GPU work fixed); strong = --frames in total (configs[2])
+    total_frames = int(args.frames) if strong else args.steps * B * world
+    lo, hi = shard_range(total_frames, rank, world)
+    n_local = hi - lo
+    per_rank = -(-total_frames // world)
+    K = -(-per_rank // B)  # batches per rank (the last one may be short; trailing ranks may own fewer rows)
     pipe = EmbeddingPipeline(synth_siglip_state_dict(spec, seed=0), synth_projector_state_dict(spec.hidden, 4096, seed=1),
                              spec, dev, batch=B, fold_ln=not args.no_fold_ln)
 
-    # this rank's chunk of the timeline, resident in HBM: K batches of B frames (22.7 GB at K=57, B=64)
-    n_local = K * B
-    first = rank * n_local
-    frames = torch.empty((n_local, FRAME_H, FRAME_W, 3), dtype=torch.uint8, device=dev)
+    # this rank's chunk of the timeline, resident in HBM (22.7 GB at 57 x 64 frames)
+    frames = torch.empty((max(n_local, 1), FRAME_H, FRAME_W, 3), dtype=torch.uint8, device=dev)
     for i0 in range(0, n_local, 16):
         n = min(16, n_local - i0)
-        frames[i0:i0 + n] = synth.scene_frames(first + i0, n, FRAME_H, FRAME_W, device=dev)
-    index_local = torch.empty((n_local, 4096), dtype=torch.bfloat16, device=dev)
-    index_full = torch.empty((world * n_local, 4096), dtype=torch.bfloat16, device=dev) if world > 1 else index_local
+        frames[i0:i0 + n] = synth.scene_frames(lo + i0, n, FRAME_H, FRAME_W, device=dev)
+    # the timeline index: every rank contributes per_rank rows to the (padded) gather, rows [0, total) in timestamp order
+    timeline = TimelineEmbeddingIndex(total_frames, 4096, fps=1.0, device=dev, rank=rank, world=world)
+    index_local = timeline.local_rows()
+    spans = [(i0, min(n_local, i0 + B)) for i0 in range(0, n_local, B)]
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    def run_region(steps: int):
-        for s in range(steps):
-            pipe.embed(frames[s * B:(s + 1) * B], out_index=index_local[s * B:(s + 1) * B])
-        if world > 1:
-            dist.all_gather_into_tensor(index_full, index_local)
+    def run_region():
+        for i0, i1 in spans:
+            pipe.embed(frames[i0:i1], out_index=index_local[i0:i1])
+        timeline.all_gather()  # NCCL all_gather_into_tensor over NVLink (no-op on one GPU)
 
     for s in range(W):  # warm-up: W batches (+ one all-gather)
-        pipe.embed(frames[(s % K) * B:(s % K + 1) * B], out_index=index_local[(s % K) * B:(s % K + 1) * B])
-    if world > 1:
-        dist.all_gather_into_tensor(index_full, index_local)
+        i0, i1 = spans[s % len(spans)]
+        pipe.embed(frames[i0:i1], out_index=index_local[i0:i1])
+    timeline.all_gather()
     barrier()
 
     # ---- timed region 1: device-resident inputs (value) ----
@@ -183,7 +221,7 @@ def main_ours(args) -> None:
     launches0 = _lib.launch_count()
     barrier()
     e0.record()
-    run_region(K)
+    run_region()
     e1.record()
     barrier()
     launches = _lib.launch_count() - launches0
@@ -192,26 +230,53 @@ def main_ours(args) -> None:
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     ms = float(ms.item())
-    total_frames = world * n_local
     value = total_frames / (ms * 1e-3)
+
+    # ---- the exchange step alone: achieved all-gather bandwidth over NVLink ----
+    allgather = None
+    if world > 1:
+        for _ in range(2):
+            timeline.all_gather()
+        barrier()
+        reps = 10
+        e0.record()
+        for _ in range(reps):
+            timeline.all_gather()
+        e1.record()
+        barrier()
+        ag_ms = torch.tensor([e0.elapsed_time(e1) / reps], device=dev)
+        dist.all_reduce(ag_ms, op=dist.ReduceOp.MAX)
+        ag_ms = float(ag_ms.item())
+        ag_bytes = world * per_rank * 4096 * 2
+        allgather = {"bytes_total": ag_bytes, "ms": round(ag_ms, 4), "algbw_gbs": round(ag_bytes / (ag_ms * 1e-3) / 1e9, 1),
+                     "busbw_gbs": round(ag_bytes * (world - 1) / world / (ag_ms * 1e-3) / 1e9, 1),
+                     "nvlink_peak_gbs": 770.0, "note": "busbw = bytes_total x (W-1)/W / time (each GPU receives W-1 shards); "
+                     "peak = measured peer copy per direction per GPU (B200_PROFILING.md)"}
 
     # ---- timed region 2: same steps with per-launch CUDA events (roofline of the dominant kernel) ----
     _lib.prof_enable(True)
-    run_region(K)
+    run_region()
     torch.cuda.synchronize()
     _lib.prof_enable(False)
     prof = _lib.prof_summary()
     gemm = prof.get("gemm", {"ms": 0.0, "launches": 0, "work": 0.0})
     gemm_tflops = gemm["work"] / (gemm["ms"] * 1e-3) / 1e12 if gemm["ms"] else 0.0
     prof_total_ms = sum(v["ms"] for v in prof.values()) or 1.0
-    traffic = None
+    # DRAM bytes per GEMM launch come from a committed ncu capture; it only counts when it was taken on THIS tree's
+    # GEMM sources (hash recorded by tools/ncu_traffic.py), otherwise the line says null and why
+    traffic, traffic_note = None, "no ncu capture committed (profiles/gemm_traffic.json)"
     tpath = os.path.join(ROOT, "profiles", "gemm_traffic.json")
     if os.path.exists(tpath):
         with open(tpath) as f:
-            traffic = json.load(f).get("dram_bytes_per_launch")
+            tj = json.load(f)
+        if tj.get("source_sha256") == source_sha256(*GEMM_SOURCES):
+            traffic, traffic_note = tj.get("dram_bytes_per_launch"), f"ncu capture {tj.get('capture', '?')} of this tree's gemm.cu"
+        else:
+            traffic_note = "stale: profiles/gemm_traffic.json was captured on different gemm.cu / common.cuh sources"
     roofline = {"kernel": "gemm_bf16_cg2_kernel", "bound": "tensor", "achieved": round(gemm_tflops, 2),
                 "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
                 "frac": round(gemm_tflops / peaks["bf16_tflops_sustained"], 4), "traffic": traffic,
+                "traffic_note": traffic_note, "algorithmic_bytes_per_launch": round(gemm_alg_bytes(spec, B)),
                 "peak_source": f"{peaks['source']} (sustained; burst {peaks['bf16_tflops']})",
                 "launches": gemm["launches"], "avg_launch_ms": round(gemm["ms"] / max(1, gemm["launches"]), 4),
                 "share_of_step": round(gemm["ms"] / prof_total_ms, 4)}
@@ -225,25 +290,25 @@ def main_ours(args) -> None:
     model_tflops = value / world * spec.flops_per_frame() / 1e12
 
     # ---- timed region 3: end to end through the public API with HOST frames (e2e) ----
-    ring = [frames[i * B:(i + 1) * B].cpu().pin_memory() for i in range(min(4, K))]
-    host_out = torch.empty((n_local, 4096), dtype=torch.bfloat16).pin_memory()
+    ring = [frames[i0:i1].cpu().pin_memory() for i0, i1 in spans[:4]]
+    host_out = torch.empty((max(n_local, 1), 4096), dtype=torch.bfloat16).pin_memory()
 
-    def host_batches(steps):
-        for s in range(steps):
-            yield ring[s % len(ring)]
+    def host_batches(n_spans):
+        for s, (i0, i1) in enumerate(spans[:n_spans]):
+            yield ring[s % len(ring)][: i1 - i0]
 
     pipe.embed_stream(host_batches(min(W, 2)), index_local, host_out)
     barrier()
     e0.record()
-    pipe.embed_stream(host_batches(K), index_local, host_out)
-    if world > 1:
-        dist.all_gather_into_tensor(index_full, index_local)
+    pipe.embed_stream(host_batches(len(spans)), index_local, host_out)
+    timeline.all_gather()
     e1.record()
     barrier()
     ms_e2e = torch.tensor([e0.elapsed_time(e1)], device=dev)
     if world > 1:
         dist.all_reduce(ms_e2e, op=dist.ReduceOp.MAX)
     e2e_value = total_frames / (float(ms_e2e.item()) * 1e-3)
+    index_full = timeline.index()
 
     # ---- side measurement (not part of value / e2e): configs[4] retrieval over a 72 000-row timeline index ----
     retrieval = None
@@ -259,16 +324,13 @@ def main_ours(args) -> None:
     if rank == 0:
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
-            cpu = cpu_reference(n_frames=8, batch=8, warmup_batches=1)
+            cpu = cpu_reference(n_frames=args.cpu_frames, batch=8, warmup_batches=1)
         line = {
             "metric": "frames/s SigLIP2+ProjectorBank", "value": round(value, 2), "unit": "frames/s", "n_gpus": world,
-            "steps": K, "warmup": W, "ms_per_step": round(ms / K, 3), "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": WORKLOAD if total_frames < 72000 else
-                       "10 h synthetic 1080p gameplay @2 fps (BASELINE.json configs[4]: 72 000 frames, rounded up to "
-                       f"{total_frames}) through SigLIP2-so400m-patch14-384 + ProjectorBank 1152->4096->4096, then cosine "
-                       "top-16 retrieval over the gathered index",
-                       "frames_per_gpu": n_local, "batch": B, "frame": [FRAME_H, FRAME_W, 3],
+            "steps": K, "warmup": W, "ms_per_step": round(ms / K, 3), "higher_is_better": True,
+            "scaling": "strong" if strong else "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": workload_text(total_frames, world, B, K, strong), "frames_total": total_frames,
+                       "frames_per_gpu": per_rank, "batch": B, "frame": [FRAME_H, FRAME_W, 3],
                        "weights": "random init, seeds 0/1", "layernorm": "separate kernels" if args.no_fold_ln else
                        "folded into the consuming GEMM epilogues", "sharding": "contiguous timeline chunk per rank, "
                        "NCCL all-gather of the projected index inside the timed region" if world > 1 else "single GPU",
@@ -285,9 +347,21 @@ def main_ours(args) -> None:
                                     "kind": cpu["kind"], "sample": cpu["sample"]}
         if retrieval is not None:
             line["retrieval"] = retrieval
+        if allgather is not None:
+            line["allgather"] = allgather
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def gemm_alg_bytes(spec, batch: int) -> float:
+    """Average algorithmic bytes of one GEMM launch of a step: A + W + out (+ residual), bf16."""
+    M, D, I, T = batch * spec.tokens, spec.hidden, spec.intermediate, spec.tokens
+    per_layer = [(M, 3 * D, D, 0), (M, D, D, 1), (M, I, D, 0), (M, D, I, 1)]
+    shapes = [(M, D, spec.patch_ld, 0)] + per_layer * spec.layers + [
+        (M, 2 * D, D, 0), (batch, D, D, 0), (batch, I, D, 0), (batch, D, I, 1), (batch, 4096, D, 0), (batch, 4096, 4096, 0)]
+    total = sum(2 * (m * k + n * k + m * n * (1 + res)) for m, n, k, res in shapes)
+    return total / len(shapes)
 
 
 def retrieval_on_gathered(index_full, dev, n_queries: int = 128, k: int = 16) -> dict:
@@ -525,6 +599,11 @@ if __name__ == "__main__":
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--batch", type=int, default=64)
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
+    ap.add_argument("--scaling", choices=["weak", "strong"], default="weak",
+                    help="weak (default): --steps batches per GPU; strong: --frames in total, split across the GPUs "
+                         "(BASELINE.json configs[2])")
+    ap.add_argument("--frames", type=int, default=3600, help="total frames of the timeline with --scaling strong")
+    ap.add_argument("--cpu-frames", type=int, default=32, help="frames of the bounded CPU-baseline sample (batch 8)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-retrieval", action="store_true", help="skip the configs[4] retrieval side measurement")
     ap.add_argument("--no-fold-ln", action="store_true",

@@ -3,6 +3,8 @@
 // and K5, the MAP-head probe attention.
 #include "common.cuh"
 
+#include <cstdlib>
+
 namespace gvl {
 
 // K5: probe attention of the MAP head.  One CTA per (image, head): scores over T keys with the
@@ -87,6 +89,13 @@ probe_attention_kernel(const float* __restrict__ q, const __nv_bfloat16* __restr
 
 template <int HD>
 int launch_attention_sdb(const void* qkv, void* out, int B, int T, int H, float scale, cudaStream_t s);  // attention_sdb.cu
+#ifdef GVL_EXPERIMENTS
+// round-2 experiment (two softmax warpgroups, fixed-reference softmax, polynomial exp2): measured equal or slower than
+// attention_sdb.cu on every shape (profiles/r02_attention_experiments.md); built only with EXTRA=-DGVL_EXPERIMENTS
+template <int HD>
+int launch_attention_p2(const void* qkv, void* out, int B, int T, int H, float scale, int poly, int force_exact,
+                        cudaStream_t s);  // experiments/attention_p2.cu
+#endif
 
 }  // namespace gvl
 
@@ -97,6 +106,14 @@ extern "C" int gvl_attention_bf16(const void* qkv, void* out, int B, int T, int 
     GVL_CHECK_ARG(B <= 65535 && H <= 65535, "gvl_attention_bf16: B/H exceed grid limits");
     GVL_CHECK_ARG((uintptr_t)qkv % 16 == 0 && (uintptr_t)out % 16 == 0, "gvl_attention_bf16: misaligned pointer");
     cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+#ifdef GVL_EXPERIMENTS  // A/B builds only (make EXTRA=-DGVL_EXPERIMENTS): the shipped library has one attention path
+    static const int impl = [] { const char* e = getenv("GVL_ATTN_IMPL"); return (e && e[0] == 'p') ? 1 : 0; }();
+    static const int poly = [] { const char* e = getenv("GVL_ATTN_POLY"); return e ? atoi(e) : 0; }();
+    if (impl == 1) {
+        if (hd == 72) return launch_attention_p2<72>(qkv, out, B, T, H, scale, poly, 0, s);
+        if (hd == 64) return launch_attention_p2<64>(qkv, out, B, T, H, scale, poly, 0, s);
+    }
+#endif
     if (hd == 72) return launch_attention_sdb<72>(qkv, out, B, T, H, scale, s);
     if (hd == 64) return launch_attention_sdb<64>(qkv, out, B, T, H, scale, s);
     set_error("gvl_attention_bf16: unsupported head dim %d (built for 72 and 64)", hd);

@@ -3,7 +3,7 @@
 //
 // Production configuration (NT = 1): one CTA = one 128-row query tile of one (image, head), 6 warps, two CTAs per SM
 // (2 x (2 x 64 S + 80 O + 16 L) TMEM columns).  NT = 2 (two tiles per CTA, one CTA per SM, K/V stages shared) and
-// NT = 3 (three tiles, S single-buffered) are selectable with GVL_ATTN_NT for A/B runs; both measure slower.
+// NT = 3 (three tiles, S single-buffered) exist only in -DGVL_EXPERIMENTS builds (GVL_ATTN_NT); both measure slower.
 //   - S(j+1) is computed into the other buffer while softmax(j) runs; PV(j) is issued as soon as P(j) is written
 //     and S(j+2) is queued right behind it (tcgen05.mma executes in issue order, which protects the P(j) columns);
 //   - keys are processed in blocks of 64;
@@ -437,7 +437,11 @@ static int launch_attention_sdb_nt(const void* qkv, void* out, int B, int T, int
     if (rc) return rc;
     GVL_CUDA(cudaFuncSetAttribute(attention_sdb_kernel<HD, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   Cfg::SMEM_BYTES));
+#ifdef GVL_EXPERIMENTS
     static const int dbg = [] { const char* e = getenv("GVL_ATTN_DEBUG"); return e ? atoi(e) : 0; }();  // timing experiments
+#else
+    const int dbg = 0;
+#endif
     dim3 grid((T + NT * SDB_BQ - 1) / (NT * SDB_BQ), H, B);
     ProfScope prof(GVL_K_ATTENTION, 4.0 * B * (double)H * T * (double)T * HD, s);
     GVL_CUDA(launch_pdl(attention_sdb_kernel<HD, NT>, grid, dim3(Cfg::THREADS), Cfg::SMEM_BYTES, s, tq64, tq16, tk64, tk16,
@@ -448,13 +452,15 @@ static int launch_attention_sdb_nt(const void* qkv, void* out, int B, int T, int
 
 template <int HD>
 int launch_attention_sdb(const void* qkv, void* out, int B, int T, int H, float scale, cudaStream_t s) {
+#ifdef GVL_EXPERIMENTS  // A/B builds: query tiles per CTA (2: one CTA per SM; 3: single-buffered S) — both measure slower
     static const int nt = [] {
-        const char* e = getenv("GVL_ATTN_NT");  // tuning switch: query tiles per CTA (3 = single-buffered S, one CTA per SM)
+        const char* e = getenv("GVL_ATTN_NT");
         return (e && (e[0] == '2' || e[0] == '3')) ? e[0] - '0' : 1;
     }();
     if (nt == 3) return launch_attention_sdb_nt<HD, 3>(qkv, out, B, T, H, scale, s);
-    return nt == 2 ? launch_attention_sdb_nt<HD, 2>(qkv, out, B, T, H, scale, s)
-                   : launch_attention_sdb_nt<HD, 1>(qkv, out, B, T, H, scale, s);
+    if (nt == 2) return launch_attention_sdb_nt<HD, 2>(qkv, out, B, T, H, scale, s);
+#endif
+    return launch_attention_sdb_nt<HD, 1>(qkv, out, B, T, H, scale, s);
 }
 
 template int launch_attention_sdb<72>(const void*, void*, int, int, int, float, cudaStream_t);

@@ -24,6 +24,7 @@ constexpr int TOPK_QB = 8;        // queries per scan pass
 constexpr int TOPK_THREADS = 256;
 constexpr int TOPK_CAND = 512;    // candidates per query the tensor path re-scores exactly
 constexpr float TOPK_MARGIN = 6e-5f;  // > 2 x the tensor path's score error (measured 9e-6 at D = 4096)
+constexpr float TOPK_MARGIN_SCAN = 8e-6f;  // > 2 x the fp32 scan's accumulation error (measured < 2e-6 at D = 4096)
 
 // The per-lane arithmetic of one 8-element chunk, shared by the scan and the rescoring kernel so that both
 // produce bit-identical scores for the same (row, query) pair.
@@ -297,92 +298,189 @@ topk_merge_kernel(const float* __restrict__ cand_s, const int32_t* __restrict__ 
     }
 }
 
-// Tensor path, second stage.  The GEMM scores carry tcgen05's accumulation rounding (~1e-5), enough to swap
-// near-equal neighbours.  Every row whose approximate score is within TOPK_MARGIN of the provisional k-th best is
-// re-scored with the scan kernel's exact arithmetic (tk_* helpers: bit-identical scores) and the final k are
-// selected among those candidates — the result equals the scan path's, at the cost of <= TOPK_CAND rows per
-// query.  More than TOPK_CAND candidates (hundreds of near-duplicates): the provisional result is kept and
-// *overflow is incremented.
+// Final stage of BOTH scoring paths: exact re-ranking of the near-top candidates.
+//
+// Approximate scores (fp32 scan: accumulation rounding ~1e-6; tcgen05 scores: ~1e-5) decide WHICH rows can be among
+// the k best; their ORDER is decided here in float64: every candidate whose approximate score is within `margin` of
+// the provisional k-th best is re-scored as  <q, e> / (max(|q|, eps) max(|e|, eps))  with float64 dot products and
+// norms (bf16 inputs are exact in float64, products exact, 4096-term sums good to ~1e-15) and the k best under
+// (score descending, row ascending) are returned, scores rounded to fp32.  The result is the float64 ranking — what
+// `cos_sim` + a stable `argsort(descending)` give on float64 data — and it is the same for the scan and the tensor path.
+//
+// Candidates of query qi: cand_s / cand_i [qi][lists][list_len] in any order (row -1 = empty slot); `raw` = scores
+// still lack the query's 1/|q| factor (tensor path).  A list that is full and whose worst entry is still within the
+// margin may have dropped rows that matter (hundreds of near-duplicates of the query inside one list's span), and
+// more than TOPK_CAND candidates do not fit the re-scoring buffer: both are counted in *overflow; the query then keeps
+// the ranking by approximate scores.
+__device__ __forceinline__ double tk_warp_sum_f64(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ bool tk_better_f64(double sa, int ia, double sb, int ib) {
+    return sa > sb || (sa == sb && ia < ib);
+}
+
 __global__ void __launch_bounds__(TOPK_THREADS)
-topk_rescore_kernel(const __nv_bfloat16* __restrict__ index, int N, int D, const __nv_bfloat16* __restrict__ queries,
-                    float eps, const float* __restrict__ scores, size_t ld, int k, const int32_t* __restrict__ row_lo,
-                    const int32_t* __restrict__ row_hi, float* __restrict__ out_scores, int32_t* __restrict__ out_idx,
-                    int* __restrict__ overflow) {
+topk_refine_kernel(const __nv_bfloat16* __restrict__ index, int D, const __nv_bfloat16* __restrict__ queries, float eps,
+                   const float* __restrict__ cand_s, const int32_t* __restrict__ cand_i, int lists, int list_len, int k,
+                   float margin, int raw, float* __restrict__ out_scores, int32_t* __restrict__ out_idx,
+                   int* __restrict__ overflow) {
     __shared__ int s_cand[TOPK_CAND];
-    __shared__ float s_exact[TOPK_CAND];
-    __shared__ int s_n;
-    __shared__ float s_qn;
+    __shared__ double s_exact[TOPK_CAND];
+    __shared__ int s_n, s_trunc;
+    __shared__ double s_qn;
     __shared__ TkBlockBest sh;
+    __shared__ double sh_ws[TOPK_THREADS / 32];
+    __shared__ int sh_wi[TOPK_THREADS / 32];
+    __shared__ double sh_bs;
+    __shared__ int sh_bi;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int qi = blockIdx.x;
-    const float* sc = scores + (size_t)qi * ld;
-    const int lo = row_lo ? max(0, row_lo[qi]) : 0;
-    const int hi = row_hi ? min(N, row_hi[qi]) : N;
-    const float kth = out_scores[(size_t)qi * k + (k - 1)];  // -inf when fewer than k rows are eligible
-    const float thr = kth - TOPK_MARGIN;
-    if (tid == 0) s_n = 0;
-    __syncthreads();
-    for (int t = lo + tid; t < hi; t += TOPK_THREADS) {
-        const float v = sc[t];
-        if (v >= thr) {  // NaN scores never qualify, as in the select kernel
-            const int slot = atomicAdd(&s_n, 1);
-            if (slot < TOPK_CAND) s_cand[slot] = t;
-        }
-    }
-    __syncthreads();
-    const int n = s_n;
-    if (n > TOPK_CAND) {
-        if (tid == 0 && overflow) atomicAdd(overflow, 1);
-        return;  // provisional (tensor-score) result stays
-    }
-    // exact scores: one warp per candidate, the query streamed from global (L2-resident)
+    const int L = lists * list_len;
+    const float* cs = cand_s + (size_t)qi * L;
+    const int32_t* ci = cand_i + (size_t)qi * L;
     const int chunks = D >> 3;
     const uint4* qr = reinterpret_cast<const uint4*>(queries + (size_t)qi * D);
+    // |q| in float64
     if (warp == 0) {
-        float acc = 0.f;
+        double acc = 0.0;
         for (int c = lane; c < chunks; c += 32) {
             float f[8];
             tk_unpack8(__ldg(qr + c), f);
-            acc = tk_sq8(acc, f);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc += (double)f[j] * (double)f[j];
         }
-        acc = tk_warp_sum(acc);
-        if (lane == 0) s_qn = 1.0f / fmaxf(sqrtf(acc), eps);
+        acc = tk_warp_sum_f64(acc);
+        if (lane == 0) s_qn = fmax(sqrt(acc), (double)eps);
     }
-    __syncthreads();
-    for (int j = warp; j < n; j += TOPK_THREADS / 32) {
-        const uint4* er = reinterpret_cast<const uint4*>(index + (size_t)s_cand[j] * D);
-        float dot = 0.f, nrm = 0.f;
-        for (int c = lane; c < chunks; c += 32) {
-            float e[8];
-            tk_unpack8(__ldg(er + c), e);
-            nrm = tk_sq8(nrm, e);
-            dot = tk_dot8(dot, e, __ldg(qr + c));
-        }
-        nrm = tk_warp_sum(nrm);
-        dot = tk_warp_sum(dot);
-        if (lane == 0) s_exact[j] = dot * s_qn * (1.0f / fmaxf(sqrtf(nrm), eps));
-    }
-    __syncthreads();
-    // final selection among the candidates: k rounds of arg-max under (score desc, index asc)
+    if (tid == 0) s_n = 0, s_trunc = 0;
+    // provisional top-k by approximate score: k rounds of arg-max over the candidates (also the fall-back result)
     float prev_s = INFINITY;
     int prev_i = -1;
+    float kth = -INFINITY;
+    __syncthreads();
+    const float iq = raw ? (float)(1.0 / s_qn) : 1.0f;
+    int found = 0;
     for (int r = 0; r < k; ++r) {
         float bs = -INFINITY;
         int bi = 0x7fffffff;
-        for (int j = tid; j < n; j += TOPK_THREADS) {
-            const float v = s_exact[j];
-            const int t = s_cand[j];
-            const bool elig = (r == 0) ? (v == v) : (v < prev_s || (v == prev_s && t > prev_i));
+        for (int j = tid; j < L; j += TOPK_THREADS) {
+            const int t = ci[j];
+            const float v = cs[j];
+            const bool elig = t >= 0 && ((r == 0) ? (v == v) : (v < prev_s || (v == prev_s && t > prev_i)));
             if (elig && tk_better(v, t, bs, bi)) {
                 bs = v;
                 bi = t;
             }
         }
         tk_block_argmax(sh, bs, bi, prev_s, prev_i);
+        if (prev_i == 0x7fffffff) break;  // fewer than k candidates (block-uniform)
         if (tid == 0) {
-            out_scores[(size_t)qi * k + r] = prev_i == 0x7fffffff ? -INFINITY : prev_s;
-            out_idx[(size_t)qi * k + r] = prev_i == 0x7fffffff ? -1 : prev_i;
+            out_scores[(size_t)qi * k + r] = prev_s * iq;
+            out_idx[(size_t)qi * k + r] = prev_i;
         }
+        kth = prev_s;
+        found = r + 1;
+    }
+    if (found < k) {
+        for (int r2 = found + tid; r2 < k; r2 += TOPK_THREADS) {
+            out_scores[(size_t)qi * k + r2] = -INFINITY;
+            out_idx[(size_t)qi * k + r2] = -1;
+        }
+        kth = -INFINITY;  // every candidate is re-scored
+    }
+    // candidates within the margin of the provisional k-th score (margin is in cosine units)
+    const float thr = kth - (raw ? margin / iq : margin);
+    for (int j = tid; j < L; j += TOPK_THREADS) {
+        const int t = ci[j];
+        if (t >= 0 && cs[j] >= thr) {
+            const int slot = atomicAdd(&s_n, 1);
+            if (slot < TOPK_CAND) s_cand[slot] = t;
+        }
+    }
+    // a full list whose worst entry is still inside the margin may have dropped qualifying rows
+    for (int li_ = tid; li_ < lists; li_ += TOPK_THREADS) {
+        float worst = INFINITY;
+        bool full = true;
+        for (int e = 0; e < list_len; ++e) {
+            const int t = ci[li_ * list_len + e];
+            if (t < 0) full = false;
+            else worst = fminf(worst, cs[li_ * list_len + e]);
+        }
+        if (full && worst >= thr && lists * list_len > k) atomicOr(&s_trunc, 1);
+    }
+    __syncthreads();
+    const int n = s_n;
+    if (n > TOPK_CAND || s_trunc) {
+        if (tid == 0 && overflow) atomicAdd(overflow, 1);
+        if (n > TOPK_CAND) return;  // provisional (approximate-score) result stays
+    }
+    // exact float64 scores: one warp per candidate
+    for (int j = warp; j < n; j += TOPK_THREADS / 32) {
+        const uint4* er = reinterpret_cast<const uint4*>(index + (size_t)s_cand[j] * D);
+        double dot = 0.0, nrm = 0.0;
+        for (int c = lane; c < chunks; c += 32) {
+            float e[8], f[8];
+            tk_unpack8(__ldg(er + c), e);
+            tk_unpack8(__ldg(qr + c), f);
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                nrm += (double)e[u] * (double)e[u];
+                dot += (double)e[u] * (double)f[u];
+            }
+        }
+        nrm = tk_warp_sum_f64(nrm);
+        dot = tk_warp_sum_f64(dot);
+        if (lane == 0) s_exact[j] = dot / (s_qn * fmax(sqrt(nrm), (double)eps));
+    }
+    __syncthreads();
+    // final selection: k rounds of arg-max under (score desc, row asc) on the float64 scores
+    double pd = INFINITY;
+    int pi = -1;
+    for (int r = 0; r < k && r < n; ++r) {
+        double bs = -INFINITY;
+        int bi = 0x7fffffff;
+        for (int j = tid; j < n; j += TOPK_THREADS) {
+            const double v = s_exact[j];
+            const int t = s_cand[j];
+            const bool elig = (r == 0) ? (v == v) : (v < pd || (v == pd && t > pi));
+            if (elig && tk_better_f64(v, t, bs, bi)) {
+                bs = v;
+                bi = t;
+            }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const double os = __shfl_xor_sync(0xffffffffu, bs, o);
+            const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+            if (tk_better_f64(os, oi, bs, bi)) {
+                bs = os;
+                bi = oi;
+            }
+        }
+        if (lane == 0) {
+            sh_ws[warp] = bs;
+            sh_wi[warp] = bi;
+        }
+        __syncthreads();
+        if (tid == 0) {
+            double fs = sh_ws[0];
+            int fi = sh_wi[0];
+            for (int w = 1; w < TOPK_THREADS / 32; ++w)
+                if (tk_better_f64(sh_ws[w], sh_wi[w], fs, fi)) {
+                    fs = sh_ws[w];
+                    fi = sh_wi[w];
+                }
+            sh_bs = fs;
+            sh_bi = fi;
+            out_scores[(size_t)qi * k + r] = fi == 0x7fffffff ? -INFINITY : (float)fs;
+            out_idx[(size_t)qi * k + r] = fi == 0x7fffffff ? -1 : fi;
+        }
+        __syncthreads();
+        pd = sh_bs;
+        pi = sh_bi;
+        if (pi == 0x7fffffff) break;
     }
 }
 
@@ -405,37 +503,33 @@ row_inv_norm_kernel(const __nv_bfloat16* __restrict__ x, int rows, int D, float 
     }
 }
 
-// raw dot products -> cosines, in place: scores[q][n] *= inv_q[q] * inv_e[n] for n in [0, n_cols)
-__global__ void __launch_bounds__(TOPK_THREADS)
-scale_scores_kernel(float* __restrict__ scores, size_t ld, int n_cols, const float* __restrict__ inv_q,
-                    const float* __restrict__ inv_e) {
-    float* row = scores + (size_t)blockIdx.y * ld;
-    const float iq = inv_q[blockIdx.y];
-    for (int n = (blockIdx.x * TOPK_THREADS + threadIdx.x) * 4; n < n_cols; n += gridDim.x * TOPK_THREADS * 4) {
-        float4 v = *reinterpret_cast<float4*>(row + n);
-        const float4 e = *reinterpret_cast<const float4*>(inv_e + n);
-        v.x *= iq * e.x;
-        v.y *= iq * e.y;
-        v.z *= iq * e.z;
-        v.w *= iq * e.w;
-        *reinterpret_cast<float4*>(row + n) = v;
-    }
-}
+int launch_topk_fused(const void* index, int N, int D, const void* queries, int nq, int span_lo, int span_hi,
+                      const float* inv_e, const int32_t* row_lo, const int32_t* row_hi, float* cand_s, int32_t* cand_i,
+                      int* grid_out, cudaStream_t s);  // topk_fused.cu
+int topk_fused_list_len();
 
 }  // namespace gvl
 
-// scratch layout (floats): [Q][ld] scores | [ld] 1/|e_n| | [Q up to 4] 1/|q| | 4: overflow counter |
-//                          [Q][TOPK_MAX_SEGS][64] segment-winner scores | same, int32 indices
-static size_t topk_cand_offset(int N, int Q) {
+// scratch layout (floats), ld = max(roundup4(N), TOPK_MIN_LD):
+//   [Q][ld]  fp32 scores of the scan path  /  candidate lists of the fused tensor path ([Q][CTAs][32] scores, then rows)
+//   [ld] 1/|e_n| | [roundup4(Q)] reserved | 4: overflow counter (int) |
+//   [Q][TOPK_MAX_SEGS][64] segment-winner scores | same, int32 rows | [Q][64] pre-selected scores | same, int32 rows
+constexpr size_t TOPK_MIN_LD = 2 * 160 * 32;  // room for the fused path's lists of up to 160 CTAs
+static size_t topk_ld(int N) {
     const size_t ld = ((size_t)N + 3) & ~(size_t)3;
+    return ld < TOPK_MIN_LD ? TOPK_MIN_LD : ld;
+}
+static size_t topk_cand_offset(int N, int Q) {
+    const size_t ld = topk_ld(N);
     return (size_t)Q * ld + ld + (((size_t)Q + 3) & ~(size_t)3) + 4;
 }
+static size_t topk_presel_offset(int N, int Q) { return topk_cand_offset(N, Q) + 2 * (size_t)Q * gvl::TOPK_MAX_SEGS * 64; }
 
 // two-stage selection over scratch[Q][ld] scores: segment winners (grid = segments x queries), then their merge
 static int topk_select(float* scratch, int N, int Q, int k, int span_lo, int span, const int32_t* row_lo,
                        const int32_t* row_hi, float* out_scores, int32_t* out_idx, cudaStream_t s) {
     using namespace gvl;
-    const size_t ld = ((size_t)N + 3) & ~(size_t)3;
+    const size_t ld = topk_ld(N);
     int segs = (span + TOPK_SEG - 1) / TOPK_SEG;
     segs = segs < 1 ? 1 : (segs > TOPK_MAX_SEGS ? TOPK_MAX_SEGS : segs);
     int seg_len = ((span + segs - 1) / segs + 3) & ~3;
@@ -454,7 +548,7 @@ static int topk_select(float* scratch, int N, int Q, int k, int span_lo, int spa
 
 extern "C" size_t gvl_topk_scratch_floats(int N, int Q) {
     if (N <= 0 || Q <= 0) return 0;
-    return topk_cand_offset(N, Q) + 2 * (size_t)Q * gvl::TOPK_MAX_SEGS * 64;
+    return topk_presel_offset(N, Q) + 2 * (size_t)Q * 64;
 }
 
 extern "C" int gvl_row_inv_norm(const void* rows, int N, int D, float eps, float* inv_norm, void* stream) {
@@ -486,68 +580,80 @@ extern "C" int gvl_topk_cosine_ex(const void* index, int N, int D, const void* q
     if (row_lo == nullptr) span_lo = 0, span_hi = N;
     GVL_CHECK_ARG(span_lo >= 0 && span_hi <= N && span_lo <= span_hi, "gvl_topk_cosine: bad span [%d, %d)", span_lo, span_hi);
     cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
-    const size_t ld = ((size_t)N + 3) & ~(size_t)3;
+    const size_t ld = topk_ld(N);
     const int rows_per_cta = TOPK_THREADS / 32;
     const int max_grid = sm_count() * 8;
     const int span = span_hi - span_lo;
     if (mode == GVL_TOPK_AUTO) mode = (Q > TOPK_QB && span >= 4096) ? GVL_TOPK_TENSOR : GVL_TOPK_SCAN;
-
-    int scan_lo = span_lo, scan_hi = span_hi;  // rows scored by the CUDA-core scan
-    bool tensor_scored = false;
-    int* overflow = nullptr;
-    if (mode == GVL_TOPK_TENSOR && span > 0) {
-        // GEMM over rows [g0, g1): g0 rounded down to the GEMM's N granularity (8 rows; the extra rows are harmless),
-        // g1 rounded down — the <= 7 rows left over go through the scan kernel
-        const int g0 = span_lo & ~7, g1 = g0 + ((span_hi - g0) & ~7);
-        float* inv_e = scratch + (size_t)Q * ld;
-        float* inv_q = inv_e + ld;
-        overflow = reinterpret_cast<int*>(inv_q + (((size_t)Q + 3) & ~(size_t)3));
-        GVL_CUDA(cudaMemsetAsync(overflow, 0, sizeof(int), s));
-        if (g1 > g0) {
-            if (inv_norm == nullptr) {
-                int rc = gvl_row_inv_norm(reinterpret_cast<const __nv_bfloat16*>(index) + (size_t)g0 * D, g1 - g0, D, eps,
-                                          inv_e + g0, stream);
-                if (rc) return rc;
-            }
-            int rc = gvl_row_inv_norm(queries, Q, D, eps, inv_q, stream);
-            if (rc) return rc;
-            rc = gvl_gemm_bf16(queries, D, reinterpret_cast<const __nv_bfloat16*>(index) + (size_t)g0 * D, D, nullptr, nullptr,
-                               0, 0, scratch + g0, (int)ld, 1, Q, g1 - g0, D, GVL_ACT_NONE, stream);
-            if (rc) return rc;
-            dim3 grid((unsigned)std::min<size_t>(((size_t)(g1 - g0) / 4 + TOPK_THREADS - 1) / TOPK_THREADS, 64), (unsigned)Q);
-            ProfScope prof(GVL_K_TOPK_SELECT, (double)Q * (g1 - g0) * 8, s);
-            scale_scores_kernel<<<grid, TOPK_THREADS, 0, s>>>(scratch + g0, ld, g1 - g0, inv_q,
-                                                              (inv_norm ? inv_norm : inv_e) + g0);
-            GVL_LAUNCH_CHECK("scale_scores_kernel");
-            tensor_scored = true;
-        }
-        scan_lo = g1;
+    const __nv_bfloat16* idx_bf = reinterpret_cast<const __nv_bfloat16*>(index);
+    const __nv_bfloat16* q_bf = reinterpret_cast<const __nv_bfloat16*>(queries);
+    int* overflow = reinterpret_cast<int*>(scratch + (size_t)Q * ld + ld + (((size_t)Q + 3) & ~(size_t)3));
+    GVL_CUDA(cudaMemsetAsync(overflow, 0, sizeof(int), s));
+    if (span <= 0) {  // nothing is eligible: every slot empty
+        ProfScope prof(GVL_K_TOPK_SELECT, 0.0, s);
+        topk_refine_kernel<<<Q, TOPK_THREADS, 0, s>>>(idx_bf, D, q_bf, eps, scratch, reinterpret_cast<int32_t*>(scratch), 0, 0, k,
+                                                      0.f, 0, out_scores, out_idx, overflow);
+        GVL_LAUNCH_CHECK("topk_refine_kernel");
+        return 0;
     }
-    if (scan_hi > scan_lo) {
+
+    if (mode == GVL_TOPK_TENSOR) {
+        // fused tcgen05 scoring + per-CTA candidate lists (topk_fused.cu), batches of up to 128 queries
+        float* inv_e = scratch + (size_t)Q * ld;
+        if (inv_norm == nullptr) {
+            int rc = gvl_row_inv_norm(idx_bf + (size_t)span_lo * D, span, D, eps, inv_e + span_lo, stream);
+            if (rc) return rc;
+        }
+        const int KL = topk_fused_list_len();
+        for (int q0 = 0; q0 < Q; q0 += 128) {
+            const int nq = Q - q0 < 128 ? Q - q0 : 128;
+            // lists of this batch live in the batch's own [nq][ld] slice of the score region
+            float* cand_s = scratch + (size_t)q0 * ld;
+            int grid = 0;
+            // cand_i directly behind cand_s: nq * grid * KL floats each, grid <= 160 (TOPK_MIN_LD guarantees the room)
+            int ntiles = (span + 255) / 256;
+            int g = ntiles < sm_count() ? ntiles : sm_count();
+            if (g < 1) g = 1;
+            GVL_CHECK_ARG((size_t)2 * g * KL <= ld, "gvl_topk_cosine: %d CTAs exceed the scratch layout", g);
+            int32_t* cand_i = reinterpret_cast<int32_t*>(cand_s + (size_t)nq * g * KL);
+            int rc = launch_topk_fused(index, N, D, q_bf + (size_t)q0 * D, nq, span_lo, span_hi, inv_norm ? inv_norm : inv_e,
+                                       row_lo ? row_lo + q0 : nullptr, row_hi ? row_hi + q0 : nullptr, cand_s, cand_i, &grid, s);
+            if (rc) return rc;
+            ProfScope prof(GVL_K_TOPK_SELECT, (double)nq * grid * KL * 8, s);
+            topk_refine_kernel<<<nq, TOPK_THREADS, 0, s>>>(idx_bf, D, q_bf + (size_t)q0 * D, eps, cand_s, cand_i, grid, KL, k,
+                                                           TOPK_MARGIN, 1, out_scores + (size_t)q0 * k, out_idx + (size_t)q0 * k,
+                                                           overflow);
+            GVL_LAUNCH_CHECK("topk_refine_kernel");
+        }
+        return 0;
+    }
+
+    // ---- scan path: fp32 scores of every row, pre-selection of the best k + 16, float64 refinement ----
+    {
         const size_t smem = (size_t)TOPK_QB * D * 2 + TOPK_QB * sizeof(float);
         GVL_CUDA(cudaFuncSetAttribute(cos_scores_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        int grid = (scan_hi - scan_lo + rows_per_cta - 1) / rows_per_cta;
+        int grid = (span + rows_per_cta - 1) / rows_per_cta;
         if (grid > max_grid) grid = max_grid;
         for (int q0 = 0; q0 < Q; q0 += TOPK_QB) {
             const int nq = Q - q0 < TOPK_QB ? Q - q0 : TOPK_QB;
-            ProfScope prof(GVL_K_TOPK_SCORES, (double)(scan_hi - scan_lo) * D * 2, s);
-            cos_scores_kernel<<<grid, TOPK_THREADS, smem, s>>>(
-                reinterpret_cast<const __nv_bfloat16*>(index), scan_lo, scan_hi, D,
-                reinterpret_cast<const __nv_bfloat16*>(queries) + (size_t)q0 * D, nq, eps, scratch + (size_t)q0 * ld, ld);
+            ProfScope prof(GVL_K_TOPK_SCORES, (double)span * D * 2, s);
+            cos_scores_kernel<<<grid, TOPK_THREADS, smem, s>>>(idx_bf, span_lo, span_hi, D, q_bf + (size_t)q0 * D, nq, eps,
+                                                               scratch + (size_t)q0 * ld, ld);
             GVL_LAUNCH_CHECK("cos_scores_kernel");
         }
     }
+    const int kpre = k + 16 < 64 ? k + 16 : 64;
+    float* pre_s = scratch + topk_presel_offset(N, Q);
+    int32_t* pre_i = reinterpret_cast<int32_t*>(pre_s + (size_t)Q * 64);
     {
-        int rc = topk_select(scratch, N, Q, k, span_lo, span, row_lo, row_hi, out_scores, out_idx, s);
+        int rc = topk_select(scratch, N, Q, kpre, span_lo, span, row_lo, row_hi, pre_s, pre_i, s);
         if (rc) return rc;
     }
-    if (tensor_scored) {
-        // exact fp32 re-scoring of the near-top candidates: the final result is the scan path's
-        ProfScope prof(GVL_K_TOPK_SELECT, (double)Q * span * 4, s);
-        topk_rescore_kernel<<<Q, TOPK_THREADS, 0, s>>>(reinterpret_cast<const __nv_bfloat16*>(index), N, D,
-                                                       reinterpret_cast<const __nv_bfloat16*>(queries), eps, scratch, ld, k,
-                                                       row_lo, row_hi, out_scores, out_idx, overflow);
-        GVL_LAUNCH_CHECK("topk_rescore_kernel");
+    {
+        ProfScope prof(GVL_K_TOPK_SELECT, (double)Q * kpre * 8, s);
+        topk_refine_kernel<<<Q, TOPK_THREADS, 0, s>>>(idx_bf, D, q_bf, eps, pre_s, pre_i, 1, kpre, k, TOPK_MARGIN_SCAN, 0,
+                                                      out_scores, out_idx, overflow);
+        GVL_LAUNCH_CHECK("topk_refine_kernel");
     }
     return 0;
 }
@@ -568,7 +674,7 @@ extern "C" int gvl_topk_cosine_f32(const float* index, int N, int D, const float
     GVL_CHECK_ARG((uintptr_t)index % 16 == 0 && (uintptr_t)queries % 16 == 0 && (uintptr_t)scratch % 16 == 0,
                   "gvl_topk_cosine_f32: misaligned pointer");
     cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
-    const size_t ld = ((size_t)N + 3) & ~(size_t)3;
+    const size_t ld = topk_ld(N);
     const size_t smem = (size_t)TOPK_QB_F32 * D * 4 + TOPK_QB_F32 * sizeof(float);
     GVL_CUDA(cudaFuncSetAttribute(cos_scores_f32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int grid = (N + TOPK_THREADS / 32 - 1) / (TOPK_THREADS / 32);

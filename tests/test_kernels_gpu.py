@@ -83,14 +83,25 @@ def test_gemm_strided_views():
     assert rel < 6e-3
 
 
-def test_gemm_layernorm_fusion():
+@pytest.mark.parametrize("case", ["plain", "outlier_channels", "common_offset"])
+def test_gemm_layernorm_fusion(case):
     """Producer GEMM writes partial row sums of what it stored; consumer GEMM on raw x with gamma-folded weights
-    reproduces Linear(LayerNorm(x)) (include/gvl.h: gvl_gemm_fusion)."""
+    reproduces Linear(LayerNorm(x)) (include/gvl.h: gvl_gemm_fusion).  The folded statistics are E[x^2] - mean^2 from
+    fp32 partial sums, so they lose precision only when a COMMON offset of all channels dwarfs their spread:
+    `outlier_channels` (massive activations of +-200 in a few channels, as trained ViT residual streams have: they
+    raise the variance itself, nothing cancels) and `common_offset` (every channel shifted by 20 standard deviations:
+    mean^2 / var = 400, relative variance error ~400 x 2^-24) must both stay inside the same tolerance; an offset of
+    hundreds of standard deviations would not, which is why EmbeddingPipeline(fold_ln=False) exists."""
     g = torch.Generator().manual_seed(11)
     M, D, N2 = 1000, 1152, 4304
     a = torch.randn(M, 592, generator=g).to(torch.bfloat16).to(DEV)
     w0 = (torch.randn(D, 592, generator=g) / 24).to(torch.bfloat16).to(DEV)
-    res = (torch.randn(M, D, generator=g) * 3 + 0.7).to(torch.bfloat16).to(DEV)
+    res = torch.randn(M, D, generator=g) * 3 + 0.7
+    if case == "outlier_channels":
+        res[:, [5, 300, 777, 1100]] += torch.tensor([200.0, -150.0, 90.0, -220.0])
+    elif case == "common_offset":
+        res += 60.0  # 20 x the spread of 3
+    res = res.to(torch.bfloat16).to(DEV)
     slots = ops.gemm_stats_slots(D)
     stats = torch.full((M, slots, 2), float("nan"), device=DEV)
     x = ops.gemm(a, w0, None, residual=res, stats_out=stats)  # x = a @ w0.T + res, bf16, + statistics
@@ -109,7 +120,7 @@ def test_gemm_layernorm_fusion():
     torch.cuda.synchronize()
     ref = siglip_ref.gelu_tanh(torch.nn.functional.layer_norm(xs, (D,), gamma, beta, 1e-6) @ w1.float().T + b1)
     mx, rel, mean = _rel_err(got, ref)
-    print(f"gemm LN fusion: max_abs={mx:.3e} rel={rel:.3e} mean={mean:.3e}")
+    print(f"gemm LN fusion [{case}]: max_abs={mx:.3e} rel={rel:.3e} mean={mean:.3e}")
     assert rel < 8e-3
 
 
@@ -143,6 +154,45 @@ def test_attention(B, T, H, hd):
     print(f"attention B={B} T={T} H={H} hd={hd}: max_abs={mx:.3e} rel={rel:.3e} mean={mean:.3e}")
     assert torch.isfinite(out.float()).all()
     assert rel < 1.5e-2 and mean < 2e-3  # P is rounded to bf16 before PV (as HF eager/SDPA do)
+
+
+def _attn_ref(qkv, B, T, H, hd):
+    D = H * hd
+    q, k, v = qkv.float().view(B, T, 3, H, hd).permute(2, 0, 3, 1, 4)
+    s = (q @ k.transpose(-1, -2)) * hd ** -0.5
+    return (torch.softmax(s, -1) @ v).transpose(1, 2).reshape(B * T, D)
+
+
+@pytest.mark.parametrize("hd", [72, 64])
+def test_attention_wide_score_range_and_exact_path(hd):
+    """The attention kernel keeps no running max: every row is exponentiated against one fixed reference (its score
+    for key 0 + 95 in log2 units) and a row whose scores leave the representable window is detected by its row sum and
+    recomputed exactly (attention_p2.cu).  (a) peaky rows — logits spread over +-60 nats, inside the window: fast path;
+    (b) key 0 scoring ~136 nats below the row maximum and (c) ~136 nats above everything else: outside the window on
+    the overflow side / far inside on the other — all three must match fp32 softmax."""
+    B, T, H = 2, 300, 2
+    D = H * hd
+    g = torch.Generator().manual_seed(hd)
+    base = (torch.randn(B * T, 3 * D, generator=g)).to(torch.bfloat16)
+    # (a) scale q up: logits ~ N(0, 18^2) nats
+    wide = base.clone().float()
+    wide[:, :D] *= 18.0
+    # (b) key 0 of every (image, head) far below: k_0 = -4 * ones, q = +4 * ones + noise  -> dot ~ -16 hd
+    low = base.clone().float()
+    low.view(B, T, 3, H, hd)[:, :, 0] = 4.0 + 0.1 * low.view(B, T, 3, H, hd)[:, :, 0]
+    low.view(B, T, 3, H, hd)[:, 0, 1] = -4.0
+    # (c) key 0 far above: k_0 = +4 * ones with the same positive queries
+    high = low.clone()
+    high.view(B, T, 3, H, hd)[:, 0, 1] = 4.0
+    for name, x in (("wide", wide), ("key0 low (exact path)", low), ("key0 high", high)):
+        qkv = x.to(torch.bfloat16).to(DEV)
+        out = ops.attention(qkv, B, T, H, hd)
+        torch.cuda.synchronize()
+        ref = _attn_ref(qkv.cpu(), B, T, H, hd)
+        mx, rel, mean = _rel_err(out, ref)
+        print(f"attention hd={hd} {name}: max_abs={mx:.3e} rel={rel:.3e} mean={mean:.3e}")
+        assert torch.isfinite(out.float()).all(), name
+        assert rel < 1.5e-2 and mean < 2e-3, name
 
 
 def test_probe_attention():
@@ -248,7 +298,7 @@ def test_topk_matches_oracle_with_ties():
 def test_topk_config5_72k_index():
     """BASELINE.json configs[4]: cosine top-16 over a 72 000-row (10 h @ 2 fps) 4096-d bf16 timeline index for 128
     queries, indices against the float64 oracle.  Rows are clustered like scene embeddings (pairwise cosine ~0.9);
-    a position may only differ from the oracle where the float64 scores are closer than fp32 accumulation noise."""
+    every one of the 2048 (query, rank) positions must hold the oracle's row (the north star's "bit-exact")."""
     N, D, Q, k = 72000, 4096, 128, 16
     g = torch.Generator(device=DEV).manual_seed(5)
     centers = torch.randn(N // 60, D, device=DEV, generator=g)
@@ -262,17 +312,9 @@ def test_topk_config5_72k_index():
     got_i = got_i.cpu().numpy().astype(np.int64)
     mism = np.argwhere(got_i != want_i)
     print(f"config 5 top-{k}: {mism.shape[0]} of {Q * k} positions differ from the float64 oracle")
-    assert np.abs(got_s.cpu().numpy() - want_s).max() < 2e-5
-    e64 = None
-    for qi, pos in mism:  # a swap is only acceptable between scores that are equal to fp32 accumulation accuracy
-        if e64 is None:
-            e64 = index.double().cpu().numpy()
-            e64 /= np.linalg.norm(e64, axis=1, keepdims=True)
-        qv = queries[qi].double().cpu().numpy()
-        qv /= np.linalg.norm(qv)
-        a, b = float(e64[got_i[qi, pos]] @ qv), float(e64[want_i[qi, pos]] @ qv)
-        assert abs(a - b) < 2e-6, f"query {qi} rank {pos}: {got_i[qi, pos]} ({a}) vs {want_i[qi, pos]} ({b})"
-    assert mism.shape[0] <= 4
+    assert np.abs(got_s.cpu().numpy() - want_s).max() < 2e-6
+    # the kernel's final ranking is done on float64 re-scored candidates (topk_refine_kernel): bit-exact indices
+    assert mism.shape[0] == 0, mism[:8]
 
 
 @pytest.mark.parametrize("mode", [ops.TOPK_SCAN, ops.TOPK_TENSOR])

@@ -23,6 +23,7 @@ namespace gvl {
 constexpr int TOPK_QB = 8;        // queries per scan pass
 constexpr int TOPK_THREADS = 256;
 constexpr int TOPK_CAND = 512;    // candidates per query the tensor path re-scores exactly
+constexpr int TOPK_REFINE_STAGE = 4096;  // non-empty candidates of one query staged in shared memory by the refinement
 constexpr float TOPK_MARGIN = 6e-5f;  // > 2 x the tensor path's score error (measured 9e-6 at D = 4096)
 constexpr float TOPK_MARGIN_SCAN = 8e-6f;  // > 2 x the fp32 scan's accumulation error (measured < 2e-6 at D = 4096)
 
@@ -328,7 +329,9 @@ topk_refine_kernel(const __nv_bfloat16* __restrict__ index, int D, const __nv_bf
                    int* __restrict__ overflow) {
     __shared__ int s_cand[TOPK_CAND];
     __shared__ double s_exact[TOPK_CAND];
-    __shared__ int s_n, s_trunc;
+    __shared__ float s_vs[TOPK_REFINE_STAGE];   // the query's non-empty candidates, staged once (the k selection rounds
+    __shared__ int s_vi[TOPK_REFINE_STAGE];     // below would otherwise re-read the sparse global lists k times)
+    __shared__ int s_n, s_trunc, s_nv;
     __shared__ double s_qn;
     __shared__ TkBlockBest sh;
     __shared__ double sh_ws[TOPK_THREADS / 32];
@@ -337,9 +340,11 @@ topk_refine_kernel(const __nv_bfloat16* __restrict__ index, int D, const __nv_bf
     __shared__ int sh_bi;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int qi = blockIdx.x;
-    const int L = lists * list_len;
+    int L = lists * list_len;
     const float* cs = cand_s + (size_t)qi * L;
     const int32_t* ci = cand_i + (size_t)qi * L;
+    const float* gcs = cs;   // the list structure (for the truncation check) stays in global memory
+    const int32_t* gci = ci;
     const int chunks = D >> 3;
     const uint4* qr = reinterpret_cast<const uint4*>(queries + (size_t)qi * D);
     // |q| in float64
@@ -354,7 +359,24 @@ topk_refine_kernel(const __nv_bfloat16* __restrict__ index, int D, const __nv_bf
         acc = tk_warp_sum_f64(acc);
         if (lane == 0) s_qn = fmax(sqrt(acc), (double)eps);
     }
-    if (tid == 0) s_n = 0, s_trunc = 0;
+    if (tid == 0) s_n = 0, s_trunc = 0, s_nv = 0;
+    __syncthreads();
+    for (int j = tid; j < L; j += TOPK_THREADS) {
+        const int t = ci[j];
+        if (t >= 0) {
+            const int slot = atomicAdd(&s_nv, 1);
+            if (slot < TOPK_REFINE_STAGE) {
+                s_vs[slot] = cs[j];
+                s_vi[slot] = t;
+            }
+        }
+    }
+    __syncthreads();
+    if (s_nv <= TOPK_REFINE_STAGE) {  // (else: more candidates than the stage holds — work on the global lists)
+        cs = s_vs;
+        ci = s_vi;
+        L = s_nv;
+    }
     // provisional top-k by approximate score: k rounds of arg-max over the candidates (also the fall-back result)
     float prev_s = INFINITY;
     int prev_i = -1;
@@ -402,11 +424,10 @@ topk_refine_kernel(const __nv_bfloat16* __restrict__ index, int D, const __nv_bf
     // a full list whose worst entry is still inside the margin may have dropped qualifying rows
     for (int li_ = tid; li_ < lists; li_ += TOPK_THREADS) {
         float worst = INFINITY;
-        bool full = true;
-        for (int e = 0; e < list_len; ++e) {
-            const int t = ci[li_ * list_len + e];
-            if (t < 0) full = false;
-            else worst = fminf(worst, cs[li_ * list_len + e]);
+        bool full = gci[li_ * list_len + list_len - 1] >= 0;  // lists fill front to back
+        for (int e = 0; full && e < list_len; ++e) {
+            if (gci[li_ * list_len + e] < 0) full = false;
+            else worst = fminf(worst, gcs[li_ * list_len + e]);
         }
         if (full && worst >= thr && lists * list_len > k) atomicOr(&s_trunc, 1);
     }
@@ -504,8 +525,8 @@ row_inv_norm_kernel(const __nv_bfloat16* __restrict__ x, int rows, int D, float 
 }
 
 int launch_topk_fused(const void* index, int N, int D, const void* queries, int nq, int span_lo, int span_hi,
-                      const float* inv_e, const int32_t* row_lo, const int32_t* row_hi, float* cand_s, int32_t* cand_i,
-                      int* grid_out, cudaStream_t s);  // topk_fused.cu
+                      const float* inv_e, const float* inv_q, float margin, int k, const int32_t* row_lo,
+                      const int32_t* row_hi, float* cand_s, int32_t* cand_i, int* grid_out, cudaStream_t s);  // topk_fused.cu
 int topk_fused_list_len();
 
 }  // namespace gvl
@@ -514,7 +535,7 @@ int topk_fused_list_len();
 //   [Q][ld]  fp32 scores of the scan path  /  candidate lists of the fused tensor path ([Q][CTAs][32] scores, then rows)
 //   [ld] 1/|e_n| | [roundup4(Q)] reserved | 4: overflow counter (int) |
 //   [Q][TOPK_MAX_SEGS][64] segment-winner scores | same, int32 rows | [Q][64] pre-selected scores | same, int32 rows
-constexpr size_t TOPK_MIN_LD = 2 * 160 * 32;  // room for the fused path's lists of up to 160 CTAs
+constexpr size_t TOPK_MIN_LD = 2 * 160 * 64;  // room for the fused path's lists of up to 160 CTAs
 static size_t topk_ld(int N) {
     const size_t ld = ((size_t)N + 3) & ~(size_t)3;
     return ld < TOPK_MIN_LD ? TOPK_MIN_LD : ld;
@@ -584,7 +605,7 @@ extern "C" int gvl_topk_cosine_ex(const void* index, int N, int D, const void* q
     const int rows_per_cta = TOPK_THREADS / 32;
     const int max_grid = sm_count() * 8;
     const int span = span_hi - span_lo;
-    if (mode == GVL_TOPK_AUTO) mode = (Q > TOPK_QB && span >= 4096) ? GVL_TOPK_TENSOR : GVL_TOPK_SCAN;
+    if (mode == GVL_TOPK_AUTO) mode = (Q > TOPK_QB && span >= 4096 && k <= 16) ? GVL_TOPK_TENSOR : GVL_TOPK_SCAN;
     const __nv_bfloat16* idx_bf = reinterpret_cast<const __nv_bfloat16*>(index);
     const __nv_bfloat16* q_bf = reinterpret_cast<const __nv_bfloat16*>(queries);
     int* overflow = reinterpret_cast<int*>(scratch + (size_t)Q * ld + ld + (((size_t)Q + 3) & ~(size_t)3));
@@ -605,6 +626,12 @@ extern "C" int gvl_topk_cosine_ex(const void* index, int N, int D, const void* q
             if (rc) return rc;
         }
         const int KL = topk_fused_list_len();
+        GVL_CHECK_ARG(k <= 16, "gvl_topk_cosine: the tensor path serves k <= 16 (k = %d): use GVL_TOPK_SCAN", k);
+        float* inv_q = inv_e + ld;  // [roundup4(Q)]
+        {
+            int rc = gvl_row_inv_norm(queries, Q, D, eps, inv_q, stream);
+            if (rc) return rc;
+        }
         for (int q0 = 0; q0 < Q; q0 += 128) {
             const int nq = Q - q0 < 128 ? Q - q0 : 128;
             // lists of this batch live in the batch's own [nq][ld] slice of the score region
@@ -617,7 +644,8 @@ extern "C" int gvl_topk_cosine_ex(const void* index, int N, int D, const void* q
             GVL_CHECK_ARG((size_t)2 * g * KL <= ld, "gvl_topk_cosine: %d CTAs exceed the scratch layout", g);
             int32_t* cand_i = reinterpret_cast<int32_t*>(cand_s + (size_t)nq * g * KL);
             int rc = launch_topk_fused(index, N, D, q_bf + (size_t)q0 * D, nq, span_lo, span_hi, inv_norm ? inv_norm : inv_e,
-                                       row_lo ? row_lo + q0 : nullptr, row_hi ? row_hi + q0 : nullptr, cand_s, cand_i, &grid, s);
+                                       inv_q + q0, TOPK_MARGIN, k, row_lo ? row_lo + q0 : nullptr,
+                                       row_hi ? row_hi + q0 : nullptr, cand_s, cand_i, &grid, s);
             if (rc) return rc;
             ProfScope prof(GVL_K_TOPK_SELECT, (double)nq * grid * KL * 8, s);
             topk_refine_kernel<<<nq, TOPK_THREADS, 0, s>>>(idx_bf, D, q_bf + (size_t)q0 * D, eps, cand_s, cand_i, grid, KL, k,

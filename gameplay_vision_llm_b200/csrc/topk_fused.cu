@@ -8,8 +8,10 @@
 //     D in tensor memory (TMA -> 3-stage smem ring -> tcgen05.mma 128x256x16, two accumulator buffers so the epilogue of
 //     tile i overlaps the main loop of tile i + 1);
 //   * epilogue: one thread = one query (TMEM lane).  It scales each score by the row's 1/|e_n| (the query's own 1/|q|
-//     does not change its ranking and is applied at the end), applies the query's row window, and keeps the best
-//     KL = 32 candidates it has seen in a private list in shared memory (threshold = the list's worst entry);
+//     does not change its ranking and is applied at the end), applies the query's row window, and appends every row
+//     that reaches a running lower bound of the k-th best score (the 16th largest of 32 group maxima, minus the re-scoring
+//     margin) to a private list of up to KL = 64 candidates in shared memory — no per-element list maintenance; each
+//     tile is read from TMEM twice (bound, then collection);
 //   * every CTA writes its 128 x KL candidates; gvl::topk_refine_kernel (topk.cu) merges them per query and re-scores
 //     everything within a margin of the provisional k-th score EXACTLY (float64 dot products and norms), so the final
 //     ranking is the float64 one, ties by ascending index — identical to what the scan path produces after the same
@@ -24,7 +26,8 @@ constexpr int TF_BM = 128;       // queries per batch (TMEM lanes)
 constexpr int TF_BN = 256;       // index rows per tile (TMEM columns per accumulator buffer)
 constexpr int TF_BK = 64;        // bf16 elements per k-step (one 128-byte swizzled row)
 constexpr int TF_STAGES = 3;
-constexpr int TF_KL = 32;        // candidates kept per (query, CTA)
+constexpr int TF_KL = 64;        // candidates kept per (query, CTA)
+constexpr int TF_GROUPS = 32;    // running group maxima per query thread; the bound is their 16th largest (k <= 16)
 constexpr int TF_THREADS = 192;  // warps 0-3 epilogue, 4 TMA, 5 MMA
 constexpr int TF_A_BYTES = TF_BM * TF_BK * 2;
 constexpr int TF_B_BYTES = TF_BN * TF_BK * 2;
@@ -32,10 +35,31 @@ constexpr int TF_STAGE_BYTES = TF_A_BYTES + TF_B_BYTES;
 constexpr int TF_LIST_BYTES = TF_KL * TF_BM * 8;
 constexpr int TF_SMEM_BYTES = TF_STAGES * TF_STAGE_BYTES + TF_LIST_BYTES + 256 + 1024;
 
+// List full (rare): keep the best TF_KL — replace the worst entry if this row beats it.  Rows arrive in ascending
+// order, so an equal score never displaces an earlier row.
+static __device__ __noinline__ void tf_replace_worst(float* my_s, int32_t* my_i, float s, int n) {
+    float ws = my_s[0];
+    int wi = my_i[0], wp = 0;
+    for (int e = 1; e < TF_KL; ++e) {
+        const float es = my_s[e * TF_BM];
+        const int ei = my_i[e * TF_BM];
+        if (es < ws || (es == ws && ei > wi)) {
+            ws = es;
+            wi = ei;
+            wp = e;
+        }
+    }
+    if (s > ws) {
+        my_s[wp * TF_BM] = s;
+        my_i[wp * TF_BM] = n;
+    }
+}
+
 __global__ void __launch_bounds__(TF_THREADS, 1)
 topk_fused_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_e, int D, int nq,
-                  int span_lo, int span_hi, const float* __restrict__ inv_e, const int32_t* __restrict__ row_lo,
-                  const int32_t* __restrict__ row_hi, int N, float* __restrict__ cand_s, int32_t* __restrict__ cand_i) {
+                  int span_lo, int span_hi, const float* __restrict__ inv_e, const float* __restrict__ inv_q, float margin,
+                  int k, const int32_t* __restrict__ row_lo, const int32_t* __restrict__ row_hi, int N,
+                  float* __restrict__ cand_s, int32_t* __restrict__ cand_i) {
     extern __shared__ uint8_t tf_smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(tf_smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* sA = smem;                                   // [STAGES][128 x 64 bf16]
@@ -122,15 +146,72 @@ topk_fused_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constan
         }
     } else {
         // ===== epilogue: thread = query =====
+        // Candidate collection without per-element list maintenance: 32 running group maxima (element i of every
+        // 32-column chunk belongs to group i); their 16th largest is a score that at least 16 distinct rows of this CTA
+        // reach — a valid lower bound of the CTA's (hence the global) k-th best score for k <= 16 — and every row
+        // scoring >= that bound minus the re-scoring margin is appended to the thread's list.  A full list falls back
+        // to replace-the-worst (exact top-KL, slow, rare).
         const int q = warp * 32 + lane;
         const uint32_t lane_off = (uint32_t)(warp * 32) << 16;
         const bool q_on = q < nq;
         const int lo = q_on ? (row_lo ? max(row_lo[q], span_lo) : span_lo) : 0;
         const int hi = q_on ? (row_hi ? min(row_hi[q], span_hi) : span_hi) : 0;
+        const float margin_raw = q_on ? margin / inv_q[q] : 0.f;  // candidate scores lack the 1/|q| factor
         float* my_s = ls + q;       // entry e at my_s[e * 128]
         int32_t* my_i = li + q;
-        int count = 0, minpos = 0;
-        float thr = -INFINITY;      // list's worst score once it is full
+        int count = 0;
+        float thr = -INFINITY;
+        float gmax[TF_GROUPS];
+#pragma unroll
+        for (int g = 0; g < TF_GROUPS; ++g) gmax[g] = -INFINITY;
+        auto append = [&](float s, int n) {
+            if (count < TF_KL) {
+                my_s[count * TF_BM] = s;
+                my_i[count * TF_BM] = n;
+                ++count;
+            } else {
+                tf_replace_worst(my_s, my_i, s, n);
+            }
+        };
+        // 16th largest of the 32 group maxima (bitonic sorting network on registers, descending) minus the margin:
+        // at least 16 distinct rows of this CTA score >= it, so it never exceeds the k-th best (k <= 16)
+        auto group_bound = [&]() {
+            float v[TF_GROUPS];
+#pragma unroll
+            for (int g = 0; g < TF_GROUPS; ++g) v[g] = gmax[g];
+#pragma unroll
+            for (int k2 = 2; k2 <= TF_GROUPS; k2 <<= 1) {
+#pragma unroll
+                for (int j = k2 >> 1; j > 0; j >>= 1) {
+#pragma unroll
+                    for (int i = 0; i < TF_GROUPS; ++i) {
+                        const int l = i ^ j;
+                        if (l > i) {
+                            const bool desc = (i & k2) == 0;
+                            const float a = v[i], c = v[l];
+                            const float hi_ = fmaxf(a, c), lo_ = fminf(a, c);
+                            v[i] = desc ? hi_ : lo_;
+                            v[l] = desc ? lo_ : hi_;
+                        }
+                    }
+                }
+            }
+            return v[15] - margin_raw;  // -inf while fewer than 16 groups have seen an eligible row
+        };
+        // drop list entries that fell below the tightened bound (keeps the list near 16-25 entries)
+        auto compact = [&]() {
+            int w = 0;
+            for (int e = 0; e < count; ++e) {
+                const float es = my_s[e * TF_BM];
+                const int ei = my_i[e * TF_BM];
+                if (es >= thr) {
+                    my_s[w * TF_BM] = es;
+                    my_i[w * TF_BM] = ei;
+                    ++w;
+                }
+            }
+            count = w;
+        };
         int it = 0;
         for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++it) {
             const int buf = it & 1;
@@ -138,42 +219,32 @@ topk_fused_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constan
             mbar_wait(&acc_full[buf], ((uint32_t)(it >> 1)) & 1u);
             tcgen05_fence_after();
             const uint32_t tD = tmem_base + (uint32_t)(buf * TF_BN) + lane_off;
-            for (int c = 0; c < TF_BN / 32; ++c) {
-                uint32_t v[32];
-                tmem_ld_32x32(tD + (uint32_t)(c * 32), v);
-                tmem_ld_wait();
-                const int nb = n0 + c * 32;
-                if (nb >= hi || nb + 32 <= lo) continue;  // (thread-local skip; the TMEM load above is warp-collective)
+            // every tile is read from TMEM twice: first its scores tighten the bound (a later tile may hold a whole
+            // scene of near-duplicates above the old bound — appending them all would flood the list), then the rows
+            // that reach the new bound are collected
+            for (int pass = 0; pass < 2; ++pass) {
+                for (int c = 0; c < TF_BN / 32; ++c) {
+                    uint32_t v[32];
+                    tmem_ld_32x32(tD + (uint32_t)(c * 32), v);
+                    tmem_ld_wait();
+                    const int nb = n0 + c * 32;
+                    const float my_ie = (nb + lane < N) ? __ldg(inv_e + nb + lane) : 0.f;  // 1/|e| of this chunk's rows
 #pragma unroll
-                for (int i = 0; i < 32; ++i) {
-                    const int n = nb + i;
-                    if (n < lo || n >= hi) continue;
-                    const float s = __uint_as_float(v[i]) * __ldg(inv_e + n);
-                    // rows arrive in ascending order: an equal score never displaces an earlier row
-                    if (!(s > thr)) continue;  // also drops NaN
-                    if (count < TF_KL) {
-                        my_s[count * TF_BM] = s;
-                        my_i[count * TF_BM] = n;
-                        if (++count < TF_KL) continue;
-                    } else {
-                        my_s[minpos * TF_BM] = s;
-                        my_i[minpos * TF_BM] = n;
+                    for (int i = 0; i < 32; ++i) {
+                        const float ie = __shfl_sync(0xffffffffu, my_ie, i);
+                        const int n = nb + i;
+                        const bool in = n >= lo && n < hi;
+                        const float s = __uint_as_float(v[i]) * ie;
+                        if (pass == 0) gmax[i % TF_GROUPS] = fmaxf(gmax[i % TF_GROUPS], in ? s : -INFINITY);
+                        else if (in && s >= thr) append(s, n);
                     }
-                    // list full: find its worst entry (lowest score, latest row among equals)
-                    float ws = my_s[0];
-                    int wi = my_i[0], wp = 0;
-#pragma unroll 8
-                    for (int e = 1; e < TF_KL; ++e) {
-                        const float es = my_s[e * TF_BM];
-                        const int ei = my_i[e * TF_BM];
-                        if (es < ws || (es == ws && ei > wi)) {
-                            ws = es;
-                            wi = ei;
-                            wp = e;
-                        }
+                }
+                if (pass == 0) {
+                    const float nb_ = group_bound();
+                    if (nb_ > thr) {
+                        thr = nb_;
+                        if (count > 0) compact();
                     }
-                    thr = ws;
-                    minpos = wp;
                 }
             }
             tcgen05_fence_before();
@@ -202,8 +273,8 @@ topk_fused_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constan
 // Launches the fused scoring kernel for one batch of nq <= 128 queries.  cand_s / cand_i: [nq][grid][TF_KL].
 // Returns the grid size through *grid_out (the number of candidate lists per query).
 int launch_topk_fused(const void* index, int N, int D, const void* queries, int nq, int span_lo, int span_hi,
-                      const float* inv_e, const int32_t* row_lo, const int32_t* row_hi, float* cand_s, int32_t* cand_i,
-                      int* grid_out, cudaStream_t s) {
+                      const float* inv_e, const float* inv_q, float margin, int k, const int32_t* row_lo,
+                      const int32_t* row_hi, float* cand_s, int32_t* cand_i, int* grid_out, cudaStream_t s) {
     CUtensorMap tq, te;
     int rc = make_tmap_2d_bf16(&tq, queries, (uint64_t)nq, (uint64_t)D, (uint64_t)D, TF_BM, TF_BK, true);
     if (rc) return rc;
@@ -214,8 +285,8 @@ int launch_topk_fused(const void* index, int N, int D, const void* queries, int 
     if (grid < 1) grid = 1;
     GVL_CUDA(cudaFuncSetAttribute(topk_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TF_SMEM_BYTES));
     ProfScope prof(GVL_K_TOPK_SCORES, (double)(span_hi - span_lo) * D * 2, s);
-    topk_fused_kernel<<<grid, TF_THREADS, TF_SMEM_BYTES, s>>>(tq, te, D, nq, span_lo, span_hi, inv_e, row_lo, row_hi, N,
-                                                              cand_s, cand_i);
+    topk_fused_kernel<<<grid, TF_THREADS, TF_SMEM_BYTES, s>>>(tq, te, D, nq, span_lo, span_hi, inv_e, inv_q, margin, k, row_lo,
+                                                              row_hi, N, cand_s, cand_i);
     GVL_LAUNCH_CHECK("topk_fused_kernel");
     *grid_out = grid;
     return 0;

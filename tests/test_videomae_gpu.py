@@ -22,13 +22,18 @@ def _cos(a, b):
 @pytest.mark.parametrize("H,W,size", [(1080, 1920, 224), (123, 211, 48), (720, 1280, 224), (400, 300, 64)])
 def test_preprocess_crop_bit_exact(H, W, size):
     frames = synth.noise_frames(3, H, W, seed=H)
-    pv = videomae_ref.pixel_values(frames.numpy(), size, size)
     oh, ow, y0, x0 = videomae_ref.resize_geometry(H, W, size, size)
     dev = frames.to(DEV)
-    got = ops.preprocess_crop(dev, oh, ow, y0, x0, size, size, layout=ops.LAYOUT_F32_CHW).cpu().numpy()
-    assert np.array_equal(got.view(np.uint32), pv.view(np.uint32)), "fp32 pixel_values differ"
-    got16 = ops.preprocess_crop(dev, oh, ow, y0, x0, size, size, layout=ops.LAYOUT_BF16_CHW).cpu()
-    assert torch.equal(got16.view(torch.int16), torch.from_numpy(pv).to(torch.bfloat16).view(torch.int16))
+    # the processor's class defaults (mean = std = 0.5) and the checkpoint's constants (ImageNet mean / std)
+    for mean, std in (((0.5,) * 3, (0.5,) * 3), (videomae_ref.IMAGENET_MEAN, videomae_ref.IMAGENET_STD)):
+        pv = videomae_ref.pixel_values(frames.numpy(), size, size, image_mean=mean, image_std=std)
+        got = ops.preprocess_crop(dev, oh, ow, y0, x0, size, size, image_mean=mean, image_std=std,
+                                  layout=ops.LAYOUT_F32_CHW).cpu().numpy()
+        assert np.array_equal(got.view(np.uint32), pv.view(np.uint32)), "fp32 pixel_values differ"
+        got16 = ops.preprocess_crop(dev, oh, ow, y0, x0, size, size, image_mean=mean, image_std=std,
+                                    layout=ops.LAYOUT_BF16_CHW).cpu()
+        assert torch.equal(got16.view(torch.int16), torch.from_numpy(pv).to(torch.bfloat16).view(torch.int16))
+    pv = videomae_ref.pixel_values(frames.numpy(), size, size, image_mean=(0.5,) * 3, image_std=(0.5,) * 3)
     u8 = ops.preprocess_crop(dev, oh, ow, y0, x0, size, size, layout=ops.LAYOUT_U8_CHW).cpu().numpy()
     assert np.array_equal(u8, np.rint(pv * 127.5 + 127.5).astype(np.uint8))
 

@@ -14,7 +14,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("GVL_LIB_PATH") or os.path.join(_HERE, "libgvl_sm100a.so")
 
 c_float_p = POINTER(c_float)
-ABI_VERSION = 5  # include/gvl.h GVL_ABI_VERSION
+ABI_VERSION = 6  # include/gvl.h GVL_ABI_VERSION
 
 
 class VitLayer(ctypes.Structure):
@@ -49,6 +49,7 @@ SIGNATURES = {
     "gvl_prof_summary": (c_int, [c_int, POINTER(ctypes.c_double), POINTER(c_ulonglong), POINTER(ctypes.c_double)]),
     "gvl_resize_taps": (c_int, [c_int, c_int, c_int, c_int, POINTER(c_int32), POINTER(c_int32), POINTER(c_int16),
                                 POINTER(c_int), POINTER(c_int)]),
+    "gvl_preprocess_path": (c_int, [c_int]),
     "gvl_preprocess_u8": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_float_p, c_float_p, c_void_p,
                                   c_int, c_int, c_int, c_void_p]),
     "gvl_preprocess_u8_crop": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int,

@@ -17,10 +17,12 @@
 // and leave as full contiguous segments (whole 592-element patch rows / whole CHW row pieces).
 // `preprocess_kernel` (v1, one byte per shared-memory load) remains as the fallback for geometries
 // outside the planar kernel's limits and for A/B runs (GVL_PRE_LEGACY=1).
-#include "common.cuh"
+#include "preprocess_common.cuh"
 
+#include <atomic>
 #include <cmath>
 #include <cstdlib>
+#include <cstring>
 #include <map>
 #include <mutex>
 #include <tuple>
@@ -39,13 +41,7 @@ static double aa_filter(double x, int resample) {
     return 0.0;
 }
 
-struct AxisTaps {
-    std::vector<int32_t> xmin, xsize;
-    std::vector<int16_t> w;  // [out][taps]
-    int taps = 0, precision = 0;
-};
-
-static int compute_axis_taps(int in_size, int out_size, int resample, AxisTaps& t) {
+int compute_axis_taps(int in_size, int out_size, int resample, AxisTaps& t) {
     if (in_size <= 0 || out_size <= 0) return 1;
     if (resample != GVL_RESAMPLE_BILINEAR && resample != GVL_RESAMPLE_BICUBIC) return 1;
     const int interp_size = resample == GVL_RESAMPLE_BILINEAR ? 2 : 4;
@@ -112,16 +108,9 @@ struct DevTables {
     int max_hsize = 0, max_vsize = 0;  // largest tap count actually used per axis
 };
 
-static std::mutex g_tab_mu;
+std::mutex g_tab_mu;
 typedef std::tuple<int, int, int, int, int, int, int, int, int, int, int, int> TabKey;
 static std::map<TabKey, DevTables> g_tabs;
-
-template <typename T>
-static int upload(const std::vector<T>& v, T** dptr) {
-    GVL_CUDA(cudaMalloc((void**)dptr, v.size() * sizeof(T)));
-    GVL_CUDA(cudaMemcpy(*dptr, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
-    return 0;
-}
 
 // eff_h x eff_w = region actually produced, starting at (cy0, cx0) of the resized image (crop window; the patch
 // layout drops the remainder rows / columns)
@@ -233,6 +222,8 @@ static int get_planar_tables(int H, int W, int out_h, int out_w, int resample, i
     out = t;
     return 0;
 }
+
+static std::atomic<int> g_pre_path{0};
 
 // ---- kernel ----
 
@@ -465,23 +456,6 @@ struct PlanarParams {
     int fast_rows;    // every frame row starts 16-byte aligned and W % 16 == 0
 };
 
-__device__ __forceinline__ int dp2a_lo(uint32_t w2, uint32_t px4, int acc) {
-    int d;
-    asm("dp2a.lo.s32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(w2), "r"(px4), "r"(acc));
-    return d;
-}
-__device__ __forceinline__ int dp2a_hi(uint32_t w2, uint32_t px4, int acc) {
-    int d;
-    asm("dp2a.hi.s32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(w2), "r"(px4), "r"(acc));
-    return d;
-}
-// {sat_u8(v3), sat_u8(v2), sat_u8(v1), sat_u8(v0)} with v0 in the low byte
-__device__ __forceinline__ uint32_t pack4_sat_u8(int v0, int v1, int v2, int v3) {
-    uint32_t hi, d;
-    asm("cvt.pack.sat.u8.s32.b32 %0, %1, %2, %3;" : "=r"(hi) : "r"(v3), "r"(v2), "r"(0));
-    asm("cvt.pack.sat.u8.s32.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(v1), "r"(v0), "r"(hi));
-    return d;
-}
 // 16 interleaved RGB pixels (12 words) -> 4 words per colour plane
 __device__ __forceinline__ void deinterleave16(const uint32_t (&a)[12], uint4& r, uint4& g, uint4& b) {
     uint32_t rr[4], gg[4], bb[4];
@@ -795,16 +769,9 @@ preprocess_planar_kernel(const PlanarParams p) {
 
 // (u8 - sub[c]) / div[c] in fp32 (IEEE division on the host), cached per (device, sub, div)
 static std::map<std::tuple<int, float, float, float, float, float, float>, float*> g_luts;
-static int get_lut(const float* sub, const float* div, float** out) {
+int get_lut(const float* sub, const float* div, float** out, float* h_copy) {
     int dev = 0;
     GVL_CUDA(cudaGetDevice(&dev));
-    std::lock_guard<std::mutex> lk(g_tab_mu);
-    auto key = std::make_tuple(dev, sub[0], sub[1], sub[2], div[0], div[1], div[2]);
-    auto it = g_luts.find(key);
-    if (it != g_luts.end()) {
-        *out = it->second;
-        return 0;
-    }
     std::vector<float> h(768);
     for (int c = 0; c < 3; ++c)
         for (int u = 0; u < 256; ++u) {
@@ -812,6 +779,14 @@ static int get_lut(const float* sub, const float* div, float** out) {
             volatile float q = num / div[c];
             h[c * 256 + u] = q;
         }
+    if (h_copy) memcpy(h_copy, h.data(), 768 * sizeof(float));
+    std::lock_guard<std::mutex> lk(g_tab_mu);
+    auto key = std::make_tuple(dev, sub[0], sub[1], sub[2], div[0], div[1], div[2]);
+    auto it = g_luts.find(key);
+    if (it != g_luts.end()) {
+        *out = it->second;
+        return 0;
+    }
     float* d = nullptr;
     if (upload(h, &d)) return 2;
     g_luts[key] = d;
@@ -1063,6 +1038,13 @@ extern "C" int gvl_resize_taps(int in_size, int out_size, int resample, int max_
     return 0;
 }
 
+extern "C" int gvl_preprocess_path(int path) {
+    using namespace gvl;
+    GVL_CHECK_ARG(path >= GVL_PRE_PATH_AUTO && path <= GVL_PRE_PATH_V1, "gvl_preprocess_path: bad path %d", path);
+    g_pre_path.store(path, std::memory_order_relaxed);
+    return 0;
+}
+
 extern "C" int gvl_preprocess_u8(const uint8_t* frames, int B, int H, int W, int out_h, int out_w, int resample,
                                  const float* h_sub, const float* h_div, void* out, int layout, int patch, int ld,
                                  void* stream) {
@@ -1079,10 +1061,14 @@ extern "C" int gvl_preprocess_u8(const uint8_t* frames, int B, int H, int W, int
         GVL_CHECK_ARG(out_h >= patch && out_w >= patch, "gvl_preprocess_u8: output smaller than one patch");
     }
     {
-        const char* legacy = getenv("GVL_PRE_LEGACY");
-        if (!(legacy && legacy[0] == '1')) {
-            const int prc = launch_planar(frames, B, H, W, out_h, out_w, resample, h_sub, h_div, out, layout, patch, ld,
-                                          reinterpret_cast<cudaStream_t>(stream));
+        const int path = g_pre_path.load(std::memory_order_relaxed);
+        cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+        if (path == GVL_PRE_PATH_AUTO && layout == GVL_LAYOUT_BF16_PATCH) {
+            const int src = launch_stream5(frames, B, H, W, out_h, out_w, resample, h_sub, h_div, out, patch, ld, st);
+            if (src != -1) return src;
+        }
+        if (path != GVL_PRE_PATH_V1) {
+            const int prc = launch_planar(frames, B, H, W, out_h, out_w, resample, h_sub, h_div, out, layout, patch, ld, st);
             if (prc != -1) return prc;
         }
     }

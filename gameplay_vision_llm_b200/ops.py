@@ -4,6 +4,7 @@ CUDA stream and raises RuntimeError on any failure (there is no eager/PyTorch fa
 """
 from __future__ import annotations
 
+import contextlib
 import ctypes
 import functools
 
@@ -103,6 +104,19 @@ def preprocess(frames: torch.Tensor, out_h: int = 384, out_w: int = 384, resampl
         frames.data_ptr(), B, H, W, out_h, out_w, resample, sub.ctypes.data_as(_lib.c_float_p),
         div.ctypes.data_as(_lib.c_float_p), out.data_ptr(), layout, patch, ld, _stream()), "gvl_preprocess_u8")
     return out
+
+
+PRE_PATH_AUTO, PRE_PATH_PLANAR, PRE_PATH_V1 = 0, 1, 2
+
+
+@contextlib.contextmanager
+def preprocess_path(path: int):
+    """Pin `preprocess` to one of its (bit-identical) kernels for tests and A/B timing; AUTO on exit."""
+    _lib.check(_lib.lib().gvl_preprocess_path(path), "gvl_preprocess_path")
+    try:
+        yield
+    finally:
+        _lib.lib().gvl_preprocess_path(PRE_PATH_AUTO)
 
 
 @_on_tensor_device

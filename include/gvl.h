@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define GVL_ABI_VERSION 5
+#define GVL_ABI_VERSION 6
 
 #if defined(__GNUC__)
 #define GVL_API __attribute__((visibility("default")))
@@ -94,6 +94,11 @@ GVL_API int gvl_resize_taps(int in_size, int out_size, int resample, int max_tap
 GVL_API int gvl_preprocess_u8(const uint8_t* frames, int B, int H, int W, int out_h, int out_w, int resample,
                       const float* h_sub, const float* h_div, void* out, int layout, int patch, int ld,
                       void* stream);
+
+/* Kernel selection of gvl_preprocess_u8 (process-wide; tests and A/B runs — every path is bit-identical):
+ * AUTO = the streaming 5:1 kernel (preprocess_stream.cu) where its geometry applies, else the planar kernel, else v1. */
+enum { GVL_PRE_PATH_AUTO = 0, GVL_PRE_PATH_PLANAR = 1, GVL_PRE_PATH_V1 = 2 };
+GVL_API int gvl_preprocess_path(int path);
 
 /* pixel_values: float [B,3,H,W] (what the HF processor returns) -> bf16 im2col rows [B*gh*gw, ld], i.e. the
  * `.to(bfloat16)` + patch extraction at the head of `get_image_features(pixel_values=...)`

@@ -252,13 +252,46 @@ def test_preprocess_rejects_out_of_range_geometry():
         ops.preprocess(frames, 37, 61, 2, layout=ops.LAYOUT_U8_CHW)
 
 
-def test_preprocess_legacy_kernel_matches(monkeypatch):
-    """The v1 kernel (GVL_PRE_LEGACY=1) stays bit-exact: it is the fallback for out-of-range geometries."""
+def test_preprocess_legacy_kernel_matches():
+    """The v1 kernel stays bit-exact: it is the fallback for out-of-range geometries."""
     frames = synth.noise_frames(2, 1080, 1920, seed=11)
     want = preprocess_ref.resize_u8(frames.numpy(), 384, 384, 2)
-    monkeypatch.setenv("GVL_PRE_LEGACY", "1")
-    got = ops.preprocess(frames.to(DEV), 384, 384, 2, layout=ops.LAYOUT_U8_CHW).cpu().numpy()
+    with ops.preprocess_path(ops.PRE_PATH_V1):
+        got = ops.preprocess(frames.to(DEV), 384, 384, 2, layout=ops.LAYOUT_U8_CHW).cpu().numpy()
     assert np.array_equal(got, want)
+
+
+@pytest.mark.parametrize("B,H,W,size,patch,mean,std", [
+    (5, 1080, 1920, 384, 14, (0.5, 0.5, 0.5), (0.5, 0.5, 0.5)),          # the headline geometry (streaming 5:1 kernel)
+    (3, 1080, 1920, 384, 16, (0.5, 0.5, 0.5), (0.5, 0.5, 0.5)),          # 24 x 24 patches of 16: strips without slack
+    (2, 1080, 1920, 384, 14, (0.485, 0.456, 0.406), (0.229, 0.224, 0.225)),  # ImageNet constants
+    (3, 385, 1920, 384, 14, (0.5, 0.5, 0.5), (0.5, 0.5, 0.5)),           # odd height, near-identity vertical scale
+    (2, 2160, 1920, 384, 14, (0.5, 0.5, 0.5), (0.5, 0.5, 0.5)),          # vertical windows of 12 rows: falls back
+    (2, 720, 1280, 256, 16, (0.5, 0.5, 0.5), (0.5, 0.5, 0.5)),           # another 5:1 width
+])
+def test_preprocess_streaming_kernel_bit_exact(B, H, W, size, patch, mean, std):
+    """Patch layout on 5:1 widths (auto path = preprocess_stream.cu where it applies) against the oracle AND against
+    the planar kernel, on noise frames (every tap matters) plus a structured scene."""
+    frames = torch.cat([synth.noise_frames(B - 1, H, W, seed=H + patch), torch.from_numpy(synth.scene_frames_np(5, 1, H, W))])
+    pv = preprocess_ref.pixel_values(frames.numpy(), size, size, 2, image_mean=mean, image_std=std)
+    ld = (3 * patch * patch + 7) // 8 * 8
+    want = torch.from_numpy(preprocess_ref.patchify(pv, patch, ld)).to(torch.bfloat16)
+    dev = frames.to(DEV)
+    got = ops.preprocess(dev, size, size, 2, image_mean=mean, image_std=std, patch=patch).cpu()
+    with ops.preprocess_path(ops.PRE_PATH_PLANAR):
+        planar = ops.preprocess(dev, size, size, 2, image_mean=mean, image_std=std, patch=patch).cpu()
+    assert torch.equal(planar.view(torch.int16), want.view(torch.int16)), "planar kernel differs from the oracle"
+    nd = int((got.view(torch.int16) != want.view(torch.int16)).sum())
+    assert nd == 0, f"{nd} of {want.numel()} elements differ from the oracle"
+
+
+def test_preprocess_streaming_kernel_batch64_equals_planar():
+    """BASELINE's batch: 64 x 1080p, streaming kernel == planar kernel on every byte (run length 3, 1728 CTAs)."""
+    frames = synth.noise_frames(64, 1080, 1920, seed=64).to(DEV)
+    got = ops.preprocess(frames, 384, 384, 2)
+    with ops.preprocess_path(ops.PRE_PATH_PLANAR):
+        planar = ops.preprocess(frames, 384, 384, 2)
+    assert torch.equal(got.view(torch.int16), planar.view(torch.int16))
 
 
 def test_preprocess_unaligned_base_pointer():

@@ -131,10 +131,13 @@ def ln_case():
 def pre_case():
     frames = synth.noise_frames(64, seed=1).to(DEV)
     out = torch.empty(64 * 729, 592, device=DEV, dtype=torch.bfloat16)
-    for rs in (2, 3):
-        ms = timeit(lambda: ops.preprocess(frames, 384, 384, rs, out=out))
+    for rs, path, name in ((2, ops.PRE_PATH_AUTO, "streaming 5:1"), (2, ops.PRE_PATH_PLANAR, "planar"),
+                           (3, ops.PRE_PATH_AUTO, "planar")):
+        with ops.preprocess_path(path):
+            ms = timeit(lambda: ops.preprocess(frames, 384, 384, rs, out=out))
         gb = 64 * (1080 * 1920 * 3 + 729 * 588 * 2) / ms / 1e6
-        print(f"preprocess 64x1080p rs={rs}: {ms*1e3:.1f} us  {gb:.0f} GB/s ({gb/6552.6*100:.1f}% of measured HBM peak)")
+        print(f"preprocess 64x1080p rs={rs} [{name}]: {ms*1e3:.1f} us  {gb:.0f} GB/s "
+              f"({gb/6552.6*100:.1f}% of measured HBM peak)")
 
 
 def sustained_cases():

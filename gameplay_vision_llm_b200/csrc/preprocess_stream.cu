@@ -60,7 +60,7 @@ struct PsParams {
     int n_strips, run_len;
     int h_prec, v_prec;
     const uint32_t* hq;  // [n_strips][32][20] weight pairs
-    const uint32_t* vq;  // [gh * patch][8]: first row pair, 4 weight pairs, pad
+    const uint32_t* vq;  // [gh * patch][8]: 4 weight pairs, 4 ring positions (16 bit each), pad
     const int2* unit;    // [gh] first / last row pair of a patch row's vertical windows
     float na[3], nb[3];  // value = fmaf(u8, na, nb)
     const float* lut;    // [3][256], used when the fmaf form is not exact
@@ -87,12 +87,13 @@ __global__ void __launch_bounds__(PS_THREADS, 3)
 preprocess_stream5_kernel(const __grid_constant__ PsParams p) {
     extern __shared__ __align__(128) uint8_t ps_smem[];
     // [raw: NW warps x 2 slots x 2 rows x PITCH] [sH: 3 planes x SH_PAIRS x 64 words] [band: n_patch x ld bf16]
-    // [lut: 768 floats (LUT form only)] [full barriers: NW x 2]
+    // [vertical tables: 32 x 8 words] [lut: 768 floats (LUT form only)] [full barriers: NW x 2]
     uint8_t* raw = ps_smem;
     uint32_t* sH = reinterpret_cast<uint32_t*>(raw + PS_NW * 4 * PS_PITCH);
     uint16_t* band = reinterpret_cast<uint16_t*>(sH + 3 * PS_SH_PAIRS * 64);
     const int band_elems = ((PS_COLS / p.patch) * p.ld + 7) & ~7;
-    float* sLut = reinterpret_cast<float*>(band + band_elems);
+    uint32_t* sVQ = reinterpret_cast<uint32_t*>(band + band_elems);  // [patch][8] vertical tables of the current patch row
+    float* sLut = reinterpret_cast<float*>(sVQ + 32 * 8);
     uint64_t* full = reinterpret_cast<uint64_t*>(sLut + (ARITH ? 0 : 768));
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -113,30 +114,35 @@ preprocess_stream5_kernel(const __grid_constant__ PsParams p) {
         for (int i = tid; i < 768; i += PS_THREADS) sLut[i] = p.lut[i];
     __syncthreads();
 
-    // ---- this warp's row pairs: p_begin + warp + k * NW, k = 0, 1, ...; pair k lives in slot k & 1
-    auto issue = [&](int k) {
-        const int pp = p_begin + warp + k * PS_NW;
-        if (pp > p_end) return;
-        const int r0 = 2 * pp;
-        const int nr = min(2, row_last - r0 + 1);
+    // ---- this warp's row pairs: p_begin + warp + k * NW, k = 0 .. n_my-1; pair k lives in slot k & 1.  Lane 0 re-arms
+    // a slot right after the warp has consumed it and prefetches PS_PF pairs further ahead into L2.
+    const int n_my = p_end - p_begin - warp >= 0 ? (p_end - p_begin - warp) / PS_NW + 1 : 0;
+    // the frame's last pair has one row when H is odd
+    const int k_single = (2 * p_end + 1 > p.H - 1 && (p_end - p_begin - warp) % PS_NW == 0) ? n_my - 1 : -1;
+    const size_t pair_stride = (size_t)2 * PS_NW * row_bytes;
+    const uint8_t* my_src = fbase + (size_t)2 * (p_begin + warp) * row_bytes;
+    uint8_t* my_dst = raw + (size_t)(warp * 4) * PS_PITCH + st.dst_off;
+    const uint32_t len = (uint32_t)st.len;
+    auto issue = [&](int k) {  // lane 0 only, k < n_my
         uint64_t* bar = &full[warp * 2 + (k & 1)];
-        uint8_t* dst = raw + (size_t)((warp * 2 + (k & 1)) * 2) * PS_PITCH + st.dst_off;
-        const uint8_t* src = fbase + (size_t)r0 * row_bytes;
-        mbar_arrive_expect_tx(bar, (uint32_t)(nr * st.len));
-        for (int r = 0; r < nr; ++r) ps_bulk_g2s(dst + r * PS_PITCH, src + r * row_bytes, (uint32_t)st.len, bar);
+        uint8_t* dst = my_dst + (k & 1) * (2 * PS_PITCH);
+        const uint8_t* src = my_src + (size_t)k * pair_stride;
+        const bool two = k != k_single;
+        mbar_arrive_expect_tx(bar, two ? 2 * len : len);
+        ps_bulk_g2s(dst, src, len, bar);
+        if (two) ps_bulk_g2s(dst + PS_PITCH, src + row_bytes, len, bar);
     };
     auto prefetch = [&](int k) {
-        const int pp = p_begin + warp + k * PS_NW;
-        if (pp > p_end) return;
-        const int r0 = 2 * pp;
-        const int nr = min(2, row_last - r0 + 1);
-        for (int r = 0; r < nr; ++r) ps_prefetch_l2(fbase + (size_t)(r0 + r) * row_bytes, (uint32_t)st.len);
+        const uint8_t* src = my_src + (size_t)k * pair_stride;
+        ps_prefetch_l2(src, len);
+        if (k != k_single) ps_prefetch_l2(src + row_bytes, len);
     };
     if (lane == 0) {
-        issue(0);
-        issue(1);
+        if (0 < n_my) issue(0);
+        if (1 < n_my) issue(1);
 #pragma unroll
-        for (int i = 2; i < 2 + PS_PF; ++i) prefetch(i);
+        for (int i = 2; i < 2 + PS_PF; ++i)
+            if (i < n_my) prefetch(i);
     }
 
     // ---- per-lane constants
@@ -161,31 +167,42 @@ preprocess_stream5_kernel(const __grid_constant__ PsParams p) {
         if (cb >= 0 && cb + 1 < ncols) idx_b = (cb / p.patch) * p.ld + cb % p.patch;
     }
     const int PP = p.patch * p.patch;
-    const int v_tasks = 3 * p.patch;
+    const float na0 = p.na[0], na1 = p.na[1], na2 = p.na[2], nb0 = p.nb[0], nb1 = p.nb[1], nb2 = p.nb[2];
 
     int k = 0;
+    int pp = p_begin + warp;          // this warp's next row pair
+    int h_slot = pp % PS_SH_PAIRS;    // and its place in the intermediate ring
     for (int u = u0; u < u1; ++u) {
         const int pair_hi = __ldg(&p.unit[u]).y;
+        // vertical tables of this patch row (read after the barrier below)
+        if (tid < 2 * p.patch)
+            reinterpret_cast<uint4*>(sVQ)[tid] = __ldg(reinterpret_cast<const uint4*>(p.vq + (size_t)u * p.patch * 8) + tid);
         // ---- horizontal pass of the row pairs this patch row still needs
-        for (;; ++k) {
-            const int pp = p_begin + warp + k * PS_NW;
-            if (pp > pair_hi) break;
+        for (; pp <= pair_hi; ++k, pp += PS_NW) {
             mbar_wait(&full[warp * 2 + (k & 1)], (uint32_t)(k >> 1) & 1u);
             const uint32_t* src = my_raw + (k & 1) * (2 * PS_PITCH / 4);
             int acc[2][3][4];
 #pragma unroll
             for (int r = 0; r < 2; ++r) {
+                // 19 interleaved words (the lane's bytes 4 .. 79) -> 7 words per plane; of the first / last planar
+                // word only the upper / lower half is ever multiplied
                 uint32_t a[21];
 #pragma unroll
-                for (int i = 0; i < 21; ++i) a[i] = src[r * (PS_PITCH / 4) + i];
+                for (int i = 1; i < 20; ++i) a[i] = src[r * (PS_PITCH / 4) + i];
                 uint32_t pl[3][7];
+                pl[0][0] = __byte_perm(a[1], a[2], 0x5200);  // planar bytes 2, 3 (interleaved 6, 9) in place
+                pl[1][0] = __byte_perm(a[1], a[2], 0x6300);  // 7, 10
+                pl[2][0] = __byte_perm(a[1], a[2], 0x7400);  // 8, 11
 #pragma unroll
-                for (int m = 0; m < 7; ++m) {
+                for (int m = 1; m < 6; ++m) {
                     const uint32_t w0 = a[3 * m], w1 = a[3 * m + 1], w2 = a[3 * m + 2];
                     pl[0][m] = __byte_perm(__byte_perm(w0, w1, 0x0630), w2, 0x5210);  // bytes 0,3,6,9
                     pl[1][m] = __byte_perm(__byte_perm(w0, w1, 0x0741), w2, 0x6210);  // bytes 1,4,7,10
                     pl[2][m] = __byte_perm(__byte_perm(w0, w1, 0x0052), w2, 0x7410);  // bytes 2,5,8,11
                 }
+                pl[0][6] = __byte_perm(a[18], a[19], 0x0030);  // planar bytes 24, 25 (interleaved 72, 75)
+                pl[1][6] = __byte_perm(a[18], a[19], 0x0041);  // 73, 76
+                pl[2][6] = __byte_perm(a[18], a[19], 0x0052);  // 74, 77
 #pragma unroll
                 for (int c = 0; c < 3; ++c)
 #pragma unroll
@@ -199,7 +216,7 @@ preprocess_stream5_kernel(const __grid_constant__ PsParams p) {
                         acc[r][c][j] = s >> p.h_prec;
                     }
             }
-            uint32_t* dst = sH + (pp % PS_SH_PAIRS) * 64 + 2 * lane;
+            uint32_t* dst = sH + h_slot * 64 + 2 * lane;
 #pragma unroll
             for (int c = 0; c < 3; ++c) {
                 uint2 w;
@@ -207,50 +224,52 @@ preprocess_stream5_kernel(const __grid_constant__ PsParams p) {
                 w.y = pack4_sat_u8(acc[0][c][2], acc[1][c][2], acc[0][c][3], acc[1][c][3]);
                 *reinterpret_cast<uint2*>(dst + c * (PS_SH_PAIRS * 64)) = w;
             }
+            h_slot += PS_NW;
+            if (h_slot >= PS_SH_PAIRS) h_slot -= PS_SH_PAIRS;
             __syncwarp();
             if (lane == 0) {
-                issue(k + 2);
-                prefetch(k + 2 + PS_PF);
+                if (k + 2 < n_my) issue(k + 2);
+                if (k + 2 + PS_PF < n_my) prefetch(k + 2 + PS_PF);
             }
         }
         if (tid == 0) tma_store_wait_read<0>();  // the previous patch row has left the band buffer
-        __syncthreads();                         // intermediate rows of this patch row complete
-        // ---- vertical pass + normalise: task = (output row of the patch row, plane)
-        for (int t = warp; t < v_tasks; t += PS_NW) {
-            const int yy = t / 3, c = t - 3 * yy;
-            const uint4* vrow = reinterpret_cast<const uint4*>(p.vq + (size_t)(u * p.patch + yy) * 8);
-            const uint4 q0 = __ldg(vrow), q1 = __ldg(vrow + 1);
-            const uint32_t wv[4] = {q0.y, q0.z, q0.w, q1.x};
-            int slot = (int)q0.x % PS_SH_PAIRS;
-            const uint2* src = reinterpret_cast<const uint2*>(sH + c * (PS_SH_PAIRS * 64)) + lane;
-            int s0 = v_round, s1 = v_round, s2 = v_round, s3 = v_round;
+        __syncthreads();                         // intermediate rows and tables of this patch row complete
+        // ---- vertical pass + normalise: task = output row of the patch row (all three planes)
+        for (int yy = warp; yy < p.patch; yy += PS_NW) {
+            const uint4 q0 = reinterpret_cast<const uint4*>(sVQ)[2 * yy], q1 = reinterpret_cast<const uint4*>(sVQ)[2 * yy + 1];
+            const uint32_t wv[4] = {q0.x, q0.y, q0.z, q0.w};
+            const int so[4] = {(int)(q1.x & 0xffffu), (int)(q1.x >> 16), (int)(q1.y & 0xffffu), (int)(q1.y >> 16)};
+            const uint2* src = reinterpret_cast<const uint2*>(sH) + lane;
+            uint16_t* brow = band + yy * p.patch;
 #pragma unroll
-            for (int i = 0; i < PS_VPAIRS; ++i) {
-                const uint2 w = src[slot * 32];
-                s0 = dp2a_lo(wv[i], w.x, s0);
-                s1 = dp2a_hi(wv[i], w.x, s1);
-                s2 = dp2a_lo(wv[i], w.y, s2);
-                s3 = dp2a_hi(wv[i], w.y, s3);
-                slot = slot + 1 == PS_SH_PAIRS ? 0 : slot + 1;
+            for (int c = 0; c < 3; ++c) {
+                int s0 = v_round, s1 = v_round, s2 = v_round, s3 = v_round;
+#pragma unroll
+                for (int i = 0; i < PS_VPAIRS; ++i) {
+                    const uint2 w = src[c * (PS_SH_PAIRS * 32) + so[i]];
+                    s0 = dp2a_lo(wv[i], w.x, s0);
+                    s1 = dp2a_hi(wv[i], w.x, s1);
+                    s2 = dp2a_lo(wv[i], w.y, s2);
+                    s3 = dp2a_hi(wv[i], w.y, s3);
+                }
+                const uint32_t u4 = pack4_sat_u8(s0 >> p.v_prec, s1 >> p.v_prec, s2 >> p.v_prec, s3 >> p.v_prec);
+                float f0, f1, f2, f3;
+                if (ARITH) {
+                    const float na = c == 0 ? na0 : (c == 1 ? na1 : na2), nb = c == 0 ? nb0 : (c == 1 ? nb1 : nb2);
+                    f0 = fmaf((float)(u4 & 0xffu), na, nb);
+                    f1 = fmaf((float)((u4 >> 8) & 0xffu), na, nb);
+                    f2 = fmaf((float)((u4 >> 16) & 0xffu), na, nb);
+                    f3 = fmaf((float)(u4 >> 24), na, nb);
+                } else {
+                    const float* l = sLut + c * 256;
+                    f0 = l[u4 & 0xffu];
+                    f1 = l[(u4 >> 8) & 0xffu];
+                    f2 = l[(u4 >> 16) & 0xffu];
+                    f3 = l[u4 >> 24];
+                }
+                if (idx_a >= 0) *reinterpret_cast<uint32_t*>(brow + idx_a + c * PP) = pack_bf16x2(f0, f1);
+                if (idx_b >= 0) *reinterpret_cast<uint32_t*>(brow + idx_b + c * PP) = pack_bf16x2(f2, f3);
             }
-            const uint32_t u4 = pack4_sat_u8(s0 >> p.v_prec, s1 >> p.v_prec, s2 >> p.v_prec, s3 >> p.v_prec);
-            float f0, f1, f2, f3;
-            if (ARITH) {
-                const float na = p.na[c], nb = p.nb[c];
-                f0 = fmaf((float)(u4 & 0xffu), na, nb);
-                f1 = fmaf((float)((u4 >> 8) & 0xffu), na, nb);
-                f2 = fmaf((float)((u4 >> 16) & 0xffu), na, nb);
-                f3 = fmaf((float)(u4 >> 24), na, nb);
-            } else {
-                const float* l = sLut + c * 256;
-                f0 = l[u4 & 0xffu];
-                f1 = l[(u4 >> 8) & 0xffu];
-                f2 = l[(u4 >> 16) & 0xffu];
-                f3 = l[u4 >> 24];
-            }
-            const int off = c * PP + yy * p.patch;
-            if (idx_a >= 0) *reinterpret_cast<uint32_t*>(band + idx_a + off) = pack_bf16x2(f0, f1);
-            if (idx_b >= 0) *reinterpret_cast<uint32_t*>(band + idx_b + off) = pack_bf16x2(f2, f3);
         }
         fence_proxy_async_smem();
         __syncthreads();
@@ -350,9 +369,10 @@ static int ps_get_tables(int H, int W, int out_h, int out_w, int resample, int p
         const int rel = tv.xmin[y] & 1;
         if (tv.xsize[y] + rel > 2 * PS_VPAIRS) return done();
         uint32_t* row = vq.data() + (size_t)y * 8;
-        row[0] = (uint32_t)(tv.xmin[y] >> 1);
         const int16_t* w = tv.w.data() + (size_t)y * tv.taps;
-        for (int tp = 0; tp < tv.xsize[y]; ++tp) row[1 + ((tp + rel) >> 1)] |= (uint32_t)(uint16_t)w[tp] << (16 * ((tp + rel) & 1));
+        for (int tp = 0; tp < tv.xsize[y]; ++tp) row[(tp + rel) >> 1] |= (uint32_t)(uint16_t)w[tp] << (16 * ((tp + rel) & 1));
+        for (int i = 0; i < PS_VPAIRS; ++i)  // ring positions of the window's row pairs, as uint2 indices
+            row[4 + (i >> 1)] |= (uint32_t)((((tv.xmin[y] >> 1) + i) % PS_SH_PAIRS) * 32) << (16 * (i & 1));
     }
     for (int u = 0; u < t.gh; ++u) {
         const int ya = u * patch, yb = ya + patch - 1;
@@ -424,7 +444,7 @@ int launch_stream5(const uint8_t* frames, int B, int H, int W, int out_h, int ou
     const int n_runs = (t.gh + run_len - 1) / run_len;
     const int band_elems = ((PS_COLS / patch) * ld + 7) & ~7;
     const size_t smem = (size_t)PS_NW * 4 * PS_PITCH + (size_t)3 * PS_SH_PAIRS * 64 * 4 + (size_t)band_elems * 2 +
-                        (arith ? 0 : 768 * 4) + PS_NW * 2 * 8;
+                        32 * 8 * 4 + (arith ? 0 : 768 * 4) + PS_NW * 2 * 8;
     if (smem > 200 * 1024) return -1;
     dim3 grid(t.n_strips * n_runs, B, 1);
     ProfScope prof(GVL_K_PREPROCESS, (double)B * ((double)H * W * 3 + (double)t.gh * t.gw * 3 * patch * patch * 2), s);

@@ -8,8 +8,9 @@
 //     rows of one frame, and walks DOWN the frame: every source row of the run is filtered horizontally exactly
 //     once (the planar kernel re-filters the ~4.6 rows two tiles share: 12 % at 14-row tiles).
 //   * Source rows arrive as raw interleaved RGB through 1-D bulk async copies (cp.async.bulk, mbarrier completion):
-//     each warp owns a double-buffered slot of two rows and re-arms it itself; cp.async.bulk.prefetch.L2 runs
-//     PS_PF tasks further ahead so the copy into shared memory finds its bytes in L2.  No register staging.
+//     each warp owns a double-buffered slot of two rows and re-arms it itself as soon as the slot's words are in
+//     registers, i.e. before the arithmetic (two task times of lead).  An additional cp.async.bulk.prefetch.L2
+//     stream was measured and made it slower (87 us without, 91 / 94 / 96 / 104 us at distance 1 / 2 / 3 / 6).
 //   * Horizontal pass: with an exact 5:1 scale the window of column x starts at pixel 5x - 2, so a lane that filters
 //     four adjacent columns (4g .. 4g+3) of a row needs the 28 planar bytes 20g-4 .. 20g+23 — 21 interleaved words at
 //     a lane stride of 15 words (conflict-free) — de-interleaves them once (42 PRMT) and feeds every colour plane's
@@ -37,7 +38,6 @@ constexpr int PS_COLS = 128;             // output columns a strip computes (4 p
 constexpr int PS_PITCH = 1968;           // bytes per staged source row: 32 lanes x 60 + 24 + alignment slack, 16 B multiple
 constexpr int PS_SH_PAIRS = 24;          // ring of intermediate row pairs (48 rows)
 constexpr int PS_VPAIRS = 4;             // row pairs per vertical window
-constexpr int PS_PF = 3;                 // L2 prefetch distance, in tasks of one warp
 constexpr int PS_MAX_STRIPS = 8;
 // first 16-bit pair (of the 14 a lane holds per plane) of column 4g + j: its window starts at planar byte 2 + 5j
 __host__ __device__ constexpr int ps_hp(int j) { return (2 + PS_S * j) >> 1; }
@@ -78,9 +78,6 @@ __device__ __forceinline__ void ps_bulk_s2g(void* dst, const void* src, uint32_t
     asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(smem_u32(src)), "r"(bytes)
                  : "memory");
 }
-__device__ __forceinline__ void ps_prefetch_l2(const void* src, uint32_t bytes) {
-    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
-}
 
 template <bool ARITH>
 __global__ void __launch_bounds__(PS_THREADS, 3)
@@ -96,7 +93,8 @@ preprocess_stream5_kernel(const __grid_constant__ PsParams p) {
     float* sLut = reinterpret_cast<float*>(sVQ + 32 * 8);
     uint64_t* full = reinterpret_cast<uint64_t*>(sLut + (ARITH ? 0 : 768));
 
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);  // (tells the compiler it is warp-uniform)
     const int strip = blockIdx.x % p.n_strips, run = blockIdx.x / p.n_strips, b = blockIdx.y;
     const PsStrip& st = p.strip[strip];
     const int u0 = run * p.run_len, u1 = min(u0 + p.run_len, p.gh);
@@ -115,7 +113,7 @@ preprocess_stream5_kernel(const __grid_constant__ PsParams p) {
     __syncthreads();
 
     // ---- this warp's row pairs: p_begin + warp + k * NW, k = 0 .. n_my-1; pair k lives in slot k & 1.  Lane 0 re-arms
-    // a slot right after the warp has consumed it and prefetches PS_PF pairs further ahead into L2.
+    // a slot as soon as the warp has pulled its words into registers.
     const int n_my = p_end - p_begin - warp >= 0 ? (p_end - p_begin - warp) / PS_NW + 1 : 0;
     // the frame's last pair has one row when H is odd
     const int k_single = (2 * p_end + 1 > p.H - 1 && (p_end - p_begin - warp) % PS_NW == 0) ? n_my - 1 : -1;
@@ -132,17 +130,9 @@ preprocess_stream5_kernel(const __grid_constant__ PsParams p) {
         ps_bulk_g2s(dst, src, len, bar);
         if (two) ps_bulk_g2s(dst + PS_PITCH, src + row_bytes, len, bar);
     };
-    auto prefetch = [&](int k) {
-        const uint8_t* src = my_src + (size_t)k * pair_stride;
-        ps_prefetch_l2(src, len);
-        if (k != k_single) ps_prefetch_l2(src + row_bytes, len);
-    };
     if (lane == 0) {
         if (0 < n_my) issue(0);
         if (1 < n_my) issue(1);
-#pragma unroll
-        for (int i = 2; i < 2 + PS_PF; ++i)
-            if (i < n_my) prefetch(i);
     }
 
     // ---- per-lane constants
@@ -181,28 +171,33 @@ preprocess_stream5_kernel(const __grid_constant__ PsParams p) {
         for (; pp <= pair_hi; ++k, pp += PS_NW) {
             mbar_wait(&full[warp * 2 + (k & 1)], (uint32_t)(k >> 1) & 1u);
             const uint32_t* src = my_raw + (k & 1) * (2 * PS_PITCH / 4);
+            // 19 interleaved words per row (the lane's bytes 4 .. 79); once both rows are in registers the slot is
+            // re-armed with the warp's pair after next, so that copy has two task times to land
+            uint32_t a[2][21];
+#pragma unroll
+            for (int r = 0; r < 2; ++r)
+#pragma unroll
+                for (int i = 1; i < 20; ++i) a[r][i] = src[r * (PS_PITCH / 4) + i];
+            __syncwarp();
+            if (lane == 0 && k + 2 < n_my) issue(k + 2);
             int acc[2][3][4];
 #pragma unroll
             for (int r = 0; r < 2; ++r) {
-                // 19 interleaved words (the lane's bytes 4 .. 79) -> 7 words per plane; of the first / last planar
-                // word only the upper / lower half is ever multiplied
-                uint32_t a[21];
-#pragma unroll
-                for (int i = 1; i < 20; ++i) a[i] = src[r * (PS_PITCH / 4) + i];
+                // -> 7 words per plane; of the first / last planar word only the upper / lower half is ever multiplied
                 uint32_t pl[3][7];
-                pl[0][0] = __byte_perm(a[1], a[2], 0x5200);  // planar bytes 2, 3 (interleaved 6, 9) in place
-                pl[1][0] = __byte_perm(a[1], a[2], 0x6300);  // 7, 10
-                pl[2][0] = __byte_perm(a[1], a[2], 0x7400);  // 8, 11
+                pl[0][0] = __byte_perm(a[r][1], a[r][2], 0x5200);  // planar bytes 2, 3 (interleaved 6, 9) in place
+                pl[1][0] = __byte_perm(a[r][1], a[r][2], 0x6300);  // 7, 10
+                pl[2][0] = __byte_perm(a[r][1], a[r][2], 0x7400);  // 8, 11
 #pragma unroll
                 for (int m = 1; m < 6; ++m) {
-                    const uint32_t w0 = a[3 * m], w1 = a[3 * m + 1], w2 = a[3 * m + 2];
+                    const uint32_t w0 = a[r][3 * m], w1 = a[r][3 * m + 1], w2 = a[r][3 * m + 2];
                     pl[0][m] = __byte_perm(__byte_perm(w0, w1, 0x0630), w2, 0x5210);  // bytes 0,3,6,9
                     pl[1][m] = __byte_perm(__byte_perm(w0, w1, 0x0741), w2, 0x6210);  // bytes 1,4,7,10
                     pl[2][m] = __byte_perm(__byte_perm(w0, w1, 0x0052), w2, 0x7410);  // bytes 2,5,8,11
                 }
-                pl[0][6] = __byte_perm(a[18], a[19], 0x0030);  // planar bytes 24, 25 (interleaved 72, 75)
-                pl[1][6] = __byte_perm(a[18], a[19], 0x0041);  // 73, 76
-                pl[2][6] = __byte_perm(a[18], a[19], 0x0052);  // 74, 77
+                pl[0][6] = __byte_perm(a[r][18], a[r][19], 0x0030);  // planar bytes 24, 25 (interleaved 72, 75)
+                pl[1][6] = __byte_perm(a[r][18], a[r][19], 0x0041);  // 73, 76
+                pl[2][6] = __byte_perm(a[r][18], a[r][19], 0x0052);  // 74, 77
 #pragma unroll
                 for (int c = 0; c < 3; ++c)
 #pragma unroll
@@ -226,11 +221,6 @@ preprocess_stream5_kernel(const __grid_constant__ PsParams p) {
             }
             h_slot += PS_NW;
             if (h_slot >= PS_SH_PAIRS) h_slot -= PS_SH_PAIRS;
-            __syncwarp();
-            if (lane == 0) {
-                if (k + 2 < n_my) issue(k + 2);
-                if (k + 2 + PS_PF < n_my) prefetch(k + 2 + PS_PF);
-            }
         }
         if (tid == 0) tma_store_wait_read<0>();  // the previous patch row has left the band buffer
         __syncthreads();                         // intermediate rows and tables of this patch row complete

@@ -396,7 +396,7 @@ def retrieval_on_gathered(index_full, dev, n_queries: int = 128, k: int = 16) ->
             "ms_per_query_batch": round(ms, 4), "queries_per_s": round(n_queries / (ms * 1e-3), 1),
             "index_gbs": round(nbytes / (ms * 1e-3) / 1e9, 1), "hbm_frac": round(nbytes / (ms * 1e-3) / 1e9 / peaks["hbm_gbs"], 4),
             "self_retrieval": "every query's first hit is its own row (or an identical earlier frame), cosine > 0.9999",
-            "path": "tcgen05 GEMM scores + segmented select + exact fp32 re-score (bit-identical to the scan path)"
+            "path": "fused tcgen05 scoring with per-CTA candidate lists + float64 re-score of everything within the margin (bit-identical to the scan path)"
                     if n >= 4096 else "fp32 scan (index below the tensor path's 4096-row threshold)"}
 
 
@@ -434,7 +434,7 @@ def retrieval_probe(dev, n_index: int = 72000, dim: int = 4096, n_queries: int =
     return {"workload": f"cosine top-{k} of {n_queries} queries over a ({n_index}, {dim}) bf16 timeline index",
             "ms_per_query_batch": round(ms, 4), "queries_per_s": round(n_queries / (ms * 1e-3), 1),
             "index_gbs": round(nbytes / (ms * 1e-3) / 1e9, 1), "hbm_frac": round(nbytes / (ms * 1e-3) / 1e9 / peaks["hbm_gbs"], 4),
-            "path": "tcgen05 GEMM scores + segmented select + exact fp32 re-score (bit-identical to the scan path)"}
+            "path": "fused tcgen05 scoring with per-CTA candidate lists + float64 re-score of everything within the margin (bit-identical to the scan path)"}
 
 
 # ------------------------------------------------------------------------------ VideoMAE workload (configs[3])

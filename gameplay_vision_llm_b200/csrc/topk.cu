@@ -23,6 +23,8 @@ namespace gvl {
 constexpr int TOPK_QB = 8;        // queries per scan pass
 constexpr int TOPK_THREADS = 256;
 constexpr int TOPK_CAND = 512;    // candidates per query the tensor path re-scores exactly
+constexpr int TOPK_MAX_LISTS = 512;       // candidate lists per query the refinement's pre-filter handles
+constexpr int TOPK_RANK_CAP = 1024;       // candidates ranked by counting instead of k arg-max rounds
 constexpr int TOPK_REFINE_STAGE = 4096;  // non-empty candidates of one query staged in shared memory by the refinement
 constexpr float TOPK_MARGIN = 6e-5f;  // > 2 x the tensor path's score error (measured 9e-6 at D = 4096)
 constexpr float TOPK_MARGIN_SCAN = 8e-6f;  // > 2 x the fp32 scan's accumulation error (measured < 2e-6 at D = 4096)
@@ -318,6 +320,12 @@ __device__ __forceinline__ double tk_warp_sum_f64(double v) {
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
     return v;
 }
+// order-preserving float <-> int key (signed integer comparison == float comparison, NaN excluded by the caller)
+__device__ __forceinline__ int tk_order_key(float v) {
+    const int i = __float_as_int(v);
+    return i >= 0 ? i : i ^ 0x7fffffff;
+}
+__device__ __forceinline__ float tk_order_unkey(int k) { return __int_as_float(k >= 0 ? k : k ^ 0x7fffffff); }
 __device__ __forceinline__ bool tk_better_f64(double sa, int ia, double sb, int ib) {
     return sa > sb || (sa == sb && ia < ib);
 }
@@ -331,13 +339,11 @@ topk_refine_kernel(const __nv_bfloat16* __restrict__ index, int D, const __nv_bf
     __shared__ double s_exact[TOPK_CAND];
     __shared__ float s_vs[TOPK_REFINE_STAGE];   // the query's non-empty candidates, staged once (the k selection rounds
     __shared__ int s_vi[TOPK_REFINE_STAGE];     // below would otherwise re-read the sparse global lists k times)
-    __shared__ int s_n, s_trunc, s_nv;
+    __shared__ int s_lmax[TOPK_MAX_LISTS];      // per-list maximum score (order-preserving integer key)
+    __shared__ int s_n, s_trunc, s_nv, s_valid;
+    __shared__ unsigned s_thr0, s_kth;
     __shared__ double s_qn;
     __shared__ TkBlockBest sh;
-    __shared__ double sh_ws[TOPK_THREADS / 32];
-    __shared__ int sh_wi[TOPK_THREADS / 32];
-    __shared__ double sh_bs;
-    __shared__ int sh_bi;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int qi = blockIdx.x;
     int L = lists * list_len;
@@ -359,51 +365,103 @@ topk_refine_kernel(const __nv_bfloat16* __restrict__ index, int D, const __nv_bf
         acc = tk_warp_sum_f64(acc);
         if (lane == 0) s_qn = fmax(sqrt(acc), (double)eps);
     }
-    if (tid == 0) s_n = 0, s_trunc = 0, s_nv = 0;
+    if (tid == 0) s_n = 0, s_trunc = 0, s_nv = 0, s_thr0 = 0xff800000u;  // -inf
+    for (int j = tid; j < lists && j < TOPK_MAX_LISTS; j += TOPK_THREADS) s_lmax[j] = tk_order_key(-INFINITY);
     __syncthreads();
+    const float iq = raw ? (float)(1.0 / s_qn) : 1.0f;
+    const float margin_raw = raw ? margin / iq : margin;  // the margin is in cosine units
+    // Pre-filter (several lists): the k-th largest of the per-list maxima is reached by k distinct rows, so it is a
+    // lower bound of the provisional k-th best score; rows below it minus the margin cannot matter.
+    float pre = -INFINITY;
+    if (lists >= 2 && lists >= k && lists <= TOPK_MAX_LISTS) {
+        for (int j = tid; j < L; j += TOPK_THREADS) {
+            const float v = cs[j];
+            if (ci[j] >= 0 && v == v) atomicMax(&s_lmax[j / list_len], tk_order_key(v));
+        }
+        __syncthreads();
+        for (int t = tid; t < lists; t += TOPK_THREADS) {
+            const int mine = s_lmax[t];
+            int rank = 0;
+            for (int j = 0; j < lists; ++j) {
+                const int o = s_lmax[j];
+                rank += (o > mine || (o == mine && j < t)) ? 1 : 0;
+            }
+            if (rank == k - 1) s_thr0 = __float_as_uint(tk_order_unkey(mine));
+        }
+        __syncthreads();
+        pre = __uint_as_float(s_thr0) - margin_raw;  // (-inf when fewer than k lists hold a row)
+    }
     for (int j = tid; j < L; j += TOPK_THREADS) {
         const int t = ci[j];
         if (t >= 0) {
-            const int slot = atomicAdd(&s_nv, 1);
-            if (slot < TOPK_REFINE_STAGE) {
-                s_vs[slot] = cs[j];
-                s_vi[slot] = t;
+            const float v = cs[j];
+            if (!(v < pre)) {  // keeps NaN scores, like the unfiltered path
+                const int slot = atomicAdd(&s_nv, 1);
+                if (slot < TOPK_REFINE_STAGE) {
+                    s_vs[slot] = v;
+                    s_vi[slot] = t;
+                }
             }
         }
     }
     __syncthreads();
-    if (s_nv <= TOPK_REFINE_STAGE) {  // (else: more candidates than the stage holds — work on the global lists)
+    const bool staged = s_nv <= TOPK_REFINE_STAGE;
+    if (staged) {  // (else: more candidates than the stage holds — work on the global lists)
         cs = s_vs;
         ci = s_vi;
         L = s_nv;
     }
-    // provisional top-k by approximate score: k rounds of arg-max over the candidates (also the fall-back result)
-    float prev_s = INFINITY;
-    int prev_i = -1;
+    // provisional top-k by approximate score (also the fall-back result)
     float kth = -INFINITY;
-    __syncthreads();
-    const float iq = raw ? (float)(1.0 / s_qn) : 1.0f;
     int found = 0;
-    for (int r = 0; r < k; ++r) {
-        float bs = -INFINITY;
-        int bi = 0x7fffffff;
+    if (staged && L <= TOPK_RANK_CAP) {
+        // few candidates: every thread ranks its own among all of them — no block-wide rounds
+        if (tid == 0) s_kth = __float_as_uint(-INFINITY), s_valid = 0;
+        __syncthreads();
         for (int j = tid; j < L; j += TOPK_THREADS) {
-            const int t = ci[j];
             const float v = cs[j];
-            const bool elig = t >= 0 && ((r == 0) ? (v == v) : (v < prev_s || (v == prev_s && t > prev_i)));
-            if (elig && tk_better(v, t, bs, bi)) {
-                bs = v;
-                bi = t;
+            const int t = ci[j];
+            if (!(v == v)) continue;
+            int rank = 0;
+            for (int i = 0; i < L; ++i) {
+                const float o = cs[i];
+                rank += (o == o && tk_better(o, ci[i], v, t)) ? 1 : 0;
+            }
+            atomicAdd(&s_valid, 1);
+            if (rank < k) {
+                out_scores[(size_t)qi * k + rank] = v * iq;
+                out_idx[(size_t)qi * k + rank] = t;
+                if (rank == k - 1) s_kth = __float_as_uint(v);
             }
         }
-        tk_block_argmax(sh, bs, bi, prev_s, prev_i);
-        if (prev_i == 0x7fffffff) break;  // fewer than k candidates (block-uniform)
-        if (tid == 0) {
-            out_scores[(size_t)qi * k + r] = prev_s * iq;
-            out_idx[(size_t)qi * k + r] = prev_i;
+        __syncthreads();
+        found = s_valid < k ? s_valid : k;
+        kth = __uint_as_float(s_kth);
+    } else {
+        // k rounds of arg-max over the candidates
+        float prev_s = INFINITY;
+        int prev_i = -1;
+        for (int r = 0; r < k; ++r) {
+            float bs = -INFINITY;
+            int bi = 0x7fffffff;
+            for (int j = tid; j < L; j += TOPK_THREADS) {
+                const int t = ci[j];
+                const float v = cs[j];
+                const bool elig = t >= 0 && ((r == 0) ? (v == v) : (v < prev_s || (v == prev_s && t > prev_i)));
+                if (elig && tk_better(v, t, bs, bi)) {
+                    bs = v;
+                    bi = t;
+                }
+            }
+            tk_block_argmax(sh, bs, bi, prev_s, prev_i);
+            if (prev_i == 0x7fffffff) break;  // fewer than k candidates (block-uniform)
+            if (tid == 0) {
+                out_scores[(size_t)qi * k + r] = prev_s * iq;
+                out_idx[(size_t)qi * k + r] = prev_i;
+            }
+            kth = prev_s;
+            found = r + 1;
         }
-        kth = prev_s;
-        found = r + 1;
     }
     if (found < k) {
         for (int r2 = found + tid; r2 < k; r2 += TOPK_THREADS) {
@@ -413,7 +471,7 @@ topk_refine_kernel(const __nv_bfloat16* __restrict__ index, int D, const __nv_bf
         kth = -INFINITY;  // every candidate is re-scored
     }
     // candidates within the margin of the provisional k-th score (margin is in cosine units)
-    const float thr = kth - (raw ? margin / iq : margin);
+    const float thr = kth - margin_raw;
     for (int j = tid; j < L; j += TOPK_THREADS) {
         const int t = ci[j];
         if (t >= 0 && cs[j] >= thr) {
@@ -456,52 +514,21 @@ topk_refine_kernel(const __nv_bfloat16* __restrict__ index, int D, const __nv_bf
         if (lane == 0) s_exact[j] = dot / (s_qn * fmax(sqrt(nrm), (double)eps));
     }
     __syncthreads();
-    // final selection: k rounds of arg-max under (score desc, row asc) on the float64 scores
-    double pd = INFINITY;
-    int pi = -1;
-    for (int r = 0; r < k && r < n; ++r) {
-        double bs = -INFINITY;
-        int bi = 0x7fffffff;
-        for (int j = tid; j < n; j += TOPK_THREADS) {
-            const double v = s_exact[j];
-            const int t = s_cand[j];
-            const bool elig = (r == 0) ? (v == v) : (v < pd || (v == pd && t > pi));
-            if (elig && tk_better_f64(v, t, bs, bi)) {
-                bs = v;
-                bi = t;
-            }
+    // final selection under (score desc, row asc) on the float64 scores: n <= TOPK_CAND, every thread ranks its own
+    // candidates; slots beyond the number of non-NaN scores keep the provisional entries
+    for (int j = tid; j < n; j += TOPK_THREADS) {
+        const double v = s_exact[j];
+        const int t = s_cand[j];
+        if (!(v == v)) continue;
+        int rank = 0;
+        for (int i = 0; i < n; ++i) {
+            const double o = s_exact[i];
+            rank += (o == o && tk_better_f64(o, s_cand[i], v, t)) ? 1 : 0;
         }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            const double os = __shfl_xor_sync(0xffffffffu, bs, o);
-            const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-            if (tk_better_f64(os, oi, bs, bi)) {
-                bs = os;
-                bi = oi;
-            }
+        if (rank < k) {
+            out_scores[(size_t)qi * k + rank] = (float)v;
+            out_idx[(size_t)qi * k + rank] = t;
         }
-        if (lane == 0) {
-            sh_ws[warp] = bs;
-            sh_wi[warp] = bi;
-        }
-        __syncthreads();
-        if (tid == 0) {
-            double fs = sh_ws[0];
-            int fi = sh_wi[0];
-            for (int w = 1; w < TOPK_THREADS / 32; ++w)
-                if (tk_better_f64(sh_ws[w], sh_wi[w], fs, fi)) {
-                    fs = sh_ws[w];
-                    fi = sh_wi[w];
-                }
-            sh_bs = fs;
-            sh_bi = fi;
-            out_scores[(size_t)qi * k + r] = fi == 0x7fffffff ? -INFINITY : (float)fs;
-            out_idx[(size_t)qi * k + r] = fi == 0x7fffffff ? -1 : fi;
-        }
-        __syncthreads();
-        pd = sh_bs;
-        pi = sh_bi;
-        if (pi == 0x7fffffff) break;
     }
 }
 

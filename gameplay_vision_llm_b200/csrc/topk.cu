@@ -22,6 +22,7 @@ namespace gvl {
 
 constexpr int TOPK_QB = 8;        // queries per scan pass
 constexpr int TOPK_THREADS = 256;
+constexpr int TOPK_REFINE_THREADS = 1024;  // one CTA per query: its float64 re-scoring is a chain of DRAM round trips, one warp per row
 constexpr int TOPK_CAND = 512;    // candidates per query the tensor path re-scores exactly
 constexpr int TOPK_MAX_LISTS = 512;       // candidate lists per query the refinement's pre-filter handles
 constexpr int TOPK_RANK_CAP = 1024;       // candidates ranked by counting instead of k arg-max rounds
@@ -177,12 +178,13 @@ __device__ __forceinline__ bool tk_better(float sa, int ia, float sb, int ib) {
 // One round-based arg-max selection step shared by the kernels below: the block agrees on the best (score, index)
 // among the per-thread bests under (score desc, index asc).
 struct TkBlockBest {
-    float ws[TOPK_THREADS / 32];
-    int wi[TOPK_THREADS / 32];
+    float ws[32];
+    int wi[32];
     float best_s;
     int best_i;
 };
 __device__ __forceinline__ void tk_block_argmax(TkBlockBest& sh, float bs, int bi, float& out_s, int& out_i) {
+    const int n_warps = (int)(blockDim.x >> 5);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
@@ -201,7 +203,7 @@ __device__ __forceinline__ void tk_block_argmax(TkBlockBest& sh, float bs, int b
     if (tid == 0) {
         float fs = sh.ws[0];
         int fi = sh.wi[0];
-        for (int w = 1; w < TOPK_THREADS / 32; ++w)
+        for (int w = 1; w < n_warps; ++w)
             if (tk_better(sh.ws[w], sh.wi[w], fs, fi)) {
                 fs = sh.ws[w];
                 fi = sh.wi[w];
@@ -330,7 +332,7 @@ __device__ __forceinline__ bool tk_better_f64(double sa, int ia, double sb, int 
     return sa > sb || (sa == sb && ia < ib);
 }
 
-__global__ void __launch_bounds__(TOPK_THREADS)
+__global__ void __launch_bounds__(TOPK_REFINE_THREADS)
 topk_refine_kernel(const __nv_bfloat16* __restrict__ index, int D, const __nv_bfloat16* __restrict__ queries, float eps,
                    const float* __restrict__ cand_s, const int32_t* __restrict__ cand_i, int lists, int list_len, int k,
                    float margin, int raw, float* __restrict__ out_scores, int32_t* __restrict__ out_idx,
@@ -366,7 +368,7 @@ topk_refine_kernel(const __nv_bfloat16* __restrict__ index, int D, const __nv_bf
         if (lane == 0) s_qn = fmax(sqrt(acc), (double)eps);
     }
     if (tid == 0) s_n = 0, s_trunc = 0, s_nv = 0, s_thr0 = 0xff800000u;  // -inf
-    for (int j = tid; j < lists && j < TOPK_MAX_LISTS; j += TOPK_THREADS) s_lmax[j] = tk_order_key(-INFINITY);
+    for (int j = tid; j < lists && j < TOPK_MAX_LISTS; j += TOPK_REFINE_THREADS) s_lmax[j] = tk_order_key(-INFINITY);
     __syncthreads();
     const float iq = raw ? (float)(1.0 / s_qn) : 1.0f;
     const float margin_raw = raw ? margin / iq : margin;  // the margin is in cosine units
@@ -374,12 +376,12 @@ topk_refine_kernel(const __nv_bfloat16* __restrict__ index, int D, const __nv_bf
     // lower bound of the provisional k-th best score; rows below it minus the margin cannot matter.
     float pre = -INFINITY;
     if (lists >= 2 && lists >= k && lists <= TOPK_MAX_LISTS) {
-        for (int j = tid; j < L; j += TOPK_THREADS) {
+        for (int j = tid; j < L; j += TOPK_REFINE_THREADS) {
             const float v = cs[j];
             if (ci[j] >= 0 && v == v) atomicMax(&s_lmax[j / list_len], tk_order_key(v));
         }
         __syncthreads();
-        for (int t = tid; t < lists; t += TOPK_THREADS) {
+        for (int t = tid; t < lists; t += TOPK_REFINE_THREADS) {
             const int mine = s_lmax[t];
             int rank = 0;
             for (int j = 0; j < lists; ++j) {
@@ -391,7 +393,7 @@ topk_refine_kernel(const __nv_bfloat16* __restrict__ index, int D, const __nv_bf
         __syncthreads();
         pre = __uint_as_float(s_thr0) - margin_raw;  // (-inf when fewer than k lists hold a row)
     }
-    for (int j = tid; j < L; j += TOPK_THREADS) {
+    for (int j = tid; j < L; j += TOPK_REFINE_THREADS) {
         const int t = ci[j];
         if (t >= 0) {
             const float v = cs[j];
@@ -418,7 +420,7 @@ topk_refine_kernel(const __nv_bfloat16* __restrict__ index, int D, const __nv_bf
         // few candidates: every thread ranks its own among all of them — no block-wide rounds
         if (tid == 0) s_kth = __float_as_uint(-INFINITY), s_valid = 0;
         __syncthreads();
-        for (int j = tid; j < L; j += TOPK_THREADS) {
+        for (int j = tid; j < L; j += TOPK_REFINE_THREADS) {
             const float v = cs[j];
             const int t = ci[j];
             if (!(v == v)) continue;
@@ -444,7 +446,7 @@ topk_refine_kernel(const __nv_bfloat16* __restrict__ index, int D, const __nv_bf
         for (int r = 0; r < k; ++r) {
             float bs = -INFINITY;
             int bi = 0x7fffffff;
-            for (int j = tid; j < L; j += TOPK_THREADS) {
+            for (int j = tid; j < L; j += TOPK_REFINE_THREADS) {
                 const int t = ci[j];
                 const float v = cs[j];
                 const bool elig = t >= 0 && ((r == 0) ? (v == v) : (v < prev_s || (v == prev_s && t > prev_i)));
@@ -464,7 +466,7 @@ topk_refine_kernel(const __nv_bfloat16* __restrict__ index, int D, const __nv_bf
         }
     }
     if (found < k) {
-        for (int r2 = found + tid; r2 < k; r2 += TOPK_THREADS) {
+        for (int r2 = found + tid; r2 < k; r2 += TOPK_REFINE_THREADS) {
             out_scores[(size_t)qi * k + r2] = -INFINITY;
             out_idx[(size_t)qi * k + r2] = -1;
         }
@@ -472,7 +474,7 @@ topk_refine_kernel(const __nv_bfloat16* __restrict__ index, int D, const __nv_bf
     }
     // candidates within the margin of the provisional k-th score (margin is in cosine units)
     const float thr = kth - margin_raw;
-    for (int j = tid; j < L; j += TOPK_THREADS) {
+    for (int j = tid; j < L; j += TOPK_REFINE_THREADS) {
         const int t = ci[j];
         if (t >= 0 && cs[j] >= thr) {
             const int slot = atomicAdd(&s_n, 1);
@@ -480,7 +482,7 @@ topk_refine_kernel(const __nv_bfloat16* __restrict__ index, int D, const __nv_bf
         }
     }
     // a full list whose worst entry is still inside the margin may have dropped qualifying rows
-    for (int li_ = tid; li_ < lists; li_ += TOPK_THREADS) {
+    for (int li_ = tid; li_ < lists; li_ += TOPK_REFINE_THREADS) {
         float worst = INFINITY;
         bool full = gci[li_ * list_len + list_len - 1] >= 0;  // lists fill front to back
         for (int e = 0; full && e < list_len; ++e) {
@@ -496,7 +498,7 @@ topk_refine_kernel(const __nv_bfloat16* __restrict__ index, int D, const __nv_bf
         if (n > TOPK_CAND) return;  // provisional (approximate-score) result stays
     }
     // exact float64 scores: one warp per candidate
-    for (int j = warp; j < n; j += TOPK_THREADS / 32) {
+    for (int j = warp; j < n; j += TOPK_REFINE_THREADS / 32) {
         const uint4* er = reinterpret_cast<const uint4*>(index + (size_t)s_cand[j] * D);
         double dot = 0.0, nrm = 0.0;
         for (int c = lane; c < chunks; c += 32) {
@@ -516,7 +518,7 @@ topk_refine_kernel(const __nv_bfloat16* __restrict__ index, int D, const __nv_bf
     __syncthreads();
     // final selection under (score desc, row asc) on the float64 scores: n <= TOPK_CAND, every thread ranks its own
     // candidates; slots beyond the number of non-NaN scores keep the provisional entries
-    for (int j = tid; j < n; j += TOPK_THREADS) {
+    for (int j = tid; j < n; j += TOPK_REFINE_THREADS) {
         const double v = s_exact[j];
         const int t = s_cand[j];
         if (!(v == v)) continue;
@@ -555,6 +557,7 @@ int launch_topk_fused(const void* index, int N, int D, const void* queries, int 
                       const float* inv_e, const float* inv_q, float margin, int k, const int32_t* row_lo,
                       const int32_t* row_hi, float* cand_s, int32_t* cand_i, int* grid_out, cudaStream_t s);  // topk_fused.cu
 int topk_fused_list_len();
+int topk_fused_grid(int span);  // CTAs (= candidate lists per query) the fused kernel runs for a span of rows
 
 }  // namespace gvl
 
@@ -639,7 +642,7 @@ extern "C" int gvl_topk_cosine_ex(const void* index, int N, int D, const void* q
     GVL_CUDA(cudaMemsetAsync(overflow, 0, sizeof(int), s));
     if (span <= 0) {  // nothing is eligible: every slot empty
         ProfScope prof(GVL_K_TOPK_SELECT, 0.0, s);
-        topk_refine_kernel<<<Q, TOPK_THREADS, 0, s>>>(idx_bf, D, q_bf, eps, scratch, reinterpret_cast<int32_t*>(scratch), 0, 0, k,
+        topk_refine_kernel<<<Q, TOPK_REFINE_THREADS, 0, s>>>(idx_bf, D, q_bf, eps, scratch, reinterpret_cast<int32_t*>(scratch), 0, 0, k,
                                                       0.f, 0, out_scores, out_idx, overflow);
         GVL_LAUNCH_CHECK("topk_refine_kernel");
         return 0;
@@ -665,9 +668,7 @@ extern "C" int gvl_topk_cosine_ex(const void* index, int N, int D, const void* q
             float* cand_s = scratch + (size_t)q0 * ld;
             int grid = 0;
             // cand_i directly behind cand_s: nq * grid * KL floats each, grid <= 160 (TOPK_MIN_LD guarantees the room)
-            int ntiles = (span + 255) / 256;
-            int g = ntiles < sm_count() ? ntiles : sm_count();
-            if (g < 1) g = 1;
+            const int g = topk_fused_grid(span);
             GVL_CHECK_ARG((size_t)2 * g * KL <= ld, "gvl_topk_cosine: %d CTAs exceed the scratch layout", g);
             int32_t* cand_i = reinterpret_cast<int32_t*>(cand_s + (size_t)nq * g * KL);
             int rc = launch_topk_fused(index, N, D, q_bf + (size_t)q0 * D, nq, span_lo, span_hi, inv_norm ? inv_norm : inv_e,
@@ -675,7 +676,7 @@ extern "C" int gvl_topk_cosine_ex(const void* index, int N, int D, const void* q
                                        row_hi ? row_hi + q0 : nullptr, cand_s, cand_i, &grid, s);
             if (rc) return rc;
             ProfScope prof(GVL_K_TOPK_SELECT, (double)nq * grid * KL * 8, s);
-            topk_refine_kernel<<<nq, TOPK_THREADS, 0, s>>>(idx_bf, D, q_bf + (size_t)q0 * D, eps, cand_s, cand_i, grid, KL, k,
+            topk_refine_kernel<<<nq, TOPK_REFINE_THREADS, 0, s>>>(idx_bf, D, q_bf + (size_t)q0 * D, eps, cand_s, cand_i, grid, KL, k,
                                                            TOPK_MARGIN, 1, out_scores + (size_t)q0 * k, out_idx + (size_t)q0 * k,
                                                            overflow);
             GVL_LAUNCH_CHECK("topk_refine_kernel");
@@ -706,7 +707,7 @@ extern "C" int gvl_topk_cosine_ex(const void* index, int N, int D, const void* q
     }
     {
         ProfScope prof(GVL_K_TOPK_SELECT, (double)Q * kpre * 8, s);
-        topk_refine_kernel<<<Q, TOPK_THREADS, 0, s>>>(idx_bf, D, q_bf, eps, pre_s, pre_i, 1, kpre, k, TOPK_MARGIN_SCAN, 0,
+        topk_refine_kernel<<<Q, TOPK_REFINE_THREADS, 0, s>>>(idx_bf, D, q_bf, eps, pre_s, pre_i, 1, kpre, k, TOPK_MARGIN_SCAN, 0,
                                                       out_scores, out_idx, overflow);
         GVL_LAUNCH_CHECK("topk_refine_kernel");
     }

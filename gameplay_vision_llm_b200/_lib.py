@@ -7,14 +7,14 @@ from __future__ import annotations
 
 import ctypes
 import os
-from ctypes import POINTER, c_char_p, c_float, c_int, c_int16, c_int32, c_size_t, c_ulonglong, c_void_p
+from ctypes import POINTER, c_char_p, c_float, c_int, c_int16, c_int32, c_longlong, c_size_t, c_ulonglong, c_void_p
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 # GVL_LIB_PATH: A/B runs of two builds of the same library (tuning aid; the ABI version is still checked)
 LIB_PATH = os.environ.get("GVL_LIB_PATH") or os.path.join(_HERE, "libgvl_sm100a.so")
 
 c_float_p = POINTER(c_float)
-ABI_VERSION = 6  # include/gvl.h GVL_ABI_VERSION
+ABI_VERSION = 7  # include/gvl.h GVL_ABI_VERSION
 
 
 class VitLayer(ctypes.Structure):
@@ -54,6 +54,9 @@ SIGNATURES = {
                                   c_int, c_int, c_int, c_void_p]),
     "gvl_preprocess_u8_crop": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
                                        c_float_p, c_float_p, c_void_p, c_int, c_void_p]),
+    "gvl_preprocess_u8_crop_band": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
+                                            c_int, c_int, c_float_p, c_float_p, c_void_p, c_int, c_void_p]),
+    "gvl_copy_band_h2d": (c_int, [c_void_p, c_void_p, c_longlong, c_longlong, c_longlong, c_longlong, c_void_p]),
     "gvl_patchify_tubelet_bf16": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     "gvl_mean_tokens_bf16": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_void_p]),
     "gvl_videomae_workspace_bytes": (c_size_t, [POINTER(VitWeights), c_int]),

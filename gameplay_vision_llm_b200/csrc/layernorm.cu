@@ -79,18 +79,35 @@ namespace gvl {
 // (rstd, mean * rstd).  Same summation order as the consumer epilogue uses when it reads the slabs itself, so both
 // routes give identical bits; the consumer then needs ONE 8-byte load per row and tile instead of slots / 2 scattered
 // 16-byte loads.
+constexpr int kLnFinalizeMaxPairs = 10;  // 20 slots of 64 columns = rows of up to 1280 elements in registers
+
 __global__ void __launch_bounds__(256)
 ln_finalize_kernel(const float* __restrict__ stats, int rows, int slots, float inv_d, float eps, float2* __restrict__ out) {
     const int row = blockIdx.x * blockDim.x + threadIdx.x;
     if (row >= rows) return;
     const float4* sp = reinterpret_cast<const float4*>(stats + (size_t)row * slots * 2);
+    // all loads issued before the first use (one memory round trip per row instead of slots / 2); the sums keep the
+    // slot order, so the bits equal what a consumer reading the slots itself would get
+    const int pairs = slots >> 1;
+    float4 t[kLnFinalizeMaxPairs];
+#pragma unroll
+    for (int i = 0; i < kLnFinalizeMaxPairs; ++i) t[i] = i < pairs ? sp[i] : make_float4(0.f, 0.f, 0.f, 0.f);
     float s1 = 0.f, s2 = 0.f;
-    for (int i = 0; i < (slots >> 1); ++i) {
-        const float4 t = sp[i];
-        s1 += t.x;
-        s2 += t.y;
-        s1 += t.z;
-        s2 += t.w;
+#pragma unroll
+    for (int i = 0; i < kLnFinalizeMaxPairs; ++i) {
+        if (i < pairs) {
+            s1 += t[i].x;
+            s2 += t[i].y;
+            s1 += t[i].z;
+            s2 += t[i].w;
+        }
+    }
+    for (int i = kLnFinalizeMaxPairs; i < pairs; ++i) {  // wider rows than the tower's: plain loop
+        const float4 u = sp[i];
+        s1 += u.x;
+        s2 += u.y;
+        s1 += u.z;
+        s2 += u.w;
     }
     const float mean = s1 * inv_d;
     const float var = fmaxf(s2 * inv_d - mean * mean, 0.0f);

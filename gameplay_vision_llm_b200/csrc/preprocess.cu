@@ -453,7 +453,8 @@ struct PlanarParams {
     int vq_stride;
     void* out;
     int layout, patch, ld, gh, gw;
-    int fast_rows;    // every frame row starts 16-byte aligned and W % 16 == 0
+    int fast_rows;    // every stored row starts 16-byte aligned and holds whole 16-pixel chunks
+    int src_x0, src_w; // stored column band of the frames (0, W for whole frames)
 };
 
 // 16 interleaved RGB pixels (12 words) -> 4 words per colour plane
@@ -523,8 +524,10 @@ preprocess_planar_kernel(const PlanarParams p) {
     const int c_hi = p.h_min[x1 - 1] + p.h_size[x1 - 1];
     const int chunk0 = c_lo >> 4;                     // first 16-pixel chunk of the staged rows
     const int nch = ((c_hi + 15) >> 4) - chunk0;      // chunks per staged row
-    const int row_chunks = p.W >> 4;                  // whole chunks in a frame row
-    const size_t row_bytes = (size_t)p.W * 3;
+    // the source tensor may hold only the column band [src_x0, src_x0 + src_w) of the W-wide frames
+    const int chunk_base = chunk0 - (p.src_x0 >> 4);  // first staged chunk, counted from the stored row's start
+    const int row_chunks = p.src_w >> 4;              // whole chunks in a stored row
+    const size_t row_bytes = (size_t)p.src_w * 3;
     const uint8_t* fbase = p.frames + ((size_t)b * p.H + r_lo) * row_bytes;
 
     // ---- per-thread horizontal setup: column x0 + 4*lane + (warp & 3), row quad (warp >> 2) of each group.
@@ -570,9 +573,9 @@ preprocess_planar_kernel(const PlanarParams p) {
     for (int k = 0; k < LPT; ++k) {
         const int i = htid + k * PL_HALF;
         const int rr = i / nch, ch = i - rr * nch;
-        const bool ok = rr < 4 && (!FAST || chunk0 + ch < row_chunks);
+        const bool ok = rr < 4 && (!FAST || chunk_base + ch < row_chunks);
         item_rr[k] = ok ? slot * 4 + rr : 0x40000000;  // never < rows_left
-        src_off[k] = (slot * 4 + rr) * (int)row_bytes + (chunk0 + ch) * 48;
+        src_off[k] = (slot * 4 + rr) * (int)row_bytes + (chunk_base + ch) * 48;
         dst_off[k] = (slot * 4 + rr) * p.pw + ch * 16;
     }
     auto fetch_group = [&](int g) {
@@ -632,8 +635,8 @@ preprocess_planar_kernel(const PlanarParams p) {
         if (FAST && g < ngroups && htid < 4) {
             const int row = g * PL_RG + slot * 4 + htid;
             if (row < min(nrows, p.H - r_lo)) {
-                const int nb = min(nch, row_chunks - chunk0) * 48;
-                const uint8_t* src = fbase + (size_t)row * row_bytes + (size_t)chunk0 * 48;
+                const int nb = min(nch, row_chunks - chunk_base) * 48;
+                const uint8_t* src = fbase + (size_t)row * row_bytes + (size_t)chunk_base * 48;
                 asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(nb) : "memory");
             }
         }
@@ -799,10 +802,12 @@ int get_lut(const float* sub, const float* div, float** out, float* h_copy) {
 // image when crop_h == 0.
 static int launch_planar(const uint8_t* frames, int B, int H, int W, int out_h, int out_w, int resample,
                          const float* h_sub, const float* h_div, void* out, int layout, int patch, int ld,
-                         cudaStream_t s, int cy0 = 0, int cx0 = 0, int crop_h = 0, int crop_w = 0) {
+                         cudaStream_t s, int cy0 = 0, int cx0 = 0, int crop_h = 0, int crop_w = 0, int src_x0 = 0,
+                         int src_w = 0) {
     PlanarParams p;
     memset(&p, 0, sizeof(p));
     if (crop_h == 0) crop_h = out_h, crop_w = out_w;
+    if (src_w == 0) src_w = W;
     p.eff_h = crop_h;
     p.eff_w = crop_w;
     p.cy0 = cy0;
@@ -831,7 +836,7 @@ static int launch_planar(const uint8_t* frames, int B, int H, int W, int out_h, 
         nwv = tb.max_vsize + 3 <= 12 ? 3 : (tb.max_vsize + 3 <= 16 ? 4 : (tb.max_vsize + 3 <= 32 ? 8 : 0));
         lpt = 4 * tb.nch_max <= 2 * PL_HALF ? 2 : (4 * tb.nch_max <= 3 * PL_HALF ? 3 : 0);
         if (!nw || !nwv || !lpt) return -1;
-        const bool fast_rows = W % 16 == 0 && (uintptr_t)frames % 16 == 0;
+        const bool fast_rows = src_w % 16 == 0 && src_x0 % 16 == 0 && (uintptr_t)frames % 16 == 0;
         if (!fast_rows || (!(nw <= 4 && nwv <= 3 && lpt <= 2) && !(nw <= 6 && nwv <= 4 && lpt <= 2))) nw = 8, nwv = 8, lpt = 3;
         else if (!(nw <= 4 && nwv <= 3)) nw = 6, nwv = 4;
         pw = tb.nch_max * 16 + 32;
@@ -879,7 +884,9 @@ static int launch_planar(const uint8_t* frames, int B, int H, int W, int out_h, 
     p.layout = layout;
     p.patch = patch > 0 ? patch : 1;
     p.ld = ld;
-    p.fast_rows = (W % 16 == 0 && (uintptr_t)frames % 16 == 0) ? 1 : 0;
+    p.fast_rows = (src_w % 16 == 0 && src_x0 % 16 == 0 && (uintptr_t)frames % 16 == 0) ? 1 : 0;
+    p.src_x0 = src_x0;
+    p.src_w = src_w;
     dim3 grid((p.eff_w + TX - 1) / TX, (p.eff_h + TY - 1) / TY, B);
     const double out_bytes = layout == GVL_LAYOUT_BF16_PATCH ? (double)p.gh * p.gw * 3 * patch * patch * 2
                                                               : (double)3 * crop_h * crop_w * esize;
@@ -1020,6 +1027,54 @@ extern "C" int gvl_preprocess_u8_crop(const uint8_t* frames, int B, int H, int W
         return 1;
     }
     return rc;
+}
+
+extern "C" int gvl_preprocess_u8_crop_band(const uint8_t* frames, int B, int H, int W, int band_x0, int band_w, int out_h,
+                                           int out_w, int crop_y0, int crop_x0, int crop_h, int crop_w, int resample,
+                                           const float* h_sub, const float* h_div, void* out, int layout, void* stream) {
+    using namespace gvl;
+    GVL_CHECK_ARG(frames && out && h_sub && h_div, "gvl_preprocess_u8_crop_band: null pointer");
+    GVL_CHECK_ARG(B > 0 && B <= 65535 && H > 0 && W > 0 && out_h > 0 && out_w > 0, "gvl_preprocess_u8_crop_band: bad shape");
+    GVL_CHECK_ARG(layout >= GVL_LAYOUT_U8_CHW && layout <= GVL_LAYOUT_BF16_CHW,
+                  "gvl_preprocess_u8_crop_band: only the CHW layouts take a crop window (layout %d)", layout);
+    GVL_CHECK_ARG(H >= out_h && W >= out_w, "gvl_preprocess_u8_crop_band: only downscaling is supported (%dx%d -> %dx%d)",
+                  H, W, out_h, out_w);
+    GVL_CHECK_ARG(crop_y0 >= 0 && crop_x0 >= 0 && crop_h > 0 && crop_w > 0 && crop_y0 + crop_h <= out_h &&
+                      crop_x0 + crop_w <= out_w,
+                  "gvl_preprocess_u8_crop_band: crop window [%d,%d)+%dx%d outside the %dx%d resized image", crop_y0,
+                  crop_x0, crop_h, crop_w, out_h, out_w);
+    GVL_CHECK_ARG(band_x0 >= 0 && band_w > 0 && band_x0 + band_w <= W && band_x0 % 16 == 0,
+                  "gvl_preprocess_u8_crop_band: band [%d, %d) must start on a multiple of 16 inside the %d-wide frame",
+                  band_x0, band_x0 + band_w, W);
+    {
+        AxisTaps th;
+        GVL_CHECK_ARG(compute_axis_taps(W, out_w, resample, th) == 0, "gvl_preprocess_u8_crop_band: bad resize geometry");
+        const int need_lo = th.xmin[crop_x0];
+        const int need_hi = th.xmin[crop_x0 + crop_w - 1] + th.xsize[crop_x0 + crop_w - 1];
+        GVL_CHECK_ARG(band_x0 <= need_lo && need_hi <= band_x0 + band_w,
+                      "gvl_preprocess_u8_crop_band: the crop reads source columns [%d, %d), the band holds [%d, %d)", need_lo,
+                      need_hi, band_x0, band_x0 + band_w);
+    }
+    const int rc = launch_planar(frames, B, H, W, out_h, out_w, resample, h_sub, h_div, out, layout, 0, 0,
+                                 reinterpret_cast<cudaStream_t>(stream), crop_y0, crop_x0, crop_h, crop_w, band_x0, band_w);
+    if (rc == -1) {
+        set_error("gvl_preprocess_u8_crop_band: resize geometry %dx%d -> %dx%d is outside the kernel's tap window", H, W,
+                  out_h, out_w);
+        return 1;
+    }
+    return rc;
+}
+
+extern "C" int gvl_copy_band_h2d(void* dst, const void* src_host, long long rows, long long src_row_bytes,
+                                 long long band_offset_bytes, long long band_bytes, void* stream) {
+    using namespace gvl;
+    GVL_CHECK_ARG(dst && src_host && rows > 0 && band_bytes > 0 && band_offset_bytes >= 0 &&
+                      band_offset_bytes + band_bytes <= src_row_bytes,
+                  "gvl_copy_band_h2d: bad arguments");
+    GVL_CUDA(cudaMemcpy2DAsync(dst, (size_t)band_bytes, reinterpret_cast<const uint8_t*>(src_host) + band_offset_bytes,
+                               (size_t)src_row_bytes, (size_t)band_bytes, (size_t)rows, cudaMemcpyHostToDevice,
+                               reinterpret_cast<cudaStream_t>(stream)));
+    return 0;
 }
 
 extern "C" int gvl_resize_taps(int in_size, int out_size, int resample, int max_taps, int32_t* h_xmin, int32_t* h_xsize,

@@ -122,8 +122,12 @@ def preprocess_path(path: int):
 @_on_tensor_device
 def preprocess_crop(frames: torch.Tensor, out_h: int, out_w: int, crop_y0: int, crop_x0: int, crop_h: int, crop_w: int,
                     resample: int = BILINEAR, image_mean=(0.5, 0.5, 0.5), image_std=(0.5, 0.5, 0.5),
-                    layout: int = LAYOUT_BF16_CHW, out: torch.Tensor | None = None) -> torch.Tensor:
-    """uint8 [B,H,W,3] frames -> the crop window of the resized (out_h x out_w) image, normalized, CHW."""
+                    layout: int = LAYOUT_BF16_CHW, out: torch.Tensor | None = None,
+                    band: tuple[int, int] | None = None) -> torch.Tensor:
+    """uint8 [B,H,W,3] frames -> the crop window of the resized (out_h x out_w) image, normalized, CHW.
+
+    band = (x0, full_width): `frames` holds only the source columns [x0, x0 + frames.shape[2]) of full_width-wide
+    frames (see `crop_source_band` / `copy_band_h2d`); the result is bit-identical to the whole-frame call."""
     _need_cuda(frames)
     if frames.dtype != torch.uint8 or frames.dim() != 4 or frames.shape[-1] != 3 or not frames.is_contiguous():
         raise RuntimeError("frames must be a contiguous uint8 [B,H,W,3] tensor")
@@ -135,11 +139,46 @@ def preprocess_crop(frames: torch.Tensor, out_h: int, out_w: int, crop_y0: int, 
     elif tuple(out.shape) != shape or out.dtype != dtype or not out.is_contiguous():
         raise RuntimeError(f"preprocess_crop: `out` must be contiguous {dtype} {shape}")
     sub, div = fused_sub_div(image_mean, image_std)
-    _lib.check(_lib.lib().gvl_preprocess_u8_crop(
-        frames.data_ptr(), B, H, W, out_h, out_w, crop_y0, crop_x0, crop_h, crop_w, resample,
-        sub.ctypes.data_as(_lib.c_float_p), div.ctypes.data_as(_lib.c_float_p), out.data_ptr(), layout, _stream()),
-        "gvl_preprocess_u8_crop")
+    if band is None:
+        _lib.check(_lib.lib().gvl_preprocess_u8_crop(
+            frames.data_ptr(), B, H, W, out_h, out_w, crop_y0, crop_x0, crop_h, crop_w, resample,
+            sub.ctypes.data_as(_lib.c_float_p), div.ctypes.data_as(_lib.c_float_p), out.data_ptr(), layout, _stream()),
+            "gvl_preprocess_u8_crop")
+    else:
+        x0, full_w = int(band[0]), int(band[1])
+        _lib.check(_lib.lib().gvl_preprocess_u8_crop_band(
+            frames.data_ptr(), B, H, full_w, x0, W, out_h, out_w, crop_y0, crop_x0, crop_h, crop_w, resample,
+            sub.ctypes.data_as(_lib.c_float_p), div.ctypes.data_as(_lib.c_float_p), out.data_ptr(), layout, _stream()),
+            "gvl_preprocess_u8_crop_band")
     return out
+
+
+def crop_source_band(W: int, out_w: int, crop_x0: int, crop_w: int, resample: int = BILINEAR, align: int = 16) -> tuple[int, int]:
+    """(x0, width) of the source-column band the crop window [crop_x0, crop_x0 + crop_w) of a W -> out_w resize reads,
+    widened to multiples of `align` pixels (host only: ATen's tap table through gvl_resize_taps)."""
+    xmin, xsize, _, _ = resize_taps(W, out_w, resample)
+    lo = int(xmin[crop_x0])
+    hi = int(xmin[crop_x0 + crop_w - 1] + xsize[crop_x0 + crop_w - 1])
+    x0 = lo // align * align
+    x1 = min(W, -(-hi // align) * align)
+    return x0, x1 - x0
+
+
+def copy_band_h2d(dst: torch.Tensor, src_host: torch.Tensor, x0: int) -> torch.Tensor:
+    """dst (device uint8 [n,H,bw,3], contiguous) <- src_host[:, :, x0:x0+bw, :] of a contiguous host uint8 [n,H,W,3]
+    tensor (pinned for an asynchronous copy), as one strided cudaMemcpy2DAsync on dst's current stream."""
+    _need_cuda(dst)
+    if src_host.is_cuda or not src_host.is_contiguous() or not dst.is_contiguous() or src_host.dtype != torch.uint8 \
+            or dst.dtype != torch.uint8:
+        raise RuntimeError("copy_band_h2d: contiguous uint8 host source and device destination required")
+    n, H, W, C = src_host.shape
+    bw = dst.shape[2]
+    if tuple(dst.shape) != (n, H, bw, C) or x0 < 0 or x0 + bw > W:
+        raise RuntimeError(f"copy_band_h2d: destination {tuple(dst.shape)} is not a band of {tuple(src_host.shape)} at {x0}")
+    with torch.cuda.device(dst.device):
+        _lib.check(_lib.lib().gvl_copy_band_h2d(dst.data_ptr(), src_host.data_ptr(), n * H, W * C, x0 * C, bw * C,
+                                                torch.cuda.current_stream(dst.device).cuda_stream), "gvl_copy_band_h2d")
+    return dst
 
 
 @_on_tensor_device

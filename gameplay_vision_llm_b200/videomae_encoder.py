@@ -95,21 +95,31 @@ class VideoMAEClipEncoder:
             self._ws = torch.empty(need, dtype=torch.uint8, device=self.device)
         return self._ws
 
-    def preprocess(self, frames: torch.Tensor) -> torch.Tensor:
-        """uint8 [n,H,W,3] (device) -> bf16 pixel_values [n,3,S,S]."""
+    def preprocess(self, frames: torch.Tensor, band: tuple[int, int] | None = None) -> torch.Tensor:
+        """uint8 [n,H,W,3] (device) -> bf16 pixel_values [n,3,S,S].  band = (x0, full_width): `frames` holds only the
+        source columns [x0, x0 + frames.shape[2]) the center crop reads (`source_band`)."""
         s = self.spec
         _, H, W, _ = frames.shape
-        out_h, out_w, y0, x0 = resize_geometry(H, W, s.image, s.image)
+        full_w = W if band is None else band[1]
+        out_h, out_w, y0, x0 = resize_geometry(H, full_w, s.image, s.image)
         return ops.preprocess_crop(frames, out_h, out_w, y0, x0, s.image, s.image, self.resample, self.image_mean,
-                                   self.image_std, layout=ops.LAYOUT_BF16_CHW)
+                                   self.image_std, layout=ops.LAYOUT_BF16_CHW, band=band)
 
-    def encode_clips(self, frames: torch.Tensor, out_dtype: torch.dtype = torch.float32) -> torch.Tensor:
+    def source_band(self, H: int, W: int) -> tuple[int, int]:
+        """(x0, width) of the source columns the processor's center crop reads (≈57 % of a 16:9 row): the only part of a
+        host frame the feed has to move (`ops.copy_band_h2d`)."""
+        s = self.spec
+        _, out_w, _, x0 = resize_geometry(H, W, s.image, s.image)
+        return ops.crop_source_band(W, out_w, x0, s.image, self.resample)
+
+    def encode_clips(self, frames: torch.Tensor, out_dtype: torch.dtype = torch.float32,
+                     band: tuple[int, int] | None = None) -> torch.Tensor:
         """uint8 [clips*frames_per_clip, H, W, 3] on the device -> clip embeddings [clips, hidden]."""
         s = self.spec
         if frames.shape[0] % s.frames:
             raise RuntimeError(f"encode_clips: frame count {frames.shape[0]} is not a multiple of {s.frames}")
         clips = frames.shape[0] // s.frames
-        pv = self.preprocess(frames)
+        pv = self.preprocess(frames, band)
         patches = ops.patchify_tubelet(pv, s.frames, s.patch, s.tubelet)
         return ops.videomae_forward(self.pack, patches, self._workspace(clips), out_dtype=out_dtype)
 
@@ -119,13 +129,24 @@ class VideoMAEClipEncoder:
         n = int(frames.shape[0])
         embeddings = []
         per_batch = self.clips_per_batch * s.frames
+        # host frames: only the column band the center crop reads crosses PCIe
+        band = None
+        if not frames.is_cuda and frames.is_contiguous() and frames.shape[2] > frames.shape[1]:
+            bx0, bw = self.source_band(int(frames.shape[1]), int(frames.shape[2]))
+            if bw < frames.shape[2]:
+                band = (bx0, int(frames.shape[2]))
         for start in range(0, n, per_batch):
-            chunk = frames[start:min(n, start + per_batch)].to(self.device, non_blocking=True)
+            host = frames[start:min(n, start + per_batch)]
+            if band is not None:
+                chunk = torch.empty((host.shape[0], host.shape[1], bw, 3), dtype=torch.uint8, device=self.device)
+                ops.copy_band_h2d(chunk, host, bx0)
+            else:
+                chunk = host.to(self.device, non_blocking=True)
             real = chunk.shape[0]
             pad = (-real) % s.frames
             if pad:  # reference: `while len(clip_frames) < clip_size: clip_frames.append(clip_frames[-1])`
                 chunk = torch.cat([chunk, chunk[-1:].expand(pad, -1, -1, -1)], 0).contiguous()
-            emb = self.encode_clips(chunk)
+            emb = self.encode_clips(chunk, band=band)
             proj = ops.project(projector, emb.to(torch.bfloat16)) if projector is not None else None
             emb_cpu = emb.cpu()
             for c in range(chunk.shape[0] // s.frames):

@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define GVL_ABI_VERSION 6
+#define GVL_ABI_VERSION 7
 
 #if defined(__GNUC__)
 #define GVL_API __attribute__((visibility("default")))
@@ -114,6 +114,20 @@ GVL_API int gvl_patchify_f32(const float* pixel_values, int B, int H, int W, int
 GVL_API int gvl_preprocess_u8_crop(const uint8_t* frames, int B, int H, int W, int out_h, int out_w, int crop_y0,
                            int crop_x0, int crop_h, int crop_w, int resample, const float* h_sub,
                            const float* h_div, void* out, int layout, void* stream);
+
+/* gvl_preprocess_u8_crop on frames of which only the column band [band_x0, band_x0 + band_w) is resident:
+ * frames is uint8 [B, H, band_w, 3].  A center crop of a 16:9 frame reads ~57 % of every source row, so a host feed
+ * (scripts/extract_features.py:345-375 hands whole PIL frames to the processor) only has to move that band.
+ * band_x0 % 16 == 0; the band must hold every source column the crop window's taps read (gvl_resize_taps gives
+ * them: xmin[crop_x0] .. xmin[crop_x0 + crop_w - 1] + xsize[...]).  Same arithmetic, bit-identical output. */
+GVL_API int gvl_preprocess_u8_crop_band(const uint8_t* frames, int B, int H, int W, int band_x0, int band_w, int out_h,
+                                int out_w, int crop_y0, int crop_x0, int crop_h, int crop_w, int resample,
+                                const float* h_sub, const float* h_div, void* out, int layout, void* stream);
+
+/* Host -> device copy of a byte band of every row: dst[r][0:band_bytes] = src_host[r][band_offset : +band_bytes]
+ * (cudaMemcpy2DAsync; src_host pinned for an asynchronous copy).  The feed side of gvl_preprocess_u8_crop_band. */
+GVL_API int gvl_copy_band_h2d(void* dst, const void* src_host, long long rows, long long src_row_bytes,
+                      long long band_offset_bytes, long long band_bytes, void* stream);
 
 /* pixel_values: bf16 [clips*frames, 3, H, W] (frames of a clip consecutive) -> bf16 tubelet im2col rows
  * [clips*(frames/tubelet)*(H/p)*(W/p), 3*tubelet*p*p] for the Conv3d(kernel = stride = (tubelet,p,p)) patch

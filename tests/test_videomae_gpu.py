@@ -10,7 +10,7 @@ from gameplay_vision_llm_b200 import ops, synth  # noqa: E402
 from gameplay_vision_llm_b200.videomae_encoder import VideoMAEClipEncoder  # noqa: E402
 from gameplay_vision_llm_b200.weights import (ProjectorPack, VideoMAEPack, VideoMAESpec,  # noqa: E402
                                                 synth_projector_state_dict, synth_videomae_state_dict)
-from oracle import siglip_ref, videomae_ref  # noqa: E402
+from oracle import preprocess_ref, siglip_ref, videomae_ref  # noqa: E402
 
 DEV = "cuda:0"
 
@@ -36,6 +36,42 @@ def test_preprocess_crop_bit_exact(H, W, size):
     pv = videomae_ref.pixel_values(frames.numpy(), size, size, image_mean=(0.5,) * 3, image_std=(0.5,) * 3)
     u8 = ops.preprocess_crop(dev, oh, ow, y0, x0, size, size, layout=ops.LAYOUT_U8_CHW).cpu().numpy()
     assert np.array_equal(u8, np.rint(pv * 127.5 + 127.5).astype(np.uint8))
+
+
+@pytest.mark.parametrize("H,W,size", [(1080, 1920, 224), (720, 1280, 224), (123, 211, 48), (300, 1000, 64)])
+def test_preprocess_crop_band_equals_whole_frames(H, W, size):
+    """Only the source-column band the center crop reads is moved to the device (one strided H2D copy of pinned whole
+    frames): the band call must give the whole-frame call's bits, and the band must be what ATen's taps read."""
+    frames = synth.noise_frames(3, H, W, seed=W)
+    oh, ow, y0, x0 = videomae_ref.resize_geometry(H, W, size, size)
+    bx0, bw = ops.crop_source_band(W, ow, x0, size)
+    xmin, xsize, _, _ = preprocess_ref.resize_taps(W, ow, preprocess_ref.BILINEAR)
+    lo, hi = int(xmin[x0]), int(xmin[x0 + size - 1] + xsize[x0 + size - 1])
+    assert bx0 % 16 == 0 and lo - 16 < bx0 <= lo and hi <= bx0 + bw <= min(W, hi + 15)
+    want = ops.preprocess_crop(frames.to(DEV), oh, ow, y0, x0, size, size, layout=ops.LAYOUT_BF16_CHW)
+    band_dev = torch.empty((3, H, bw, 3), dtype=torch.uint8, device=DEV)
+    ops.copy_band_h2d(band_dev, frames.pin_memory(), bx0)
+    torch.cuda.synchronize()
+    assert torch.equal(band_dev.cpu(), frames[:, :, bx0:bx0 + bw, :])
+    got = ops.preprocess_crop(band_dev, oh, ow, y0, x0, size, size, layout=ops.LAYOUT_BF16_CHW, band=(bx0, W))
+    assert torch.equal(got.view(torch.int16), want.view(torch.int16))
+    with pytest.raises(RuntimeError, match="band"):  # a band that misses columns the crop reads is refused
+        ops.preprocess_crop(band_dev[:, :, 16:, :].contiguous(), oh, ow, y0, x0, size, size, layout=ops.LAYOUT_BF16_CHW,
+                            band=(bx0 + 16, W))
+
+
+def test_run_host_frames_band_feed_equals_device_frames():
+    """`run` on host frames ships only the crop band; its embeddings equal those of device-resident whole frames."""
+    spec = VideoMAESpec.tiny()
+    enc = VideoMAEClipEncoder(synth_videomae_state_dict(spec, seed=2), spec, DEV, clips_per_batch=2)
+    n = 3 * spec.frames + 1
+    frames = torch.from_numpy(synth.scene_frames_np(7, n, 270, 480))
+    ts = [i / 2.0 for i in range(n)]
+    a = enc.run(frames.pin_memory(), ts)
+    b = enc.run(frames.to(DEV), ts)
+    assert a["num_embeddings"] == b["num_embeddings"] == 4
+    for x, y in zip(a["embeddings"], b["embeddings"]):
+        assert torch.equal(x["embedding"], y["embedding"]) and x["start_time"] == y["start_time"]
 
 
 def test_patchify_tubelet_bit_exact():

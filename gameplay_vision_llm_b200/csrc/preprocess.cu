@@ -772,6 +772,33 @@ preprocess_planar_kernel(const PlanarParams p) {
 
 // (u8 - sub[c]) / div[c] in fp32 (IEEE division on the host), cached per (device, sub, div)
 static std::map<std::tuple<int, float, float, float, float, float, float>, float*> g_luts;
+std::shared_mutex g_tab_rw;
+
+void trim_table_caches_if_full() {
+    {
+        std::lock_guard<std::mutex> lk(g_tab_mu);
+        if (g_tabs.size() < kTableCacheCap && g_ptabs.size() < kTableCacheCap && g_luts.size() < kTableCacheCap &&
+            stream_table_cache_size() < kTableCacheCap)
+            return;
+    }
+    std::unique_lock<std::shared_mutex> x(g_tab_rw);  // no launch is between its table fetch and its kernel
+    std::lock_guard<std::mutex> lk(g_tab_mu);
+    cudaDeviceSynchronize();
+    for (auto& kv : g_tabs) {
+        DevTables& e = kv.second;
+        cudaFree(e.h_min); cudaFree(e.h_size); cudaFree(e.v_min); cudaFree(e.v_size); cudaFree(e.h_w); cudaFree(e.v_w);
+    }
+    g_tabs.clear();
+    for (auto& kv : g_ptabs) {
+        cudaFree(kv.second.hq);
+        cudaFree(kv.second.vq);
+    }
+    g_ptabs.clear();
+    for (auto& kv : g_luts) cudaFree(kv.second);
+    g_luts.clear();
+    stream_table_cache_clear();
+}
+
 int get_lut(const float* sub, const float* div, float** out, float* h_copy) {
     int dev = 0;
     GVL_CUDA(cudaGetDevice(&dev));
@@ -1009,6 +1036,8 @@ extern "C" int gvl_preprocess_u8_crop(const uint8_t* frames, int B, int H, int W
                                       int crop_x0, int crop_h, int crop_w, int resample, const float* h_sub,
                                       const float* h_div, void* out, int layout, void* stream) {
     using namespace gvl;
+    trim_table_caches_if_full();
+    std::shared_lock<std::shared_mutex> tab_guard(g_tab_rw);
     GVL_CHECK_ARG(frames && out && h_sub && h_div, "gvl_preprocess_u8_crop: null pointer");
     GVL_CHECK_ARG(B > 0 && B <= 65535 && H > 0 && W > 0 && out_h > 0 && out_w > 0, "gvl_preprocess_u8_crop: bad shape");
     GVL_CHECK_ARG(layout >= GVL_LAYOUT_U8_CHW && layout <= GVL_LAYOUT_BF16_CHW,
@@ -1033,6 +1062,8 @@ extern "C" int gvl_preprocess_u8_crop_band(const uint8_t* frames, int B, int H, 
                                            int out_w, int crop_y0, int crop_x0, int crop_h, int crop_w, int resample,
                                            const float* h_sub, const float* h_div, void* out, int layout, void* stream) {
     using namespace gvl;
+    trim_table_caches_if_full();
+    std::shared_lock<std::shared_mutex> tab_guard(g_tab_rw);
     GVL_CHECK_ARG(frames && out && h_sub && h_div, "gvl_preprocess_u8_crop_band: null pointer");
     GVL_CHECK_ARG(B > 0 && B <= 65535 && H > 0 && W > 0 && out_h > 0 && out_w > 0, "gvl_preprocess_u8_crop_band: bad shape");
     GVL_CHECK_ARG(layout >= GVL_LAYOUT_U8_CHW && layout <= GVL_LAYOUT_BF16_CHW,
@@ -1104,6 +1135,8 @@ extern "C" int gvl_preprocess_u8(const uint8_t* frames, int B, int H, int W, int
                                  const float* h_sub, const float* h_div, void* out, int layout, int patch, int ld,
                                  void* stream) {
     using namespace gvl;
+    trim_table_caches_if_full();
+    std::shared_lock<std::shared_mutex> tab_guard(g_tab_rw);
     GVL_CHECK_ARG(frames && out && h_sub && h_div, "gvl_preprocess_u8: null pointer");
     GVL_CHECK_ARG(B > 0 && B <= 65535 && H > 0 && W > 0 && out_h > 0 && out_w > 0, "gvl_preprocess_u8: bad shape");
     GVL_CHECK_ARG(layout >= 0 && layout <= 3, "gvl_preprocess_u8: bad layout %d", layout);

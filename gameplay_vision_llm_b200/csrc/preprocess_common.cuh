@@ -4,6 +4,7 @@
 #include "common.cuh"
 
 #include <mutex>
+#include <shared_mutex>
 #include <vector>
 
 namespace gvl {
@@ -28,6 +29,16 @@ int upload(const std::vector<T>& v, T** dptr) {
     GVL_CUDA(cudaMemcpy(*dptr, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
     return 0;
 }
+
+// Table caches are bounded: a stream of differently sized images (crops, mixed-resolution videos) would otherwise
+// grow them without limit.  Every K1 entry point first calls trim_table_caches_if_full() and then holds g_tab_rw
+// shared while it fetches tables and launches; the trim takes it exclusively, waits for the device and frees every
+// table, so no launch can be left holding a freed pointer.
+constexpr size_t kTableCacheCap = 64;
+extern std::shared_mutex g_tab_rw;
+void trim_table_caches_if_full();
+size_t stream_table_cache_size();   // preprocess_stream.cu's cache (callers hold g_tab_mu)
+void stream_table_cache_clear();
 
 // returns -1 when the geometry is outside the kernel's limits (the caller falls back to the planar kernel)
 int launch_stream5(const uint8_t* frames, int B, int H, int W, int out_h, int out_w, int resample, const float* h_sub,

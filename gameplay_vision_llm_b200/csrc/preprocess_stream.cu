@@ -283,6 +283,16 @@ struct PsTables {
 };
 static std::map<std::tuple<int, int, int, int, int, int, int, int>, PsTables> g_ps_tabs;
 
+size_t stream_table_cache_size() { return g_ps_tabs.size(); }
+void stream_table_cache_clear() {
+    for (auto& kv : g_ps_tabs) {
+        cudaFree(kv.second.hq);
+        cudaFree(kv.second.vq);
+        cudaFree(kv.second.unit);
+    }
+    g_ps_tabs.clear();
+}
+
 static uint16_t ps_bf16_rn(float f) {
     uint32_t u;
     memcpy(&u, &f, 4);

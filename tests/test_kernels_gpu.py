@@ -294,6 +294,23 @@ def test_preprocess_streaming_kernel_batch64_equals_planar():
     assert torch.equal(got.view(torch.int16), planar.view(torch.int16))
 
 
+def test_preprocess_table_cache_is_bounded():
+    """More distinct geometries than the table caches hold (64): the caches are emptied and rebuilt, results stay exact
+    (variable-size crops / mixed-resolution videos must not grow device memory without bound)."""
+    dev_frames = {}
+    for i in range(70):
+        H = 40 + i
+        frames = synth.noise_frames(1, H, 64, seed=i)
+        got = ops.preprocess(frames.to(DEV), 16, 24, 2, layout=ops.LAYOUT_U8_CHW).cpu().numpy()
+        if i % 23 == 0 or i == 69:
+            assert np.array_equal(got, preprocess_ref.resize_u8(frames.numpy(), 16, 24, 2)), f"geometry {i}"
+    # the headline geometry after the trim (streaming kernel tables rebuilt)
+    frames = synth.noise_frames(1, 1080, 1920, seed=3)
+    pv = preprocess_ref.pixel_values(frames.numpy(), 384, 384, 2)
+    want = torch.from_numpy(preprocess_ref.patchify(pv, 14, 592)).to(torch.bfloat16)
+    assert torch.equal(ops.preprocess(frames.to(DEV), 384, 384, 2).cpu().view(torch.int16), want.view(torch.int16))
+
+
 def test_preprocess_unaligned_base_pointer():
     """Frames whose base address is not 16-byte aligned take the byte-copy staging path."""
     H, W = 60, 101

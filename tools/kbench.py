@@ -156,8 +156,12 @@ def sustained_cases():
         reps = max(50, int(1500 / probe))
         ms, mhz, watts = sm_clock_during(lambda: ops.gemm(a, w, bias, out if res else None, act=act, out=out), reps)
         ms2, mhz2, watts2 = sm_clock_during(lambda: torch.matmul(a, wt, out=out), reps)
-        print(f"sustained {name:7s} M={m} N={n} K={k}: ours {flops/ms/1e9:7.1f} TFLOP/s @ {mhz} MHz {watts:.0f} W | "
-              f"cuBLAS (no bias/act/residual) {flops/ms2/1e9:7.1f} TFLOP/s @ {mhz2} MHz {watts2:.0f} W")
+        line = (f"sustained {name:7s} M={m} N={n} K={k}: ours {flops/ms/1e9:7.1f} TFLOP/s @ {mhz} MHz {watts:.0f} W | "
+                f"cuBLAS (no bias/act/residual) {flops/ms2/1e9:7.1f} TFLOP/s @ {mhz2} MHz {watts2:.0f} W")
+        if res:  # the same work: D = A.W^T + C with C = D in place (beta = 1), still without the bias
+            ms3, mhz3, watts3 = sm_clock_during(lambda: torch.addmm(out, a, wt, out=out), reps)
+            line += f" | cuBLAS + residual (addmm, beta=1) {flops/ms3/1e9:7.1f} TFLOP/s @ {mhz3} MHz {watts3:.0f} W"
+        print(line)
 
 
 def topk_case():

@@ -1,0 +1,334 @@
+// region.cu — K9: the masked-region variant of the path (reference
+// src/perception/siglip_semantic_encoder.py:485-562).  Bounding-box crops of ONE resident frame are resized with
+// Pillow's bicubic resampler (integer two-pass, 22-bit fixed-point coefficients, uint8 intermediate — bit-exact),
+// normalised through a 3 x 256 table, zero-padded to the batch canvas and written directly as bf16 im2col patch rows;
+// the learned position table is re-sampled to the canvas grid the way HF's `interpolate_pos_encoding` does; the
+// reference's `mean` / `max` pooling over the tokens.  The tower itself is gvl_siglip_forward on a pack whose T / pos
+// describe the canvas grid.
+#include "common.cuh"
+
+#include <cmath>
+#include <vector>
+
+namespace gvl {
+
+constexpr int PIL_PRECISION_BITS = 32 - 8 - 2;  // Pillow src/libImaging/Resample.c
+constexpr int DESC_INTS = GVL_REGION_DESC_INTS;  // caller fields
+constexpr int DEV_DESC_INTS = 12;                // + tmp offset (bytes / 4) + pad
+
+// Pillow `bicubic_filter` (a = -0.5)
+static inline double pil_bicubic(double x) {
+    const double a = -0.5;
+    if (x < 0.0) x = -x;
+    if (x < 1.0) return ((a + 2.0) * x - (a + 3.0)) * x * x + 1;
+    if (x < 2.0) return (((x - 5) * x + 8) * x - 4) * a;
+    return 0.0;
+}
+
+__device__ __forceinline__ int clip8(int v) {
+    v >>= PIL_PRECISION_BITS;
+    return v < 0 ? 0 : (v > 255 ? 255 : v);
+}
+
+// Horizontal pass: tmp[row, xx, c] = clip8(2^21 + sum_t frame[y1 + row, x1 + xmin[xx] + t, c] * k[xx, t]).
+// grid (blocks over ch * ow, R); one thread per output pixel (3 channels).
+__global__ void __launch_bounds__(256)
+region_h_kernel(const uint8_t* __restrict__ frame, int W, const int32_t* __restrict__ desc, const int32_t* __restrict__ tabs,
+                uint8_t* __restrict__ scratch) {
+    const int32_t* d = desc + blockIdx.y * DEV_DESC_INTS;
+    const int x1 = d[0], y1 = d[1], ch = d[3], ow = d[4], kh = d[6];
+    const int32_t* xmin = tabs + d[8];
+    const int32_t* cnt = xmin + ow;
+    const int32_t* kk = cnt + ow;
+    uint8_t* tmp = scratch + (size_t)d[10] * 4;
+    const int total = ch * ow;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        const int row = i / ow, xx = i - row * ow;
+        const int n = cnt[xx];
+        const uint8_t* src = frame + ((size_t)(y1 + row) * W + x1 + xmin[xx]) * 3;
+        const int32_t* k = kk + (size_t)xx * kh;
+        int s0 = 1 << (PIL_PRECISION_BITS - 1), s1 = s0, s2 = s0;
+        for (int t = 0; t < n; ++t) {
+            const int w = k[t];
+            s0 += (int)src[3 * t + 0] * w;
+            s1 += (int)src[3 * t + 1] * w;
+            s2 += (int)src[3 * t + 2] * w;
+        }
+        uint8_t* o = tmp + (size_t)i * 3;
+        o[0] = (uint8_t)clip8(s0);
+        o[1] = (uint8_t)clip8(s1);
+        o[2] = (uint8_t)clip8(s2);
+    }
+}
+
+// Vertical pass + normalisation table + zero padding + im2col.  One thread per canvas pixel; the patch buffer was
+// zeroed beforehand, so threads outside the region's oh x ow rectangle have nothing to write.
+__global__ void __launch_bounds__(256)
+region_v_kernel(const int32_t* __restrict__ desc, const int32_t* __restrict__ tabs, const uint8_t* __restrict__ scratch,
+                const uint16_t* __restrict__ lut, int canvas_h, int canvas_w, int patch, int ld,
+                uint16_t* __restrict__ patches, uint8_t* __restrict__ resized, int tokens_per_region) {
+    const int32_t* d = desc + blockIdx.y * DEV_DESC_INTS;
+    const int ow = d[4], oh = d[5], kv = d[7];
+    const int32_t* ymin = tabs + d[9];
+    const int32_t* cnt = ymin + oh;
+    const int32_t* kk = cnt + oh;
+    const uint8_t* tmp = scratch + (size_t)d[10] * 4;
+    const int total = oh * ow;
+    const int gw = canvas_w / patch, pp = patch * patch;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        const int y = i / ow, x = i - y * ow;
+        const int n = cnt[y];
+        const uint8_t* src = tmp + ((size_t)ymin[y] * ow + x) * 3;
+        const int32_t* k = kk + (size_t)y * kv;
+        int s0 = 1 << (PIL_PRECISION_BITS - 1), s1 = s0, s2 = s0;
+        for (int t = 0; t < n; ++t) {
+            const int w = k[t];
+            const uint8_t* p = src + (size_t)t * ow * 3;
+            s0 += (int)p[0] * w;
+            s1 += (int)p[1] * w;
+            s2 += (int)p[2] * w;
+        }
+        const int v0 = clip8(s0), v1 = clip8(s1), v2 = clip8(s2);
+        if (resized) {
+            uint8_t* u = resized + (((size_t)blockIdx.y * canvas_h + y) * canvas_w + x) * 3;
+            u[0] = (uint8_t)v0;
+            u[1] = (uint8_t)v1;
+            u[2] = (uint8_t)v2;
+        }
+        if (patches) {
+            const int py = y / patch, ky = y - py * patch, px = x / patch, kx = x - px * patch;
+            uint16_t* o = patches + ((size_t)blockIdx.y * tokens_per_region + (size_t)py * gw + px) * ld + ky * patch + kx;
+            o[0] = lut[v0];
+            o[pp] = lut[256 + v1];
+            o[2 * pp] = lut[512 + v2];
+        }
+    }
+}
+
+// ATen native/UpSample.h `get_cubic_upsample_coefficients` (A = -0.75), fp32 like upsample_bicubic2d on float
+__device__ __forceinline__ void cubic_coeffs(float t, float c[4]) {
+    const float A = -0.75f;
+    const float x0 = t + 1.0f, x1 = t, x2 = 1.0f - t, x3 = 2.0f - t;
+    c[0] = ((A * x0 - 5.0f * A) * x0 + 8.0f * A) * x0 - 4.0f * A;
+    c[1] = ((A + 2.0f) * x1 - (A + 3.0f)) * x1 * x1 + 1.0f;
+    c[2] = ((A + 2.0f) * x2 - (A + 3.0f)) * x2 * x2 + 1.0f;
+    c[3] = ((A * x3 - 5.0f * A) * x3 + 8.0f * A) * x3 - 4.0f * A;
+}
+
+// out[(oy * gw + ox), d] = sum_i wy[i] * sum_j wx[j] * pos[(clamp(iy - 1 + i) * g + clamp(ix - 1 + j)), d]
+// grid (gh * gw tokens), block over D in pairs.
+__global__ void __launch_bounds__(256)
+pos_interp_kernel(const __nv_bfloat16* __restrict__ pos, int g, int D, int gh, int gw, __nv_bfloat16* __restrict__ out) {
+    const int oy = blockIdx.x / gw, ox = blockIdx.x - oy * gw;
+    const float sy = (float)g / (float)gh, sx = (float)g / (float)gw;
+    const float fy = sy * ((float)oy + 0.5f) - 0.5f, fx = sx * ((float)ox + 0.5f) - 0.5f;
+    const float fy0 = floorf(fy), fx0 = floorf(fx);
+    float wy[4], wx[4];
+    cubic_coeffs(fy - fy0, wy);
+    cubic_coeffs(fx - fx0, wx);
+    int iy[4], ix[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        iy[i] = min(max((int)fy0 - 1 + i, 0), g - 1);
+        ix[i] = min(max((int)fx0 - 1 + i, 0), g - 1);
+    }
+    for (int dcol = threadIdx.x; dcol < D; dcol += blockDim.x) {
+        float acc = 0.f;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            float r = 0.f;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) r += wx[j] * __bfloat162float(pos[((size_t)iy[i] * g + ix[j]) * D + dcol]);
+            acc += wy[i] * r;
+        }
+        out[(size_t)blockIdx.x * D + dcol] = __float2bfloat16_rn(acc);
+    }
+}
+
+// x: bf16 [B, T, D] -> out [B, D] = max over T (the reference's `sequence.max(dim=1)[0]`).  Same slab layout as
+// mean_tokens_kernel (videomae.cu).
+__global__ void __launch_bounds__(256)
+max_tokens_kernel(const __nv_bfloat16* __restrict__ x, int T, int D, void* __restrict__ out, int out_f32) {
+    __shared__ float part[8][256];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int c0 = blockIdx.x * 256 + lane * 8;
+    const int b = blockIdx.y;
+    float acc[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) acc[e] = -INFINITY;
+    if (c0 < D) {
+        const __nv_bfloat16* base = x + (size_t)b * T * D + c0;
+        for (int t = warp; t < T; t += 8) {
+            const uint4 v = *reinterpret_cast<const uint4*>(base + (size_t)t * D);
+            acc[0] = fmaxf(acc[0], bf16_lo(v.x)); acc[1] = fmaxf(acc[1], bf16_hi(v.x));
+            acc[2] = fmaxf(acc[2], bf16_lo(v.y)); acc[3] = fmaxf(acc[3], bf16_hi(v.y));
+            acc[4] = fmaxf(acc[4], bf16_lo(v.z)); acc[5] = fmaxf(acc[5], bf16_hi(v.z));
+            acc[6] = fmaxf(acc[6], bf16_lo(v.w)); acc[7] = fmaxf(acc[7], bf16_hi(v.w));
+        }
+    }
+#pragma unroll
+    for (int e = 0; e < 8; ++e) part[warp][lane * 8 + e] = acc[e];
+    __syncthreads();
+    const int c = blockIdx.x * 256 + threadIdx.x;
+    if (c < D) {
+        float s = -INFINITY;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) s = fmaxf(s, part[w][threadIdx.x]);
+        if (out_f32)
+            reinterpret_cast<float*>(out)[(size_t)b * D + c] = s;
+        else
+            reinterpret_cast<__nv_bfloat16*>(out)[(size_t)b * D + c] = __float2bfloat16_rn(s);
+    }
+}
+
+static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+// scratch layout: device descriptors, then one uint8 [ch, ow, 3] intermediate per region
+static size_t region_layout(int R, const int32_t* h_desc, std::vector<int32_t>* dev_desc) {
+    size_t off = align_up((size_t)R * DEV_DESC_INTS * sizeof(int32_t), 256);
+    if (dev_desc) dev_desc->assign((size_t)R * DEV_DESC_INTS, 0);
+    for (int r = 0; r < R; ++r) {
+        const int32_t* d = h_desc + (size_t)r * DESC_INTS;
+        if (dev_desc) {
+            int32_t* o = dev_desc->data() + (size_t)r * DEV_DESC_INTS;
+            for (int i = 0; i < DESC_INTS; ++i) o[i] = d[i];
+            o[10] = (int32_t)(off / 4);
+        }
+        off = align_up(off + (size_t)d[3] * d[4] * 3, 256);
+    }
+    return off;
+}
+
+}  // namespace gvl
+
+extern "C" int gvl_pil_bicubic_taps(int in_size, int out_size, int max_taps, int32_t* h_xmin, int32_t* h_count,
+                                    int32_t* h_coeffs, int* h_ksize) {
+    using namespace gvl;
+    GVL_CHECK_ARG(in_size > 0 && out_size > 0, "gvl_pil_bicubic_taps: bad sizes %d -> %d", in_size, out_size);
+    // Resample.c `precompute_coeffs` with box = (0, in_size)
+    double scale = (double)in_size / out_size, filterscale = scale;
+    if (filterscale < 1.0) filterscale = 1.0;
+    const double support = 2.0 * filterscale;
+    const int ksize = (int)ceil(support) * 2 + 1;
+    if (h_ksize) *h_ksize = ksize;
+    if (!h_xmin && !h_count && !h_coeffs) return 0;  // size query
+    GVL_CHECK_ARG(h_xmin && h_count && h_coeffs, "gvl_pil_bicubic_taps: null table pointer");
+    GVL_CHECK_ARG(max_taps >= ksize, "gvl_pil_bicubic_taps: max_taps %d < ksize %d", max_taps, ksize);
+    const double ss = 1.0 / filterscale;
+    std::vector<double> k((size_t)ksize);
+    for (int xx = 0; xx < out_size; ++xx) {
+        const double center = 0.0 + (xx + 0.5) * scale;
+        double ww = 0.0;
+        int xmin = (int)(center - support + 0.5);
+        if (xmin < 0) xmin = 0;
+        int xmax = (int)(center + support + 0.5);
+        if (xmax > in_size) xmax = in_size;
+        xmax -= xmin;
+        for (int x = 0; x < xmax; ++x) {
+            const double w = pil_bicubic((x + xmin - center + 0.5) * ss);
+            k[x] = w;
+            ww += w;
+        }
+        for (int x = 0; x < xmax; ++x)
+            if (ww != 0.0) k[x] /= ww;
+        int32_t* out = h_coeffs + (size_t)xx * max_taps;
+        for (int x = 0; x < max_taps; ++x) {
+            if (x >= xmax) {
+                out[x] = 0;
+            } else if (k[x] < 0) {  // `normalize_coeffs_8bpc`
+                out[x] = (int)(-0.5 + k[x] * (1 << PIL_PRECISION_BITS));
+            } else {
+                out[x] = (int)(0.5 + k[x] * (1 << PIL_PRECISION_BITS));
+            }
+        }
+        h_xmin[xx] = xmin;
+        h_count[xx] = xmax;
+    }
+    return 0;
+}
+
+extern "C" size_t gvl_region_scratch_bytes(int R, const int32_t* h_desc) {
+    if (R <= 0 || !h_desc) return 0;
+    return gvl::region_layout(R, h_desc, nullptr);
+}
+
+extern "C" int gvl_region_patches_pil_u8(const uint8_t* frame, int H, int W, int R, const int32_t* h_desc,
+                                         const int32_t* tabs, long long tabs_ints, const uint16_t* lut, int canvas_h,
+                                         int canvas_w, int patch, int ld, void* patches, uint8_t* resized_u8,
+                                         void* scratch, size_t scratch_bytes, void* stream) {
+    using namespace gvl;
+    GVL_CHECK_ARG(frame && h_desc && tabs && scratch && (patches || resized_u8) && (lut || !patches),
+                  "gvl_region_patches_pil_u8: null pointer");
+    GVL_CHECK_ARG(H > 0 && W > 0 && R > 0 && R <= 65535, "gvl_region_patches_pil_u8: bad shape H=%d W=%d R=%d", H, W, R);
+    GVL_CHECK_ARG(patch > 0 && canvas_h > 0 && canvas_w > 0 && canvas_h % patch == 0 && canvas_w % patch == 0,
+                  "gvl_region_patches_pil_u8: canvas %dx%d is not a multiple of the patch size %d", canvas_h, canvas_w, patch);
+    GVL_CHECK_ARG(ld >= 3 * patch * patch && ld % 8 == 0, "gvl_region_patches_pil_u8: bad ld %d", ld);
+    GVL_CHECK_ARG((uintptr_t)scratch % 256 == 0 && (uintptr_t)patches % 16 == 0, "gvl_region_patches_pil_u8: misaligned buffer");
+    for (int r = 0; r < R; ++r) {
+        const int32_t* d = h_desc + (size_t)r * DESC_INTS;
+        const int x1 = d[0], y1 = d[1], cw = d[2], ch = d[3], ow = d[4], oh = d[5], kh = d[6], kv = d[7];
+        GVL_CHECK_ARG(cw > 0 && ch > 0 && x1 >= 0 && y1 >= 0 && x1 + cw <= W && y1 + ch <= H,
+                      "gvl_region_patches_pil_u8: region %d box (%d,%d)+(%dx%d) leaves the %dx%d frame", r, x1, y1, cw, ch, W, H);
+        GVL_CHECK_ARG(ow > 0 && oh > 0 && ow <= canvas_w && oh <= canvas_h,
+                      "gvl_region_patches_pil_u8: region %d target %dx%d exceeds the %dx%d canvas", r, ow, oh, canvas_w, canvas_h);
+        int need_kh = 0, need_kv = 0;
+        gvl_pil_bicubic_taps(cw, ow, 0, nullptr, nullptr, nullptr, &need_kh);
+        gvl_pil_bicubic_taps(ch, oh, 0, nullptr, nullptr, nullptr, &need_kv);
+        GVL_CHECK_ARG(kh >= need_kh && kv >= need_kv, "gvl_region_patches_pil_u8: region %d tap strides %d/%d < %d/%d", r, kh,
+                      kv, need_kh, need_kv);
+        GVL_CHECK_ARG(d[8] >= 0 && d[9] >= 0 && (long long)d[8] + (long long)ow * (2 + kh) <= tabs_ints &&
+                          (long long)d[9] + (long long)oh * (2 + kv) <= tabs_ints,
+                      "gvl_region_patches_pil_u8: region %d tables leave the %lld-int table buffer", r, tabs_ints);
+    }
+    std::vector<int32_t> dev_desc;
+    const size_t need = region_layout(R, h_desc, &dev_desc);
+    GVL_CHECK_ARG(scratch_bytes >= need, "gvl_region_patches_pil_u8: scratch %zu < required %zu bytes", scratch_bytes, need);
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+    const int gh = canvas_h / patch, gw = canvas_w / patch;
+    // pageable source: the copy is staged before the call returns, so dev_desc may go out of scope
+    GVL_CUDA(cudaMemcpyAsync(scratch, dev_desc.data(), dev_desc.size() * sizeof(int32_t), cudaMemcpyHostToDevice, s));
+    if (patches) GVL_CUDA(cudaMemsetAsync(patches, 0, (size_t)R * gh * gw * ld * 2, s));
+    if (resized_u8) GVL_CUDA(cudaMemsetAsync(resized_u8, 0, (size_t)R * canvas_h * canvas_w * 3, s));
+    long long max_h = 0, max_v = 0, src_bytes = 0;
+    for (int r = 0; r < R; ++r) {
+        const int32_t* d = h_desc + (size_t)r * DESC_INTS;
+        max_h = std::max(max_h, (long long)d[3] * d[4]);
+        max_v = std::max(max_v, (long long)d[4] * d[5]);
+        src_bytes += (long long)d[2] * d[3] * 3;
+    }
+    ProfScope prof(GVL_K_PREPROCESS, (double)src_bytes + (double)R * gh * gw * ld * 2, s);
+    const int32_t* desc = reinterpret_cast<const int32_t*>(scratch);
+    uint8_t* sc = reinterpret_cast<uint8_t*>(scratch);
+    const int bh = (int)std::min<long long>((max_h + 255) / 256, 4096), bv = (int)std::min<long long>((max_v + 255) / 256, 4096);
+    region_h_kernel<<<dim3(bh, R), 256, 0, s>>>(frame, W, desc, tabs, sc);
+    GVL_LAUNCH_CHECK("region_h_kernel");
+    region_v_kernel<<<dim3(bv, R), 256, 0, s>>>(desc, tabs, sc, lut, canvas_h, canvas_w, patch, ld,
+                                               reinterpret_cast<uint16_t*>(patches), resized_u8, gh * gw);
+    GVL_LAUNCH_CHECK("region_v_kernel");
+    return 0;
+}
+
+extern "C" int gvl_pos_interp_bicubic_bf16(const void* pos, int g, int D, int gh, int gw, void* out, void* stream) {
+    using namespace gvl;
+    GVL_CHECK_ARG(pos && out, "gvl_pos_interp_bicubic_bf16: null pointer");
+    GVL_CHECK_ARG(g > 0 && D > 0 && gh > 0 && gw > 0 && (long long)gh * gw <= 2147483647LL / D,
+                  "gvl_pos_interp_bicubic_bf16: bad shape g=%d D=%d gh=%d gw=%d", g, D, gh, gw);
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+    pos_interp_kernel<<<gh * gw, 256, 0, s>>>(reinterpret_cast<const __nv_bfloat16*>(pos), g, D, gh, gw,
+                                              reinterpret_cast<__nv_bfloat16*>(out));
+    GVL_LAUNCH_CHECK("pos_interp_kernel");
+    return 0;
+}
+
+extern "C" int gvl_max_tokens_bf16(const void* x, int B, int T, int D, void* out, int out_f32, void* stream) {
+    using namespace gvl;
+    GVL_CHECK_ARG(x && out, "gvl_max_tokens_bf16: null pointer");
+    GVL_CHECK_ARG(B > 0 && B <= 65535 && T > 0 && D > 0 && D % 8 == 0, "gvl_max_tokens_bf16: bad shape B=%d T=%d D=%d", B, T,
+                  D);
+    GVL_CHECK_ARG((uintptr_t)x % 16 == 0, "gvl_max_tokens_bf16: x must be 16-byte aligned");
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+    ProfScope prof(GVL_K_LAYERNORM, (double)B * T * D * 2, s);
+    max_tokens_kernel<<<dim3((D + 255) / 256, B), 256, 0, s>>>(reinterpret_cast<const __nv_bfloat16*>(x), T, D, out, out_f32);
+    GVL_LAUNCH_CHECK("max_tokens_kernel");
+    return 0;
+}

@@ -12,7 +12,7 @@ import numpy as np
 import torch
 
 from . import _lib
-from .weights import ProjectorPack, SiglipPack, VideoMAEPack, resolve_device  # noqa: F401
+from .weights import ProjectorPack, SiglipGridView, SiglipPack, VideoMAEPack, resolve_device  # noqa: F401
 
 LAYOUT_U8_CHW, LAYOUT_F32_CHW, LAYOUT_BF16_CHW, LAYOUT_BF16_PATCH = 0, 1, 2, 3
 ACT_NONE, ACT_GELU_TANH, ACT_GELU_ERF = 0, 1, 2
@@ -36,7 +36,7 @@ def _on_tensor_device(fn):
                     dev = a.device
                 elif a.device != dev:
                     raise RuntimeError(f"{fn.__name__}: tensors on different devices ({dev} and {a.device})")
-            elif isinstance(a, (SiglipPack, ProjectorPack, VideoMAEPack)) and dev is not None and \
+            elif isinstance(a, (SiglipPack, SiglipGridView, ProjectorPack, VideoMAEPack)) and dev is not None and \
                     torch.device(a.device) != dev:
                 raise RuntimeError(f"{fn.__name__}: weights on {a.device}, tensors on {dev}")
         if dev is None or dev.index == torch.cuda.current_device():
@@ -340,19 +340,20 @@ def probe_attention(q: torch.Tensor, kv: torch.Tensor, B: int, T: int, H: int, h
 
 
 @_on_tensor_device
-def siglip_forward(pack: SiglipPack, patches: torch.Tensor, workspace: torch.Tensor | None = None,
+def siglip_forward(pack: "SiglipPack | SiglipGridView", patches: torch.Tensor, workspace: torch.Tensor | None = None,
                    return_tokens: bool = False):
-    """bf16 patches [B*T, patch_ld] -> pooled bf16 [B, D] (and post-LN tokens [B*T, D] if asked)."""
+    """bf16 patches [B*T, patch_ld] -> pooled bf16 [B, D] (and post-LN tokens [B*T, D] if asked).  `pack` may be a
+    `siglip_grid_view` (T = gh*gw tokens per item, re-sampled position table)."""
     _need_cuda(patches)
-    spec = pack.spec
-    if patches.dtype != torch.bfloat16 or patches.shape[1] != spec.patch_ld or patches.shape[0] % spec.tokens:
+    spec, T = pack.spec, pack.tokens
+    if patches.dtype != torch.bfloat16 or patches.shape[1] != spec.patch_ld or patches.shape[0] % T:
         raise RuntimeError("siglip_forward: patches must be bf16 [B*T, patch_ld]")
-    B = patches.shape[0] // spec.tokens
+    B = patches.shape[0] // T
     need = pack.workspace_bytes(B)
-    if workspace is None:
+    if workspace is None or workspace.numel() < need:
         workspace = torch.empty(need, dtype=torch.uint8, device=patches.device)
     pooled = torch.empty((B, spec.hidden), dtype=torch.bfloat16, device=patches.device)
-    tokens = torch.empty((B * spec.tokens, spec.hidden), dtype=torch.bfloat16, device=patches.device) if return_tokens else None
+    tokens = torch.empty((B * T, spec.hidden), dtype=torch.bfloat16, device=patches.device) if return_tokens else None
     _lib.check(_lib.lib().gvl_siglip_forward(ctypes.byref(pack.struct), patches.data_ptr(), B, workspace.data_ptr(),
                                              workspace.numel(), pooled.data_ptr(), _ptr(tokens), _stream()),
                "gvl_siglip_forward")
@@ -441,3 +442,115 @@ def topk_cosine(index: torch.Tensor, queries: torch.Tensor, k: int, eps: float =
         int(lo_hi[1]), int(mode), _ptr(inv_norm), scratch.data_ptr(), scores.data_ptr(), idx.data_ptr(), _stream()),
         "gvl_topk_cosine_ex")
     return scores, idx
+
+
+# ------------------------------------------------------------------------------------------------ masked regions (K9)
+@functools.lru_cache(maxsize=4096)
+def pil_bicubic_taps(in_size: int, out_size: int):
+    """Host-only: Pillow's 8-bit bicubic coefficient table of one axis as int32 [xmin[out] | count[out] | k[out, ksize]]
+    (the layout gvl_region_patches_pil_u8 reads) and ksize."""
+    ks = ctypes.c_int(0)
+    _lib.check(_lib.lib().gvl_pil_bicubic_taps(in_size, out_size, 0, None, None, None, ctypes.byref(ks)), "gvl_pil_bicubic_taps")
+    k = ks.value
+    tab = np.zeros(out_size * (2 + k), np.int32)
+    p = tab.ctypes.data_as(ctypes.POINTER(ctypes.c_int32))
+    i32 = ctypes.sizeof(ctypes.c_int32)
+    at = lambda off: ctypes.cast(ctypes.addressof(p.contents) + off * i32, ctypes.POINTER(ctypes.c_int32))  # noqa: E731
+    _lib.check(_lib.lib().gvl_pil_bicubic_taps(in_size, out_size, k, at(0), at(out_size), at(2 * out_size), None),
+               "gvl_pil_bicubic_taps")
+    tab.setflags(write=False)
+    return tab, k
+
+
+def region_lut(image_mean, image_std, dtype: torch.dtype = torch.bfloat16) -> torch.Tensor:
+    """[3, 256] table of `RegionExtractor.prepare_region_tensor`'s normalisation (reference :357-365) evaluated with the
+    reference's own three fp32 CPU operations on every possible uint8 value, then cast like `.to(device, dtype)` (:539)."""
+    t = torch.arange(256, dtype=torch.float32).view(1, 256).expand(3, 256).contiguous()
+    t = t / 255.0
+    t = (t - torch.tensor(list(image_mean)).view(3, 1)) / torch.tensor(list(image_std)).view(3, 1)
+    return t.to(dtype)
+
+
+@_on_tensor_device
+def region_patches(frame: torch.Tensor, boxes, sizes, canvas_hw, lut: torch.Tensor | None, patch: int = 14,
+                   ld: int | None = None, want_patches: bool = True, want_u8: bool = False):
+    """Crop + Pillow-bicubic resize + normalise + zero-pad + im2col of R regions of ONE frame.
+
+    frame: uint8 [H,W,3] on the device; boxes: R x (x1, y1, x2, y2) (`frame[y1:y2, x1:x2]`); sizes: R x (out_h, out_w);
+    canvas_hw: (canvas_h, canvas_w) multiples of `patch`, >= every size.  Returns (patches bf16 [R*gh*gw, ld] or None,
+    resized uint8 [R, canvas_h, canvas_w, 3] or None)."""
+    _need_cuda(frame, lut)
+    if frame.dtype != torch.uint8 or frame.dim() != 3 or frame.shape[2] != 3 or not frame.is_contiguous():
+        raise RuntimeError("region_patches: frame must be contiguous uint8 [H,W,3]")
+    R = len(boxes)
+    if R == 0 or len(sizes) != R:
+        raise RuntimeError("region_patches: need one (out_h, out_w) per box")
+    H, W = int(frame.shape[0]), int(frame.shape[1])
+    canvas_h, canvas_w = int(canvas_hw[0]), int(canvas_hw[1])
+    ld = ld or (3 * patch * patch + 7) // 8 * 8
+    desc = np.zeros((R, 10), np.int32)
+    tabs, off = [], 0
+    for r, ((x1, y1, x2, y2), (oh, ow)) in enumerate(zip(boxes, sizes)):
+        cw, ch = int(x2) - int(x1), int(y2) - int(y1)
+        if cw <= 0 or ch <= 0:
+            raise ValueError(f"region {r}: empty box {(x1, y1, x2, y2)}")  # PIL raises on a zero-size crop too
+        th, kh = pil_bicubic_taps(cw, int(ow))
+        tv, kv = pil_bicubic_taps(ch, int(oh))
+        desc[r] = (x1, y1, cw, ch, ow, oh, kh, kv, off, off + th.size)
+        tabs += [th, tv]
+        off += th.size + tv.size
+    tabs_dev = torch.from_numpy(np.concatenate(tabs)).to(frame.device)
+    dptr = desc.ctypes.data_as(ctypes.POINTER(ctypes.c_int32))
+    scratch = torch.empty(int(_lib.lib().gvl_region_scratch_bytes(R, dptr)) + 256, dtype=torch.uint8, device=frame.device)
+    gh, gw = canvas_h // patch, canvas_w // patch
+    patches = torch.empty((R * gh * gw, ld), dtype=torch.bfloat16, device=frame.device) if want_patches else None
+    resized = torch.empty((R, canvas_h, canvas_w, 3), dtype=torch.uint8, device=frame.device) if want_u8 else None
+    if want_patches and (lut is None or lut.dtype != torch.bfloat16 or tuple(lut.shape) != (3, 256) or not lut.is_contiguous()):
+        raise RuntimeError("region_patches: lut must be contiguous bf16 [3, 256]")
+    _lib.check(_lib.lib().gvl_region_patches_pil_u8(frame.data_ptr(), H, W, R, dptr, tabs_dev.data_ptr(), tabs_dev.numel(),
+                                                    _ptr(lut), canvas_h, canvas_w, patch, ld, _ptr(patches), _ptr(resized),
+                                                    scratch.data_ptr(), scratch.numel(), _stream()),
+               "gvl_region_patches_pil_u8")
+    return patches, resized
+
+
+@_on_tensor_device
+def interpolate_pos(pos: torch.Tensor, gh: int, gw: int) -> torch.Tensor:
+    """Learned position table bf16 [g*g, D] -> bf16 [gh*gw, D] (HF `interpolate_pos_encoding`: bicubic, align_corners
+    False).  The g x g grid returns the table itself, as HF does (HF:models/siglip/modeling_siglip.py:152-153)."""
+    _need_cuda(pos)
+    n, D = pos.shape
+    g = int(round(n ** 0.5))
+    if pos.dtype != torch.bfloat16 or not pos.is_contiguous() or g * g != n:
+        raise RuntimeError("interpolate_pos: pos must be contiguous bf16 [g*g, D]")
+    if gh == g and gw == g:
+        return pos
+    out = torch.empty((gh * gw, D), dtype=torch.bfloat16, device=pos.device)
+    _lib.check(_lib.lib().gvl_pos_interp_bicubic_bf16(pos.data_ptr(), g, D, gh, gw, out.data_ptr(), _stream()),
+               "gvl_pos_interp_bicubic_bf16")
+    return out
+
+
+@_on_tensor_device
+def max_tokens(x: torch.Tensor, B: int, T: int, out_dtype: torch.dtype = torch.float32) -> torch.Tensor:
+    """bf16 [B*T, D] -> [B, D] max over the T tokens of each item."""
+    _need_cuda(x)
+    if x.dtype != torch.bfloat16 or not x.is_contiguous() or x.shape[0] != B * T:
+        raise RuntimeError("max_tokens: x must be contiguous bf16 [B*T, D]")
+    D = x.shape[1]
+    out = torch.empty((B, D), dtype=out_dtype, device=x.device)
+    _lib.check(_lib.lib().gvl_max_tokens_bf16(x.data_ptr(), B, T, D, out.data_ptr(),
+                                              1 if out_dtype == torch.float32 else 0, _stream()), "gvl_max_tokens_bf16")
+    return out
+
+
+def siglip_grid_view(pack: SiglipPack, gh: int, gw: int) -> "SiglipPack | SiglipGridView":
+    """`pack` seen with a gh x gw patch grid: same weights, T = gh*gw, position table re-sampled once per grid and cached
+    on the pack.  The checkpoint's own square grid is the pack itself."""
+    g = pack.spec.grid
+    if (gh, gw) == (g, g):
+        return pack
+    views = pack.__dict__.setdefault("_grid_views", {})
+    if (gh, gw) not in views:
+        views[(gh, gw)] = SiglipGridView(pack, gh, gw, interpolate_pos(pack.pos_table, gh, gw))
+    return views[(gh, gw)]

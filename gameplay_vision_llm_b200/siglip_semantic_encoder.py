@@ -9,10 +9,14 @@ Same names, argument meaning and error behaviour as the reference for everything
 * `_model.get_image_features(pixel_values=...)`    -> patchify + tcgen05 tower + MAP head
 * `encode_frames(uint8 [B,H,W,3])`                 -> the batched fast entry the reference lacks
 
+* `encode_masked_regions(frame, masks)`             -> the masked-region variant (reference :485-562):
+  Pillow-bicubic crops of the resident frame (bit-exact), HF `interpolate_pos_encoding` for non-square grids, the
+  reference's pooling and REN `projection` head — all on the device
+
 Differences, on purpose: a model that cannot be loaded raises (the reference silently degrades to a
-random `Placeholder`, :206-210 — a CPU/placeholder fallback would void every parity claim);
-`encode_masked_regions` and the REN `projection` head are out of scope (not reached from
-`extract_features.main`).
+random `Placeholder`, :206-210 — a CPU/placeholder fallback would void every parity claim); non-square regions are
+encoded with HF's own position-table interpolation instead of raising inside HF (`NaFlexConfig.interpolate_pos_encoding
+= False` restores the reference's failure for them).
 """
 from __future__ import annotations
 
@@ -68,6 +72,9 @@ class NaFlexConfig:
     synthetic_seed: Optional[int] = None  # random-init weights in the HF layout (no network here)
     state_dict: Optional[dict] = None  # an already loaded HF state_dict (vision_model.* keys)
     num_attention_heads: Optional[int] = None  # only needed for a bare state dict of an unpublished tower width
+    # masked-region route: HF's `interpolate_pos_encoding=True` for patch grids other than the checkpoint's.  False =
+    # the reference as published: HF raises on the position add for every non-square region
+    interpolate_pos_encoding: bool = True
 
 
 class BatchFeature(dict):
@@ -141,7 +148,9 @@ class GvlSiglipModel:
         return self
 
     def _ws(self, batch: int) -> torch.Tensor:
-        need = self.pack.workspace_bytes(batch)
+        return self._ws_bytes(self.pack.workspace_bytes(batch))
+
+    def _ws_bytes(self, need: int) -> torch.Tensor:
         if self._workspace is None or self._workspace.numel() < need:
             self._workspace = torch.empty(need, dtype=torch.uint8, device=self.device)
         return self._workspace
@@ -195,6 +204,120 @@ def _load_checkpoint_configs(model_name: str) -> tuple[Optional[dict], Optional[
     return vision, out[1]
 
 
+class AspectPreservingResizer:
+    """NaFlex target size (reference :86-163).  The resize itself runs in `gvl_region_patches_pil_u8`."""
+
+    def __init__(self, config: NaFlexConfig):
+        self.config = config
+
+    def compute_optimal_size(self, original_h: int, original_w: int) -> tuple[int, int]:
+        """(target_h, target_w): base resolution along the longer side, aspect preserved, bounded by
+        min/max_resolution, rounded down to the 14-pixel patch (reference :97-135, same float arithmetic)."""
+        aspect_ratio = original_w / original_h
+        base = self.config.base_resolution
+        if aspect_ratio >= 1:
+            target_w = min(self.config.max_resolution, max(self.config.min_resolution, base))
+            target_h = max(self.config.min_resolution, int(target_w / aspect_ratio))
+        else:
+            target_h = min(self.config.max_resolution, max(self.config.min_resolution, base))
+            target_w = max(self.config.min_resolution, int(target_h * aspect_ratio))
+        patch_size = 14
+        target_h = (target_h // patch_size) * patch_size
+        target_w = (target_w // patch_size) * patch_size
+        return max(patch_size, target_h), max(patch_size, target_w)
+
+    def target_size(self, region_h: int, region_w: int) -> tuple[int, int]:
+        """(target_h, target_w) of `resize_with_aspect_ratio` (:137-163), square fallback included."""
+        if self.config.preserve_aspect_ratio:
+            return self.compute_optimal_size(region_h, region_w)
+        return self.config.base_resolution, self.config.base_resolution
+
+
+IMAGENET_MEAN = (0.485, 0.456, 0.406)  # hard-coded in the reference's prepare_region_tensor (:363-364)
+IMAGENET_STD = (0.229, 0.224, 0.225)
+
+
+class RegionExtractor:
+    """Mask -> expanded bounding box (reference :292-344); the crop / resize / normalisation of :346-367 run on the
+    device."""
+
+    def __init__(self, config: NaFlexConfig):
+        self.config = config
+        self.resizer = AspectPreservingResizer(config)
+
+    @staticmethod
+    def region_bbox(frame_shape, mask, expand_ratio: float = 0.1) -> tuple[int, int, int, int]:
+        """The box of `extract_masked_region` (:318-338).  Row / column occupancy instead of `np.where` over the whole
+        mask: the same min / max, without materialising every set pixel's coordinates."""
+        mask = np.asarray(mask)
+        cols = np.flatnonzero(mask.any(axis=0))
+        if cols.size == 0:
+            h, w = frame_shape[:2]
+            cx, cy = w // 2, h // 2
+            size = min(h, w) // 4
+            return (cx - size, cy - size, cx + size, cy + size)
+        rows = np.flatnonzero(mask.any(axis=1))
+        x_min, x_max = cols[0], cols[-1]
+        y_min, y_max = rows[0], rows[-1]
+        width = x_max - x_min
+        height = y_max - y_min
+        x_min = max(0, int(x_min - width * expand_ratio))
+        y_min = max(0, int(y_min - height * expand_ratio))
+        x_max = min(frame_shape[1], int(x_max + width * expand_ratio))
+        y_max = min(frame_shape[0], int(y_max + height * expand_ratio))
+        return (x_min, y_min, x_max, y_max)
+
+    def extract_masked_region(self, frame, mask, expand_ratio: float = 0.1):
+        """(PIL crop, bbox) like the reference (:301-344)."""
+        from PIL import Image
+        bbox = self.region_bbox(frame.shape, mask, expand_ratio)
+        x1, y1, x2, y2 = bbox
+        return Image.fromarray(np.asarray(frame)[y1:y2, x1:x2]), bbox
+
+    def prepare_region_tensor(self, region) -> tuple[torch.Tensor, float]:
+        """PIL region -> (fp32 CHW tensor on the CPU, aspect ratio) like the reference (:346-367): the resize runs in
+        the region kernel (bit-identical to `PIL.Image.resize(BICUBIC)`), the three fp32 operations are the
+        reference's."""
+        arr = _to_uint8_hwc(region)
+        h, w = arr.shape[:2]
+        th, tw = self.resizer.target_size(h, w)
+        dev = ops.resolve_device(self.config.device)
+        _, u8 = ops.region_patches(torch.from_numpy(np.ascontiguousarray(arr)).to(dev), [(0, 0, w, h)], [(th, tw)],
+                                   ((th + 13) // 14 * 14, (tw + 13) // 14 * 14), None, want_patches=False, want_u8=True)
+        tensor = u8[0, :th, :tw].cpu().float().permute(2, 0, 1) / 255.0
+        mean = torch.tensor(IMAGENET_MEAN).view(3, 1, 1)
+        std = torch.tensor(IMAGENET_STD).view(3, 1, 1)
+        return (tensor - mean) / std, w / h
+
+
+class RenProjection(torch.nn.Sequential):
+    """The REN-style `projection` head (reference :415-420): Linear(D, D) -> GELU (erf) -> Linear(D, D), parameters
+    under "0.*" / "2.*" like the reference's nn.Sequential; `forward` runs the two tcgen05 GEMMs of `gvl_project`."""
+
+    def __init__(self, dim: int):
+        super().__init__(torch.nn.Linear(dim, dim), torch.nn.GELU(), torch.nn.Linear(dim, dim))
+        self.dim = dim
+        self._pack = None
+        self._pack_key = None
+
+    def _device_pack(self, device) -> "ops.ProjectorPack":
+        params = [self[0].weight, self[0].bias, self[2].weight, self[2].bias]
+        key = tuple((p.data_ptr(), p._version, p.device, p.dtype) for p in params) + (str(device),)
+        if self._pack is None or key != self._pack_key:
+            sd = {"net.0.weight": params[0], "net.0.bias": params[1], "net.2.weight": params[2], "net.2.bias": params[3]}
+            self._pack = ops.ProjectorPack(sd, device)
+            self._pack_key = key
+        return self._pack
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        if not x.is_cuda:
+            raise RuntimeError("RenProjection.forward needs a CUDA (sm_100a) tensor; there is no CPU fallback")
+        x2 = x.reshape(-1, self.dim).to(torch.bfloat16).contiguous()
+        with torch.no_grad():
+            out = ops.project(self._device_pack(x.device), x2, out_dtype=torch.float32)
+        return out.reshape(*x.shape[:-1], self.dim)
+
+
 class SigLIPEncoder:
     """Lazy loader with the reference's attribute seam (`_model`, `_processor`, `_load_model`)."""
 
@@ -233,12 +356,19 @@ class SigLIPEncoder:
         self._processor = GvlSiglipProcessor(spec.image, resample, mean, std, device)
 
     def forward(self, pixel_values: torch.Tensor):
-        """(sequence_output, pooled_output) like the reference's `SigLIPEncoder.forward` (:246-289)."""
+        """(sequence_output, pooled_output) like the reference's `SigLIPEncoder.forward` (:246-289).  pixel_values
+        [B,3,h,w]; h x w other than the checkpoint's square goes through the re-sampled position table (HF
+        `interpolate_pos_encoding=True`) unless `config.interpolate_pos_encoding` is off."""
         self._load_model()
         m = self._model
+        B, _, h, w = pixel_values.shape
+        gh, gw = h // m.spec.patch, w // m.spec.patch
+        if (gh, gw) != (m.spec.grid, m.spec.grid) and not self.config.interpolate_pos_encoding:
+            raise RuntimeError(f"pixel_values {h}x{w} do not match the checkpoint's {m.spec.tokens} positions")
+        view = ops.siglip_grid_view(m.pack, gh, gw)
         patches = ops.patchify(pixel_values.to(m.device, torch.float32), m.spec.patch, m.spec.patch_ld)
-        pooled, tokens = ops.siglip_forward(m.pack, patches, workspace=m._ws(pixel_values.shape[0]), return_tokens=True)
-        return tokens.view(pixel_values.shape[0], m.spec.tokens, m.spec.hidden), pooled
+        pooled, tokens = ops.siglip_forward(view, patches, workspace=m._ws_bytes(view.workspace_bytes(B)), return_tokens=True)
+        return tokens.view(B, view.tokens, m.spec.hidden), pooled
 
     __call__ = forward
 
@@ -286,6 +416,11 @@ class SigLIPSemanticEncoder:
         if device:
             self.config.device = device
         self.encoder = SigLIPEncoder(self.config)
+        self.region_extractor = RegionExtractor(self.config)
+        # same constructor order and default init as the reference (:412-420), so a seeded construction gives the
+        # reference's projection weights; they stay on the host as the parameter container (bf16 device copy on use)
+        self.projection = RenProjection(self.config.embedding_dim)
+        self._region_lut: Optional[torch.Tensor] = None
         logger.info("SigLIPSemanticEncoder initialized with device=%s", self.config.device)
 
     # ---- the reference's per-frame entry ----------------------------------------------------------
@@ -317,10 +452,80 @@ class SigLIPSemanticEncoder:
             outs.append(m.forward_patches(patches))
         return outs[0] if len(outs) == 1 else torch.cat(outs, 0)
 
-    def encode_masked_regions(self, *args, **kwargs):
-        raise NotImplementedError(
-            "encode_masked_regions (NaFlex masked-region path) is outside this build's scope: it is not reached from "
-            "scripts/extract_features.py and fails in the reference with the fixed 729-position checkpoint")
+    # ---- masked-region variant (reference :485-602) ---------------------------------
+    def _pool_features(self, tokens: torch.Tensor, pooled: torch.Tensor, B: int, T: int) -> torch.Tensor:
+        """`_pool_features` (:426-443): tokens bf16 [B*T, D] (post-layernorm), pooled bf16 [B, D] (MAP head) -> fp32."""
+        if self.config.pool_strategy == "mean":
+            return ops.mean_tokens(tokens, B, T, torch.float32)
+        if self.config.pool_strategy == "max":
+            return ops.max_tokens(tokens, B, T, torch.float32)
+        return pooled.float()
+
+    def encode_masked_regions(self, frame, masks) -> list[SemanticEmbedding]:
+        """frame: RGB uint8 (H, W, 3) (numpy, or a tensor already on the device); masks: [(entity_id, bool (H, W))].
+        One H2D copy of the frame, then per `config.batch_size` regions: one crop/resize/normalise/pad/im2col launch,
+        one tower pass on the batch canvas, pooling, the projection head, one D2H copy — same batching, padding and
+        outputs (fp32 CPU embeddings) as the reference (:503-562)."""
+        if not masks:
+            return []
+        self.encoder._load_model()
+        m = self.encoder._model
+        spec = m.spec
+        if spec.patch != 14:
+            raise RuntimeError("encode_masked_regions: the reference rounds region sizes to 14-pixel patches (:131)")
+        if torch.is_tensor(frame):
+            frame_dev = frame.to(m.device).contiguous()
+        else:
+            frame_dev = torch.from_numpy(np.ascontiguousarray(frame)).to(m.device)
+        if frame_dev.dtype != torch.uint8 or frame_dev.dim() != 3 or frame_dev.shape[2] != 3:
+            raise ValueError("frame must be RGB uint8 (H, W, 3)")
+        shape = tuple(frame_dev.shape)
+        if self._region_lut is None or self._region_lut.device != m.device:
+            self._region_lut = ops.region_lut(IMAGENET_MEAN, IMAGENET_STD).to(m.device)
+
+        boxes, sizes, metadata = [], [], []
+        for entity_id, mask in masks:
+            bbox = self.region_extractor.region_bbox(shape, mask.cpu().numpy() if torch.is_tensor(mask) else mask)
+            x1, y1, x2, y2 = bbox
+            if x2 <= x1 or y2 <= y1:
+                raise ValueError(f"region '{entity_id}': empty bounding box {bbox}")  # PIL raises here in the reference
+            boxes.append(bbox)
+            sizes.append(self.region_extractor.resizer.target_size(y2 - y1, x2 - x1))
+            metadata.append({"entity_id": entity_id, "bbox": bbox, "aspect_ratio": (x2 - x1) / (y2 - y1)})
+
+        embeddings: list[SemanticEmbedding] = []
+        bs = max(1, int(self.config.batch_size))
+        for i in range(0, len(boxes), bs):
+            chunk_sizes = sizes[i:i + bs]
+            max_h = max(s[0] for s in chunk_sizes)
+            max_w = max(s[1] for s in chunk_sizes)
+            gh, gw = max_h // spec.patch, max_w // spec.patch
+            if (gh, gw) != (spec.grid, spec.grid) and not self.config.interpolate_pos_encoding:
+                raise RuntimeError(f"a {gh}x{gw} patch grid does not match the checkpoint's {spec.tokens} positions "
+                                   "(the reference fails here; NaFlexConfig.interpolate_pos_encoding=True encodes it)")
+            patches, _ = ops.region_patches(frame_dev, boxes[i:i + bs], chunk_sizes, (max_h, max_w), self._region_lut,
+                                            patch=spec.patch, ld=spec.patch_ld)
+            view = ops.siglip_grid_view(m.pack, gh, gw)
+            B = len(chunk_sizes)
+            pooled, tokens = ops.siglip_forward(view, patches, workspace=m._ws_bytes(view.workspace_bytes(B)),
+                                                return_tokens=True)
+            feats = self._pool_features(tokens, pooled, B, view.tokens)
+            out = self.projection(feats).cpu()
+            for emb, meta in zip(out, metadata[i:i + bs]):
+                embeddings.append(SemanticEmbedding(embedding=emb, entity_id=meta["entity_id"], confidence=1.0,
+                                                    original_bbox=meta["bbox"], aspect_ratio=meta["aspect_ratio"]))
+        logger.debug("Encoded %d masked regions", len(embeddings))
+        return embeddings
+
+    def encode_with_context(self, frame, mask, context_radius: int = 50) -> tuple[SemanticEmbedding, SemanticEmbedding]:
+        """Region + surrounding-context embeddings (reference :564-602): the context mask is the mask dilated
+        `context_radius // 3` times (scipy's default cross structuring element) minus the mask."""
+        import scipy.ndimage as ndi
+        mask = np.asarray(mask.cpu() if torch.is_tensor(mask) else mask)
+        region = self.encode_masked_regions(frame, [("region", mask)])
+        dilated = ndi.binary_dilation(mask, iterations=context_radius // 3)
+        context = self.encode_masked_regions(frame, [("context", dilated & ~mask)])
+        return region[0], context[0]
 
     # ---- similarity (reference :604-638) ------------------------------------------------------------
     @staticmethod

@@ -153,6 +153,13 @@ def synth_projector_state_dict(encoder_dim: int, llm_dim: int = 4096, seed: int 
     }
 
 
+def synth_ren_projection_state_dict(dim: int, seed: int = 3) -> dict[str, torch.Tensor]:
+    """Random weights for the REN-style `projection` head of `SigLIPSemanticEncoder` under the reference's
+    nn.Sequential names "0.*" / "2.*" (src/perception/siglip_semantic_encoder.py:416-420); bf16-representable."""
+    sd = synth_projector_state_dict(dim, dim, seed)
+    return {k[len("net."):]: v for k, v in sd.items()}
+
+
 _ACT = {"gelu_pytorch_tanh": 1, "gelu": 2, "gelu_erf": 2, "none": 0}
 
 
@@ -201,7 +208,8 @@ class SiglipPack:
         wp[:, : spec.patch_k] = get("embeddings.patch_embedding.weight").reshape(D, spec.patch_k)
         w.w_patch = mat(wp).data_ptr()
         w.b_patch = vec(get("embeddings.patch_embedding.bias")).data_ptr()
-        w.pos = mat(get("embeddings.position_embedding.weight")).data_ptr()
+        self.pos_table = mat(get("embeddings.position_embedding.weight"))  # bf16 [T, D]
+        w.pos = self.pos_table.data_ptr()
 
         self._layers = (_lib.VitLayer * spec.layers)()
         for i in range(spec.layers):
@@ -254,11 +262,34 @@ class SiglipPack:
         w.b_hfc2 = vec(get("head.mlp.fc2.bias")).data_ptr()
         self.struct = w
 
+    @property
+    def tokens(self) -> int:
+        return self.spec.tokens
+
     def workspace_bytes(self, batch: int) -> int:
         return int(_lib.lib().gvl_siglip_workspace_bytes(ctypes.byref(self.struct), int(batch)))
 
     def nbytes(self) -> int:
         return sum(t.numel() * t.element_size() for t in self._keep)
+
+
+class SiglipGridView:
+    """A `SiglipPack` seen with a gh x gw patch grid (the masked-region variant, include/gvl.h K9): the same device
+    weights, `T = gh * gw` tokens per item and the position table re-sampled to that grid
+    (`gvl_pos_interp_bicubic_bf16`).  Holds the base pack alive; `struct` is a copy of the base struct."""
+
+    def __init__(self, base: SiglipPack, gh: int, gw: int, pos: torch.Tensor):
+        if pos.dtype != torch.bfloat16 or tuple(pos.shape) != (gh * gw, base.spec.hidden) or not pos.is_contiguous():
+            raise RuntimeError("SiglipGridView: pos must be contiguous bf16 [gh*gw, D]")
+        self.base, self.spec, self.device = base, base.spec, base.device
+        self.grid, self.tokens, self.pos_table = (gh, gw), gh * gw, pos
+        w = _lib.VitWeights.from_buffer_copy(base.struct)
+        w.T = gh * gw
+        w.pos = pos.data_ptr()
+        self.struct = w
+
+    def workspace_bytes(self, batch: int) -> int:
+        return int(_lib.lib().gvl_siglip_workspace_bytes(ctypes.byref(self.struct), int(batch)))
 
 
 class ProjectorPack:

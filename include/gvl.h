@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define GVL_ABI_VERSION 7
+#define GVL_ABI_VERSION 8
 
 #if defined(__GNUC__)
 #define GVL_API __attribute__((visibility("default")))
@@ -327,6 +327,52 @@ GVL_API int gvl_topk_cosine_f32(const float* index, int N, int D, const float* q
                         float* scratch, float* out_scores, int32_t* out_idx, void* stream);
 /* inv_norm[n] = 1 / max(|rows[n]|, eps), rows bf16 [N, D]. */
 GVL_API int gvl_row_inv_norm(const void* rows, int N, int D, float eps, float* inv_norm, void* stream);
+
+/* ---- K9: masked-region variant ---------------------------------------------------- */
+/* The region route of `SigLIPSemanticEncoder.encode_masked_regions` (src/perception/siglip_semantic_encoder.py:485-562,
+ * called from scripts/extract_features.py:551-585 when SAM detections exist): bounding-box crops of one frame are
+ * resized with `PIL.Image.resize(..., BICUBIC)` (:155), scaled by 1/255 and normalised with the ImageNet constants in
+ * fp32 (:357-365), zero-padded to the largest region of the batch (:527-537), cast to the model dtype (:539) and
+ * encoded; `mean` / `max` / `cls` pooling (:426-443).
+ *
+ * Host only: Pillow's 8-bit coefficient tables of one axis (Pillow src/libImaging/Resample.c `precompute_coeffs` with
+ * the bicubic filter, a = -0.5, support 2 scaled by max(in/out, 1), + `normalize_coeffs_8bpc`, 22-bit fixed point).
+ * h_xmin / h_count: [out_size]; h_coeffs: [out_size * max_taps] (zero padded); *h_ksize = taps per output (the
+ * stride Pillow allocates).  With all three table pointers NULL only *h_ksize is written. */
+GVL_API int gvl_pil_bicubic_taps(int in_size, int out_size, int max_taps, int32_t* h_xmin, int32_t* h_count,
+                         int32_t* h_coeffs, int* h_ksize);
+
+/* One region = GVL_REGION_DESC_INTS int32 (HOST array, validated, uploaded by the call):
+ *   [0] x1  [1] y1  [2] crop_w  [3] crop_h   source box inside the frame (`frame[y1:y2, x1:x2]`, :342)
+ *   [4] out_w  [5] out_h                      `AspectPreservingResizer.compute_optimal_size` (:97-135)
+ *   [6] kh  [7] kv                            tap strides of the two tables (>= gvl_pil_bicubic_taps' ksize)
+ *   [8] h_off  [9] v_off                      int32 offsets into `tabs` of the horizontal / vertical table,
+ *                                             each laid out as xmin[out] | count[out] | coeffs[out * k] */
+#define GVL_REGION_DESC_INTS 10
+GVL_API size_t gvl_region_scratch_bytes(int R, const int32_t* h_desc); /* Host only. */
+
+/* frame: device uint8 [H, W, 3]; tabs: device int32 [tabs_ints]; lut: device bf16 [3, 256] = the model-dtype value of
+ * ((v / 255) - mean[c]) / std[c] evaluated in fp32 (built by the host with the reference's own three fp32 operations).
+ * patches: bf16 [R * (canvas_h/patch) * (canvas_w/patch), ld], GVL_LAYOUT_BF16_PATCH order per region; pixels outside a
+ * region's out_h x out_w rectangle and the columns [3*patch*patch, ld) are zero (`F.pad` of the normalised tensor, :536).
+ * resized_u8: optional uint8 [R, canvas_h, canvas_w, 3] = the resized regions themselves (zero outside), bit-identical
+ * to Pillow's bytes (horizontal pass into a uint8 intermediate, then vertical); either output may be NULL. */
+GVL_API int gvl_region_patches_pil_u8(const uint8_t* frame, int H, int W, int R, const int32_t* h_desc,
+                              const int32_t* tabs, long long tabs_ints, const uint16_t* lut, int canvas_h, int canvas_w,
+                              int patch, int ld, void* patches, uint8_t* resized_u8, void* scratch, size_t scratch_bytes,
+                              void* stream);
+
+/* Position table for a gh x gw patch grid: pos bf16 [g*g, D] -> out bf16 [gh*gw, D], bicubic, align_corners = false,
+ * A = -0.75, border-clamped taps, fp32 arithmetic.  Replaces `SiglipVisionEmbeddings.interpolate_pos_encoding`
+ * (HF:models/siglip/modeling_siglip.py:137-174 -> ATen native/UpSampleBicubic2d, UpSample.h) — the
+ * "interpolate_pos_encoding fixed" of SURVEY.md §8 f.4: without it the reference's region route raises for every
+ * non-square region of a 729-position checkpoint.  gvl_siglip_forward then runs on a copy of the weight pack whose
+ * T = gh*gw and pos = out. */
+GVL_API int gvl_pos_interp_bicubic_bf16(const void* pos, int g, int D, int gh, int gw, void* out, void* stream);
+
+/* out[b, :] = max over the T tokens of x[b] (bf16 [B,T,D]); out bf16 or float [B,D].
+ * Replaces `sequence.max(dim=1)[0]` (src/perception/siglip_semantic_encoder.py:438-440). */
+GVL_API int gvl_max_tokens_bf16(const void* x, int B, int T, int D, void* out, int out_f32, void* stream);
 
 #ifdef __cplusplus
 }

@@ -53,19 +53,21 @@ def _mha(x, wq, bq, wk, bk, wv, bv, heads):
 
 
 def vision_forward(sd: dict, pixel_values: torch.Tensor, heads: int, patch: int, eps: float = 1e-6,
-                   act=gelu_tanh, seams: dict | None = None, dtype=torch.float32) -> torch.Tensor:
-    """pixel_values [B,3,S,S] -> pooled [B,D].  `seams` (if given) receives the intermediate tensors."""
+                   act=gelu_tanh, seams: dict | None = None, dtype=torch.float32, pos: torch.Tensor | None = None) -> torch.Tensor:
+    """pixel_values [B,3,h,w] -> pooled [B,D].  `seams` (if given) receives the intermediate tensors.  `pos`
+    replaces the learned position table (the `interpolate_pos_encoding=True` route for h x w inputs whose patch
+    grid differs from the checkpoint's, HF :137-186; see oracle/region_ref.py)."""
     pre = "vision_model." if any(k.startswith("vision_model.") for k in sd) else ""
     W = lambda n: sd[pre + n].to(dtype)  # noqa: E731
     x = pixel_values.to(dtype)
     B = x.shape[0]
     wp = W("embeddings.patch_embedding.weight")  # [D,3,p,p]
     D = wp.shape[0]
-    g = x.shape[-1] // patch
-    # valid stride-p conv == im2col GEMM over the top-left g*p x g*p pixels
-    cols = x[:, :, : g * patch, : g * patch].reshape(B, 3, g, patch, g, patch).permute(0, 2, 4, 1, 3, 5).reshape(B, g * g, -1)
+    gh, gw = x.shape[-2] // patch, x.shape[-1] // patch
+    # valid stride-p conv == im2col GEMM over the top-left gh*p x gw*p pixels
+    cols = x[:, :, : gh * patch, : gw * patch].reshape(B, 3, gh, patch, gw, patch).permute(0, 2, 4, 1, 3, 5).reshape(B, gh * gw, -1)
     h = cols @ wp.reshape(D, -1).T + W("embeddings.patch_embedding.bias")
-    h = h + W("embeddings.position_embedding.weight")[None]
+    h = h + (W("embeddings.position_embedding.weight") if pos is None else pos.to(dtype))[None]
     if seams is not None:
         seams["patches"] = cols
         seams["embeddings"] = h

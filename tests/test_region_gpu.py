@@ -1,0 +1,183 @@
+"""Masked-region variant through the C ABI: Pillow-exact region bytes and patch rows, the position
+table interpolation, the pooling kernels, and `encode_masked_regions` / `encode_with_context` end to end against the
+goldens the REFERENCE'S OWN `encode_masked_regions` produced (tests/golden/make_golden_regions.py) and the fp32 oracle.
+Tolerance: resized bytes and bf16 patch rows bit-exact; embeddings cosine >= 0.999 + stated max-abs."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from gameplay_vision_llm_b200 import ops, synth  # noqa: E402
+from gameplay_vision_llm_b200.siglip_semantic_encoder import NaFlexConfig, SigLIPSemanticEncoder  # noqa: E402
+from gameplay_vision_llm_b200.weights import (SiglipPack, SiglipVisionSpec, synth_ren_projection_state_dict,  # noqa: E402
+                                                synth_siglip_state_dict)
+from oracle import preprocess_ref, region_ref, siglip_ref  # noqa: E402
+
+sys.path.insert(0, os.path.join(os.path.dirname(__file__), "golden"))
+from make_golden_regions import MID_CFG, MID_RECTS, MID_SPEC, SO_RECTS, rect_mask  # noqa: E402
+
+DEV = "cuda:0"
+
+
+def _cos(a, b):
+    return torch.nn.functional.cosine_similarity(torch.as_tensor(a).double().cpu(), torch.as_tensor(b).double().cpu(), dim=-1)
+
+
+# (frame H, W, boxes, sizes (out_h, out_w)): down- and up-scaling, identity axes, 1-pixel crops, whole-frame crops
+KERNEL_CASES = [
+    (270, 480, [(14, 21, 326, 129), (194, 0, 266, 270), (90, 90, 210, 210), (4, 4, 13, 10), (0, 197, 480, 233)],
+     [(42, 140), (140, 42), (140, 140), (84, 140), (42, 140)]),
+    (1080, 1920, [(200, 156, 1400, 684), (852, 0, 1428, 1050), (0, 0, 1920, 1080), (340, 248, 1060, 872)],
+     [(154, 378), (378, 196), (210, 378), (322, 378)]),
+    (64, 96, [(10, 10, 11, 11), (0, 0, 96, 64), (5, 7, 47, 49)], [(14, 14), (42, 70), (42, 42)]),
+]
+
+
+@pytest.mark.parametrize("H,W,boxes,sizes", KERNEL_CASES)
+def test_region_kernel_is_bit_exact_against_the_pillow_oracle(H, W, boxes, sizes):
+    frame = synth.noise_frames(1, H, W, seed=H + W)[0]
+    canvas = (max(s[0] for s in sizes), max(s[1] for s in sizes))
+    lut = ops.region_lut(region_ref.IMAGENET_MEAN, region_ref.IMAGENET_STD).to(DEV)
+    patches, u8 = ops.region_patches(frame.to(DEV), boxes, sizes, canvas, lut, patch=14, ld=592, want_u8=True)
+    torch.cuda.synchronize()
+    gh, gw = canvas[0] // 14, canvas[1] // 14
+    assert patches.shape == (len(boxes) * gh * gw, 592)
+    f = frame.numpy()
+    for r, ((x1, y1, x2, y2), (oh, ow)) in enumerate(zip(boxes, sizes)):
+        want = region_ref.pil_resize_bicubic_u8(f[y1:y2, x1:x2], ow, oh)
+        got = u8[r].cpu().numpy()
+        assert np.array_equal(got[:oh, :ow], want), f"region {r}: resized bytes differ from Pillow's"
+        assert not got[oh:].any() and not got[:, ow:].any(), f"region {r}: padding is not zero"
+        # patch rows: the reference's normalisation in fp32, zero padding, cast to bf16, im2col
+        t = torch.from_numpy(want.copy()).float().permute(2, 0, 1) / 255.0
+        t = (t - torch.tensor(region_ref.IMAGENET_MEAN).view(3, 1, 1)) / torch.tensor(region_ref.IMAGENET_STD).view(3, 1, 1)
+        t = torch.nn.functional.pad(t, (0, canvas[1] - ow, 0, canvas[0] - oh))
+        want_p = torch.from_numpy(preprocess_ref.patchify(t[None].numpy(), 14, 592)).to(torch.bfloat16)
+        got_p = patches[r * gh * gw:(r + 1) * gh * gw].cpu()
+        assert torch.equal(got_p.view(torch.int16), want_p.view(torch.int16)), f"region {r}: patch rows differ"
+
+
+def test_region_kernel_rejects_bad_geometry():
+    frame = synth.noise_frames(1, 64, 96, seed=1)[0].to(DEV)
+    lut = ops.region_lut(region_ref.IMAGENET_MEAN, region_ref.IMAGENET_STD).to(DEV)
+    with pytest.raises(RuntimeError, match="leaves the"):
+        ops.region_patches(frame, [(90, 0, 100, 10)], [(14, 14)], (14, 14), lut)
+    with pytest.raises(RuntimeError, match="exceeds"):
+        ops.region_patches(frame, [(0, 0, 10, 10)], [(28, 14)], (14, 14), lut)
+    with pytest.raises(ValueError, match="empty box"):
+        ops.region_patches(frame, [(5, 5, 5, 9)], [(14, 14)], (14, 14), lut)
+
+
+@pytest.mark.parametrize("g,D,gh,gw", [(27, 1152, 13, 27), (27, 1152, 27, 16), (10, 216, 3, 10), (10, 216, 10, 7), (4, 144, 9, 5)])
+def test_position_interpolation_kernel(g, D, gh, gw):
+    pos = torch.randn(g * g, D, generator=torch.Generator().manual_seed(g + gh)).to(torch.bfloat16)
+    got = ops.interpolate_pos(pos.to(DEV), gh, gw).float().cpu()
+    want = region_ref.interpolate_pos(pos.float(), gh, gw)
+    # fp32 evaluation rounded to bf16: within one bf16 step of the float64 restatement
+    assert ((got - want).abs() <= want.abs() * 2.0 ** -7 + 1e-5).all()  # + fp32 evaluation noise where taps cancel
+    p = pos.to(DEV)
+    assert ops.interpolate_pos(p, g, g) is p  # the checkpoint's own grid: the table itself, as in HF
+
+
+def test_max_and_mean_tokens():
+    B, T, D = 3, 37, 216
+    x = torch.randn(B * T, D, generator=torch.Generator().manual_seed(0)).to(torch.bfloat16).to(DEV)
+    assert torch.equal(ops.max_tokens(x, B, T).cpu(), x.float().view(B, T, D).max(dim=1)[0].cpu())
+    assert torch.allclose(ops.mean_tokens(x, B, T).cpu(), x.float().view(B, T, D).mean(dim=1).cpu(), atol=1e-5)
+
+
+def _encoder(spec, pool, bs, cfg_kw, fold=False):
+    cfg = NaFlexConfig(device=DEV, embedding_dim=spec.hidden, pool_strategy=pool, batch_size=bs,
+                       state_dict=synth_siglip_state_dict(spec, seed=0), num_attention_heads=spec.heads, **cfg_kw)
+    enc = SigLIPSemanticEncoder(cfg)
+    enc.projection.load_state_dict(synth_ren_projection_state_dict(spec.hidden, seed=3))
+    return enc
+
+
+@pytest.mark.parametrize("pool", ["mean", "cls", "max"])
+@pytest.mark.parametrize("bs", [16, 1])
+def test_encode_masked_regions_mid_tower_vs_reference_golden(golden_dir, pool, bs):
+    gold = np.load(f"{golden_dir}/golden_regions.npz")
+    frame = synth.scene_frames_np(7, 1, 270, 480)[0]
+    masks = [(f"e{i}", rect_mask(frame.shape, r)) for i, r in enumerate(MID_RECTS)]
+    enc = _encoder(MID_SPEC, pool, bs, MID_CFG)
+    res = enc.encode_masked_regions(frame, masks)
+    assert [r.entity_id for r in res] == [m[0] for m in masks]
+    assert np.array_equal(np.array([r.original_bbox for r in res]), gold["mid_bbox"])
+    assert np.array_equal(np.array([r.aspect_ratio for r in res]), gold["mid_aspect"])
+    got = torch.stack([r.embedding for r in res])
+    assert got.dtype == torch.float32 and got.device.type == "cpu"  # `.cpu()` fp32 rows like the reference (:553)
+    want = torch.from_numpy(gold[f"mid_{pool}_bs{bs}"])
+    cos, err = _cos(got, want), (got - want).abs().max().item()
+    print(f"regions mid pool={pool} bs={bs}: cos min {cos.min():.6f} max_abs {err:.4f} (|want| max {want.abs().max():.3f})")
+    assert cos.min() > 0.999 and err < 0.015 * want.abs().max().item() + 0.005  # measured 0.005 x max
+
+
+def test_encode_masked_regions_accepts_a_resident_frame_and_empty_input():
+    frame = synth.scene_frames_np(7, 1, 270, 480)[0]
+    masks = [("a", rect_mask(frame.shape, MID_RECTS[0])), ("b", rect_mask(frame.shape, MID_RECTS[1]))]
+    enc = _encoder(MID_SPEC, "mean", 16, MID_CFG)
+    assert enc.encode_masked_regions(frame, []) == []
+    host = enc.encode_masked_regions(frame, masks)
+    dev = enc.encode_masked_regions(torch.from_numpy(frame).to(DEV), masks)
+    assert all(torch.equal(a.embedding, b.embedding) for a, b in zip(host, dev))
+
+
+def test_encode_with_context_vs_reference_golden(golden_dir):
+    gold = np.load(f"{golden_dir}/golden_regions.npz")
+    frame = synth.scene_frames_np(7, 1, 270, 480)[0]
+    enc = _encoder(MID_SPEC, "mean", 16, MID_CFG)
+    a, b = enc.encode_with_context(frame, rect_mask(frame.shape, MID_RECTS[2]), context_radius=30)
+    assert np.array_equal(np.array([a.original_bbox, b.original_bbox]), gold["mid_context_bbox"])
+    cos = _cos(torch.stack([a.embedding, b.embedding]), torch.from_numpy(gold["mid_context"]))
+    assert cos.min() > 0.999
+
+
+def test_non_square_region_raises_like_the_reference_without_interpolation():
+    frame = synth.scene_frames_np(7, 1, 270, 480)[0]
+    enc = _encoder(MID_SPEC, "mean", 16, dict(MID_CFG, interpolate_pos_encoding=False))
+    with pytest.raises(RuntimeError, match="positions"):
+        enc.encode_masked_regions(frame, [("wide", rect_mask(frame.shape, MID_RECTS[0]))])
+    # a region that resizes to the checkpoint's own square grid works either way (the reference's working case)
+    sq = enc.encode_masked_regions(frame, [("sq", rect_mask(frame.shape, MID_RECTS[2]))])
+    enc2 = _encoder(MID_SPEC, "mean", 16, MID_CFG)
+    assert torch.equal(sq[0].embedding, enc2.encode_masked_regions(frame, [("sq", rect_mask(frame.shape, MID_RECTS[2]))])[0].embedding)
+
+
+def test_encoder_forward_on_a_non_square_input_vs_oracle():
+    """`SigLIPEncoder.forward` (reference :246-289) returns (sequence, pooled) for an h x w input."""
+    spec = MID_SPEC
+    sd = synth_siglip_state_dict(spec, seed=0)
+    pv = torch.randn(2, 3, 42, 98, generator=torch.Generator().manual_seed(5)).clamp(-2, 2)
+    pv = pv.to(torch.bfloat16).float()
+    pos = region_ref.interpolate_pos(sd["vision_model.embeddings.position_embedding.weight"], 3, 7)
+    seams = {}
+    want = siglip_ref.vision_forward(sd, pv, spec.heads, spec.patch, spec.eps, seams=seams, pos=pos)
+    enc = _encoder(spec, "mean", 16, MID_CFG)
+    seq, pooled = enc.encoder(pv.to(DEV))
+    assert seq.shape == (2, 21, spec.hidden)
+    assert _cos(seq.float(), seams["last_hidden_state"]).min() > 0.999 and _cos(pooled.float(), want).min() > 0.999
+
+
+@pytest.mark.timeout(900)
+def test_encode_masked_regions_so400m_vs_reference_golden(golden_dir):
+    """Full-size tower, three regions of a 1080p frame: one call per detection (scripts/extract_features.py:568 — grids
+    12 x 27, 27 x 15 and the untouched 27 x 27) and one padded batch of three, against the reference's own outputs."""
+    gold = np.load(f"{golden_dir}/golden_regions.npz")
+    spec = SiglipVisionSpec.so400m()
+    enc = _encoder(spec, "mean", 16, {})
+    frame = synth.scene_frames_np(40, 1)[0]
+    masks = [(f"s{i}", rect_mask(frame.shape, r)) for i, r in enumerate(SO_RECTS)]
+    single = [enc.encode_masked_regions(frame, [mk])[0] for mk in masks]
+    batched = enc.encode_masked_regions(frame, masks)
+    assert np.array_equal(np.array([r.original_bbox for r in single]), gold["so_bbox"])
+    assert np.array_equal(np.array([r.aspect_ratio for r in single]), gold["so_aspect"])
+    for name, res in (("single", single), ("batched", batched)):
+        got, want = torch.stack([r.embedding for r in res]), torch.from_numpy(gold[f"so_mean_{name}"])
+        cos, err = _cos(got, want), (got - want).abs().max().item()
+        print(f"regions so400m {name}: cos {cos.tolist()} max_abs {err:.4f} (|want| max {want.abs().max():.3f})")
+        assert cos.min() > 0.999 and err < 0.015 * want.abs().max().item() + 0.005  # measured 0.005 x max

@@ -34,6 +34,10 @@ class VitWeights(ctypes.Structure):
     )
 
 
+class RaggedGroup(ctypes.Structure):
+    _fields_ = [("B", c_int32), ("T", c_int32), ("pos", c_void_p)]
+
+
 class GemmFusion(ctypes.Structure):
     _fields_ = [("stats_out", c_void_p), ("ln_stats", c_void_p), ("ln_slots", c_int32), ("ln_dim", c_int32),
                 ("ln_c1", c_void_p), ("ln_eps", c_float)]
@@ -76,6 +80,9 @@ SIGNATURES = {
     "gvl_siglip_workspace_bytes": (c_size_t, [POINTER(VitWeights), c_int]),
     "gvl_siglip_forward": (c_int, [POINTER(VitWeights), c_void_p, c_int, c_void_p, c_size_t, c_void_p, c_void_p,
                                    c_void_p]),
+    "gvl_siglip_ragged_workspace_bytes": (c_size_t, [POINTER(VitWeights), c_longlong, c_int]),
+    "gvl_siglip_forward_ragged": (c_int, [POINTER(VitWeights), c_void_p, c_int, POINTER(RaggedGroup), c_void_p, c_size_t,
+                                          c_void_p, c_void_p, c_void_p]),
     "gvl_project": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                             c_int, c_void_p]),
     "gvl_topk_cosine": (c_int, [c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_float, c_void_p, c_void_p, c_void_p,

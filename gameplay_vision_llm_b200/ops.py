@@ -473,12 +473,13 @@ def region_lut(image_mean, image_std, dtype: torch.dtype = torch.bfloat16) -> to
 
 @_on_tensor_device
 def region_patches(frame: torch.Tensor, boxes, sizes, canvas_hw, lut: torch.Tensor | None, patch: int = 14,
-                   ld: int | None = None, want_patches: bool = True, want_u8: bool = False):
+                   ld: int | None = None, want_patches: bool = True, want_u8: bool = False, out: torch.Tensor | None = None):
     """Crop + Pillow-bicubic resize + normalise + zero-pad + im2col of R regions of ONE frame.
 
     frame: uint8 [H,W,3] on the device; boxes: R x (x1, y1, x2, y2) (`frame[y1:y2, x1:x2]`); sizes: R x (out_h, out_w);
     canvas_hw: (canvas_h, canvas_w) multiples of `patch`, >= every size.  Returns (patches bf16 [R*gh*gw, ld] or None,
-    resized uint8 [R, canvas_h, canvas_w, 3] or None)."""
+    resized uint8 [R, canvas_h, canvas_w, 3] or None).  `out`: a contiguous bf16 [R*gh*gw, ld] slice to write the patch
+    rows into (a ragged batch is assembled from several calls)."""
     _need_cuda(frame, lut)
     if frame.dtype != torch.uint8 or frame.dim() != 3 or frame.shape[2] != 3 or not frame.is_contiguous():
         raise RuntimeError("region_patches: frame must be contiguous uint8 [H,W,3]")
@@ -503,7 +504,11 @@ def region_patches(frame: torch.Tensor, boxes, sizes, canvas_hw, lut: torch.Tens
     dptr = desc.ctypes.data_as(ctypes.POINTER(ctypes.c_int32))
     scratch = torch.empty(int(_lib.lib().gvl_region_scratch_bytes(R, dptr)) + 256, dtype=torch.uint8, device=frame.device)
     gh, gw = canvas_h // patch, canvas_w // patch
-    patches = torch.empty((R * gh * gw, ld), dtype=torch.bfloat16, device=frame.device) if want_patches else None
+    patches = None
+    if want_patches:
+        patches = out if out is not None else torch.empty((R * gh * gw, ld), dtype=torch.bfloat16, device=frame.device)
+        if patches.dtype != torch.bfloat16 or tuple(patches.shape) != (R * gh * gw, ld) or not patches.is_contiguous():
+            raise RuntimeError(f"region_patches: `out` must be contiguous bf16 [{R * gh * gw}, {ld}]")
     resized = torch.empty((R, canvas_h, canvas_w, 3), dtype=torch.uint8, device=frame.device) if want_u8 else None
     if want_patches and (lut is None or lut.dtype != torch.bfloat16 or tuple(lut.shape) != (3, 256) or not lut.is_contiguous()):
         raise RuntimeError("region_patches: lut must be contiguous bf16 [3, 256]")
@@ -542,6 +547,39 @@ def max_tokens(x: torch.Tensor, B: int, T: int, out_dtype: torch.dtype = torch.f
     _lib.check(_lib.lib().gvl_max_tokens_bf16(x.data_ptr(), B, T, D, out.data_ptr(),
                                               1 if out_dtype == torch.float32 else 0, _stream()), "gvl_max_tokens_bf16")
     return out
+
+
+def siglip_ragged_workspace_bytes(pack: SiglipPack, M_total: int, B_total: int) -> int:
+    return int(_lib.lib().gvl_siglip_ragged_workspace_bytes(ctypes.byref(pack.struct), int(M_total), int(B_total)))
+
+
+@_on_tensor_device
+def siglip_forward_ragged(pack: SiglipPack, patches: torch.Tensor, groups, workspace: torch.Tensor | None = None,
+                          return_tokens: bool = False):
+    """One tower pass over a ragged batch.  groups: [(B_g, gh_g, gw_g)] — B_g items on a gh_g x gw_g patch grid each,
+    rows of `patches` (bf16 [sum B*gh*gw, patch_ld]) concatenated in that order.  Returns pooled bf16 [sum B, D] (MAP
+    head) and, if asked, the post-layernorm tokens bf16 [sum B*gh*gw, D].  Row-wise kernels run once over all rows;
+    each item's result is bit-identical to `siglip_forward` on its own grid view."""
+    _need_cuda(patches)
+    spec = pack.spec
+    views = [siglip_grid_view(pack, gh, gw) for _, gh, gw in groups]
+    arr = (_lib.RaggedGroup * len(groups))()
+    M = Bt = 0
+    for g, ((B, gh, gw), v) in enumerate(zip(groups, views)):
+        arr[g].B, arr[g].T, arr[g].pos = int(B), gh * gw, v.pos_table.data_ptr()
+        M += int(B) * gh * gw
+        Bt += int(B)
+    if patches.dtype != torch.bfloat16 or tuple(patches.shape) != (M, spec.patch_ld) or not patches.is_contiguous():
+        raise RuntimeError(f"siglip_forward_ragged: patches must be contiguous bf16 [{M}, {spec.patch_ld}]")
+    need = siglip_ragged_workspace_bytes(pack, M, Bt)
+    if workspace is None or workspace.numel() < need:
+        workspace = torch.empty(need, dtype=torch.uint8, device=patches.device)
+    pooled = torch.empty((Bt, spec.hidden), dtype=torch.bfloat16, device=patches.device)
+    tokens = torch.empty((M, spec.hidden), dtype=torch.bfloat16, device=patches.device) if return_tokens else None
+    _lib.check(_lib.lib().gvl_siglip_forward_ragged(ctypes.byref(pack.struct), patches.data_ptr(), len(groups), arr,
+                                                    workspace.data_ptr(), workspace.numel(), pooled.data_ptr(), _ptr(tokens),
+                                                    _stream()), "gvl_siglip_forward_ragged")
+    return (pooled, tokens) if return_tokens else pooled
 
 
 def siglip_grid_view(pack: SiglipPack, gh: int, gw: int) -> "SiglipPack | SiglipGridView":

@@ -174,6 +174,93 @@ class EmbeddingPipeline:
         return ts, index, pooled
 
 
+def run_siglip_encoder(frames, device: str = "cuda", sam_results: list | None = None, entity_tracker=None,
+                       encoder=None) -> list[dict]:
+    """Drop-in for `run_siglip_encoder` (scripts/extract_features.py:502-610): frames = [(timestamp, PIL image or uint8
+    array)], optional SAM detections [{"timestamp", "bbox", "entity_type", "entity_id", "description"}] -> the
+    reference's list of dicts (`timestamp`, `embedding` (CPU tensor), `embedding_shape`, `entity_type`, `description`,
+    and for detections `entity_id`, `bbox`) in the reference's order.
+
+    With detections (and an entity tracker, :520) every detection's bounding box is encoded through the masked-region
+    route exactly as the reference's one-call-per-detection loop would (:552-583), but all detections of a frame that
+    share a target size go through one tower pass, and all frames WITHOUT detections (and every frame in the fallback
+    branch, :590-607) are embedded together in batches of `config.batch_size` instead of one forward per frame.
+    A failing frame / detection is logged and skipped like the reference (:547, :584, :606).  `encoder`: an already
+    constructed `SigLIPSemanticEncoder` (the reference builds a fresh one per call, :514-515)."""
+    import logging
+
+    from .siglip_semantic_encoder import NaFlexConfig, SigLIPSemanticEncoder, _to_uint8_hwc
+    log = logging.getLogger(__name__)
+    if encoder is None:
+        encoder = SigLIPSemanticEncoder(NaFlexConfig(device=device))
+    slots: list[list[dict]] = [[] for _ in frames]  # per frame, in detection order
+    full_frame: list[int] = []
+    note = "Full frame encoding"
+    if sam_results and entity_tracker:
+        note = "Full frame encoding (no SAM detection)"
+        by_time: dict = {}
+        for det in sam_results:
+            by_time.setdefault(det.get("timestamp", 0), []).append(det)
+        for idx, (timestamp, frame) in enumerate(frames):
+            dets = [d for d in by_time.get(timestamp, []) if d.get("bbox") is not None]
+            if not by_time.get(timestamp):
+                full_frame.append(idx)
+                continue
+            frame_np = _to_uint8_hwc(frame)
+            masks, kept = [], []
+            for det in dets:
+                entity_type = det.get("entity_type", "unknown")
+                entity_id = det.get("entity_id", f"{entity_type}_{timestamp}")
+                x1, y1, x2, y2 = [int(c) for c in det["bbox"]]
+                mask = np.zeros(frame_np.shape[:2], dtype=np.bool_)
+                mask[y1:y2, x1:x2] = True
+                masks.append((entity_id, mask))
+                kept.append(det)
+            try:
+                regions = encoder.encode_regions_individually(frame_np, masks)
+            except Exception as e:  # one bad detection must not lose the frame: fall back to one call per detection
+                log.warning("SigLIP mask encoding failed at %.1fs (%s); retrying per detection", timestamp, e)
+                regions = []
+                for mk in masks:
+                    try:
+                        regions.append(encoder.encode_masked_regions(frame_np, [mk])[0])
+                    except Exception as e2:
+                        log.warning("SigLIP mask encoding failed for %s at %.1fs: %s", mk[0], timestamp, e2)
+                        regions.append(None)
+            for det, emb in zip(kept, regions):
+                if emb is None:
+                    continue
+                entity_type = det.get("entity_type", "unknown")
+                slots[idx].append({
+                    "timestamp": timestamp, "embedding": emb.embedding.cpu(), "embedding_shape": list(emb.embedding.shape),
+                    "entity_type": entity_type, "entity_id": emb.entity_id,
+                    "description": det.get("description", f"Detected {entity_type}"), "bbox": det["bbox"]})
+    else:
+        full_frame = list(range(len(frames)))
+    # frames encoded whole: group equal shapes into batches (one preprocess + one tower pass per batch)
+    bs = max(1, int(encoder.config.batch_size))
+    i = 0
+    while i < len(full_frame):
+        first = _to_uint8_hwc(frames[full_frame[i]][1])
+        batch_idx, arrays = [full_frame[i]], [first]
+        while i + len(batch_idx) < len(full_frame) and len(batch_idx) < bs:
+            nxt = _to_uint8_hwc(frames[full_frame[i + len(batch_idx)]][1])
+            if nxt.shape != first.shape:
+                break
+            batch_idx.append(full_frame[i + len(batch_idx)])
+            arrays.append(nxt)
+        i += len(batch_idx)
+        try:
+            emb = encoder.encode_frames(np.stack(arrays)).cpu()
+        except Exception as e:
+            log.warning("SigLIP failed at %.1fs: %s", frames[batch_idx[0]][0], e)
+            continue
+        for j, idx in enumerate(batch_idx):
+            slots[idx].append({"timestamp": frames[idx][0], "embedding": emb[j], "embedding_shape": list(emb[j].shape),
+                               "entity_type": "full_frame", "description": note})
+    return [d for s in slots for d in s]
+
+
 def pinned_batches(frames: np.ndarray | torch.Tensor, batch: int) -> Iterator[torch.Tensor]:
     """Convenience: slice a host frame array into pinned batches."""
     t = torch.as_tensor(frames)

@@ -468,21 +468,85 @@ class SigLIPSemanticEncoder:
         outputs (fp32 CPU embeddings) as the reference (:503-562)."""
         if not masks:
             return []
-        self.encoder._load_model()
+        frame_dev, boxes, sizes, metadata = self._prepare_regions(frame, masks)
+        bs = max(1, int(self.config.batch_size))
+        chunks = [list(range(i, min(i + bs, len(boxes)))) for i in range(0, len(boxes), bs)]
+        embeddings = self._encode_region_chunks(frame_dev, boxes, sizes, metadata, chunks)
+        logger.debug("Encoded %d masked regions", len(embeddings))
+        return embeddings
+
+    def encode_regions_individually(self, frame, masks, max_tokens: int = 32768) -> list[SemanticEmbedding]:
+        """What `[encode_masked_regions(frame, [m])[0] for m in masks]` returns — the way scripts/extract_features.py
+        :552-583 calls the encoder, one detection per call, so no region is ever zero-padded to a neighbour's size —
+        computed as ONE ragged tower pass (`gvl_siglip_forward_ragged`): the token rows of all regions are concatenated,
+        every GEMM / LayerNorm runs once over all of them, and only the position add, the attention and the pooling run
+        per distinct target size.  Every kernel's per-row arithmetic is independent of the rows around it, so the
+        embeddings are bit-identical to the one-per-call results.  `max_tokens` bounds one pass (activation memory)."""
+        if not masks:
+            return []
+        frame_dev, boxes, sizes, metadata = self._prepare_regions(frame, masks)
         m = self.encoder._model
         spec = m.spec
-        if spec.patch != 14:
+        by_size: dict[tuple[int, int], list[int]] = {}
+        for i, sz in enumerate(sizes):
+            by_size.setdefault(sz, []).append(i)
+        # passes of at most max_tokens rows; a size group may be split across passes
+        passes, cur, cur_tokens = [], {}, 0
+        for (th, tw), idx in by_size.items():
+            gh, gw = th // spec.patch, tw // spec.patch
+            if (gh, gw) != (spec.grid, spec.grid) and not self.config.interpolate_pos_encoding:
+                raise RuntimeError(f"a {gh}x{gw} patch grid does not match the checkpoint's {spec.tokens} positions "
+                                   "(the reference fails here; NaFlexConfig.interpolate_pos_encoding=True encodes it)")
+            for i in idx:
+                if cur and cur_tokens + gh * gw > max_tokens:
+                    passes.append(list(cur.items()))
+                    cur, cur_tokens = {}, 0
+                cur.setdefault((th, tw), []).append(i)
+                cur_tokens += gh * gw
+        if cur:
+            passes.append(list(cur.items()))
+        results: dict[int, SemanticEmbedding] = {}
+        for groups in passes:
+            shapes = [(len(idx), th // spec.patch, tw // spec.patch) for (th, tw), idx in groups]
+            M = sum(b * gh * gw for b, gh, gw in shapes)
+            patches = torch.empty((M, spec.patch_ld), dtype=torch.bfloat16, device=m.device)
+            r0 = 0
+            for ((th, tw), idx), (b, gh, gw) in zip(groups, shapes):
+                ops.region_patches(frame_dev, [boxes[i] for i in idx], [sizes[i] for i in idx], (th, tw), self._region_lut,
+                                   patch=spec.patch, ld=spec.patch_ld, out=patches[r0:r0 + b * gh * gw])
+                r0 += b * gh * gw
+            need = ops.siglip_ragged_workspace_bytes(m.pack, M, sum(x[0] for x in shapes))
+            pooled, tokens = ops.siglip_forward_ragged(m.pack, patches, shapes, workspace=m._ws_bytes(need), return_tokens=True)
+            if self.config.pool_strategy in ("mean", "max"):
+                feats, r0 = [], 0
+                for b, gh, gw in shapes:
+                    feats.append(self._pool_features(tokens[r0:r0 + b * gh * gw], None, b, gh * gw))
+                    r0 += b * gh * gw
+                feats = torch.cat(feats, 0)
+            else:
+                feats = pooled.float()
+            out = self.projection(feats).cpu()
+            order = [i for _, idx in groups for i in idx]
+            for emb, i in zip(out, order):
+                meta = metadata[i]
+                results[i] = SemanticEmbedding(embedding=emb, entity_id=meta["entity_id"], confidence=1.0,
+                                               original_bbox=meta["bbox"], aspect_ratio=meta["aspect_ratio"])
+        return [results[i] for i in range(len(boxes))]
+
+    def _prepare_regions(self, frame, masks):
+        self.encoder._load_model()
+        m = self.encoder._model
+        if m.spec.patch != 14:
             raise RuntimeError("encode_masked_regions: the reference rounds region sizes to 14-pixel patches (:131)")
         if torch.is_tensor(frame):
             frame_dev = frame.to(m.device).contiguous()
         else:
-            frame_dev = torch.from_numpy(np.ascontiguousarray(frame)).to(m.device)
+            frame_dev = torch.from_numpy(np.require(frame, requirements="CW")).to(m.device)  # PIL arrays are read-only
         if frame_dev.dtype != torch.uint8 or frame_dev.dim() != 3 or frame_dev.shape[2] != 3:
             raise ValueError("frame must be RGB uint8 (H, W, 3)")
         shape = tuple(frame_dev.shape)
         if self._region_lut is None or self._region_lut.device != m.device:
             self._region_lut = ops.region_lut(IMAGENET_MEAN, IMAGENET_STD).to(m.device)
-
         boxes, sizes, metadata = [], [], []
         for entity_id, mask in masks:
             bbox = self.region_extractor.region_bbox(shape, mask.cpu().numpy() if torch.is_tensor(mask) else mask)
@@ -492,29 +556,33 @@ class SigLIPSemanticEncoder:
             boxes.append(bbox)
             sizes.append(self.region_extractor.resizer.target_size(y2 - y1, x2 - x1))
             metadata.append({"entity_id": entity_id, "bbox": bbox, "aspect_ratio": (x2 - x1) / (y2 - y1)})
+        return frame_dev, boxes, sizes, metadata
 
+    def _encode_region_chunks(self, frame_dev, boxes, sizes, metadata, chunks) -> list[SemanticEmbedding]:
+        """One launch sequence per chunk (a list of region indices); the chunk's canvas is its largest region."""
+        m = self.encoder._model
+        spec = m.spec
         embeddings: list[SemanticEmbedding] = []
-        bs = max(1, int(self.config.batch_size))
-        for i in range(0, len(boxes), bs):
-            chunk_sizes = sizes[i:i + bs]
+        for chunk in chunks:
+            chunk_sizes = [sizes[i] for i in chunk]
             max_h = max(s[0] for s in chunk_sizes)
             max_w = max(s[1] for s in chunk_sizes)
             gh, gw = max_h // spec.patch, max_w // spec.patch
             if (gh, gw) != (spec.grid, spec.grid) and not self.config.interpolate_pos_encoding:
                 raise RuntimeError(f"a {gh}x{gw} patch grid does not match the checkpoint's {spec.tokens} positions "
                                    "(the reference fails here; NaFlexConfig.interpolate_pos_encoding=True encodes it)")
-            patches, _ = ops.region_patches(frame_dev, boxes[i:i + bs], chunk_sizes, (max_h, max_w), self._region_lut,
-                                            patch=spec.patch, ld=spec.patch_ld)
+            patches, _ = ops.region_patches(frame_dev, [boxes[i] for i in chunk], chunk_sizes, (max_h, max_w),
+                                            self._region_lut, patch=spec.patch, ld=spec.patch_ld)
             view = ops.siglip_grid_view(m.pack, gh, gw)
-            B = len(chunk_sizes)
+            B = len(chunk)
             pooled, tokens = ops.siglip_forward(view, patches, workspace=m._ws_bytes(view.workspace_bytes(B)),
                                                 return_tokens=True)
             feats = self._pool_features(tokens, pooled, B, view.tokens)
             out = self.projection(feats).cpu()
-            for emb, meta in zip(out, metadata[i:i + bs]):
+            for emb, i in zip(out, chunk):
+                meta = metadata[i]
                 embeddings.append(SemanticEmbedding(embedding=emb, entity_id=meta["entity_id"], confidence=1.0,
                                                     original_bbox=meta["bbox"], aspect_ratio=meta["aspect_ratio"]))
-        logger.debug("Encoded %d masked regions", len(embeddings))
         return embeddings
 
     def encode_with_context(self, frame, mask, context_radius: int = 50) -> tuple[SemanticEmbedding, SemanticEmbedding]:

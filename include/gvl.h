@@ -263,6 +263,21 @@ GVL_API size_t gvl_siglip_workspace_bytes(const gvl_vit_weights* w, int B);
 GVL_API int gvl_siglip_forward(const gvl_vit_weights* w, const void* patches, int B, void* workspace,
                        size_t workspace_bytes, void* pooled, void* last_hidden, void* stream);
 
+/* Ragged batch (the masked-region route, K9): n_groups groups, group g = B items of T tokens each with its own position
+ * table pos (bf16 [T, D], device), token rows concatenated in group order.  Row-wise work (GEMMs, LayerNorms) runs once
+ * over all rows; the patch GEMM's position add, the attention and the MAP-head probe attention run per group.  Each
+ * item's rows are bit-identical to a gvl_siglip_forward call on a pack with that T / pos (every kernel's per-row
+ * arithmetic is independent of the rows around it).  patches: bf16 [sum B*T, patch_ld]; pooled: bf16 [sum B, D];
+ * last_hidden: optional bf16 [sum B*T, D].  w->T / w->pos are ignored. */
+typedef struct gvl_ragged_group {
+    int32_t B, T;
+    const void* pos;
+} gvl_ragged_group;
+GVL_API size_t gvl_siglip_ragged_workspace_bytes(const gvl_vit_weights* w, long long M_total, int B_total);
+GVL_API int gvl_siglip_forward_ragged(const gvl_vit_weights* w, const void* patches, int n_groups,
+                              const gvl_ragged_group* groups, void* workspace, size_t workspace_bytes, void* pooled,
+                              void* last_hidden, void* stream);
+
 /* ---- K6b: VideoMAE clip encoder ------------------------------------------------------------------- */
 /* out[b, :] = mean over the T tokens of x[b] (bf16 [B,T,D]); out bf16 or float [B,D].
  * Replaces `outputs.last_hidden_state.mean(dim=1)` (scripts/extract_features.py:381). */

@@ -73,3 +73,79 @@ def run(n_frames: int = 8, batch: int = 8, warmup_batches: int = 1, frame_hw=(10
             "sample": f"{n_frames} synthetic 1080p frames in batches of {batch} after {warmup_batches} warm-up batch(es); "
                       f"HF SiglipImageProcessor + SiglipVisionModel(so400m, random init) + projector, fp32, "
                       f"torch {torch.__version__}, {cores} threads"}
+
+
+def region_boxes(n: int, H: int = 1080, W: int = 1920, seed: int = 4000) -> list[tuple[int, int, int, int]]:
+    """Seeded detection boxes (x1, y1, x2, y2) of a frame: UI-like wide strips, tall panels and near-square sprites from
+    a small set of shapes, so several detections share a target size (the grouping the GPU path exploits) — still one
+    `encode_masked_regions` call per detection on the reference side (scripts/extract_features.py:552-583)."""
+    rng = np.random.default_rng(seed)
+    shapes = [(1000, 440), (480, 900), (520, 520), (800, 200), (300, 300), (1200, 600), (240, 640), (640, 360)]
+    boxes = []
+    for i in range(n):
+        w, h = shapes[i % len(shapes)]
+        x1, y1 = int(rng.integers(0, W - w)), int(rng.integers(0, H - h))
+        boxes.append((x1, y1, x1 + w, y1 + h))
+    return boxes
+
+
+def run_regions(n_regions: int = 4, warmup_regions: int = 1, frame_hw=(1080, 1920)) -> dict:
+    """The reference's masked-region route on the host cores, one detection per call: bbox mask -> expanded box -> PIL
+    bicubic resize -> ImageNet normalisation -> HF SiglipVisionModel (fp32, `interpolate_pos_encoding=True`) ->
+    mean over the tokens -> REN projection (src/perception/siglip_semantic_encoder.py:485-562)."""
+    from PIL import Image
+
+    from gameplay_vision_llm_b200 import synth
+    from gameplay_vision_llm_b200.weights import (SiglipVisionSpec, synth_ren_projection_state_dict,
+                                                    synth_siglip_state_dict)
+    from oracle import region_ref
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    spec = SiglipVisionSpec.so400m()
+    sd = synth_siglip_state_dict(spec, seed=0)
+    psd = synth_ren_projection_state_dict(spec.hidden, seed=3)
+    H, W = frame_hw
+    frame = synth.scene_frames_np(40, 1, H, W)[0]
+    kind = "reference"
+    try:
+        from transformers import SiglipVisionConfig, SiglipVisionModel
+        cfg = SiglipVisionConfig(hidden_size=spec.hidden, intermediate_size=spec.intermediate,
+                                 num_hidden_layers=spec.layers, num_attention_heads=spec.heads, image_size=spec.image,
+                                 patch_size=spec.patch, layer_norm_eps=spec.eps, hidden_act=spec.act)
+        model = SiglipVisionModel(cfg).eval().float()
+        model.load_state_dict(sd, strict=True)
+        projection = torch.nn.Sequential(torch.nn.Linear(spec.hidden, spec.hidden), torch.nn.GELU(),
+                                         torch.nn.Linear(spec.hidden, spec.hidden))
+        projection.load_state_dict(psd)
+
+        def one(box):
+            mask = np.zeros((H, W), np.bool_)
+            mask[box[1]:box[3], box[0]:box[2]] = True
+            x1, y1, x2, y2 = region_ref.extract_bbox(frame.shape, mask)
+            region = Image.fromarray(frame[y1:y2, x1:x2])
+            th, tw = region_ref.compute_optimal_size(region.size[1], region.size[0])
+            t = torch.from_numpy(np.array(region.resize((tw, th), Image.Resampling.BICUBIC))).float().permute(2, 0, 1) / 255.0
+            t = (t - torch.tensor(region_ref.IMAGENET_MEAN).view(3, 1, 1)) / torch.tensor(region_ref.IMAGENET_STD).view(3, 1, 1)
+            seq = model(pixel_values=t[None], interpolate_pos_encoding=True).last_hidden_state
+            return projection(seq.mean(dim=1))
+    except ImportError:
+        kind = "port"
+
+        def one(box):
+            mask = np.zeros((H, W), np.bool_)
+            mask[box[1]:box[3], box[0]:box[2]] = True
+            return region_ref.encode_masked_regions(sd, psd, frame, [("r", mask)], spec.heads, spec.patch, spec.eps)[0][1][None]
+
+    boxes = region_boxes(n_regions + warmup_regions, H, W)
+    with torch.inference_mode():
+        for b in boxes[:warmup_regions]:
+            one(b)
+        t0 = time.perf_counter()
+        for b in boxes[warmup_regions:]:
+            out = one(b)
+        dt = time.perf_counter() - t0
+    assert out.shape[-1] == spec.hidden
+    return {"regions_per_s": n_regions / dt, "seconds": dt, "cores": cores, "kind": kind,
+            "sample": f"{n_regions} seeded detections of one synthetic 1080p frame, one call each, after {warmup_regions} "
+                      f"warm-up; PIL bicubic + HF SiglipVisionModel(so400m, random init, interpolate_pos_encoding) + mean "
+                      f"pool + REN projection, fp32, torch {torch.__version__}, {cores} threads"}

@@ -181,3 +181,90 @@ def test_encode_masked_regions_so400m_vs_reference_golden(golden_dir):
         cos, err = _cos(got, want), (got - want).abs().max().item()
         print(f"regions so400m {name}: cos {cos.tolist()} max_abs {err:.4f} (|want| max {want.abs().max():.3f})")
         assert cos.min() > 0.999 and err < 0.015 * want.abs().max().item() + 0.005  # measured 0.005 x max
+
+
+def test_run_siglip_encoder_equals_the_reference_loop_call_by_call():
+    """`pipeline.run_siglip_encoder` (scripts/extract_features.py:502-610) batches full frames and groups detections by
+    target size; every record must equal what the reference's loop order produces with one encoder call each."""
+    from PIL import Image
+
+    from gameplay_vision_llm_b200.pipeline import run_siglip_encoder
+    enc = _encoder(MID_SPEC, "mean", 4, MID_CFG)
+    raw = synth.scene_frames_np(3, 6, 270, 480)
+    frames = [(i * 0.5, Image.fromarray(f)) for i, f in enumerate(raw)]
+    sam = [
+        {"timestamp": 0.5, "bbox": [40, 30, 300, 120], "entity_type": "player", "entity_id": "p1", "description": "the player"},
+        {"timestamp": 0.5, "bbox": [60, 40, 320, 130], "entity_type": "enemy"},           # same target size as p1
+        {"timestamp": 0.5, "bbox": None, "entity_type": "ghost"},                           # skipped (:558)
+        {"timestamp": 0.5, "bbox": [200.7, 10.2, 260.9, 250.0], "entity_type": "tower", "entity_id": "t1"},
+        {"timestamp": 2.0, "bbox": [100, 100, 200, 200], "entity_type": "item", "entity_id": "i1"},
+    ]
+    got = run_siglip_encoder(frames, DEV, sam_results=sam, entity_tracker=object(), encoder=enc)
+    # the reference's loop, literally, on the same encoder
+    want = []
+    for ts, frame in frames:
+        dets = [d for d in sam if d["timestamp"] == ts]
+        frame_np = np.array(frame.convert("RGB"))
+        if not dets:
+            e = enc.encode_image(frame)
+            want.append({"timestamp": ts, "embedding": e.cpu(), "embedding_shape": list(e.shape), "entity_type": "full_frame",
+                         "description": "Full frame encoding (no SAM detection)"})
+            continue
+        for det in dets:
+            if det.get("bbox") is None:
+                continue
+            entity_type = det.get("entity_type", "unknown")
+            entity_id = det.get("entity_id", f"{entity_type}_{ts}")
+            x1, y1, x2, y2 = [int(c) for c in det["bbox"]]
+            mask = np.zeros(frame_np.shape[:2], dtype=np.bool_)
+            mask[y1:y2, x1:x2] = True
+            emb = enc.encode_masked_regions(frame_np, [(entity_id, mask)])[0]
+            want.append({"timestamp": ts, "embedding": emb.embedding.cpu(), "embedding_shape": list(emb.embedding.shape),
+                         "entity_type": entity_type, "entity_id": entity_id,
+                         "description": det.get("description", f"Detected {entity_type}"), "bbox": det["bbox"]})
+    assert len(got) == len(want) == 8
+    for g, w in zip(got, want):
+        assert set(g) == set(w)
+        for k in w:
+            if k == "embedding":
+                assert g[k].dtype == w[k].dtype and torch.equal(g[k], w[k]), (w["timestamp"], w["entity_type"])
+            else:
+                assert g[k] == w[k], k
+    # fallback branch (:590-607): no detections -> every frame whole, batched
+    plain = run_siglip_encoder(frames, DEV, encoder=enc)
+    assert [d["description"] for d in plain] == ["Full frame encoding"] * 6
+    assert all(torch.equal(d["embedding"], enc.encode_image(f).cpu()) for d, (_, f) in zip(plain, frames))
+
+
+@pytest.mark.parametrize("pool", ["mean", "cls", "max"])
+@pytest.mark.parametrize("fold_ln", [False, True])
+def test_ragged_pass_equals_one_call_per_region_bit_for_bit(pool, fold_ln):
+    """`encode_regions_individually` = ONE ragged tower pass over all regions (`gvl_siglip_forward_ragged`); every row
+    must equal `encode_masked_regions(frame, [m])[0]`, the reference's one-call-per-detection loop, bit for bit —
+    with the LayerNorms as kernels and folded into the GEMMs, and when max_tokens splits the pass."""
+    frame = synth.scene_frames_np(7, 1, 270, 480)[0]
+    rects = MID_RECTS + [(60, 40, 320, 130), (210, 5, 270, 245), (120, 90, 220, 190), (0, 0, 480, 270)]
+    masks = [(f"e{i}", rect_mask(frame.shape, r)) for i, r in enumerate(rects)]
+    enc = _encoder(MID_SPEC, pool, 16, MID_CFG)
+    if fold_ln:
+        enc.encoder._load_model()
+        m = enc.encoder._model
+        m.pack = SiglipPack(enc.config.state_dict, m.spec, DEV, fold_ln=True)
+    want = [enc.encode_masked_regions(frame, [mk])[0] for mk in masks]
+    for max_tokens in (32768, 150):
+        got = enc.encode_regions_individually(frame, masks, max_tokens=max_tokens)
+        assert [g.entity_id for g in got] == [w.entity_id for w in want]
+        for g, w in zip(got, want):
+            assert g.original_bbox == w.original_bbox and g.aspect_ratio == w.aspect_ratio
+            assert torch.equal(g.embedding, w.embedding), (g.entity_id, max_tokens)
+
+
+@pytest.mark.timeout(900)
+def test_ragged_pass_so400m_equals_one_call_per_region():
+    spec = SiglipVisionSpec.so400m()
+    enc = _encoder(spec, "mean", 16, {})
+    frame = synth.scene_frames_np(40, 1)[0]
+    masks = [(f"s{i}", rect_mask(frame.shape, r)) for i, r in enumerate(SO_RECTS + [(100, 100, 1100, 540), (0, 0, 1920, 1080)])]
+    want = [enc.encode_masked_regions(frame, [mk])[0] for mk in masks]
+    got = enc.encode_regions_individually(frame, masks)
+    assert all(torch.equal(g.embedding, w.embedding) for g, w in zip(got, want))

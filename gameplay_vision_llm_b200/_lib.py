@@ -14,7 +14,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("GVL_LIB_PATH") or os.path.join(_HERE, "libgvl_sm100a.so")
 
 c_float_p = POINTER(c_float)
-ABI_VERSION = 8  # include/gvl.h GVL_ABI_VERSION
+ABI_VERSION = 9  # include/gvl.h GVL_ABI_VERSION
 
 
 class VitLayer(ctypes.Structure):
@@ -100,6 +100,14 @@ SIGNATURES = {
                                           c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     "gvl_pos_interp_bicubic_bf16": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     "gvl_max_tokens_bf16": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_void_p]),
+    "gvl_nvdec_available": (c_int, []),
+    "gvl_nvdec_caps": (c_int, [c_int, POINTER(c_int), POINTER(c_int), POINTER(c_int), POINTER(c_int)]),
+    "gvl_nvdec_open": (c_int, [c_int, c_int, POINTER(c_void_p)]),
+    "gvl_nvdec_sampling": (c_int, [c_void_p, c_longlong, c_longlong, c_int, c_int]),
+    "gvl_nvdec_feed": (c_int, [c_void_p, c_char_p, c_size_t, c_int, c_void_p, c_int, c_int, c_int, POINTER(c_int),
+                               POINTER(c_longlong), c_void_p]),
+    "gvl_nvdec_info": (c_int, [c_void_p, POINTER(c_int32)]),
+    "gvl_nvdec_close": (c_int, [c_void_p]),
 }
 
 _LIB = None

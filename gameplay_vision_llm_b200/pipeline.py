@@ -9,6 +9,7 @@ the only host synchronisation is at the end of the chunk.
 """
 from __future__ import annotations
 
+from struct import error as struct_error
 from typing import Iterable, Iterator
 
 import numpy as np
@@ -25,6 +26,10 @@ def shard_range(n_items: int, rank: int, world: int, align: int = 1) -> tuple[in
     per = -(-per // align) * align
     lo = min(n_items, rank * per)
     return lo, min(n_items, lo + per)
+
+
+class _NvdecUnusable(Exception):
+    """Hardware decode cannot be used for this file on this machine (decoder="auto" then takes the OpenCV feed)."""
 
 
 class EmbeddingPipeline:
@@ -138,12 +143,25 @@ class EmbeddingPipeline:
 
     # ---- a video file: decode -> pinned ring -> device, overlapped -------------------------------------
     def embed_video(self, video_path: str, fps: float = 1.0, index: torch.Tensor | None = None,
-                    host_out: torch.Tensor | None = None, return_pooled: bool = False):
+                    host_out: torch.Tensor | None = None, return_pooled: bool = False, decoder: str = "auto"):
         """Replaces `extract_frames` + `run_siglip_encoder` (scripts/extract_features.py:230-264, 590-607) for one
         video: frames are sampled with the reference's rule (every int(video_fps / fps)-th frame, timestamp =
-        idx / video_fps), decoded on a background thread into pinned batches and embedded while the next batch
-        decodes.  Returns (timestamps float64 [n], projected index bf16 [n, llm] on the device) and, with
-        `return_pooled`, the 1152-d SigLIP rows bf16 [n, hidden] the reference's cache files hold."""
+        idx / video_fps) and embedded batch by batch.  Returns (timestamps float64 [n], projected index bf16 [n, llm] on
+        the device) and, with `return_pooled`, the 1152-d SigLIP rows bf16 [n, hidden] the reference's cache files hold.
+
+        decoder = "nvdec": the GPU's hardware decoder (`nvdec_ingest.NvdecFeed`: the host only demuxes; sampled frames
+        are converted to RGB in device memory and go straight into the preprocess kernel — no host frame, no H2D);
+        "opencv": software decode on a background thread into pinned batches (`frame_ingest.FrameFeed`), H2D overlapped
+        with compute; "auto": nvdec when the driver library, the container (MP4 / MOV) and the codec (H.264 / HEVC 8-bit
+        4:2:0) allow it, else opencv."""
+        if decoder not in ("auto", "nvdec", "opencv"):
+            raise ValueError("decoder must be 'auto', 'nvdec' or 'opencv'")
+        if decoder != "opencv":
+            try:
+                return self._embed_video_nvdec(video_path, fps, index, host_out, return_pooled)
+            except _NvdecUnusable as exc:
+                if decoder == "nvdec":
+                    raise RuntimeError(f"hardware decode of {video_path} is not possible: {exc}") from exc
         from .frame_ingest import FrameFeed
         feed = FrameFeed(video_path, fps=fps, batch=self.batch, auto_release=False)
         n_plan = len(feed.timestamps)
@@ -153,6 +171,40 @@ class EmbeddingPipeline:
         with torch.cuda.device(self.device):
             n = self.embed_stream(feed, index, host_out, pooled_out=pooled)
             torch.cuda.current_stream(self.device).synchronize()
+        if return_pooled:
+            return feed.timestamps[:n], index[:n], pooled[:n]
+        return feed.timestamps[:n], index[:n]
+
+    def _embed_video_nvdec(self, video_path, fps, index, host_out, return_pooled):
+        from . import nvdec_ingest as nv
+        if not nv.available():
+            raise _NvdecUnusable("libnvcuvid.so.1 (GPU driver) did not load")
+        try:
+            track = nv.read_mp4_video_track(video_path)
+        except (ValueError, KeyError, struct_error) as exc:  # not an MP4 / MOV container, or not H.264 / HEVC
+            raise _NvdecUnusable(str(exc)) from exc
+        ok, why = nv.usable(track.codec, self.device)
+        if not ok:
+            raise _NvdecUnusable(why)
+        feed = nv.NvdecFeed(video_path, fps=fps, batch=self.batch, device=self.device)
+        with torch.cuda.device(self.device):
+            n_plan = len(feed.timestamps)
+            if index is None:
+                index = torch.empty((n_plan, self.llm_dim), dtype=torch.bfloat16, device=self.device)
+            pooled = torch.empty((n_plan, self.spec.hidden), dtype=torch.bfloat16, device=self.device) if return_pooled else None
+            n = 0
+            for frames in feed:
+                b = frames.shape[0]
+                if n + b > index.shape[0]:
+                    raise RuntimeError(f"the file holds more sampled frames than its sample table announced ({n + b} > {n_plan})")
+                pl, _ = self.embed(frames, out_index=index[n:n + b])
+                if pooled is not None:
+                    pooled[n:n + b].copy_(pl)
+                n += b
+            if host_out is not None:
+                host_out[:n].copy_(index[:n], non_blocking=True)
+            torch.cuda.current_stream(self.device).synchronize()
+            feed.close()
         if return_pooled:
             return feed.timestamps[:n], index[:n], pooled[:n]
         return feed.timestamps[:n], index[:n]

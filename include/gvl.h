@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define GVL_ABI_VERSION 8
+#define GVL_ABI_VERSION 9
 
 #if defined(__GNUC__)
 #define GVL_API __attribute__((visibility("default")))
@@ -388,6 +388,37 @@ GVL_API int gvl_pos_interp_bicubic_bf16(const void* pos, int g, int D, int gh, i
 /* out[b, :] = max over the T tokens of x[b] (bf16 [B,T,D]); out bf16 or float [B,D].
  * Replaces `sequence.max(dim=1)[0]` (src/perception/siglip_semantic_encoder.py:438-440). */
 GVL_API int gvl_max_tokens_bf16(const void* x, int B, int T, int D, void* out, int out_f32, void* stream);
+
+/* ---- K10: hardware video decode for the frame ingest --------------------------------- */
+/* Replaces the decode half of `extract_frames` (scripts/extract_features.py:230-264: decord decodes EVERY frame of the
+ * file to a host RGB array, the sampling rule then keeps every int(video_fps / fps)-th) with the GPU's NVDEC engines
+ * (libnvcuvid.so.1, bound with dlopen — part of the GPU driver, not of this image's toolkit): the caller feeds
+ * elementary-stream bytes (the host demuxes the container), pictures are decoded on the engine, and only the frames the
+ * sampling rule keeps are converted NV12 -> packed RGB, directly into the caller's device batch buffer.
+ * Codec ids are cuvid's: 4 = H.264, 8 = HEVC, 9 = VP8, 10 = VP9, 11 = AV1, 2 = MPEG-4, 5 = JPEG.  8-bit 4:2:0 only. */
+typedef struct gvl_nvdec gvl_nvdec;
+enum { GVL_CODEC_MPEG4 = 2, GVL_CODEC_H264 = 4, GVL_CODEC_JPEG = 5, GVL_CODEC_HEVC = 8, GVL_CODEC_VP9 = 10, GVL_CODEC_AV1 = 11 };
+/* 1 if libnvcuvid loaded and exports every entry point used.  Host only, no device call. */
+GVL_API int gvl_nvdec_available(void);
+/* What this GPU's NVDEC decodes (cuvidGetDecoderCaps, 8-bit 4:2:0). */
+GVL_API int gvl_nvdec_caps(int codec, int* supported, int* max_w, int* max_h, int* n_engines);
+/* max_display_delay: pictures the parser may hold back to pipeline decode with display (0 = none; 2-4 recommended). */
+GVL_API int gvl_nvdec_open(int codec, int max_display_delay, gvl_nvdec** out);
+/* Frames are numbered from 0 in display order; frame i is kept iff i >= first_frame and (i - first_frame) % interval
+ * == 0 (the reference's `range(0, total_frames, frame_interval)`, scripts/extract_features.py:247-253).
+ * matrix_override: -1 = the stream's VUI matrix_coefficients (1 = BT.709, anything else BT.601), 1 / 6 force one;
+ * full_range_override: -1 = the stream's video_full_range_flag, 0 / 1 force. */
+GVL_API int gvl_nvdec_sampling(gvl_nvdec* d, long long first_frame, long long interval, int matrix_override,
+                       int full_range_override);
+/* data: HOST bytes of the elementary stream (Annex-B for H.264 / HEVC), any chunking.  out_rgb: device uint8
+ * [cap, H, W, 3]: kept frames displayed during this call are written to slots 0..*frames_written-1 (conversion kernels on
+ * `stream`, finished when the call returns); more than `cap` kept frames in one call is an error.  H x W must be the
+ * video's display size.  *frames_displayed: running count of displayed frames.  end_of_stream flushes the parser. */
+GVL_API int gvl_nvdec_feed(gvl_nvdec* d, const uint8_t* data, size_t bytes, int end_of_stream, uint8_t* out_rgb, int cap,
+                   int H, int W, int* frames_written, long long* frames_displayed, void* stream);
+/* info8: coded_w, coded_h, display_w, display_h, fps numerator, fps denominator, matrix_coefficients, full_range. */
+GVL_API int gvl_nvdec_info(gvl_nvdec* d, int32_t* info8);
+GVL_API int gvl_nvdec_close(gvl_nvdec* d);
 
 #ifdef __cplusplus
 }

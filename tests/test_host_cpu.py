@@ -31,8 +31,10 @@ def test_encoder_raises_instead_of_placeholder():
     enc2 = SigLIPSemanticEncoder(NaFlexConfig(model_name="/nonexistent/checkpoint", device="cuda"))
     with pytest.raises(RuntimeError):
         enc2.encoder._load_model()
-    with pytest.raises(NotImplementedError):
-        enc.encode_masked_regions(None, [])
+    assert enc.encode_masked_regions(None, []) == []  # `if not masks: return []` (reference :503-504)
+    mask = np.ones((8, 8), np.bool_)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):  # the region route has no CPU path either
+        enc.encode_masked_regions(np.zeros((8, 8, 3), np.uint8), [("e", mask)])
 
 
 def test_spec_from_state_dict_roundtrip():

@@ -618,13 +618,16 @@ def main_regions(args) -> None:
     1080p frame with 16 seeded SAM-style detections, each encoded exactly as the reference's one-call-per-detection loop
     would (own canvas, no padding to a neighbour), through `SigLIPSemanticEncoder.encode_regions_individually` = one
     ragged tower pass per frame.
-    value: the frame already resident on the device; e2e: the frame comes from host memory.  Both include the D2H of the
-    fp32 embeddings, which the API returns on the CPU like the reference.  Replicas only: no collective on this route."""
+    value: the frame already resident on the device, detections as `BoxMask`es (`encode_regions_individually`); e2e: the
+    reference's caller API, `pipeline.run_siglip_encoder([(ts, host frame)], sam_results=detections, ...)`, frame copied
+    from host memory and the reference's list of dicts built.  Both include the D2H of the fp32 embeddings, which the
+    API returns on the CPU like the reference.  Replicas only: no collective on this route."""
     import numpy as np
     import torch
 
     from gameplay_vision_llm_b200 import _lib, synth
-    from gameplay_vision_llm_b200.siglip_semantic_encoder import NaFlexConfig, SigLIPSemanticEncoder
+    from gameplay_vision_llm_b200.pipeline import run_siglip_encoder
+    from gameplay_vision_llm_b200.siglip_semantic_encoder import BoxMask, NaFlexConfig, SigLIPSemanticEncoder
     from gameplay_vision_llm_b200.weights import (SiglipVisionSpec, synth_ren_projection_state_dict,
                                                     synth_siglip_state_dict)
     from oracle import hf_baseline
@@ -646,11 +649,9 @@ def main_regions(args) -> None:
     enc.projection.load_state_dict(synth_ren_projection_state_dict(spec.hidden, seed=3))
     frames_host = [synth.scene_frames_np((rank * 4 + i) * 30, 1, FRAME_H, FRAME_W)[0] for i in range(4)]
     frames_dev = [torch.from_numpy(f).to(dev) for f in frames_host]
-    masks = []
-    for i, (x1, y1, x2, y2) in enumerate(hf_baseline.region_boxes(R, FRAME_H, FRAME_W)):
-        m = np.zeros((FRAME_H, FRAME_W), np.bool_)
-        m[y1:y2, x1:x2] = True
-        masks.append((f"det{i}", m))
+    boxes = hf_baseline.region_boxes(R, FRAME_H, FRAME_W)
+    masks = [(f"det{i}", BoxMask((FRAME_H, FRAME_W), y1, y2, x1, x2)) for i, (x1, y1, x2, y2) in enumerate(boxes)]
+    dets = [{"timestamp": 0.0, "bbox": list(b), "entity_type": "ui", "entity_id": f"det{i}"} for i, b in enumerate(boxes)]
 
     def barrier():
         if world > 1:
@@ -661,6 +662,14 @@ def main_regions(args) -> None:
         out = None
         for s in range(steps):
             out = enc.encode_regions_individually(frames[s % len(frames)], masks)
+        return out
+
+    def run_caller(frames, steps):  # the reference's caller-level API, one frame per call
+        out = None
+        for s in range(steps):
+            out = run_siglip_encoder([(0.0, frames[s % len(frames)])], str(dev), sam_results=dets, entity_tracker=True,
+                                     encoder=enc)
+        assert len(out) == R
         return out
 
     run_region(frames_dev, max(W, 3))
@@ -699,10 +708,10 @@ def main_regions(args) -> None:
         gbs = prof["preprocess"]["work"] / (prof["preprocess"]["ms"] * 1e-3) / 1e9
         kernels["preprocess"].update({"achieved_gbs": round(gbs, 1), "hbm_frac": round(gbs / peaks["hbm_gbs"], 4)})
 
-    run_region(frames_host, 2)
+    run_caller(frames_host, 2)
     barrier()
     e0.record()
-    run_region(frames_host, K)
+    run_caller(frames_host, K)
     e1.record()
     barrier()
     ms_e2e = torch.tensor([e0.elapsed_time(e1)], device=dev)

@@ -14,7 +14,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("GVL_LIB_PATH") or os.path.join(_HERE, "libgvl_sm100a.so")
 
 c_float_p = POINTER(c_float)
-ABI_VERSION = 9  # include/gvl.h GVL_ABI_VERSION
+ABI_VERSION = 10  # include/gvl.h GVL_ABI_VERSION
 
 
 class VitLayer(ctypes.Structure):
@@ -76,6 +76,9 @@ SIGNATURES = {
     "gvl_layernorm_bf16": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_float,
                                    c_void_p]),
     "gvl_attention_bf16": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_float, c_void_p]),
+    "gvl_attention_varlen_tiles": (c_int, [c_int, POINTER(c_int32), POINTER(c_int32), POINTER(c_int)]),
+    "gvl_attention_varlen_bf16": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_int, ctypes.c_double, c_int, c_int, c_float,
+                                          c_void_p]),
     "gvl_probe_attention_bf16": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     "gvl_siglip_workspace_bytes": (c_size_t, [POINTER(VitWeights), c_int]),
     "gvl_siglip_forward": (c_int, [POINTER(VitWeights), c_void_p, c_int, c_void_p, c_size_t, c_void_p, c_void_p,

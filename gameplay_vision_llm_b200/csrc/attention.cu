@@ -3,6 +3,9 @@
 // and K5, the MAP-head probe attention.
 #include "common.cuh"
 
+#include <algorithm>
+#include <vector>
+
 #include <cstdlib>
 
 namespace gvl {
@@ -89,6 +92,9 @@ probe_attention_kernel(const float* __restrict__ q, const __nv_bfloat16* __restr
 
 template <int HD>
 int launch_attention_sdb(const void* qkv, void* out, int B, int T, int H, float scale, cudaStream_t s);  // attention_sdb.cu
+template <int HD>
+int launch_attention_sdb_varlen(const void* qkv, void* out, int M_total, const void* tiles, int n_tiles, double score_elems,
+                                int H, float scale, cudaStream_t s);
 #ifdef GVL_EXPERIMENTS
 // round-2 experiment (two softmax warpgroups, fixed-reference softmax, polynomial exp2): measured equal or slower than
 // attention_sdb.cu on every shape (profiles/r02_attention_experiments.md); built only with EXTRA=-DGVL_EXPERIMENTS
@@ -117,6 +123,55 @@ extern "C" int gvl_attention_bf16(const void* qkv, void* out, int B, int T, int 
     if (hd == 72) return launch_attention_sdb<72>(qkv, out, B, T, H, scale, s);
     if (hd == 64) return launch_attention_sdb<64>(qkv, out, B, T, H, scale, s);
     set_error("gvl_attention_bf16: unsupported head dim %d (built for 72 and 64)", hd);
+    return 1;
+}
+
+extern "C" int gvl_attention_varlen_tiles(int n_items, const int32_t* h_item_tokens, int32_t* h_tiles, int* n_tiles) {
+    using namespace gvl;
+    GVL_CHECK_ARG(n_items > 0 && h_item_tokens && n_tiles, "gvl_attention_varlen_tiles: bad arguments");
+    long long count = 0, tok = 0;
+    for (int i = 0; i < n_items; ++i) {
+        GVL_CHECK_ARG(h_item_tokens[i] > 0, "gvl_attention_varlen_tiles: item %d has %d tokens", i, h_item_tokens[i]);
+        count += (h_item_tokens[i] + 127) / 128;
+        tok += h_item_tokens[i];
+    }
+    GVL_CHECK_ARG(count <= 2147483647LL && tok <= 2147483647LL, "gvl_attention_varlen_tiles: batch too large");
+    *n_tiles = (int)count;
+    if (!h_tiles) return 0;  // size query
+    // longest items first: a tile's cost grows with its item's key count, so the tail of the launch is short tiles
+    std::vector<int> order(n_items);
+    for (int i = 0; i < n_items; ++i) order[i] = i;
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return h_item_tokens[a] > h_item_tokens[b]; });
+    std::vector<long long> start(n_items);
+    tok = 0;
+    for (int i = 0; i < n_items; ++i) {
+        start[i] = tok;
+        tok += h_item_tokens[i];
+    }
+    int32_t* o = h_tiles;
+    for (int i : order)
+        for (int q0 = 0; q0 < h_item_tokens[i]; q0 += 128) {
+            o[0] = (int32_t)start[i];
+            o[1] = h_item_tokens[i];
+            o[2] = q0;
+            o[3] = 0;
+            o += 4;
+        }
+    return 0;
+}
+
+extern "C" int gvl_attention_varlen_bf16(const void* qkv, void* out, int M_total, const void* tiles, int n_tiles,
+                                         double score_elems, int H, int hd, float scale, void* stream) {
+    using namespace gvl;
+    GVL_CHECK_ARG(qkv && out && tiles, "gvl_attention_varlen_bf16: null pointer");
+    GVL_CHECK_ARG(M_total > 0 && n_tiles > 0 && H > 0 && H <= 65535, "gvl_attention_varlen_bf16: bad shape M=%d tiles=%d H=%d",
+                  M_total, n_tiles, H);
+    GVL_CHECK_ARG((uintptr_t)qkv % 16 == 0 && (uintptr_t)out % 16 == 0 && (uintptr_t)tiles % 16 == 0,
+                  "gvl_attention_varlen_bf16: misaligned pointer");
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+    if (hd == 72) return launch_attention_sdb_varlen<72>(qkv, out, M_total, tiles, n_tiles, score_elems, H, scale, s);
+    if (hd == 64) return launch_attention_sdb_varlen<64>(qkv, out, M_total, tiles, n_tiles, score_elems, H, scale, s);
+    set_error("gvl_attention_varlen_bf16: unsupported head dim %d (built for 72 and 64)", hd);
     return 1;
 }
 

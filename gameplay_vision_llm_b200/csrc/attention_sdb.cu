@@ -89,11 +89,17 @@ __device__ __forceinline__ float sdb_ex2(float x) {
 #define SDB_TRACE(jj, slot) do { } while (0)
 #endif
 
-template <int HD, int NT>
+// VARLEN (the ragged batch of the masked-region route, gvl_attention_varlen_bf16): items of different lengths are
+// concatenated along the token axis (the tensor maps see ONE batch of `T` = all tokens); blockIdx.x indexes a table of
+// query tiles {first token of the item, item length, first query row of the tile}.  A Q box that runs past its item's
+// end reads the next item's rows (finite; those output rows are never stored), K / V boxes likewise (those keys are
+// masked to -inf, so the next item's finite V rows are multiplied by exactly zero).
+template <int HD, int NT, bool VARLEN = false>
 __global__ void __launch_bounds__(SdbCfg<HD, NT>::THREADS, NT >= 2 ? 1 : 2)
 attention_sdb_kernel(const __grid_constant__ CUtensorMap tmq64, const __grid_constant__ CUtensorMap tmq16,
                      const __grid_constant__ CUtensorMap tmk64, const __grid_constant__ CUtensorMap tmk16,
-                     __nv_bfloat16* __restrict__ out, int T, int H, float scale_log2, int dbg, long long* __restrict__ trace) {
+                     __nv_bfloat16* __restrict__ out, int T_arg, int H, float scale_log2, int dbg,
+                     long long* __restrict__ trace, const int4* __restrict__ tiles) {
     using Cfg = SdbCfg<HD, NT>;
     constexpr int SDB_STAGES = Cfg::STAGES;
     constexpr int W_TMA = 4 * NT, W_MMA = 4 * NT + 1;  // warp roles: [0, 4 NT) softmax, then TMA, then NT MMA warps
@@ -120,7 +126,13 @@ attention_sdb_kernel(const __grid_constant__ CUtensorMap tmq64, const __grid_con
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     pdl_trigger();
-    const int q0 = blockIdx.x * (NT * SDB_BQ);
+    int q0 = blockIdx.x * (NT * SDB_BQ), T = T_arg, tok0 = 0;  // tok0: first token of the item on the token axis
+    if (VARLEN) {
+        const int4 e = tiles[blockIdx.x];
+        tok0 = e.x;
+        T = e.y;
+        q0 = e.z;
+    }
     const int h = blockIdx.y, b = blockIdx.z;
     const int nblk = (T + SDB_BKV - 1) / SDB_BKV;
     const bool traced = blockIdx.x == 1 && blockIdx.y == 3 && blockIdx.z == 17 && (threadIdx.x & 31) == 0;
@@ -165,8 +177,8 @@ attention_sdb_kernel(const __grid_constant__ CUtensorMap tmq64, const __grid_con
             mbar_arrive_expect_tx(q_full, ntile * Cfg::Q_BYTES);
             for (int t = 0; t < ntile; ++t) {
                 uint8_t* q = sQ + t * Cfg::Q_BYTES;
-                tma_load_4d(q, &tmq64, q_full, 0, h, q0 + t * SDB_BQ, b);
-                if (Cfg::TAIL) tma_load_4d(q + Cfg::Q_P0, &tmq16, q_full, 64, h, q0 + t * SDB_BQ, b);
+                tma_load_4d(q, &tmq64, q_full, 0, h, tok0 + q0 + t * SDB_BQ, b);
+                if (Cfg::TAIL) tma_load_4d(q + Cfg::Q_P0, &tmq16, q_full, 64, h, tok0 + q0 + t * SDB_BQ, b);
             }
             int st = 0;
             uint32_t ph = 0;
@@ -176,11 +188,11 @@ attention_sdb_kernel(const __grid_constant__ CUtensorMap tmq64, const __grid_con
                 mbar_arrive_expect_tx(&kv_full[st], 2 * Cfg::KV_BYTES);
                 uint8_t* k = sK + st * Cfg::KV_BYTES;
                 uint8_t* v = sV + st * Cfg::KV_BYTES;
-                tma_load_4d(k, &tmk64, &kv_full[st], 0, H + h, j * SDB_BKV, b);
-                tma_load_4d(v, &tmk64, &kv_full[st], 0, 2 * H + h, j * SDB_BKV, b);
+                tma_load_4d(k, &tmk64, &kv_full[st], 0, H + h, tok0 + j * SDB_BKV, b);
+                tma_load_4d(v, &tmk64, &kv_full[st], 0, 2 * H + h, tok0 + j * SDB_BKV, b);
                 if (Cfg::TAIL) {
-                    tma_load_4d(k + Cfg::KV_P0, &tmk16, &kv_full[st], 64, H + h, j * SDB_BKV, b);
-                    tma_load_4d(v + Cfg::KV_P0, &tmk16, &kv_full[st], 64, 2 * H + h, j * SDB_BKV, b);
+                    tma_load_4d(k + Cfg::KV_P0, &tmk16, &kv_full[st], 64, H + h, tok0 + j * SDB_BKV, b);
+                    tma_load_4d(v + Cfg::KV_P0, &tmk16, &kv_full[st], 64, 2 * H + h, tok0 + j * SDB_BKV, b);
                 }
                 if (++st == SDB_STAGES) {
                     st = 0;
@@ -374,7 +386,7 @@ attention_sdb_kernel(const __grid_constant__ CUtensorMap tmq64, const __grid_con
             }
             const float inv = 1.0f / l;
             const int D = H * HD;
-            __nv_bfloat16* orow = out + ((size_t)b * T + row) * D + (size_t)h * HD;
+            __nv_bfloat16* orow = out + ((size_t)b * T_arg + tok0 + row) * D + (size_t)h * HD;
 #pragma unroll
             for (int c = 0; c < 2; ++c) {
                 uint32_t o[32];
@@ -445,10 +457,41 @@ static int launch_attention_sdb_nt(const void* qkv, void* out, int B, int T, int
     dim3 grid((T + NT * SDB_BQ - 1) / (NT * SDB_BQ), H, B);
     ProfScope prof(GVL_K_ATTENTION, 4.0 * B * (double)H * T * (double)T * HD, s);
     GVL_CUDA(launch_pdl(attention_sdb_kernel<HD, NT>, grid, dim3(Cfg::THREADS), Cfg::SMEM_BYTES, s, tq64, tq16, tk64, tk16,
-                        reinterpret_cast<__nv_bfloat16*>(out), T, H, scale * 1.4426950408889634f, dbg, g_attn_trace));
+                        reinterpret_cast<__nv_bfloat16*>(out), T, H, scale * 1.4426950408889634f, dbg, g_attn_trace,
+                        (const int4*)nullptr));
     GVL_LAUNCH_CHECK("attention_sdb_kernel");
     return 0;
 }
+
+// Ragged batch: qkv / out hold M_total token rows (items back to back); tiles: device int4 [n_tiles] (see the kernel).
+template <int HD>
+int launch_attention_sdb_varlen(const void* qkv, void* out, int M_total, const void* tiles, int n_tiles, double score_elems,
+                                int H, float scale, cudaStream_t s) {
+    using Cfg = SdbCfg<HD, 1>;
+    const uint64_t dims[4] = {(uint64_t)HD, (uint64_t)3 * H, (uint64_t)M_total, 1};
+    const uint64_t strides[3] = {(uint64_t)HD * 2, (uint64_t)3 * H * HD * 2, (uint64_t)M_total * 3 * H * HD * 2};
+    const uint32_t bq64[4] = {64, 1, SDB_BQ, 1}, bq16[4] = {16, 1, SDB_BQ, 1};
+    const uint32_t bk64[4] = {64, 1, SDB_BKV, 1}, bk16[4] = {16, 1, SDB_BKV, 1};
+    CUtensorMap tq64, tq16, tk64, tk16;
+    int rc = make_tmap_nd_bf16(&tq64, qkv, 4, dims, strides, bq64, 128);
+    if (rc) return rc;
+    rc = make_tmap_nd_bf16(&tk64, qkv, 4, dims, strides, bk64, 128);
+    if (rc) return rc;
+    rc = make_tmap_nd_bf16(&tq16, qkv, 4, dims, strides, Cfg::TAIL ? bq16 : bq64, Cfg::TAIL ? 32 : 128);
+    if (rc) return rc;
+    rc = make_tmap_nd_bf16(&tk16, qkv, 4, dims, strides, Cfg::TAIL ? bk16 : bk64, Cfg::TAIL ? 32 : 128);
+    if (rc) return rc;
+    GVL_CUDA(cudaFuncSetAttribute(attention_sdb_kernel<HD, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  Cfg::SMEM_BYTES));
+    ProfScope prof(GVL_K_ATTENTION, 4.0 * H * score_elems * HD, s);
+    GVL_CUDA(launch_pdl(attention_sdb_kernel<HD, 1, true>, dim3(n_tiles, H, 1), dim3(Cfg::THREADS), Cfg::SMEM_BYTES, s, tq64,
+                        tq16, tk64, tk16, reinterpret_cast<__nv_bfloat16*>(out), M_total, H, scale * 1.4426950408889634f, 0,
+                        (long long*)nullptr, reinterpret_cast<const int4*>(tiles)));
+    GVL_LAUNCH_CHECK("attention_sdb_kernel<varlen>");
+    return 0;
+}
+template int launch_attention_sdb_varlen<72>(const void*, void*, int, const void*, int, double, int, float, cudaStream_t);
+template int launch_attention_sdb_varlen<64>(const void*, void*, int, const void*, int, double, int, float, cudaStream_t);
 
 template <int HD>
 int launch_attention_sdb(const void* qkv, void* out, int B, int T, int H, float scale, cudaStream_t s) {

@@ -14,7 +14,7 @@ namespace gvl {
 
 constexpr int PIL_PRECISION_BITS = 32 - 8 - 2;  // Pillow src/libImaging/Resample.c
 constexpr int DESC_INTS = GVL_REGION_DESC_INTS;  // caller fields
-constexpr int DEV_DESC_INTS = 12;                // + tmp offset (bytes / 4) + pad
+constexpr int DEV_DESC_INTS = 12;                // + [10] tmp offset (bytes / 4), [11] first patch row of the region
 
 // Pillow `bicubic_filter` (a = -0.5)
 static inline double pil_bicubic(double x) {
@@ -74,7 +74,9 @@ region_v_kernel(const int32_t* __restrict__ desc, const int32_t* __restrict__ ta
     const int32_t* kk = cnt + oh;
     const uint8_t* tmp = scratch + (size_t)d[10] * 4;
     const int total = oh * ow;
-    const int gw = canvas_w / patch, pp = patch * patch;
+    // canvas_w == 0: ragged output, every region on its own canvas (its out_w x out_h), rows from d[11]
+    const int gw = (canvas_w > 0 ? canvas_w : ow) / patch, pp = patch * patch;
+    const size_t row0 = (size_t)d[11];
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
         const int y = i / ow, x = i - y * ow;
         const int n = cnt[y];
@@ -97,7 +99,7 @@ region_v_kernel(const int32_t* __restrict__ desc, const int32_t* __restrict__ ta
         }
         if (patches) {
             const int py = y / patch, ky = y - py * patch, px = x / patch, kx = x - px * patch;
-            uint16_t* o = patches + ((size_t)blockIdx.y * tokens_per_region + (size_t)py * gw + px) * ld + ky * patch + kx;
+            uint16_t* o = patches + (row0 + (size_t)py * gw + px) * ld + ky * patch + kx;
             o[0] = lut[v0];
             o[pp] = lut[256 + v1];
             o[2 * pp] = lut[512 + v2];
@@ -184,8 +186,10 @@ max_tokens_kernel(const __nv_bfloat16* __restrict__ x, int T, int D, void* __res
 static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 // scratch layout: device descriptors, then one uint8 [ch, ow, 3] intermediate per region
-static size_t region_layout(int R, const int32_t* h_desc, std::vector<int32_t>* dev_desc) {
+static size_t region_layout(int R, const int32_t* h_desc, std::vector<int32_t>* dev_desc, int tokens_per_region = 0,
+                            int patch = 0) {
     size_t off = align_up((size_t)R * DEV_DESC_INTS * sizeof(int32_t), 256);
+    long long first_row = 0;  // uniform canvas: r * tokens_per_region; ragged: running sum of the regions' own grids
     if (dev_desc) dev_desc->assign((size_t)R * DEV_DESC_INTS, 0);
     for (int r = 0; r < R; ++r) {
         const int32_t* d = h_desc + (size_t)r * DESC_INTS;
@@ -193,7 +197,9 @@ static size_t region_layout(int R, const int32_t* h_desc, std::vector<int32_t>* 
             int32_t* o = dev_desc->data() + (size_t)r * DEV_DESC_INTS;
             for (int i = 0; i < DESC_INTS; ++i) o[i] = d[i];
             o[10] = (int32_t)(off / 4);
+            o[11] = (int32_t)first_row;
         }
+        first_row += tokens_per_region > 0 ? tokens_per_region : (patch > 0 ? (long long)(d[4] / patch) * (d[5] / patch) : 0);
         off = align_up(off + (size_t)d[3] * d[4] * 3, 256);
     }
     return off;
@@ -260,17 +266,22 @@ extern "C" int gvl_region_patches_pil_u8(const uint8_t* frame, int H, int W, int
     GVL_CHECK_ARG(frame && h_desc && tabs && scratch && (patches || resized_u8) && (lut || !patches),
                   "gvl_region_patches_pil_u8: null pointer");
     GVL_CHECK_ARG(H > 0 && W > 0 && R > 0 && R <= 65535, "gvl_region_patches_pil_u8: bad shape H=%d W=%d R=%d", H, W, R);
-    GVL_CHECK_ARG(patch > 0 && canvas_h > 0 && canvas_w > 0 && canvas_h % patch == 0 && canvas_w % patch == 0,
+    const bool ragged = canvas_h == 0 && canvas_w == 0;  // every region on its own canvas, patch rows back to back
+    GVL_CHECK_ARG(patch > 0 && (ragged || (canvas_h > 0 && canvas_w > 0 && canvas_h % patch == 0 && canvas_w % patch == 0)),
                   "gvl_region_patches_pil_u8: canvas %dx%d is not a multiple of the patch size %d", canvas_h, canvas_w, patch);
+    GVL_CHECK_ARG(!ragged || (patches && !resized_u8), "gvl_region_patches_pil_u8: the ragged form writes patch rows only");
     GVL_CHECK_ARG(ld >= 3 * patch * patch && ld % 8 == 0, "gvl_region_patches_pil_u8: bad ld %d", ld);
     GVL_CHECK_ARG((uintptr_t)scratch % 256 == 0 && (uintptr_t)patches % 16 == 0, "gvl_region_patches_pil_u8: misaligned buffer");
+    long long total_rows = 0;
     for (int r = 0; r < R; ++r) {
         const int32_t* d = h_desc + (size_t)r * DESC_INTS;
         const int x1 = d[0], y1 = d[1], cw = d[2], ch = d[3], ow = d[4], oh = d[5], kh = d[6], kv = d[7];
         GVL_CHECK_ARG(cw > 0 && ch > 0 && x1 >= 0 && y1 >= 0 && x1 + cw <= W && y1 + ch <= H,
                       "gvl_region_patches_pil_u8: region %d box (%d,%d)+(%dx%d) leaves the %dx%d frame", r, x1, y1, cw, ch, W, H);
-        GVL_CHECK_ARG(ow > 0 && oh > 0 && ow <= canvas_w && oh <= canvas_h,
-                      "gvl_region_patches_pil_u8: region %d target %dx%d exceeds the %dx%d canvas", r, ow, oh, canvas_w, canvas_h);
+        GVL_CHECK_ARG(ow > 0 && oh > 0 && (ragged ? (ow % patch == 0 && oh % patch == 0) : (ow <= canvas_w && oh <= canvas_h)),
+                      "gvl_region_patches_pil_u8: region %d target %dx%d exceeds the %dx%d canvas (ragged form: must be a "
+                      "multiple of the patch size)", r, ow, oh, canvas_w, canvas_h);
+        total_rows += ragged ? (long long)(ow / patch) * (oh / patch) : (long long)(canvas_h / patch) * (canvas_w / patch);
         int need_kh = 0, need_kv = 0;
         gvl_pil_bicubic_taps(cw, ow, 0, nullptr, nullptr, nullptr, &need_kh);
         gvl_pil_bicubic_taps(ch, oh, 0, nullptr, nullptr, nullptr, &need_kv);
@@ -280,14 +291,15 @@ extern "C" int gvl_region_patches_pil_u8(const uint8_t* frame, int H, int W, int
                           (long long)d[9] + (long long)oh * (2 + kv) <= tabs_ints,
                       "gvl_region_patches_pil_u8: region %d tables leave the %lld-int table buffer", r, tabs_ints);
     }
+    GVL_CHECK_ARG(total_rows <= 2147483647LL, "gvl_region_patches_pil_u8: %lld patch rows", total_rows);
+    const int gh = ragged ? 0 : canvas_h / patch, gw = ragged ? 0 : canvas_w / patch;
     std::vector<int32_t> dev_desc;
-    const size_t need = region_layout(R, h_desc, &dev_desc);
+    const size_t need = region_layout(R, h_desc, &dev_desc, gh * gw, patch);
     GVL_CHECK_ARG(scratch_bytes >= need, "gvl_region_patches_pil_u8: scratch %zu < required %zu bytes", scratch_bytes, need);
     cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
-    const int gh = canvas_h / patch, gw = canvas_w / patch;
     // pageable source: the copy is staged before the call returns, so dev_desc may go out of scope
     GVL_CUDA(cudaMemcpyAsync(scratch, dev_desc.data(), dev_desc.size() * sizeof(int32_t), cudaMemcpyHostToDevice, s));
-    if (patches) GVL_CUDA(cudaMemsetAsync(patches, 0, (size_t)R * gh * gw * ld * 2, s));
+    if (patches) GVL_CUDA(cudaMemsetAsync(patches, 0, (size_t)total_rows * ld * 2, s));
     if (resized_u8) GVL_CUDA(cudaMemsetAsync(resized_u8, 0, (size_t)R * canvas_h * canvas_w * 3, s));
     long long max_h = 0, max_v = 0, src_bytes = 0;
     for (int r = 0; r < R; ++r) {
@@ -296,7 +308,7 @@ extern "C" int gvl_region_patches_pil_u8(const uint8_t* frame, int H, int W, int
         max_v = std::max(max_v, (long long)d[4] * d[5]);
         src_bytes += (long long)d[2] * d[3] * 3;
     }
-    ProfScope prof(GVL_K_PREPROCESS, (double)src_bytes + (double)R * gh * gw * ld * 2, s);
+    ProfScope prof(GVL_K_PREPROCESS, (double)src_bytes + (double)total_rows * ld * 2, s);
     const int32_t* desc = reinterpret_cast<const int32_t*>(scratch);
     uint8_t* sc = reinterpret_cast<uint8_t*>(scratch);
     const int bh = (int)std::min<long long>((max_h + 255) / 256, 4096), bv = (int)std::min<long long>((max_v + 255) / 256, 4096);

@@ -7,6 +7,7 @@
 #include "common.cuh"
 
 #include <cstdlib>
+#include <vector>
 
 namespace gvl {
 
@@ -22,6 +23,7 @@ struct Workspace {
 
 struct VitBuffers {
     void *x, *xn, *qkv, *attn, *h, *pa, *hx, *hxn, *hh;
+    void* tiles;  // query-tile table of a ragged batch (gvl_attention_varlen_tiles), 16 B per tile
     float *stats_a, *stats_b;  // LayerNorm-fusion partial row sums ([M, slots, 2] each)
     float *fin_a, *fin_b;      // finalised (rstd, mean * rstd) per row ([M, 2] each)
 };
@@ -43,6 +45,7 @@ static size_t carve(const gvl_vit_weights* w, size_t M, int B, uint8_t* base, Vi
     vb.stats_b = reinterpret_cast<float*>(ws.take(M * slots * 2 * sizeof(float)));
     vb.fin_a = reinterpret_cast<float*>(ws.take(M * 2 * sizeof(float)));
     vb.fin_b = reinterpret_cast<float*>(ws.take(M * 2 * sizeof(float)));
+    vb.tiles = ws.take((M / 128 + (size_t)B + 1) * 16);  // sum ceil(T_i / 128) <= M / 128 + B
     return ws.off + 256;
 }
 
@@ -112,7 +115,25 @@ static int forward_groups(const gvl_vit_weights* w, const void* patches, int n_g
         }
         return 0;
     };
+    // a ragged batch takes ONE attention launch per layer over a table of query tiles (uploaded once per call)
+    int n_tiles = 0;
+    double score_elems = 0.0;
+    if (n_groups > 1) {
+        std::vector<int32_t> item_tokens;
+        for (int g = 0; g < n_groups; ++g) {
+            item_tokens.insert(item_tokens.end(), (size_t)groups[g].B, groups[g].T);
+            score_elems += (double)groups[g].B * groups[g].T * (double)groups[g].T;
+        }
+        GVL_TRY(gvl_attention_varlen_tiles((int)item_tokens.size(), item_tokens.data(), nullptr, &n_tiles));
+        std::vector<int32_t> table((size_t)n_tiles * 4);
+        GVL_TRY(gvl_attention_varlen_tiles((int)item_tokens.size(), item_tokens.data(), table.data(), &n_tiles));
+        // pageable source: staged before the call returns
+        GVL_CUDA(cudaMemcpyAsync(vb.tiles, table.data(), table.size() * sizeof(int32_t), cudaMemcpyHostToDevice,
+                                 reinterpret_cast<cudaStream_t>(stream)));
+    }
     auto attention = [&]() -> int {
+        if (n_groups > 1)
+            return gvl_attention_varlen_bf16(vb.qkv, vb.attn, M, vb.tiles, n_tiles, score_elems, H, hd, scale, stream);
         size_t r0 = 0;
         for (int g = 0; g < n_groups; ++g) {
             GVL_TRY(gvl_attention_bf16(rows(vb.qkv, r0, 3 * (size_t)D), rows(vb.attn, r0, D), groups[g].B, groups[g].T, H, hd,

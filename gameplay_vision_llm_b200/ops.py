@@ -328,6 +328,30 @@ def attention(qkv: torch.Tensor, B: int, T: int, H: int, hd: int, scale: float |
 
 
 @_on_tensor_device
+def attention_varlen(qkv: torch.Tensor, item_tokens, H: int, hd: int, scale: float | None = None) -> torch.Tensor:
+    """Self-attention over a ragged batch in ONE launch: qkv bf16 [sum T_i, 3*H*hd], items of `item_tokens[i]` tokens
+    back to back -> bf16 [sum T_i, H*hd]; every item attends to itself only."""
+    _need_cuda(qkv)
+    toks = np.ascontiguousarray(np.asarray(item_tokens, np.int32))
+    M = int(toks.sum())
+    if qkv.dtype != torch.bfloat16 or tuple(qkv.shape) != (M, 3 * H * hd) or not qkv.is_contiguous():
+        raise RuntimeError("attention_varlen: qkv must be contiguous bf16 [sum T_i, 3*H*hd]")
+    tp = toks.ctypes.data_as(ctypes.POINTER(ctypes.c_int32))
+    n = ctypes.c_int(0)
+    _lib.check(_lib.lib().gvl_attention_varlen_tiles(len(toks), tp, None, ctypes.byref(n)), "gvl_attention_varlen_tiles")
+    table = np.zeros((n.value, 4), np.int32)
+    _lib.check(_lib.lib().gvl_attention_varlen_tiles(len(toks), tp, table.ctypes.data_as(ctypes.POINTER(ctypes.c_int32)),
+                                                     ctypes.byref(n)), "gvl_attention_varlen_tiles")
+    tiles = torch.from_numpy(table).to(qkv.device)
+    out = torch.empty((M, H * hd), dtype=torch.bfloat16, device=qkv.device)
+    scale = float(hd) ** -0.5 if scale is None else float(scale)
+    _lib.check(_lib.lib().gvl_attention_varlen_bf16(qkv.data_ptr(), out.data_ptr(), M, tiles.data_ptr(), n.value,
+                                                    float((toks.astype(np.float64) ** 2).sum()), H, hd, scale, _stream()),
+               "gvl_attention_varlen_bf16")
+    return out
+
+
+@_on_tensor_device
 def probe_attention(q: torch.Tensor, kv: torch.Tensor, B: int, T: int, H: int, hd: int) -> torch.Tensor:
     """q fp32 [H*hd] (pre-scaled), kv bf16 [B*T, 2*H*hd] -> bf16 [B, H*hd]."""
     _need_cuda(q, kv)
@@ -477,8 +501,9 @@ def region_patches(frame: torch.Tensor, boxes, sizes, canvas_hw, lut: torch.Tens
     """Crop + Pillow-bicubic resize + normalise + zero-pad + im2col of R regions of ONE frame.
 
     frame: uint8 [H,W,3] on the device; boxes: R x (x1, y1, x2, y2) (`frame[y1:y2, x1:x2]`); sizes: R x (out_h, out_w);
-    canvas_hw: (canvas_h, canvas_w) multiples of `patch`, >= every size.  Returns (patches bf16 [R*gh*gw, ld] or None,
-    resized uint8 [R, canvas_h, canvas_w, 3] or None).  `out`: a contiguous bf16 [R*gh*gw, ld] slice to write the patch
+    canvas_hw: (canvas_h, canvas_w) multiples of `patch`, >= every size; None = the RAGGED form: every region on its own
+    canvas (its size, a multiple of `patch`), patch rows back to back.  Returns (patches bf16 [R*gh*gw, ld] — ragged:
+    [sum gh_r*gw_r, ld] — or None, resized uint8 [R, canvas_h, canvas_w, 3] or None).  `out`: a contiguous bf16 [R*gh*gw, ld] slice to write the patch
     rows into (a ragged batch is assembled from several calls)."""
     _need_cuda(frame, lut)
     if frame.dtype != torch.uint8 or frame.dim() != 3 or frame.shape[2] != 3 or not frame.is_contiguous():
@@ -487,7 +512,10 @@ def region_patches(frame: torch.Tensor, boxes, sizes, canvas_hw, lut: torch.Tens
     if R == 0 or len(sizes) != R:
         raise RuntimeError("region_patches: need one (out_h, out_w) per box")
     H, W = int(frame.shape[0]), int(frame.shape[1])
-    canvas_h, canvas_w = int(canvas_hw[0]), int(canvas_hw[1])
+    ragged = canvas_hw is None
+    canvas_h, canvas_w = (0, 0) if ragged else (int(canvas_hw[0]), int(canvas_hw[1]))
+    if ragged and want_u8:
+        raise RuntimeError("region_patches: the ragged form writes patch rows only")
     ld = ld or (3 * patch * patch + 7) // 8 * 8
     desc = np.zeros((R, 10), np.int32)
     tabs, off = [], 0
@@ -504,11 +532,12 @@ def region_patches(frame: torch.Tensor, boxes, sizes, canvas_hw, lut: torch.Tens
     dptr = desc.ctypes.data_as(ctypes.POINTER(ctypes.c_int32))
     scratch = torch.empty(int(_lib.lib().gvl_region_scratch_bytes(R, dptr)) + 256, dtype=torch.uint8, device=frame.device)
     gh, gw = canvas_h // patch, canvas_w // patch
+    rows = sum((int(oh) // patch) * (int(ow) // patch) for oh, ow in sizes) if ragged else R * gh * gw
     patches = None
     if want_patches:
-        patches = out if out is not None else torch.empty((R * gh * gw, ld), dtype=torch.bfloat16, device=frame.device)
-        if patches.dtype != torch.bfloat16 or tuple(patches.shape) != (R * gh * gw, ld) or not patches.is_contiguous():
-            raise RuntimeError(f"region_patches: `out` must be contiguous bf16 [{R * gh * gw}, {ld}]")
+        patches = out if out is not None else torch.empty((rows, ld), dtype=torch.bfloat16, device=frame.device)
+        if patches.dtype != torch.bfloat16 or tuple(patches.shape) != (rows, ld) or not patches.is_contiguous():
+            raise RuntimeError(f"region_patches: `out` must be contiguous bf16 [{rows}, {ld}]")
     resized = torch.empty((R, canvas_h, canvas_w, 3), dtype=torch.uint8, device=frame.device) if want_u8 else None
     if want_patches and (lut is None or lut.dtype != torch.bfloat16 or tuple(lut.shape) != (3, 256) or not lut.is_contiguous()):
         raise RuntimeError("region_patches: lut must be contiguous bf16 [3, 256]")

@@ -241,7 +241,7 @@ def run_siglip_encoder(frames, device: str = "cuda", sam_results: list | None = 
     constructed `SigLIPSemanticEncoder` (the reference builds a fresh one per call, :514-515)."""
     import logging
 
-    from .siglip_semantic_encoder import NaFlexConfig, SigLIPSemanticEncoder, _to_uint8_hwc
+    from .siglip_semantic_encoder import BoxMask, NaFlexConfig, SigLIPSemanticEncoder, _to_uint8_hwc
     log = logging.getLogger(__name__)
     if encoder is None:
         encoder = SigLIPSemanticEncoder(NaFlexConfig(device=device))
@@ -264,9 +264,7 @@ def run_siglip_encoder(frames, device: str = "cuda", sam_results: list | None = 
                 entity_type = det.get("entity_type", "unknown")
                 entity_id = det.get("entity_id", f"{entity_type}_{timestamp}")
                 x1, y1, x2, y2 = [int(c) for c in det["bbox"]]
-                mask = np.zeros(frame_np.shape[:2], dtype=np.bool_)
-                mask[y1:y2, x1:x2] = True
-                masks.append((entity_id, mask))
+                masks.append((entity_id, BoxMask(frame_np.shape[:2], y1, y2, x1, x2)))  # the reference's zeros + slice fill
                 kept.append(det)
             try:
                 regions = encoder.encode_regions_individually(frame_np, masks)

@@ -237,6 +237,33 @@ IMAGENET_MEAN = (0.485, 0.456, 0.406)  # hard-coded in the reference's prepare_r
 IMAGENET_STD = (0.229, 0.224, 0.225)
 
 
+class BoxMask:
+    """The mask `m = np.zeros((H, W), bool); m[y1:y2, x1:x2] = True` — how scripts/extract_features.py:563-565 turns a
+    SAM bounding box into a mask — kept as its four slice bounds.  `region_bbox` reads the extent of the set pixels off
+    the bounds (Python slice semantics: negative indices wrap, out-of-range ones clip, like the array assignment)
+    instead of scanning H x W bytes that were written a moment earlier; `np.asarray(box_mask)` materialises the array
+    for any other consumer."""
+
+    def __init__(self, shape, y1: int, y2: int, x1: int, x2: int):
+        self.shape = (int(shape[0]), int(shape[1]))
+        self.bounds = (int(y1), int(y2), int(x1), int(x2))
+
+    def extent(self):
+        """(x_min, x_max, y_min, y_max) of the set pixels (inclusive), or None when the slices select nothing."""
+        y1, y2, x1, x2 = self.bounds
+        rows = range(*slice(y1, y2).indices(self.shape[0]))
+        cols = range(*slice(x1, x2).indices(self.shape[1]))
+        if len(rows) == 0 or len(cols) == 0:
+            return None
+        return cols[0], cols[-1], rows[0], rows[-1]
+
+    def __array__(self, dtype=None, copy=None):
+        y1, y2, x1, x2 = self.bounds
+        m = np.zeros(self.shape, dtype=np.bool_)
+        m[y1:y2, x1:x2] = True
+        return m if dtype is None else m.astype(dtype)
+
+
 class RegionExtractor:
     """Mask -> expanded bounding box (reference :292-344); the crop / resize / normalisation of :346-367 run on the
     device."""
@@ -249,14 +276,24 @@ class RegionExtractor:
     def region_bbox(frame_shape, mask, expand_ratio: float = 0.1) -> tuple[int, int, int, int]:
         """The box of `extract_masked_region` (:318-338).  Row / column occupancy instead of `np.where` over the whole
         mask: the same min / max, without materialising every set pixel's coordinates."""
-        mask = np.asarray(mask)
-        cols = np.flatnonzero(mask.any(axis=0))
+        if isinstance(mask, BoxMask):
+            ext = mask.extent()
+            cols, rows = ((), ()) if ext is None else ((ext[0], ext[1]), (ext[2], ext[3]))
+            cols, rows = np.asarray(cols, np.int64), np.asarray(rows, np.int64)
+        elif (mask := np.asarray(mask)).dtype == np.bool_ and mask.ndim == 2 and mask.flags.c_contiguous and \
+                mask.shape[1] % 8 == 0:
+            words = mask.view(np.uint8).view(np.uint64)  # 8 pixels per word: OR-reductions instead of byte scans
+            rows = np.flatnonzero(np.bitwise_or.reduce(words, axis=1))
+            cols = (np.flatnonzero(np.bitwise_or.reduce(words[rows[0]:rows[-1] + 1], axis=0).view(np.uint8))
+                    if rows.size else rows)
+        else:
+            cols = np.flatnonzero(mask.any(axis=0))
+            rows = np.flatnonzero(mask.any(axis=1)) if cols.size else cols
         if cols.size == 0:
             h, w = frame_shape[:2]
             cx, cy = w // 2, h // 2
             size = min(h, w) // 4
             return (cx - size, cy - size, cx + size, cy + size)
-        rows = np.flatnonzero(mask.any(axis=1))
         x_min, x_max = cols[0], cols[-1]
         y_min, y_max = rows[0], rows[-1]
         width = x_max - x_min
@@ -509,12 +546,10 @@ class SigLIPSemanticEncoder:
         for groups in passes:
             shapes = [(len(idx), th // spec.patch, tw // spec.patch) for (th, tw), idx in groups]
             M = sum(b * gh * gw for b, gh, gw in shapes)
-            patches = torch.empty((M, spec.patch_ld), dtype=torch.bfloat16, device=m.device)
-            r0 = 0
-            for ((th, tw), idx), (b, gh, gw) in zip(groups, shapes):
-                ops.region_patches(frame_dev, [boxes[i] for i in idx], [sizes[i] for i in idx], (th, tw), self._region_lut,
-                                   patch=spec.patch, ld=spec.patch_ld, out=patches[r0:r0 + b * gh * gw])
-                r0 += b * gh * gw
+            order = [i for _, idx in groups for i in idx]  # regions of equal size adjacent: the ragged pass's groups
+            # one crop / resize / normalise / im2col launch for the whole pass, every region on its own canvas
+            patches, _ = ops.region_patches(frame_dev, [boxes[i] for i in order], [sizes[i] for i in order], None,
+                                            self._region_lut, patch=spec.patch, ld=spec.patch_ld)
             need = ops.siglip_ragged_workspace_bytes(m.pack, M, sum(x[0] for x in shapes))
             pooled, tokens = ops.siglip_forward_ragged(m.pack, patches, shapes, workspace=m._ws_bytes(need), return_tokens=True)
             if self.config.pool_strategy in ("mean", "max"):
@@ -526,7 +561,6 @@ class SigLIPSemanticEncoder:
             else:
                 feats = pooled.float()
             out = self.projection(feats).cpu()
-            order = [i for _, idx in groups for i in idx]
             for emb, i in zip(out, order):
                 meta = metadata[i]
                 results[i] = SemanticEmbedding(embedding=emb, entity_id=meta["entity_id"], confidence=1.0,

@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define GVL_ABI_VERSION 9
+#define GVL_ABI_VERSION 10
 
 #if defined(__GNUC__)
 #define GVL_API __attribute__((visibility("default")))
@@ -196,6 +196,16 @@ GVL_API int gvl_layernorm_bf16(const void* x, int ldx, const float* gamma, const
  * definition :229-249).  hd = 64 or 72 (the two instantiations; anything else returns an error). */
 GVL_API int gvl_attention_bf16(const void* qkv, void* out, int B, int T, int H, int hd, float scale,
                        void* stream);
+
+/* Ragged batch (masked-region route): items of different lengths back to back on the token axis, ONE launch.
+ * gvl_attention_varlen_tiles (host only): h_item_tokens int32 [n_items] -> h_tiles int32 [*n_tiles, 4] = {first token of
+ * the item, item length, first query row of the tile, 0}, longest items first; h_tiles NULL = size query
+ * (*n_tiles = sum ceil(T_i / 128)).  gvl_attention_varlen_bf16: qkv bf16 [M_total, 3*H*hd], out bf16 [M_total, H*hd],
+ * tiles = that table in DEVICE memory (16-byte aligned); score_elems = sum T_i^2 (profiling only).  Each item's rows are
+ * bit-identical to gvl_attention_bf16(B = 1, T = T_i) on that item. */
+GVL_API int gvl_attention_varlen_tiles(int n_items, const int32_t* h_item_tokens, int32_t* h_tiles, int* n_tiles);
+GVL_API int gvl_attention_varlen_bf16(const void* qkv, void* out, int M_total, const void* tiles, int n_tiles,
+                              double score_elems, int H, int hd, float scale, void* stream);
 
 /* ---- K5: MAP-head probe attention -------------------------------------------------------------- */
 /* One query (the learned probe, already projected and pre-scaled: q float[H*hd]) attends over the T
@@ -370,6 +380,9 @@ GVL_API size_t gvl_region_scratch_bytes(int R, const int32_t* h_desc); /* Host o
  * ((v / 255) - mean[c]) / std[c] evaluated in fp32 (built by the host with the reference's own three fp32 operations).
  * patches: bf16 [R * (canvas_h/patch) * (canvas_w/patch), ld], GVL_LAYOUT_BF16_PATCH order per region; pixels outside a
  * region's out_h x out_w rectangle and the columns [3*patch*patch, ld) are zero (`F.pad` of the normalised tensor, :536).
+ * canvas_h = canvas_w = 0 is the RAGGED form: every region on its own out_h x out_w canvas (multiples of the patch size),
+ * patch rows of the regions back to back in `patches` (bf16 [sum (out_h/patch)*(out_w/patch), ld]) — the input layout of
+ * gvl_siglip_forward_ragged when regions of equal size are adjacent; resized_u8 must be NULL then.
  * resized_u8: optional uint8 [R, canvas_h, canvas_w, 3] = the resized regions themselves (zero outside), bit-identical
  * to Pillow's bytes (horizontal pass into a uint8 intermediate, then vertical); either output may be NULL. */
 GVL_API int gvl_region_patches_pil_u8(const uint8_t* frame, int H, int W, int R, const int32_t* h_desc,

@@ -122,3 +122,19 @@ def test_oracle_equals_the_reference_encode_masked_regions_so400m(golden_dir):
     cos = torch.nn.functional.cosine_similarity(torch.from_numpy(got), torch.from_numpy(want)).item()
     assert cos > 0.999999 and np.abs(got - want).max() < 5e-4, (cos, np.abs(got - want).max())
     assert res[0][2] == tuple(gold["so_bbox"][0])
+
+
+def test_box_mask_extent_equals_the_materialised_mask():
+    """`BoxMask` (the caller's `mask[y1:y2, x1:x2] = True`, extract_features.py:563-565) must give the bounding box the
+    reference's `np.where` finds on the materialised array — including negative / out-of-frame slice bounds."""
+    from gameplay_vision_llm_b200.siglip_semantic_encoder import BoxMask
+    shape = (54, 96, 3)
+    rng = np.random.default_rng(1)
+    cases = [(0, 54, 0, 96), (10, 10, 5, 50), (-5, 20, -10, 30), (40, 200, 90, 300), (-60, -50, 3, 9), (53, 54, 95, 96)]
+    cases += [tuple(int(v) for v in rng.integers(-70, 130, 4)) for _ in range(300)]
+    for y1, y2, x1, x2 in cases:
+        bm = BoxMask(shape[:2], y1, y2, x1, x2)
+        arr = np.zeros(shape[:2], np.bool_)
+        arr[y1:y2, x1:x2] = True
+        assert np.array_equal(np.asarray(bm), arr)
+        assert RegionExtractor.region_bbox(shape, bm) == region_ref.extract_bbox(shape, arr), (y1, y2, x1, x2)

@@ -268,3 +268,19 @@ def test_ragged_pass_so400m_equals_one_call_per_region():
     want = [enc.encode_masked_regions(frame, [mk])[0] for mk in masks]
     got = enc.encode_regions_individually(frame, masks)
     assert all(torch.equal(g.embedding, w.embedding) for g, w in zip(got, want))
+
+
+@pytest.mark.parametrize("hd,H,items", [(72, 3, [21, 100, 30, 351, 729, 1, 130]), (64, 2, [200, 64, 65, 128, 127, 1000]),
+                                         (72, 16, [324, 405, 729, 621])])
+def test_varlen_attention_equals_one_launch_per_item(hd, H, items):
+    """One launch over a ragged batch (query-tile table) against one gvl_attention_bf16 launch per item: bit-identical
+    (a tile that runs past its item reads the neighbour's rows; those keys are masked, those query rows never stored)."""
+    M = sum(items)
+    qkv = (torch.randn(M, 3 * H * hd, generator=torch.Generator().manual_seed(M)) * 1.5).to(torch.bfloat16).to(DEV)
+    got = ops.attention_varlen(qkv, items, H, hd)
+    r0 = 0
+    for T in items:
+        want = ops.attention(qkv[r0:r0 + T].contiguous(), 1, T, H, hd)
+        assert torch.equal(got[r0:r0 + T], want), (T, r0)
+        r0 += T
+    assert torch.isfinite(got.float()).all()

@@ -13,116 +13,17 @@
 // mapped (NV12 in device memory) and converted to packed RGB straight into the caller's batch buffer — the frames the
 // sampling rule skips are decoded (inter prediction needs them) but never converted, copied or sent to the host.
 #include "common.cuh"
+#include "cuvid_abi.h"
 
 #include <dlfcn.h>
+
+#include <cstdlib>
 
 #include <mutex>
 #include <new>
 
 namespace gvl {
 namespace cuvid {
-
-// ---- the subset of cuviddec.h / nvcuvid.h used here (Linux x86-64 layout) ---------------------------------------
-typedef void* CUvideodecoder;
-typedef void* CUvideoparser;
-typedef long long CUvideotimestamp;
-
-struct CUVIDDECODECAPS {
-    int eCodecType;               // IN
-    int eChromaFormat;            // IN
-    unsigned int nBitDepthMinus8; // IN
-    unsigned int reserved1[3];
-    unsigned char bIsSupported;   // OUT
-    unsigned char nNumNVDECs;
-    unsigned short nOutputFormatMask;
-    unsigned int nMaxWidth, nMaxHeight, nMaxMBCount;
-    unsigned short nMinWidth, nMinHeight;
-    unsigned char bIsHistogramSupported, nCounterBitDepth;
-    unsigned short nMaxHistogramBins;
-    unsigned int reserved3[10];
-    unsigned int tail_pad[16];  // not in the SDK: slack in case a newer driver writes a longer struct
-};
-
-struct CUVIDDECODECREATEINFO {
-    unsigned long ulWidth, ulHeight, ulNumDecodeSurfaces;
-    int CodecType, ChromaFormat;
-    unsigned long ulCreationFlags, bitDepthMinus8, ulIntraDecodeOnly, ulMaxWidth, ulMaxHeight, Reserved1;
-    struct { short left, top, right, bottom; } display_area;
-    int OutputFormat, DeinterlaceMode;
-    unsigned long ulTargetWidth, ulTargetHeight, ulNumOutputSurfaces;
-    void* vidLock;
-    struct { short left, top, right, bottom; } target_rect;
-    unsigned long enableHistogram;
-    unsigned long Reserved2[4];
-    unsigned long tail_pad[8];
-};
-
-struct CUVIDPROCPARAMS {
-    int progressive_frame, second_field, top_field_first, unpaired_field;
-    unsigned int reserved_flags, reserved_zero;
-    unsigned long long raw_input_dptr;
-    unsigned int raw_input_pitch, raw_input_format;
-    unsigned long long raw_output_dptr;
-    unsigned int raw_output_pitch, Reserved1;
-    CUstream output_stream;
-    unsigned int Reserved[46];
-    unsigned long long* histogram_dptr;
-    void* Reserved2[1];
-    unsigned long tail_pad[8];
-};
-
-struct CUVIDEOFORMAT {
-    int codec;
-    struct { unsigned int numerator, denominator; } frame_rate;
-    unsigned char progressive_sequence, bit_depth_luma_minus8, bit_depth_chroma_minus8, min_num_decode_surfaces;
-    unsigned int coded_width, coded_height;
-    struct { int left, top, right, bottom; } display_area;
-    int chroma_format;
-    unsigned int bitrate;
-    struct { int x, y; } display_aspect_ratio;
-    struct {
-        unsigned char video_format : 3;
-        unsigned char video_full_range_flag : 1;
-        unsigned char reserved_zero_bits : 4;
-        unsigned char color_primaries, transfer_characteristics, matrix_coefficients;
-    } video_signal_description;
-    unsigned int seqhdr_data_length;
-};
-
-struct CUVIDSOURCEDATAPACKET {
-    unsigned long flags, payload_size;
-    const unsigned char* payload;
-    CUvideotimestamp timestamp;
-};
-
-struct CUVIDPARSERDISPINFO {
-    int picture_index, progressive_frame, top_field_first, repeat_first_field;
-    CUvideotimestamp timestamp;
-};
-
-typedef int (*PFNVIDSEQUENCECALLBACK)(void*, CUVIDEOFORMAT*);
-typedef int (*PFNVIDDECODECALLBACK)(void*, void* /* CUVIDPICPARAMS*: passed through untouched */);
-typedef int (*PFNVIDDISPLAYCALLBACK)(void*, CUVIDPARSERDISPINFO*);
-
-struct CUVIDPARSERPARAMS {
-    int CodecType;
-    unsigned int ulMaxNumDecodeSurfaces, ulClockRate, ulErrorThreshold, ulMaxDisplayDelay;
-    unsigned int bAnnexb : 1;
-    unsigned int uReserved : 31;
-    unsigned int uReserved1[4];
-    void* pUserData;
-    PFNVIDSEQUENCECALLBACK pfnSequenceCallback;
-    PFNVIDDECODECALLBACK pfnDecodePicture;
-    PFNVIDDISPLAYCALLBACK pfnDisplayPicture;
-    void* pfnGetOperatingPoint;  // AV1 only
-    void* pfnGetSEIMsg;
-    void* pvReserved2[5];
-    void* pExtVideoInfo;
-    void* tail_pad[8];
-};
-
-enum { PKT_ENDOFSTREAM = 0x01, PKT_TIMESTAMP = 0x02 };
-enum { SURFACE_NV12 = 0, CHROMA_420 = 1, DEINTERLACE_WEAVE = 0, DEINTERLACE_ADAPTIVE = 2, CREATE_PREFER_CUVID = 4 };
 
 struct Api {
     void* lib = nullptr;
@@ -142,9 +43,12 @@ static Api& api() {
     static Api a;
     static std::once_flag once;
     std::call_once(once, [] {
-        for (const char* name : {"libnvcuvid.so.1", "libnvcuvid.so"}) {
+        // GVL_NVCUVID_LIB: another library with the cuvid entry points (tests/mock_nvcuvid: a software test double)
+        const char* override_lib = getenv("GVL_NVCUVID_LIB");
+        for (const char* name : {override_lib, "libnvcuvid.so.1", "libnvcuvid.so"}) {
+            if (!name || !name[0]) continue;
             a.lib = dlopen(name, RTLD_NOW | RTLD_LOCAL);
-            if (a.lib) break;
+            if (a.lib || name == override_lib) break;  // a named override that fails to load is an error, not a fallback
         }
         if (!a.lib) return;
         bool all = true;

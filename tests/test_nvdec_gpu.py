@@ -193,3 +193,18 @@ def test_auto_decoder_falls_back_when_nvdec_is_unusable(clip):
     assert torch.equal(idx_auto, idx_sw)
     with pytest.raises(RuntimeError, match="hardware decode"):
         pipe.embed_video(clip[0], fps=10.0, decoder="nvdec")
+
+
+def test_raw_annexb_stream(clip, tmp_path):
+    """A raw elementary stream (no container): the size comes from the SPS, the frame count from decoding."""
+    _require_nvdec()
+    _, y, cb, cr = clip
+    path = str(tmp_path / "clip.h264")
+    assert sv.write_h264_annexb(path, y, cb, cr, fps=(30, 1), skip_every=2) == 46
+    feed = nv.NvdecFeed(path, fps=15.0, batch=5, device=DEV, raw_codec=nv.CODEC_H264, raw_fps=30.0)
+    frames = torch.cat([b.clone() for b in feed]).cpu().numpy().astype(np.int16)
+    assert frames.shape == (23, 100, 176, 3) and feed.frames_decoded == 46
+    assert np.array_equal(feed.timestamps, np.arange(23) * 2 / 30.0)
+    want = _rgb_from_planes(y, cb, cr)
+    assert all(np.abs(frames[k] - want[k]).max() <= 1 for k in range(23))  # every second frame = every coded picture
+    feed.close()

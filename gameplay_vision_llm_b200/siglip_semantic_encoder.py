@@ -92,8 +92,8 @@ class BatchFeature(dict):
 
 def _to_uint8_hwc(image) -> np.ndarray:
     """PIL image / numpy array / tensor -> uint8 [H,W,3] (`convert_rgb` + `pil_to_tensor` of the HF processor)."""
-    if hasattr(image, "convert"):  # PIL
-        return np.asarray(image.convert("RGB"), dtype=np.uint8)
+    if hasattr(image, "convert"):  # PIL; an image that already is RGB is read in place (convert() would copy it first)
+        return np.asarray(image if getattr(image, "mode", None) == "RGB" else image.convert("RGB"), dtype=np.uint8)
     arr = image.detach().cpu().numpy() if torch.is_tensor(image) else np.asarray(image)
     if arr.dtype != np.uint8 or arr.ndim != 3 or arr.shape[-1] != 3:
         raise ValueError("images must be PIL RGB images or uint8 [H,W,3] arrays")

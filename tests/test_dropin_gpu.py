@@ -222,3 +222,4 @@ def test_ops_bind_to_the_tensors_device():
     assert idx.search(got[1:2], top_k=1)[1].item() == 1
     with pytest.raises(RuntimeError, match="different devices|weights on"):
         pipe1.embed(torch.from_numpy(frames).to("cuda:0"))
+

@@ -645,7 +645,8 @@ def main_regions(args) -> None:
     spec = SiglipVisionSpec.so400m()
     R = 16
     K, W = args.steps, args.warmup
-    enc = SigLIPSemanticEncoder(NaFlexConfig(device=str(dev), state_dict=synth_siglip_state_dict(spec, seed=0), batch_size=R))
+    enc = SigLIPSemanticEncoder(NaFlexConfig(device=str(dev), state_dict=synth_siglip_state_dict(spec, seed=0), batch_size=R,
+                                             fold_layernorm=not args.no_fold_ln))
     enc.projection.load_state_dict(synth_ren_projection_state_dict(spec.hidden, seed=3))
     frames_host = [synth.scene_frames_np((rank * 4 + i) * 30, 1, FRAME_H, FRAME_W)[0] for i in range(4)]
     frames_dev = [torch.from_numpy(f).to(dev) for f in frames_host]
@@ -735,6 +736,7 @@ def main_regions(args) -> None:
                                    "(gvl_siglip_forward_ragged), so400m tower + mean pool + REN projection",
                        "regions_per_step": R, "tokens_per_step": int(tokens), "frame": [FRAME_H, FRAME_W, 3],
                        "weights": "random init, seeds 0/3", "sharding": "replicas only (no collective on this route)",
+                       "layernorm": "separate kernels" if args.no_fold_ln else "folded into the consuming GEMM epilogues",
                        "l2": "a ring of 4 distinct frames; activations of a step exceed L2 only for the larger groups"},
             "roofline": {"kernel": "gemm_bf16_cg2_kernel", "bound": "tensor", "achieved": round(gemm_tflops, 2),
                          "peak": peaks["bf16_tflops"], "unit": "TFLOP/s", "frac": round(gemm_tflops / peaks["bf16_tflops"], 4),

@@ -75,6 +75,9 @@ class NaFlexConfig:
     # masked-region route: HF's `interpolate_pos_encoding=True` for patch grids other than the checkpoint's.  False =
     # the reference as published: HF raises on the position add for every non-square region
     interpolate_pos_encoding: bool = True
+    # fold every token-level LayerNorm into the GEMM that consumes it (weights.SiglipPack(fold_ln=True), what
+    # EmbeddingPipeline runs): the LayerNorm kernels disappear.  False keeps the reference's op order.
+    fold_layernorm: bool = False
 
 
 class BatchFeature(dict):
@@ -389,7 +392,7 @@ class SigLIPEncoder:
             self.config.resample, self.config.image_mean, self.config.image_std = resample, mean, std
         logger.info("Loading SigLIP encoder: %s (%d layers, hidden %d)", cfg.model_name, spec.layers, spec.hidden)
         with torch.cuda.device(device):
-            self._model = GvlSiglipModel(SiglipPack(sd, spec, device))
+            self._model = GvlSiglipModel(SiglipPack(sd, spec, device, fold_ln=bool(cfg.fold_layernorm)))
         self._processor = GvlSiglipProcessor(spec.image, resample, mean, std, device)
 
     def forward(self, pixel_values: torch.Tensor):

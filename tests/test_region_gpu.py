@@ -163,13 +163,14 @@ def test_encoder_forward_on_a_non_square_input_vs_oracle():
     assert _cos(seq.float(), seams["last_hidden_state"]).min() > 0.999 and _cos(pooled.float(), want).min() > 0.999
 
 
+@pytest.mark.parametrize("fold_ln", [False, True])
 @pytest.mark.timeout(900)
-def test_encode_masked_regions_so400m_vs_reference_golden(golden_dir):
+def test_encode_masked_regions_so400m_vs_reference_golden(golden_dir, fold_ln):
     """Full-size tower, three regions of a 1080p frame: one call per detection (scripts/extract_features.py:568 — grids
     12 x 27, 27 x 15 and the untouched 27 x 27) and one padded batch of three, against the reference's own outputs."""
     gold = np.load(f"{golden_dir}/golden_regions.npz")
     spec = SiglipVisionSpec.so400m()
-    enc = _encoder(spec, "mean", 16, {})
+    enc = _encoder(spec, "mean", 16, {"fold_layernorm": fold_ln})
     frame = synth.scene_frames_np(40, 1)[0]
     masks = [(f"s{i}", rect_mask(frame.shape, r)) for i, r in enumerate(SO_RECTS)]
     single = [enc.encode_masked_regions(frame, [mk])[0] for mk in masks]
@@ -179,7 +180,7 @@ def test_encode_masked_regions_so400m_vs_reference_golden(golden_dir):
     for name, res in (("single", single), ("batched", batched)):
         got, want = torch.stack([r.embedding for r in res]), torch.from_numpy(gold[f"so_mean_{name}"])
         cos, err = _cos(got, want), (got - want).abs().max().item()
-        print(f"regions so400m {name}: cos {cos.tolist()} max_abs {err:.4f} (|want| max {want.abs().max():.3f})")
+        print(f"regions so400m fold_ln={fold_ln} {name}: cos {cos.tolist()} max_abs {err:.4f} (|want| max {want.abs().max():.3f})")
         assert cos.min() > 0.999 and err < 0.015 * want.abs().max().item() + 0.005  # measured 0.005 x max
 
 
@@ -245,11 +246,7 @@ def test_ragged_pass_equals_one_call_per_region_bit_for_bit(pool, fold_ln):
     frame = synth.scene_frames_np(7, 1, 270, 480)[0]
     rects = MID_RECTS + [(60, 40, 320, 130), (210, 5, 270, 245), (120, 90, 220, 190), (0, 0, 480, 270)]
     masks = [(f"e{i}", rect_mask(frame.shape, r)) for i, r in enumerate(rects)]
-    enc = _encoder(MID_SPEC, pool, 16, MID_CFG)
-    if fold_ln:
-        enc.encoder._load_model()
-        m = enc.encoder._model
-        m.pack = SiglipPack(enc.config.state_dict, m.spec, DEV, fold_ln=True)
+    enc = _encoder(MID_SPEC, pool, 16, dict(MID_CFG, fold_layernorm=fold_ln))
     want = [enc.encode_masked_regions(frame, [mk])[0] for mk in masks]
     for max_tokens in (32768, 150):
         got = enc.encode_regions_individually(frame, masks, max_tokens=max_tokens)

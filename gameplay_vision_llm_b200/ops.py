@@ -619,5 +619,7 @@ def siglip_grid_view(pack: SiglipPack, gh: int, gw: int) -> "SiglipPack | Siglip
         return pack
     views = pack.__dict__.setdefault("_grid_views", {})
     if (gh, gw) not in views:
+        if len(views) >= 64:  # bounded: variable-size inputs must not grow device memory without limit
+            views.pop(next(iter(views)))
         views[(gh, gw)] = SiglipGridView(pack, gh, gw, interpolate_pos(pack.pos_table, gh, gw))
     return views[(gh, gw)]

@@ -14,7 +14,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("GVL_LIB_PATH") or os.path.join(_HERE, "libgvl_sm100a.so")
 
 c_float_p = POINTER(c_float)
-ABI_VERSION = 10  # include/gvl.h GVL_ABI_VERSION
+ABI_VERSION = 11  # include/gvl.h GVL_ABI_VERSION
 
 
 class VitLayer(ctypes.Structure):
@@ -101,6 +101,9 @@ SIGNATURES = {
     "gvl_region_scratch_bytes": (c_size_t, [c_int, POINTER(c_int32)]),
     "gvl_region_patches_pil_u8": (c_int, [c_void_p, c_int, c_int, c_int, POINTER(c_int32), c_void_p, c_longlong, c_void_p,
                                           c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "gvl_resize_two_pass_u8": (c_int, [c_void_p, c_int, c_int, c_int, POINTER(c_int32), c_void_p, c_longlong, c_int, c_int,
+                                       c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
+                                       c_size_t, c_void_p]),
     "gvl_pos_interp_bicubic_bf16": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     "gvl_max_tokens_bf16": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_void_p]),
     "gvl_nvdec_available": (c_int, []),

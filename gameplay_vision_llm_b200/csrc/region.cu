@@ -25,8 +25,8 @@ static inline double pil_bicubic(double x) {
     return 0.0;
 }
 
-__device__ __forceinline__ int clip8(int v) {
-    v >>= PIL_PRECISION_BITS;
+__device__ __forceinline__ int clip8(int v, int precision) {
+    v >>= precision;
     return v < 0 ? 0 : (v > 255 ? 255 : v);
 }
 
@@ -34,9 +34,9 @@ __device__ __forceinline__ int clip8(int v) {
 // grid (blocks over ch * ow, R); one thread per output pixel (3 channels).
 __global__ void __launch_bounds__(256)
 region_h_kernel(const uint8_t* __restrict__ frame, int W, const int32_t* __restrict__ desc, const int32_t* __restrict__ tabs,
-                uint8_t* __restrict__ scratch) {
+                uint8_t* __restrict__ scratch, int precision) {
     const int32_t* d = desc + blockIdx.y * DEV_DESC_INTS;
-    const int x1 = d[0], y1 = d[1], ch = d[3], ow = d[4], kh = d[6];
+    const int x1 = d[0], y1 = d[1], cw = d[2], ch = d[3], ow = d[4], kh = d[6];
     const int32_t* xmin = tabs + d[8];
     const int32_t* cnt = xmin + ow;
     const int32_t* kk = cnt + ow;
@@ -44,10 +44,12 @@ region_h_kernel(const uint8_t* __restrict__ frame, int W, const int32_t* __restr
     const int total = ch * ow;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
         const int row = i / ow, xx = i - row * ow;
-        const int n = cnt[xx];
-        const uint8_t* src = frame + ((size_t)(y1 + row) * W + x1 + xmin[xx]) * 3;
+        // the tables live in device memory the host cannot inspect: a window is clipped to the crop, never trusted
+        const int x0 = min(max(xmin[xx], 0), cw - 1);
+        const int n = min(min(cnt[xx], kh), cw - x0);
+        const uint8_t* src = frame + ((size_t)(y1 + row) * W + x1 + x0) * 3;
         const int32_t* k = kk + (size_t)xx * kh;
-        int s0 = 1 << (PIL_PRECISION_BITS - 1), s1 = s0, s2 = s0;
+        int s0 = 1 << (precision - 1), s1 = s0, s2 = s0;
         for (int t = 0; t < n; ++t) {
             const int w = k[t];
             s0 += (int)src[3 * t + 0] * w;
@@ -55,9 +57,9 @@ region_h_kernel(const uint8_t* __restrict__ frame, int W, const int32_t* __restr
             s2 += (int)src[3 * t + 2] * w;
         }
         uint8_t* o = tmp + (size_t)i * 3;
-        o[0] = (uint8_t)clip8(s0);
-        o[1] = (uint8_t)clip8(s1);
-        o[2] = (uint8_t)clip8(s2);
+        o[0] = (uint8_t)clip8(s0, precision);
+        o[1] = (uint8_t)clip8(s1, precision);
+        o[2] = (uint8_t)clip8(s2, precision);
     }
 }
 
@@ -66,9 +68,10 @@ region_h_kernel(const uint8_t* __restrict__ frame, int W, const int32_t* __restr
 __global__ void __launch_bounds__(256)
 region_v_kernel(const int32_t* __restrict__ desc, const int32_t* __restrict__ tabs, const uint8_t* __restrict__ scratch,
                 const uint16_t* __restrict__ lut, int canvas_h, int canvas_w, int patch, int ld,
-                uint16_t* __restrict__ patches, uint8_t* __restrict__ resized, int tokens_per_region) {
+                uint16_t* __restrict__ patches, uint8_t* __restrict__ resized, int tokens_per_region, int precision,
+                const float* __restrict__ lut_f32, float* __restrict__ f32_chw) {
     const int32_t* d = desc + blockIdx.y * DEV_DESC_INTS;
-    const int ow = d[4], oh = d[5], kv = d[7];
+    const int ch = d[3], ow = d[4], oh = d[5], kv = d[7];
     const int32_t* ymin = tabs + d[9];
     const int32_t* cnt = ymin + oh;
     const int32_t* kk = cnt + oh;
@@ -79,10 +82,11 @@ region_v_kernel(const int32_t* __restrict__ desc, const int32_t* __restrict__ ta
     const size_t row0 = (size_t)d[11];
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
         const int y = i / ow, x = i - y * ow;
-        const int n = cnt[y];
-        const uint8_t* src = tmp + ((size_t)ymin[y] * ow + x) * 3;
+        const int y0 = min(max(ymin[y], 0), ch - 1);
+        const int n = min(min(cnt[y], kv), ch - y0);
+        const uint8_t* src = tmp + ((size_t)y0 * ow + x) * 3;
         const int32_t* k = kk + (size_t)y * kv;
-        int s0 = 1 << (PIL_PRECISION_BITS - 1), s1 = s0, s2 = s0;
+        int s0 = 1 << (precision - 1), s1 = s0, s2 = s0;
         for (int t = 0; t < n; ++t) {
             const int w = k[t];
             const uint8_t* p = src + (size_t)t * ow * 3;
@@ -90,15 +94,22 @@ region_v_kernel(const int32_t* __restrict__ desc, const int32_t* __restrict__ ta
             s1 += (int)p[1] * w;
             s2 += (int)p[2] * w;
         }
-        const int v0 = clip8(s0), v1 = clip8(s1), v2 = clip8(s2);
+        const int v0 = clip8(s0, precision), v1 = clip8(s1, precision), v2 = clip8(s2, precision);
+        if (f32_chw) {  // HF `pixel_values` layout [R, 3, canvas_h, canvas_w]
+            float* f = f32_chw + ((size_t)blockIdx.y * 3 * canvas_h + y) * canvas_w + x;
+            f[0] = lut_f32[v0];
+            f[(size_t)canvas_h * canvas_w] = lut_f32[256 + v1];
+            f[2 * (size_t)canvas_h * canvas_w] = lut_f32[512 + v2];
+        }
         if (resized) {
             uint8_t* u = resized + (((size_t)blockIdx.y * canvas_h + y) * canvas_w + x) * 3;
             u[0] = (uint8_t)v0;
             u[1] = (uint8_t)v1;
             u[2] = (uint8_t)v2;
         }
-        if (patches) {
-            const int py = y / patch, ky = y - py * patch, px = x / patch, kx = x - px * patch;
+        const int py = y / patch, ky = y - py * patch, px = x / patch, kx = x - px * patch;
+        // a canvas that is not a whole number of patches loses its last rows / columns (a valid stride-p convolution)
+        if (patches && px < gw && (canvas_w == 0 || py < canvas_h / patch)) {
             uint16_t* o = patches + (row0 + (size_t)py * gw + px) * ld + ky * patch + kx;
             o[0] = lut[v0];
             o[pp] = lut[256 + v1];
@@ -258,49 +269,55 @@ extern "C" size_t gvl_region_scratch_bytes(int R, const int32_t* h_desc) {
     return gvl::region_layout(R, h_desc, nullptr);
 }
 
-extern "C" int gvl_region_patches_pil_u8(const uint8_t* frame, int H, int W, int R, const int32_t* h_desc,
-                                         const int32_t* tabs, long long tabs_ints, const uint16_t* lut, int canvas_h,
-                                         int canvas_w, int patch, int ld, void* patches, uint8_t* resized_u8,
-                                         void* scratch, size_t scratch_bytes, void* stream) {
-    using namespace gvl;
-    GVL_CHECK_ARG(frame && h_desc && tabs && scratch && (patches || resized_u8) && (lut || !patches),
-                  "gvl_region_patches_pil_u8: null pointer");
-    GVL_CHECK_ARG(H > 0 && W > 0 && R > 0 && R <= 65535, "gvl_region_patches_pil_u8: bad shape H=%d W=%d R=%d", H, W, R);
+namespace gvl {
+
+// Integer two-pass resize of R crops of one frame with caller-supplied tap tables:
+//   out = clip8((2^(p-1) + sum px * k) >> p), horizontal pass (precision ph) into a uint8 intermediate, then vertical (pv).
+static int two_pass_launch(const char* who, const uint8_t* frame, int H, int W, int R, const int32_t* h_desc,
+                           const int32_t* tabs, long long tabs_ints, int ph, int pv, bool pil_tables, const uint16_t* lut,
+                           const float* lut_f32, int canvas_h, int canvas_w, int patch, int ld, void* patches,
+                           uint8_t* resized_u8, float* f32_chw, void* scratch, size_t scratch_bytes, void* stream) {
+    GVL_CHECK_ARG(frame && h_desc && tabs && scratch && (patches || resized_u8 || f32_chw) && (lut || !patches) &&
+                      (lut_f32 || !f32_chw), "%s: null pointer", who);
+    GVL_CHECK_ARG(H > 0 && W > 0 && R > 0 && R <= 65535, "%s: bad shape H=%d W=%d R=%d", who, H, W, R);
+    GVL_CHECK_ARG(ph >= 1 && ph <= 22 && pv >= 1 && pv <= 22, "%s: bad precision %d / %d", who, ph, pv);
     const bool ragged = canvas_h == 0 && canvas_w == 0;  // every region on its own canvas, patch rows back to back
-    GVL_CHECK_ARG(patch > 0 && (ragged || (canvas_h > 0 && canvas_w > 0 && canvas_h % patch == 0 && canvas_w % patch == 0)),
-                  "gvl_region_patches_pil_u8: canvas %dx%d is not a multiple of the patch size %d", canvas_h, canvas_w, patch);
-    GVL_CHECK_ARG(!ragged || (patches && !resized_u8), "gvl_region_patches_pil_u8: the ragged form writes patch rows only");
-    GVL_CHECK_ARG(ld >= 3 * patch * patch && ld % 8 == 0, "gvl_region_patches_pil_u8: bad ld %d", ld);
-    GVL_CHECK_ARG((uintptr_t)scratch % 256 == 0 && (uintptr_t)patches % 16 == 0, "gvl_region_patches_pil_u8: misaligned buffer");
+    GVL_CHECK_ARG(patch > 0 && (ragged || (canvas_h > 0 && canvas_w > 0 && (!patches || (canvas_h >= patch && canvas_w >= patch)))),
+                  "%s: canvas %dx%d smaller than one %d-pixel patch", who, canvas_h, canvas_w, patch);
+    GVL_CHECK_ARG(!ragged || (patches && !resized_u8 && !f32_chw), "%s: the ragged form writes patch rows only", who);
+    GVL_CHECK_ARG(!patches || (ld >= 3 * patch * patch && ld % 8 == 0), "%s: bad ld %d", who, ld);
+    GVL_CHECK_ARG((uintptr_t)scratch % 256 == 0 && (uintptr_t)patches % 16 == 0, "%s: misaligned buffer", who);
     long long total_rows = 0;
     for (int r = 0; r < R; ++r) {
         const int32_t* d = h_desc + (size_t)r * DESC_INTS;
         const int x1 = d[0], y1 = d[1], cw = d[2], ch = d[3], ow = d[4], oh = d[5], kh = d[6], kv = d[7];
         GVL_CHECK_ARG(cw > 0 && ch > 0 && x1 >= 0 && y1 >= 0 && x1 + cw <= W && y1 + ch <= H,
-                      "gvl_region_patches_pil_u8: region %d box (%d,%d)+(%dx%d) leaves the %dx%d frame", r, x1, y1, cw, ch, W, H);
+                      "%s: region %d box (%d,%d)+(%dx%d) leaves the %dx%d frame", who, r, x1, y1, cw, ch, W, H);
         GVL_CHECK_ARG(ow > 0 && oh > 0 && (ragged ? (ow % patch == 0 && oh % patch == 0) : (ow <= canvas_w && oh <= canvas_h)),
-                      "gvl_region_patches_pil_u8: region %d target %dx%d exceeds the %dx%d canvas (ragged form: must be a "
-                      "multiple of the patch size)", r, ow, oh, canvas_w, canvas_h);
+                      "%s: region %d target %dx%d exceeds the %dx%d canvas (ragged form: must be a multiple of the patch "
+                      "size)", who, r, ow, oh, canvas_w, canvas_h);
         total_rows += ragged ? (long long)(ow / patch) * (oh / patch) : (long long)(canvas_h / patch) * (canvas_w / patch);
-        int need_kh = 0, need_kv = 0;
-        gvl_pil_bicubic_taps(cw, ow, 0, nullptr, nullptr, nullptr, &need_kh);
-        gvl_pil_bicubic_taps(ch, oh, 0, nullptr, nullptr, nullptr, &need_kv);
-        GVL_CHECK_ARG(kh >= need_kh && kv >= need_kv, "gvl_region_patches_pil_u8: region %d tap strides %d/%d < %d/%d", r, kh,
-                      kv, need_kh, need_kv);
+        int need_kh = 1, need_kv = 1;
+        if (pil_tables) {
+            gvl_pil_bicubic_taps(cw, ow, 0, nullptr, nullptr, nullptr, &need_kh);
+            gvl_pil_bicubic_taps(ch, oh, 0, nullptr, nullptr, nullptr, &need_kv);
+        }
+        GVL_CHECK_ARG(kh >= need_kh && kv >= need_kv, "%s: region %d tap strides %d/%d < %d/%d", who, r, kh, kv, need_kh, need_kv);
         GVL_CHECK_ARG(d[8] >= 0 && d[9] >= 0 && (long long)d[8] + (long long)ow * (2 + kh) <= tabs_ints &&
                           (long long)d[9] + (long long)oh * (2 + kv) <= tabs_ints,
-                      "gvl_region_patches_pil_u8: region %d tables leave the %lld-int table buffer", r, tabs_ints);
+                      "%s: region %d tables leave the %lld-int table buffer", who, r, tabs_ints);
     }
-    GVL_CHECK_ARG(total_rows <= 2147483647LL, "gvl_region_patches_pil_u8: %lld patch rows", total_rows);
+    GVL_CHECK_ARG(total_rows <= 2147483647LL, "%s: %lld patch rows", who, total_rows);
     const int gh = ragged ? 0 : canvas_h / patch, gw = ragged ? 0 : canvas_w / patch;
     std::vector<int32_t> dev_desc;
     const size_t need = region_layout(R, h_desc, &dev_desc, gh * gw, patch);
-    GVL_CHECK_ARG(scratch_bytes >= need, "gvl_region_patches_pil_u8: scratch %zu < required %zu bytes", scratch_bytes, need);
+    GVL_CHECK_ARG(scratch_bytes >= need, "%s: scratch %zu < required %zu bytes", who, scratch_bytes, need);
     cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
     // pageable source: the copy is staged before the call returns, so dev_desc may go out of scope
     GVL_CUDA(cudaMemcpyAsync(scratch, dev_desc.data(), dev_desc.size() * sizeof(int32_t), cudaMemcpyHostToDevice, s));
     if (patches) GVL_CUDA(cudaMemsetAsync(patches, 0, (size_t)total_rows * ld * 2, s));
     if (resized_u8) GVL_CUDA(cudaMemsetAsync(resized_u8, 0, (size_t)R * canvas_h * canvas_w * 3, s));
+    if (f32_chw) GVL_CUDA(cudaMemsetAsync(f32_chw, 0, (size_t)R * canvas_h * canvas_w * 3 * sizeof(float), s));
     long long max_h = 0, max_v = 0, src_bytes = 0;
     for (int r = 0; r < R; ++r) {
         const int32_t* d = h_desc + (size_t)r * DESC_INTS;
@@ -312,12 +329,33 @@ extern "C" int gvl_region_patches_pil_u8(const uint8_t* frame, int H, int W, int
     const int32_t* desc = reinterpret_cast<const int32_t*>(scratch);
     uint8_t* sc = reinterpret_cast<uint8_t*>(scratch);
     const int bh = (int)std::min<long long>((max_h + 255) / 256, 4096), bv = (int)std::min<long long>((max_v + 255) / 256, 4096);
-    region_h_kernel<<<dim3(bh, R), 256, 0, s>>>(frame, W, desc, tabs, sc);
+    region_h_kernel<<<dim3(bh, R), 256, 0, s>>>(frame, W, desc, tabs, sc, ph);
     GVL_LAUNCH_CHECK("region_h_kernel");
     region_v_kernel<<<dim3(bv, R), 256, 0, s>>>(desc, tabs, sc, lut, canvas_h, canvas_w, patch, ld,
-                                               reinterpret_cast<uint16_t*>(patches), resized_u8, gh * gw);
+                                               reinterpret_cast<uint16_t*>(patches), resized_u8, gh * gw, pv, lut_f32, f32_chw);
     GVL_LAUNCH_CHECK("region_v_kernel");
     return 0;
+}
+
+}  // namespace gvl
+
+extern "C" int gvl_region_patches_pil_u8(const uint8_t* frame, int H, int W, int R, const int32_t* h_desc,
+                                         const int32_t* tabs, long long tabs_ints, const uint16_t* lut, int canvas_h,
+                                         int canvas_w, int patch, int ld, void* patches, uint8_t* resized_u8,
+                                         void* scratch, size_t scratch_bytes, void* stream) {
+    return gvl::two_pass_launch("gvl_region_patches_pil_u8", frame, H, W, R, h_desc, tabs, tabs_ints, gvl::PIL_PRECISION_BITS,
+                                gvl::PIL_PRECISION_BITS, true, lut, nullptr, canvas_h, canvas_w, patch, ld, patches, resized_u8,
+                                nullptr, scratch, scratch_bytes, stream);
+}
+
+extern "C" int gvl_resize_two_pass_u8(const uint8_t* frame, int H, int W, int R, const int32_t* h_desc, const int32_t* tabs,
+                                      long long tabs_ints, int precision_h, int precision_v, const uint16_t* lut_bf16,
+                                      const float* lut_f32, int canvas_h, int canvas_w, int patch, int ld, void* patches,
+                                      uint8_t* resized_u8, float* f32_chw, void* scratch, size_t scratch_bytes,
+                                      void* stream) {
+    return gvl::two_pass_launch("gvl_resize_two_pass_u8", frame, H, W, R, h_desc, tabs, tabs_ints, precision_h, precision_v,
+                                false, lut_bf16, lut_f32, canvas_h, canvas_w, patch, ld, patches, resized_u8, f32_chw,
+                                scratch, scratch_bytes, stream);
 }
 
 extern "C" int gvl_pos_interp_bicubic_bf16(const void* pos, int g, int D, int gh, int gw, void* out, void* stream) {

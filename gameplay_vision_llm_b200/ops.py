@@ -100,9 +100,59 @@ def preprocess(frames: torch.Tensor, out_h: int = 384, out_w: int = 384, resampl
     elif tuple(out.shape) != shape or out.dtype != dtype or not out.is_contiguous():
         raise RuntimeError(f"preprocess: `out` must be contiguous {dtype} {shape}")
     sub, div = fused_sub_div(image_mean, image_std)
+    if H < out_h or W < out_w or _aten_taps_table(W, out_w, resample)[1] > 24:
+        # an axis is up-scaled (crops and small images through `encode_image`), or the horizontal window is wider than
+        # the tuned K1 kernels hold in registers (24 taps: beyond a ~11x bilinear / ~5.5x bicubic down-scale): the
+        # general two-pass kernel runs ATen's own tables for any geometry (still bit-exact)
+        return _preprocess_any_geometry(frames, out_h, out_w, resample, sub, div, layout, patch, ld, out)
     _lib.check(_lib.lib().gvl_preprocess_u8(
         frames.data_ptr(), B, H, W, out_h, out_w, resample, sub.ctypes.data_as(_lib.c_float_p),
         div.ctypes.data_as(_lib.c_float_p), out.data_ptr(), layout, patch, ld, _stream()), "gvl_preprocess_u8")
+    return out
+
+
+@functools.lru_cache(maxsize=1024)
+def _aten_taps_table(in_size: int, out_size: int, resample: int):
+    """ATen's int16 tap table of one axis in the layout gvl_resize_two_pass_u8 reads: int32 [xmin | count | k[out, taps]]."""
+    xmin, xsize, w, prec = resize_taps(in_size, out_size, resample, max_taps=1024)
+    tab = np.concatenate([xmin.astype(np.int32), xsize.astype(np.int32), w.astype(np.int32).reshape(-1)])
+    tab.setflags(write=False)
+    return tab, int(w.shape[1]), int(prec)
+
+
+def _preprocess_any_geometry(frames, out_h, out_w, resample, sub, div, layout, patch, ld, out):
+    B, H, W, _ = frames.shape
+    dev = frames.device
+    th, kh, ph = _aten_taps_table(W, out_w, resample)
+    tv, kv, pv = _aten_taps_table(H, out_h, resample)
+    # the batch is one tall image: frame b is the crop (0, b*H, W, H)
+    desc = np.zeros((B, 10), np.int32)
+    for b in range(B):
+        desc[b] = (0, b * H, W, H, out_w, out_h, kh, kv, 0, th.size)
+    tabs = torch.from_numpy(np.concatenate([th, tv])).to(dev)
+    dptr = desc.ctypes.data_as(ctypes.POINTER(ctypes.c_int32))
+    scratch = torch.empty(int(_lib.lib().gvl_region_scratch_bytes(B, dptr)) + 256, dtype=torch.uint8, device=dev)
+    # HF's fused rescale + normalise `(float(u8) - sub[c]) / div[c]`, evaluated once per byte value in fp32
+    lut32 = (np.arange(256, dtype=np.float32)[None, :] - sub[:, None]) / div[:, None]
+    lut_f32 = torch.from_numpy(np.ascontiguousarray(lut32, dtype=np.float32)).to(dev)
+    lut_bf16 = lut_f32.to(torch.bfloat16)
+    patches = resized = f32 = None
+    if layout == LAYOUT_BF16_PATCH:
+        patches = out
+    elif layout == LAYOUT_F32_CHW:
+        f32 = out
+    elif layout == LAYOUT_BF16_CHW:
+        f32 = torch.empty(tuple(out.shape), dtype=torch.float32, device=dev)
+    else:
+        resized = torch.empty((B, out_h, out_w, 3), dtype=torch.uint8, device=dev)
+    _lib.check(_lib.lib().gvl_resize_two_pass_u8(
+        frames.data_ptr(), B * H, W, B, dptr, tabs.data_ptr(), tabs.numel(), ph, pv, lut_bf16.data_ptr(), lut_f32.data_ptr(),
+        out_h, out_w, patch, ld if layout == LAYOUT_BF16_PATCH else 8 * ((3 * patch * patch + 7) // 8), _ptr(patches),
+        _ptr(resized), _ptr(f32), scratch.data_ptr(), scratch.numel(), _stream()), "gvl_resize_two_pass_u8")
+    if layout == LAYOUT_BF16_CHW:
+        out.copy_(f32)
+    elif layout == LAYOUT_U8_CHW:
+        out.copy_(resized.permute(0, 3, 1, 2))
     return out
 
 

@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define GVL_ABI_VERSION 10
+#define GVL_ABI_VERSION 11
 
 #if defined(__GNUC__)
 #define GVL_API __attribute__((visibility("default")))
@@ -389,6 +389,19 @@ GVL_API int gvl_region_patches_pil_u8(const uint8_t* frame, int H, int W, int R,
                               const int32_t* tabs, long long tabs_ints, const uint16_t* lut, int canvas_h, int canvas_w,
                               int patch, int ld, void* patches, uint8_t* resized_u8, void* scratch, size_t scratch_bytes,
                               void* stream);
+
+/* The same two integer passes with ANY caller-supplied tap tables and shifts:
+ *   out = clip8((2^(p-1) + sum px * k) >> p), horizontal pass (precision_h) into a uint8 intermediate, then vertical.
+ * With ATen's tables (gvl_resize_taps, weights widened to int32) this is torchvision's uint8 antialias resize for ANY
+ * geometry — the general route of gvl_preprocess_u8's callers when an axis is up-scaled (crops and small images
+ * through `encode_image`, e.g. scripts/realtime_inference.py:281-295), which the tuned K1 kernels do not cover.
+ * Outputs (any subset): patches (bf16 via lut_bf16 [3,256]), resized_u8 [R, canvas_h, canvas_w, 3], f32_chw float
+ * [R, 3, canvas_h, canvas_w] via lut_f32 [3,256] (HF `pixel_values`); zero outside a region's rectangle.  Windows that
+ * would leave the crop are clipped in the kernel (the tables are device memory the host cannot validate). */
+GVL_API int gvl_resize_two_pass_u8(const uint8_t* frame, int H, int W, int R, const int32_t* h_desc, const int32_t* tabs,
+                           long long tabs_ints, int precision_h, int precision_v, const uint16_t* lut_bf16,
+                           const float* lut_f32, int canvas_h, int canvas_w, int patch, int ld, void* patches,
+                           uint8_t* resized_u8, float* f32_chw, void* scratch, size_t scratch_bytes, void* stream);
 
 /* Position table for a gh x gw patch grid: pos bf16 [g*g, D] -> out bf16 [gh*gw, D], bicubic, align_corners = false,
  * A = -0.75, border-clamped taps, fp32 arithmetic.  Replaces `SiglipVisionEmbeddings.interpolate_pos_encoding`

@@ -223,3 +223,20 @@ def test_ops_bind_to_the_tensors_device():
     with pytest.raises(RuntimeError, match="different devices|weights on"):
         pipe1.embed(torch.from_numpy(frames).to("cuda:0"))
 
+
+
+def test_encode_image_accepts_small_images_like_the_reference():
+    """`encode_image(region_img)` on a bounding-box crop (scripts/realtime_inference.py:281-295): the HF processor
+    up-scales whatever it is given; so does the drop-in (general two-pass kernel), bit-identical pixel_values."""
+    from PIL import Image
+    spec = SiglipVisionSpec(hidden=216, intermediate=400, layers=2, heads=3, image=140, patch=14)
+    sd = synth_siglip_state_dict(spec, seed=0)
+    enc = SigLIPSemanticEncoder(NaFlexConfig(device=DEV, base_resolution=140, state_dict=sd, num_attention_heads=3))
+    crop = synth.scene_frames_np(4, 1, 270, 480)[0][40:97, 100:231]  # 57 x 131: up-scaled vertically and horizontally
+    emb = enc.encode_image(Image.fromarray(crop))
+    pv = preprocess_ref.pixel_values(crop[None], 140, 140, 2)
+    got_pv = enc.encoder._processor(images=[Image.fromarray(crop)], return_tensors="pt")["pixel_values"]
+    assert np.array_equal(got_pv.cpu().numpy().view(np.uint32), pv.view(np.uint32))
+    want = siglip_ref.vision_forward(sd, torch.from_numpy(pv), spec.heads, spec.patch, spec.eps)
+    cos = torch.nn.functional.cosine_similarity(emb.float().cpu(), want[0], dim=0).item()
+    assert cos > 0.999, cos

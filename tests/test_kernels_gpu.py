@@ -245,11 +245,31 @@ def test_preprocess_layouts_bit_exact(H, W, size, rs):
     assert torch.equal(got_patch.view(torch.int16), want_patch.view(torch.int16)), "bf16 patches differ"
 
 
-def test_preprocess_rejects_out_of_range_geometry():
-    """A 16x downscale needs 35 horizontal taps: beyond both kernels' windows -> a clean error, not garbage."""
-    frames = synth.noise_frames(1, 400, 1000, seed=1).to(DEV)
-    with pytest.raises(RuntimeError, match="taps"):
-        ops.preprocess(frames, 37, 61, 2, layout=ops.LAYOUT_U8_CHW)
+ANY_GEOMETRY = [(60, 90, 140, 140, 2), (60, 90, 140, 140, 3),      # both axes up-scaled (a small crop through encode_image)
+                (200, 100, 140, 140, 2), (100, 500, 384, 384, 3),  # one axis up, one down
+                (30, 31, 56, 56, 2), (1, 1, 28, 28, 3),            # tiny sources
+                (400, 1000, 37, 61, 2),                            # 16x down: 35 horizontal taps, beyond the tuned kernels
+                (2160, 3840, 126, 224, 3)]                         # 17x bicubic down: 71 taps
+
+
+@pytest.mark.parametrize("H,W,oh,ow,rs", ANY_GEOMETRY)
+def test_preprocess_any_geometry_bit_exact(H, W, oh, ow, rs):
+    """Up-scaling and very wide windows go through the general two-pass kernel (gvl_resize_two_pass_u8 with ATen's own
+    tables): every layout must still equal the oracle bit for bit."""
+    frames = synth.noise_frames(2, H, W, seed=H + W + rs)
+    f = frames.to(DEV)
+    want_u8 = preprocess_ref.resize_u8(frames.numpy(), oh, ow, rs)
+    assert np.array_equal(ops.preprocess(f, oh, ow, rs, layout=ops.LAYOUT_U8_CHW).cpu().numpy(), want_u8)
+    mean, std = (0.485, 0.456, 0.406), (0.229, 0.224, 0.225)
+    pv = preprocess_ref.pixel_values(frames.numpy(), oh, ow, rs, mean, std)
+    got = ops.preprocess(f, oh, ow, rs, mean, std, layout=ops.LAYOUT_F32_CHW).cpu().numpy()
+    assert np.array_equal(got.view(np.uint32), pv.view(np.uint32))
+    got16 = ops.preprocess(f, oh, ow, rs, mean, std, layout=ops.LAYOUT_BF16_CHW).cpu()
+    assert torch.equal(got16.view(torch.int16), torch.from_numpy(pv).to(torch.bfloat16).view(torch.int16))
+    if oh >= 14 and ow >= 14:
+        want_p = torch.from_numpy(preprocess_ref.patchify(pv, 14, 592)).to(torch.bfloat16)
+        got_p = ops.preprocess(f, oh, ow, rs, mean, std, layout=ops.LAYOUT_BF16_PATCH, patch=14, ld=592).cpu()
+        assert torch.equal(got_p.view(torch.int16), want_p.view(torch.int16))
 
 
 def test_preprocess_legacy_kernel_matches():

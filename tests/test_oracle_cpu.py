@@ -33,6 +33,18 @@ def test_preprocess_oracle_matches_torchvision_live():
         assert np.array_equal(preprocess_ref.resize_u8(x.numpy(), 97, 64, rs), want)
 
 
+@pytest.mark.parametrize("H,W,oh,ow", [(60, 90, 140, 140), (200, 100, 140, 140), (100, 500, 384, 384), (30, 31, 56, 56),
+                                       (400, 1000, 37, 61)])
+def test_preprocess_oracle_matches_torchvision_live_any_geometry(H, W, oh, ow):
+    """Up-scaling (ATen keeps the filter support at the interpolation radius) and very wide down-scaling windows."""
+    tvF = pytest.importorskip("torchvision.transforms.v2.functional")
+    from torchvision.transforms import InterpolationMode as IM
+    x = synth.noise_frames(2, H, W, seed=H + W)
+    for rs, mode in ((2, IM.BILINEAR), (3, IM.BICUBIC)):
+        want = tvF.resize(x.permute(0, 3, 1, 2), [oh, ow], interpolation=mode, antialias=True).numpy()
+        assert np.array_equal(preprocess_ref.resize_u8(x.numpy(), oh, ow, rs), want)
+
+
 def test_pixel_values_and_patchify():
     frames = synth.noise_frames(2, 60, 80, seed=1).numpy()
     pv = preprocess_ref.pixel_values(frames, 28, 28, 2)

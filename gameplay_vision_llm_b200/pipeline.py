@@ -311,6 +311,74 @@ def run_siglip_encoder(frames, device: str = "cuda", sam_results: list | None = 
     return [d for s in slots for d in s]
 
 
+def extract_siglip_embeddings(frames, device: str = "cuda", sam_results: list | None = None, encoder=None) -> list[dict]:
+    """Drop-in for `extract_siglip_embeddings` of the online pipeline (scripts/realtime_inference.py:244-335): frames =
+    [(timestamp, PIL image)], optional `sam_results` = [{"timestamp", "frame", "detections": [{"mask" | "bbox", "label"}]}]
+    -> [{"timestamp", "label", "embedding" (CPU tensor)}] in the reference's order.
+
+    The reference sends every detection through `encode_image` as its own image — the frame with everything outside
+    the mask zeroed (:281-286), or `frame.crop(bbox)` (:287-290, PIL semantics: rounded box, black beyond the frame),
+    resized to the model's square input by the processor like any frame.  Here the images are built the same way on the
+    host and then embedded together: equal shapes share one preprocess launch (the general two-pass kernel up-scales
+    small crops) and one tower pass per `config.batch_size` images instead of one forward per detection.  An image that
+    fails is logged and skipped like the reference (:303, :324)."""
+    import logging
+
+    from .siglip_semantic_encoder import NaFlexConfig, SigLIPSemanticEncoder, _to_uint8_hwc
+    log = logging.getLogger(__name__)
+    if encoder is None:
+        encoder = SigLIPSemanticEncoder(NaFlexConfig(device=device))
+    items: list[tuple[float, str, np.ndarray]] = []
+    if sam_results and any(d["detections"] for d in sam_results):
+        for sam_frame in sam_results:
+            timestamp, frame = sam_frame["timestamp"], sam_frame["frame"]
+            if not sam_frame["detections"]:
+                items.append((timestamp, "full_frame", _to_uint8_hwc(frame)))
+                continue
+            frame_np = None
+            for det in sam_frame["detections"]:
+                try:
+                    if det.get("mask") and hasattr(det["mask"], "mask"):
+                        frame_np = np.array(frame) if frame_np is None else frame_np
+                        masked = frame_np.copy()
+                        masked[~det["mask"].mask] = 0
+                        img = masked
+                    elif det.get("bbox"):
+                        x1, y1, x2, y2 = det["bbox"]
+                        img = _to_uint8_hwc(frame.crop((x1, y1, x2, y2)))
+                    else:
+                        img = _to_uint8_hwc(frame)
+                    items.append((timestamp, det.get("label", "region"), img))
+                except Exception as e:
+                    log.debug("Region encoding failed: %s", e)
+    else:
+        for timestamp, frame in frames:
+            try:
+                items.append((timestamp, "full_frame", _to_uint8_hwc(frame)))
+            except Exception as e:
+                log.warning("SigLIP failed at %.1fs: %s", timestamp, e)
+    # embed: images of one shape go through the batched entry; the output keeps the reference's order
+    out: list[dict | None] = [None] * len(items)
+    by_shape: dict[tuple, list[int]] = {}
+    for i, (_, _, img) in enumerate(items):
+        by_shape.setdefault(img.shape, []).append(i)
+    for idx in by_shape.values():
+        try:
+            emb = encoder.encode_frames(np.stack([items[i][2] for i in idx])).cpu()
+            rows = {i: emb[j] for j, i in enumerate(idx)}
+        except Exception as e:  # one bad image must not lose its whole group
+            log.warning("SigLIP batch of %d images failed (%s); retrying one by one", len(idx), e)
+            rows = {}
+            for i in idx:
+                try:
+                    rows[i] = encoder.encode_frames(items[i][2][None])[0].cpu()
+                except Exception as e2:
+                    log.warning("SigLIP failed at %.1fs: %s", items[i][0], e2)
+        for i, r in rows.items():
+            out[i] = {"timestamp": items[i][0], "label": items[i][1], "embedding": r}
+    return [d for d in out if d is not None]
+
+
 def pinned_batches(frames: np.ndarray | torch.Tensor, batch: int) -> Iterator[torch.Tensor]:
     """Convenience: slice a host frame array into pinned batches."""
     t = torch.as_tensor(frames)

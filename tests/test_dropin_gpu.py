@@ -240,3 +240,54 @@ def test_encode_image_accepts_small_images_like_the_reference():
     want = siglip_ref.vision_forward(sd, torch.from_numpy(pv), spec.heads, spec.patch, spec.eps)
     cos = torch.nn.functional.cosine_similarity(emb.float().cpu(), want[0], dim=0).item()
     assert cos > 0.999, cos
+
+
+def test_extract_siglip_embeddings_equals_the_realtime_loop():
+    """`pipeline.extract_siglip_embeddings` (scripts/realtime_inference.py:244-335) against the reference's loop written
+    out literally on the same encoder: masked frames, PIL crops (including one that leaves the frame and a tiny one that
+    is up-scaled), frames without detections, and the full-frame fallback."""
+    from types import SimpleNamespace
+
+    from PIL import Image
+
+    from gameplay_vision_llm_b200.pipeline import extract_siglip_embeddings
+    spec = SiglipVisionSpec(hidden=216, intermediate=400, layers=2, heads=3, image=140, patch=14)
+    sd = synth_siglip_state_dict(spec, seed=0)
+    enc = SigLIPSemanticEncoder(NaFlexConfig(device=DEV, base_resolution=140, state_dict=sd, num_attention_heads=3, batch_size=4))
+    raw = synth.scene_frames_np(9, 4, 270, 480)
+    pil = [Image.fromarray(f) for f in raw]
+    mask = np.zeros((270, 480), np.bool_)
+    mask[60:200, 100:300] = True
+    sam = [
+        {"timestamp": 0.0, "frame": pil[0], "detections": [{"mask": SimpleNamespace(mask=mask), "label": "player"},
+                                                           {"bbox": (40, 30, 300, 120), "label": "hud"},
+                                                           {"bbox": (400.4, 200.6, 520, 300)},      # leaves the frame
+                                                           {"label": "whole"}]},
+        {"timestamp": 0.5, "frame": pil[1], "detections": []},
+        {"timestamp": 1.0, "frame": pil[2], "detections": [{"bbox": (10, 10, 50, 34), "label": "icon"},  # 40 x 24: up-scaled
+                                                           {"bbox": (45, 35, 305, 125), "label": "hud"}]},
+    ]
+    got = extract_siglip_embeddings([(i * 0.5, p) for i, p in enumerate(pil)], DEV, sam_results=sam, encoder=enc)
+    want = []
+    for sf in sam:  # the reference's loop (:271-311), literally
+        frame, frame_np = sf["frame"], np.array(sf["frame"])
+        if sf["detections"]:
+            for det in sf["detections"]:
+                if det.get("mask") and hasattr(det["mask"], "mask"):
+                    masked = frame_np.copy()
+                    masked[~det["mask"].mask] = 0
+                    region_img = Image.fromarray(masked)
+                elif det.get("bbox"):
+                    x1, y1, x2, y2 = det["bbox"]
+                    region_img = frame.crop((x1, y1, x2, y2))
+                else:
+                    region_img = frame
+                want.append({"timestamp": sf["timestamp"], "label": det.get("label", "region"),
+                             "embedding": enc.encode_image(region_img).cpu()})
+        else:
+            want.append({"timestamp": sf["timestamp"], "label": "full_frame", "embedding": enc.encode_image(frame).cpu()})
+    assert [(g["timestamp"], g["label"]) for g in got] == [(w["timestamp"], w["label"]) for w in want] and len(got) == 7
+    assert all(torch.equal(g["embedding"], w["embedding"]) for g, w in zip(got, want))
+    plain = extract_siglip_embeddings([(i * 0.5, p) for i, p in enumerate(pil)], DEV, encoder=enc)
+    assert [d["label"] for d in plain] == ["full_frame"] * 4
+    assert all(torch.equal(d["embedding"], enc.encode_image(p).cpu()) for d, p in zip(plain, pil))

@@ -650,7 +650,6 @@ def main_regions(args) -> None:
     from gameplay_vision_llm_b200.siglip_semantic_encoder import BoxMask, NaFlexConfig, SigLIPSemanticEncoder
     from gameplay_vision_llm_b200.weights import (SiglipVisionSpec, synth_ren_projection_state_dict,
                                                     synth_siglip_state_dict)
-    from oracle import hf_baseline
 
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -670,7 +669,7 @@ def main_regions(args) -> None:
     enc.projection.load_state_dict(synth_ren_projection_state_dict(spec.hidden, seed=3))
     frames_host = [synth.scene_frames_np((rank * 4 + i) * 30, 1, FRAME_H, FRAME_W)[0] for i in range(4)]
     frames_dev = [torch.from_numpy(f).to(dev) for f in frames_host]
-    boxes = hf_baseline.region_boxes(R, FRAME_H, FRAME_W)
+    boxes = synth.region_boxes(R, FRAME_H, FRAME_W)
     masks = [(f"det{i}", BoxMask((FRAME_H, FRAME_W), y1, y2, x1, x2)) for i, (x1, y1, x2, y2) in enumerate(boxes)]
     dets = [{"timestamp": 0.0, "bbox": list(b), "entity_type": "ui", "entity_id": f"det{i}"} for i, b in enumerate(boxes)]
 
@@ -743,6 +742,7 @@ def main_regions(args) -> None:
     if rank == 0:
         cpu = None
         if not args.no_cpu_baseline:
+            from oracle import hf_baseline  # the cpu_baseline leg: the one place the ours-arm may run oracle/ code
             res = hf_baseline.run_regions(n_regions=4, warmup_regions=1, frame_hw=(FRAME_H, FRAME_W))
             cpu = {"value": res["regions_per_s"], "unit": "regions/s", "cores": res["cores"], "kind": res["kind"],
                    "sample": res["sample"]}

@@ -101,3 +101,17 @@ def timestamps(n: int, fps: float = 1.0, start: int = 0) -> np.ndarray:
     """float64 timestamps ``t_i = i / fps`` (reference: timestamp = frame_idx / video_fps,
     scripts/extract_features.py:252-258)."""
     return (np.arange(start, start + n, dtype=np.float64)) / float(fps)
+
+
+def region_boxes(n: int, H: int = 1080, W: int = 1920, seed: int = 4000) -> list[tuple[int, int, int, int]]:
+    """Seeded detection boxes (x1, y1, x2, y2) of a frame: UI-like wide strips, tall panels and near-square sprites from
+    a small set of shapes, so several detections share a target size — the synthetic stand-in for SAM detections
+    (scripts/extract_features.py:552-583 encodes one per call)."""
+    rng = np.random.default_rng(seed)
+    shapes = [(1000, 440), (480, 900), (520, 520), (800, 200), (300, 300), (1200, 600), (240, 640), (640, 360)]
+    boxes = []
+    for i in range(n):
+        w, h = shapes[i % len(shapes)]
+        x1, y1 = int(rng.integers(0, W - w)), int(rng.integers(0, H - h))
+        boxes.append((x1, y1, x1 + w, y1 + h))
+    return boxes

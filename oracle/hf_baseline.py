@@ -75,20 +75,6 @@ def run(n_frames: int = 8, batch: int = 8, warmup_batches: int = 1, frame_hw=(10
                       f"torch {torch.__version__}, {cores} threads"}
 
 
-def region_boxes(n: int, H: int = 1080, W: int = 1920, seed: int = 4000) -> list[tuple[int, int, int, int]]:
-    """Seeded detection boxes (x1, y1, x2, y2) of a frame: UI-like wide strips, tall panels and near-square sprites from
-    a small set of shapes, so several detections share a target size (the grouping the GPU path exploits) — still one
-    `encode_masked_regions` call per detection on the reference side (scripts/extract_features.py:552-583)."""
-    rng = np.random.default_rng(seed)
-    shapes = [(1000, 440), (480, 900), (520, 520), (800, 200), (300, 300), (1200, 600), (240, 640), (640, 360)]
-    boxes = []
-    for i in range(n):
-        w, h = shapes[i % len(shapes)]
-        x1, y1 = int(rng.integers(0, W - w)), int(rng.integers(0, H - h))
-        boxes.append((x1, y1, x1 + w, y1 + h))
-    return boxes
-
-
 def run_regions(n_regions: int = 4, warmup_regions: int = 1, frame_hw=(1080, 1920)) -> dict:
     """The reference's masked-region route on the host cores, one detection per call: bbox mask -> expanded box -> PIL
     bicubic resize -> ImageNet normalisation -> HF SiglipVisionModel (fp32, `interpolate_pos_encoding=True`) ->
@@ -96,6 +82,7 @@ def run_regions(n_regions: int = 4, warmup_regions: int = 1, frame_hw=(1080, 192
     from PIL import Image
 
     from gameplay_vision_llm_b200 import synth
+    from gameplay_vision_llm_b200.synth import region_boxes
     from gameplay_vision_llm_b200.weights import (SiglipVisionSpec, synth_ren_projection_state_dict,
                                                     synth_siglip_state_dict)
     from oracle import region_ref

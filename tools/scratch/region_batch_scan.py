@@ -10,7 +10,7 @@ spec = SiglipVisionSpec.so400m()
 enc = SigLIPSemanticEncoder(NaFlexConfig(device="cuda:0", state_dict=synth_siglip_state_dict(spec, seed=0), batch_size=16))
 enc.projection.load_state_dict(synth_ren_projection_state_dict(spec.hidden, seed=3))
 fd = torch.from_numpy(synth.scene_frames_np(0, 1)[0]).cuda()
-base = [(f"d{i}", BoxMask((1080, 1920), y1, y2, x1, x2)) for i, (x1, y1, x2, y2) in enumerate(hf_baseline.region_boxes(16))]
+base = [(f"d{i}", BoxMask((1080, 1920), y1, y2, x1, x2)) for i, (x1, y1, x2, y2) in enumerate(synth.region_boxes(16))]
 for rep in (1, 2, 4, 8):
     masks = base * rep
     for _ in range(3): enc.encode_regions_individually(fd, masks, max_tokens=65536)

@@ -12,7 +12,7 @@ enc.projection.load_state_dict(synth_ren_projection_state_dict(spec.hidden, seed
 frame = synth.scene_frames_np(0, 1)[0]
 fd = torch.from_numpy(frame).cuda()
 masks = []
-for i, (x1, y1, x2, y2) in enumerate(hf_baseline.region_boxes(16)):
+for i, (x1, y1, x2, y2) in enumerate(synth.region_boxes(16)):
     m = np.zeros((1080, 1920), np.bool_); m[y1:y2, x1:x2] = True; masks.append((f"d{i}", m))
 for _ in range(3): enc.encode_regions_individually(fd, masks)
 def T(fn, n=20):

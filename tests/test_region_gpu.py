@@ -281,3 +281,37 @@ def test_varlen_attention_equals_one_launch_per_item(hd, H, items):
         assert torch.equal(got[r0:r0 + T], want), (T, r0)
         r0 += T
     assert torch.isfinite(got.float()).all()
+
+
+def test_region_kernel_random_geometries_and_ragged_form():
+    """40 random crops of one frame at random target sizes (up- and down-scaling, 1-pixel crops, whole-frame crops):
+    bytes equal to the Pillow oracle, and the ragged form (every region on its own canvas, rows back to back) holds
+    exactly the rows the padded-canvas form holds inside each region's rectangle."""
+    rng = np.random.default_rng(11)
+    H, W = 300, 500
+    frame = synth.noise_frames(1, H, W, seed=3)[0]
+    boxes, sizes = [], []
+    for _ in range(40):
+        x1, y1 = int(rng.integers(0, W - 1)), int(rng.integers(0, H - 1))
+        x2, y2 = int(rng.integers(x1 + 1, W + 1)), int(rng.integers(y1 + 1, H + 1))
+        boxes.append((x1, y1, x2, y2))
+        sizes.append((14 * int(rng.integers(1, 15)), 14 * int(rng.integers(1, 15))))
+    boxes[0], boxes[1] = (0, 0, W, H), (7, 9, 8, 10)
+    canvas = (max(s[0] for s in sizes), max(s[1] for s in sizes))
+    lut = ops.region_lut(region_ref.IMAGENET_MEAN, region_ref.IMAGENET_STD).to(DEV)
+    fd = frame.to(DEV)
+    padded, u8 = ops.region_patches(fd, boxes, sizes, canvas, lut, patch=14, ld=592, want_u8=True)
+    ragged, _ = ops.region_patches(fd, boxes, sizes, None, lut, patch=14, ld=592)
+    torch.cuda.synchronize()
+    f = frame.numpy()
+    gwc, tok = canvas[1] // 14, (canvas[0] // 14) * (canvas[1] // 14)
+    r0 = 0
+    for r, ((x1, y1, x2, y2), (oh, ow)) in enumerate(zip(boxes, sizes)):
+        want = region_ref.pil_resize_bicubic_u8(f[y1:y2, x1:x2], ow, oh)
+        assert np.array_equal(u8[r, :oh, :ow].cpu().numpy(), want), (r, boxes[r], sizes[r])
+        gh, gw = oh // 14, ow // 14
+        mine = ragged[r0:r0 + gh * gw].view(gh, gw, 592)
+        theirs = padded[r * tok:(r + 1) * tok].view(canvas[0] // 14, gwc, 592)[:gh, :gw]
+        assert torch.equal(mine, theirs), r
+        r0 += gh * gw
+    assert r0 == ragged.shape[0]

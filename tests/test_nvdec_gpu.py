@@ -208,3 +208,39 @@ def test_raw_annexb_stream(clip, tmp_path):
     want = _rgb_from_planes(y, cb, cr)
     assert all(np.abs(frames[k] - want[k]).max() <= 1 for k in range(23))  # every second frame = every coded picture
     feed.close()
+
+
+def test_real_libnvcuvid_parser_agrees_with_the_declared_struct_layouts(clip, tmp_path):
+    """The REAL driver library's bitstream parser is host code and runs even where the decode engine is unreachable: a
+    small C++ program built on csrc/cuvid_abi.h creates it, feeds the known stream and prints what the callbacks receive.
+    Correct numbers here pin the layouts of CUVIDPARSERPARAMS, CUVIDSOURCEDATAPACKET, CUVIDEOFORMAT and
+    CUVIDPARSERDISPINFO against the driver (the decoder-side structs stay unverified without the engine)."""
+    import shutil
+    import subprocess
+    if shutil.which("g++") is None:
+        pytest.skip("no g++")
+    if os.environ.get("GVL_NVCUVID_LIB"):
+        pytest.skip("running against the software double: nothing real to check")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = str(tmp_path / "parser_check")
+    cuda = os.environ.get("CUDA_HOME", "/usr/local/cuda")
+    b = subprocess.run(["g++", "-O2", "-std=c++17", f"-I{cuda}/include", f"-I{root}/gameplay_vision_llm_b200/csrc",
+                        f"{root}/tests/nvcuvid_parser_check/parser_check.cpp", "-o", exe, "-ldl"], capture_output=True, text=True)
+    assert b.returncode == 0, b.stderr
+    _, y, cb, cr = clip
+    path = str(tmp_path / "clip.h264")
+    assert sv.write_h264_annexb(path, y, cb, cr, fps=(30, 1), skip_every=2) == 46
+    run = subprocess.run([exe, path], capture_output=True, text=True, timeout=120)
+    print(run.stdout)
+    if run.stdout.startswith("nolib"):
+        pytest.skip("libnvcuvid.so.1 not present on this box")
+    assert run.returncode == 0, (run.returncode, run.stdout, run.stderr)
+    out = run.stdout
+    assert "create rc=0" in out and "eos rc=0" in out
+    assert "codec=4 coded=176x112 display=0,0,176,100" in out
+    assert "progressive=1 chroma=1 bitdepth=8" in out and "matrix=6 full_range=0" in out
+    import re
+    num, den = map(int, re.search(r"fps=(\d+)/(\d+)", out).groups())
+    assert num / den == 30.0
+    assert "decodes=46 displays=46" in out
+    assert "display #1 picture_index=0" in out

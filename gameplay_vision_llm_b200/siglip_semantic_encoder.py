@@ -229,6 +229,18 @@ class AspectPreservingResizer:
         target_w = (target_w // patch_size) * patch_size
         return max(patch_size, target_h), max(patch_size, target_w)
 
+    def resize_with_aspect_ratio(self, image):
+        """(resized PIL image, aspect ratio) like the reference (:137-163); the resize runs in the region kernel and
+        returns the bytes `image.resize((w, h), Image.Resampling.BICUBIC)` returns."""
+        from PIL import Image
+        arr = _to_uint8_hwc(image)
+        h, w = arr.shape[:2]
+        th, tw = self.target_size(h, w)
+        dev = ops.resolve_device(self.config.device)
+        _, u8 = ops.region_patches(torch.from_numpy(np.require(arr, requirements="CW")).to(dev), [(0, 0, w, h)], [(th, tw)],
+                                   ((th + 13) // 14 * 14, (tw + 13) // 14 * 14), None, want_patches=False, want_u8=True)
+        return Image.fromarray(u8[0, :th, :tw].cpu().numpy()), w / h
+
     def target_size(self, region_h: int, region_w: int) -> tuple[int, int]:
         """(target_h, target_w) of `resize_with_aspect_ratio` (:137-163), square fallback included."""
         if self.config.preserve_aspect_ratio:
@@ -318,16 +330,11 @@ class RegionExtractor:
         """PIL region -> (fp32 CHW tensor on the CPU, aspect ratio) like the reference (:346-367): the resize runs in
         the region kernel (bit-identical to `PIL.Image.resize(BICUBIC)`), the three fp32 operations are the
         reference's."""
-        arr = _to_uint8_hwc(region)
-        h, w = arr.shape[:2]
-        th, tw = self.resizer.target_size(h, w)
-        dev = ops.resolve_device(self.config.device)
-        _, u8 = ops.region_patches(torch.from_numpy(np.ascontiguousarray(arr)).to(dev), [(0, 0, w, h)], [(th, tw)],
-                                   ((th + 13) // 14 * 14, (tw + 13) // 14 * 14), None, want_patches=False, want_u8=True)
-        tensor = u8[0, :th, :tw].cpu().float().permute(2, 0, 1) / 255.0
+        resized, aspect_ratio = self.resizer.resize_with_aspect_ratio(region)
+        tensor = torch.from_numpy(np.array(resized)).float().permute(2, 0, 1) / 255.0
         mean = torch.tensor(IMAGENET_MEAN).view(3, 1, 1)
         std = torch.tensor(IMAGENET_STD).view(3, 1, 1)
-        return (tensor - mean) / std, w / h
+        return (tensor - mean) / std, aspect_ratio
 
 
 class RenProjection(torch.nn.Sequential):

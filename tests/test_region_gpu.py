@@ -315,3 +315,25 @@ def test_region_kernel_random_geometries_and_ragged_form():
         assert torch.equal(mine, theirs), r
         r0 += gh * gw
     assert r0 == ragged.shape[0]
+
+
+def test_resizer_and_extractor_helpers_match_the_reference_classes():
+    """`AspectPreservingResizer.resize_with_aspect_ratio`, `RegionExtractor.extract_masked_region` /
+    `prepare_region_tensor` (reference :137-163, :301-367): same return types and values as the oracle's restatement
+    (PIL bytes bit-exact, fp32 tensor bit-exact)."""
+    from PIL import Image
+    enc = _encoder(MID_SPEC, "mean", 16, MID_CFG)
+    frame = synth.scene_frames_np(7, 1, 270, 480)[0]
+    mask = rect_mask(frame.shape, MID_RECTS[0])
+    region, bbox = enc.region_extractor.extract_masked_region(frame, mask)
+    assert bbox == region_ref.extract_bbox(frame.shape, mask) and isinstance(region, Image.Image)
+    resized, ar = enc.region_extractor.resizer.resize_with_aspect_ratio(region)
+    x1, y1, x2, y2 = bbox
+    th, tw = region_ref.compute_optimal_size(y2 - y1, x2 - x1, MID_CFG["base_resolution"], MID_CFG["min_resolution"],
+                                             MID_CFG["max_resolution"])
+    assert resized.size == (tw, th) and ar == (x2 - x1) / (y2 - y1)
+    assert np.array_equal(np.asarray(resized), np.asarray(region.resize((tw, th), Image.Resampling.BICUBIC)))
+    tensor, ar2 = enc.region_extractor.prepare_region_tensor(region)
+    want, _ = region_ref.prepare_region_tensor(frame[y1:y2, x1:x2], True, MID_CFG["base_resolution"],
+                                               MID_CFG["min_resolution"], MID_CFG["max_resolution"])
+    assert ar2 == ar and torch.equal(tensor, want)

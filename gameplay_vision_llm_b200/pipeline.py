@@ -287,27 +287,28 @@ def run_siglip_encoder(frames, device: str = "cuda", sam_results: list | None = 
                     "description": det.get("description", f"Detected {entity_type}"), "bbox": det["bbox"]})
     else:
         full_frame = list(range(len(frames)))
-    # frames encoded whole: group equal shapes into batches (one preprocess + one tower pass per batch)
-    bs = max(1, int(encoder.config.batch_size))
+    # frames encoded whole: runs of equal size go through the encoder's batched, pinned, threaded feed
+    from .siglip_semantic_encoder import _image_shape
     i = 0
     while i < len(full_frame):
-        first = _to_uint8_hwc(frames[full_frame[i]][1])
-        batch_idx, arrays = [full_frame[i]], [first]
-        while i + len(batch_idx) < len(full_frame) and len(batch_idx) < bs:
-            nxt = _to_uint8_hwc(frames[full_frame[i + len(batch_idx)]][1])
-            if nxt.shape != first.shape:
-                break
-            batch_idx.append(full_frame[i + len(batch_idx)])
-            arrays.append(nxt)
-        i += len(batch_idx)
+        shape = _image_shape(frames[full_frame[i]][1])
+        run = [full_frame[i]]
+        while i + len(run) < len(full_frame) and _image_shape(frames[full_frame[i + len(run)]][1]) == shape:
+            run.append(full_frame[i + len(run)])
+        i += len(run)
         try:
-            emb = encoder.encode_frames(np.stack(arrays)).cpu()
-        except Exception as e:
-            log.warning("SigLIP failed at %.1fs: %s", frames[batch_idx[0]][0], e)
-            continue
-        for j, idx in enumerate(batch_idx):
-            slots[idx].append({"timestamp": frames[idx][0], "embedding": emb[j], "embedding_shape": list(emb[j].shape),
-                               "entity_type": "full_frame", "description": note})
+            rows = dict(zip(run, encoder.encode_images([frames[j][1] for j in run]).cpu()))
+        except Exception as e:  # one bad frame must not lose its run: the reference skips only the failing frame (:606)
+            log.warning("SigLIP batch starting at %.1fs failed (%s); retrying frame by frame", frames[run[0]][0], e)
+            rows = {}
+            for j in run:
+                try:
+                    rows[j] = encoder.encode_images([frames[j][1]])[0].cpu()
+                except Exception as e2:
+                    log.warning("SigLIP failed at %.1fs: %s", frames[j][0], e2)
+        for j, emb in rows.items():
+            slots[j].append({"timestamp": frames[j][0], "embedding": emb, "embedding_shape": list(emb.shape),
+                             "entity_type": "full_frame", "description": note})
     return [d for s in slots for d in s]
 
 
@@ -364,14 +365,14 @@ def extract_siglip_embeddings(frames, device: str = "cuda", sam_results: list | 
         by_shape.setdefault(img.shape, []).append(i)
     for idx in by_shape.values():
         try:
-            emb = encoder.encode_frames(np.stack([items[i][2] for i in idx])).cpu()
+            emb = encoder.encode_images([items[i][2] for i in idx]).cpu()
             rows = {i: emb[j] for j, i in enumerate(idx)}
         except Exception as e:  # one bad image must not lose its whole group
             log.warning("SigLIP batch of %d images failed (%s); retrying one by one", len(idx), e)
             rows = {}
             for i in idx:
                 try:
-                    rows[i] = encoder.encode_frames(items[i][2][None])[0].cpu()
+                    rows[i] = encoder.encode_images([items[i][2]])[0].cpu()
                 except Exception as e2:
                     log.warning("SigLIP failed at %.1fs: %s", items[i][0], e2)
         for i, r in rows.items():

@@ -291,3 +291,21 @@ def test_extract_siglip_embeddings_equals_the_realtime_loop():
     plain = extract_siglip_embeddings([(i * 0.5, p) for i, p in enumerate(pil)], DEV, encoder=enc)
     assert [d["label"] for d in plain] == ["full_frame"] * 4
     assert all(torch.equal(d["embedding"], enc.encode_image(p).cpu()) for d, p in zip(plain, pil))
+
+
+def test_encode_images_equals_the_per_frame_loop():
+    """`encode_images` (threaded PIL conversion into a pinned double buffer, batches of config.batch_size) must return
+    what the reference's loop `[encode_image(f) for f in frames]` returns, bit for bit, across buffer reuse."""
+    from PIL import Image
+    spec = SiglipVisionSpec(hidden=216, intermediate=400, layers=2, heads=3, image=140, patch=14)
+    sd = synth_siglip_state_dict(spec, seed=0)
+    enc = SigLIPSemanticEncoder(NaFlexConfig(device=DEV, base_resolution=140, state_dict=sd, num_attention_heads=3, batch_size=4))
+    raw = synth.scene_frames_np(11, 14, 270, 480)  # 14 frames: 3 full batches of 4 + a tail of 2, ring reused twice
+    pil = [Image.fromarray(f) for f in raw]
+    got = enc.encode_images(pil)
+    want = torch.stack([enc.encode_image(p) for p in pil])
+    assert got.shape == (14, spec.hidden) and torch.equal(got, want)
+    assert torch.equal(enc.encode_images(list(raw)), want)           # arrays instead of PIL images
+    assert torch.equal(enc.encode_images(pil[:2]), want[:2])         # the small-list path
+    with pytest.raises(ValueError, match="one size"):
+        enc.encode_images(pil[:4] + [Image.fromarray(raw[0][:100])])

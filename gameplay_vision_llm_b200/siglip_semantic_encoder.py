@@ -103,6 +103,21 @@ def _to_uint8_hwc(image) -> np.ndarray:
     return arr
 
 
+def _rgbx_view(image):
+    """Zero-copy uint8 [H, W, 4] view of a PIL "RGB" image's own pixel storage (Pillow keeps RGB as 4 bytes per pixel and
+    exports it through the Arrow C data interface since 11.2), or None when that is not available.  `np.asarray(image)`
+    instead packs the pixels into a bytes object under the GIL (1.7 ms per 1080p frame, not parallelisable)."""
+    if getattr(image, "mode", None) != "RGB" or not hasattr(image, "__arrow_c_array__"):
+        return None
+    try:
+        import pyarrow as pa
+        flat = pa.array(image).flatten().to_numpy(zero_copy_only=True)
+    except Exception:
+        return None
+    w, h = image.size
+    return flat.reshape(h, w, 4) if flat.size == h * w * 4 else None
+
+
 def _image_shape(image) -> tuple[int, int, int]:
     """(H, W, 3) of a PIL image / array without converting it."""
     if hasattr(image, "convert"):
@@ -121,14 +136,38 @@ class GvlSiglipProcessor:
         self.size = {"height": size, "width": size}
         self.resample, self.image_mean, self.image_std = resample, tuple(image_mean), tuple(image_std)
         self.device = device
+        self._stage: Optional[tuple] = None  # (pinned uint8 [H,W,4], event of the copy that last read it)
+
+    def _upload_rgbx(self, view: np.ndarray) -> torch.Tensor:
+        """One PIL "RGB" image (its zero-copy RGBX storage) -> uint8 [1,H,W,3] on the device: a flat memcpy into a
+        reused pinned buffer, an asynchronous copy, the padding byte dropped on the device — instead of Pillow's
+        `tobytes` packing (1.7 ms per 1080p frame) followed by a pageable copy."""
+        if self._stage is None or tuple(self._stage[0].shape) != view.shape:
+            self._stage = (torch.empty(view.shape, dtype=torch.uint8).pin_memory(), None)
+        host, event = self._stage
+        if event is not None:
+            event.synchronize()
+        np.copyto(host.numpy(), view)
+        with torch.cuda.device(self.device):
+            dev = host.to(self.device, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(torch.cuda.current_stream(self.device))
+        self._stage = (host, ev)
+        return dev[None, ..., :3].contiguous()
 
     def __call__(self, images=None, return_tensors: str = "pt", **kwargs) -> BatchFeature:
         if images is None:
             raise ValueError("images is required")
         if not isinstance(images, (list, tuple)):
             images = [images]
-        arrays = [_to_uint8_hwc(im) for im in images]
         s = self.size["height"]
+        if len(images) == 1:  # the per-frame loop's call (`encode_image`, reference :474-477)
+            view = _rgbx_view(images[0])
+            if view is not None:
+                return BatchFeature({"pixel_values": ops.preprocess(self._upload_rgbx(view), s, s, self.resample,
+                                                                    self.image_mean, self.image_std,
+                                                                    layout=ops.LAYOUT_F32_CHW)})
+        arrays = [_to_uint8_hwc(im) for im in images]
         outs = []
         # frames of equal shape go through one launch (HF groups by shape the same way)
         i = 0
@@ -523,22 +562,31 @@ class SigLIPSemanticEncoder:
         bs = max(1, int(self.config.batch_size))
         if len(images) < 4:  # a handful of images (odd-sized crops): not worth a pinned ring of their size
             return self.encode_frames(np.stack([_to_uint8_hwc(im) for im in images]))
-        ring = self._pinned_ring(bs, shape)
+        # PIL "RGB" images hand out their RGBX storage without a copy: the pool then only does flat 8 MB memcpys (GIL
+        # released) into the pinned buffer, and the padding byte is dropped on the device
+        views = [_rgbx_view(im) for im in images]
+        rgbx = all(v is not None for v in views)
+        ring = self._pinned_ring(bs, shape[:2] + (4,) if rgbx else shape)
         pool = self._convert_pool()
         outs = []
         with torch.cuda.device(m.device):
             stream = torch.cuda.current_stream(m.device)
             for k, i0 in enumerate(range(0, len(images), bs)):
-                chunk = images[i0:i0 + bs]
+                chunk = views[i0:i0 + bs] if rgbx else images[i0:i0 + bs]
                 host, event = ring[k % 2]
                 if event is not None:
                     event.synchronize()  # the copy that last read this buffer has finished
                 view = host.numpy()
-                list(pool.map(lambda a: np.copyto(view[a[0]], _to_uint8_hwc(a[1])), enumerate(chunk)))
+                if rgbx:
+                    list(pool.map(lambda a: np.copyto(view[a[0]], a[1]), enumerate(chunk)))
+                else:
+                    list(pool.map(lambda a: np.copyto(view[a[0]], _to_uint8_hwc(a[1])), enumerate(chunk)))
                 dev = host[:len(chunk)].to(m.device, non_blocking=True)
                 ev = torch.cuda.Event()
                 ev.record(stream)
                 ring[k % 2] = (host, ev)
+                if rgbx:
+                    dev = dev[..., :3].contiguous()
                 patches = ops.preprocess(dev, m.spec.image, m.spec.image, self.config.resample, self.config.image_mean,
                                          self.config.image_std, layout=ops.LAYOUT_BF16_PATCH, patch=m.spec.patch,
                                          ld=m.spec.patch_ld)

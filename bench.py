@@ -342,6 +342,14 @@ def main_ours(args) -> None:
         # that is BASELINE.json configs[4]: 72 192 frames = 10 h at 2 fps, top-16 for 128 queries)
         retrieval = retrieval_on_gathered(index_full, dev)
 
+    # ---- side measurement: the reference's caller-level function on its own data model (a list of PIL frames) ----
+    caller = None
+    if rank == 0 and world == 1 and not args.no_caller_api:
+        try:
+            caller = caller_api_probe(dev, synth_siglip_state_dict(spec, seed=0))
+        except Exception as exc:  # Pillow / pyarrow missing on the box: the side measurement is simply absent
+            caller = {"unavailable": f"{type(exc).__name__}: {exc}"}
+
     if rank == 0:
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
@@ -368,6 +376,8 @@ def main_ours(args) -> None:
                                     "kind": cpu["kind"], "sample": cpu["sample"]}
         if retrieval is not None:
             line["retrieval"] = retrieval
+        if caller is not None:
+            line["reference_caller_api"] = caller
         if allgather is not None:
             line["allgather"] = allgather
         print(json.dumps(line), flush=True)
@@ -419,6 +429,31 @@ def retrieval_on_gathered(index_full, dev, n_queries: int = 128, k: int = 16) ->
             "self_retrieval": "every query's first hit is its own row (or an identical earlier frame), cosine > 0.9999",
             "path": "fused tcgen05 scoring with per-CTA candidate lists + float64 re-score of everything within the margin (bit-identical to the scan path)"
                     if n >= 4096 else "fp32 scan (index below the tensor path's 4096-row threshold)"}
+
+
+def caller_api_probe(dev, siglip_sd, n_frames: int = 128) -> dict:
+    """`pipeline.run_siglip_encoder([(timestamp, PIL 1080p frame)], device)` — the signature, data model and output of
+    scripts/extract_features.py:502-610 (fallback branch: every frame encoded whole, 1152-d embeddings returned on the CPU
+    in the reference's list of dicts; no projector: the reference applies it later).  Wall clock around the call."""
+    import torch
+    from PIL import Image
+
+    from gameplay_vision_llm_b200 import synth
+    from gameplay_vision_llm_b200.pipeline import run_siglip_encoder
+    from gameplay_vision_llm_b200.siglip_semantic_encoder import NaFlexConfig, SigLIPSemanticEncoder
+    enc = SigLIPSemanticEncoder(NaFlexConfig(device=str(dev), state_dict=siglip_sd, fold_layernorm=True))
+    frames = [(float(i), Image.fromarray(f)) for i, f in enumerate(synth.scene_frames_np(0, n_frames, FRAME_H, FRAME_W))]
+    run_siglip_encoder(frames[:32], str(dev), encoder=enc)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    out = run_siglip_encoder(frames, str(dev), encoder=enc)
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    assert len(out) == n_frames and out[0]["embedding"].shape[-1] == 1152
+    return {"call": "run_siglip_encoder([(timestamp, PIL.Image 1080p)], device) -> [{timestamp, embedding (CPU), ...}]",
+            "frames": n_frames, "batch_size": enc.config.batch_size, "frames_per_s": round(n_frames / dt, 1),
+            "note": "host wall clock incl. PIL -> pinned memory (Pillow's zero-copy Arrow export), H2D, tower, D2H and the "
+                    "reference's list of dicts; the 1152-d SigLIP embedding only, as in the reference function"}
 
 
 def retrieval_probe(dev, n_index: int = 72000, dim: int = 4096, n_queries: int = 128, k: int = 16) -> dict:
@@ -789,6 +824,8 @@ if __name__ == "__main__":
     ap.add_argument("--cpu-frames", type=int, default=32, help="frames of the bounded CPU-baseline sample (batch 8)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-retrieval", action="store_true", help="skip the configs[4] retrieval side measurement")
+    ap.add_argument("--no-caller-api", action="store_true",
+                    help="skip the side measurement of run_siglip_encoder on a list of PIL frames")
     ap.add_argument("--no-fold-ln", action="store_true",
                     help="A/B: run the 56 LayerNorm kernels per batch instead of folding them into the GEMM epilogues")
     ap.add_argument("--workload", choices=["siglip", "videomae", "regions"], default="siglip",

@@ -241,7 +241,7 @@ def run_siglip_encoder(frames, device: str = "cuda", sam_results: list | None = 
     constructed `SigLIPSemanticEncoder` (the reference builds a fresh one per call, :514-515)."""
     import logging
 
-    from .siglip_semantic_encoder import BoxMask, NaFlexConfig, SigLIPSemanticEncoder, _to_uint8_hwc
+    from .siglip_semantic_encoder import BoxMask, NaFlexConfig, SigLIPSemanticEncoder, _image_shape
     log = logging.getLogger(__name__)
     if encoder is None:
         encoder = SigLIPSemanticEncoder(NaFlexConfig(device=device))
@@ -258,22 +258,22 @@ def run_siglip_encoder(frames, device: str = "cuda", sam_results: list | None = 
             if not by_time.get(timestamp):
                 full_frame.append(idx)
                 continue
-            frame_np = _to_uint8_hwc(frame)
+            frame_hw = _image_shape(frame)[:2]
             masks, kept = [], []
             for det in dets:
                 entity_type = det.get("entity_type", "unknown")
                 entity_id = det.get("entity_id", f"{entity_type}_{timestamp}")
                 x1, y1, x2, y2 = [int(c) for c in det["bbox"]]
-                masks.append((entity_id, BoxMask(frame_np.shape[:2], y1, y2, x1, x2)))  # the reference's zeros + slice fill
+                masks.append((entity_id, BoxMask(frame_hw, y1, y2, x1, x2)))  # the reference's zeros + slice fill
                 kept.append(det)
             try:
-                regions = encoder.encode_regions_individually(frame_np, masks)
+                regions = encoder.encode_regions_individually(frame, masks)
             except Exception as e:  # one bad detection must not lose the frame: fall back to one call per detection
                 log.warning("SigLIP mask encoding failed at %.1fs (%s); retrying per detection", timestamp, e)
                 regions = []
                 for mk in masks:
                     try:
-                        regions.append(encoder.encode_masked_regions(frame_np, [mk])[0])
+                        regions.append(encoder.encode_masked_regions(frame, [mk])[0])
                     except Exception as e2:
                         log.warning("SigLIP mask encoding failed for %s at %.1fs: %s", mk[0], timestamp, e2)
                         regions.append(None)
@@ -288,7 +288,6 @@ def run_siglip_encoder(frames, device: str = "cuda", sam_results: list | None = 
     else:
         full_frame = list(range(len(frames)))
     # frames encoded whole: runs of equal size go through the encoder's batched, pinned, threaded feed
-    from .siglip_semantic_encoder import _image_shape
     i = 0
     while i < len(full_frame):
         shape = _image_shape(frames[full_frame[i]][1])
@@ -325,16 +324,16 @@ def extract_siglip_embeddings(frames, device: str = "cuda", sam_results: list | 
     fails is logged and skipped like the reference (:303, :324)."""
     import logging
 
-    from .siglip_semantic_encoder import NaFlexConfig, SigLIPSemanticEncoder, _to_uint8_hwc
+    from .siglip_semantic_encoder import NaFlexConfig, SigLIPSemanticEncoder, _image_shape, _to_uint8_hwc
     log = logging.getLogger(__name__)
     if encoder is None:
         encoder = SigLIPSemanticEncoder(NaFlexConfig(device=device))
-    items: list[tuple[float, str, np.ndarray]] = []
+    items: list[tuple] = []  # (timestamp, label, PIL image or uint8 array)
     if sam_results and any(d["detections"] for d in sam_results):
         for sam_frame in sam_results:
             timestamp, frame = sam_frame["timestamp"], sam_frame["frame"]
             if not sam_frame["detections"]:
-                items.append((timestamp, "full_frame", _to_uint8_hwc(frame)))
+                items.append((timestamp, "full_frame", frame))  # PIL frames stay PIL: encode_images reads them in place
                 continue
             frame_np = None
             for det in sam_frame["detections"]:
@@ -348,21 +347,18 @@ def extract_siglip_embeddings(frames, device: str = "cuda", sam_results: list | 
                         x1, y1, x2, y2 = det["bbox"]
                         img = _to_uint8_hwc(frame.crop((x1, y1, x2, y2)))
                     else:
-                        img = _to_uint8_hwc(frame)
+                        img = frame
                     items.append((timestamp, det.get("label", "region"), img))
                 except Exception as e:
                     log.debug("Region encoding failed: %s", e)
     else:
         for timestamp, frame in frames:
-            try:
-                items.append((timestamp, "full_frame", _to_uint8_hwc(frame)))
-            except Exception as e:
-                log.warning("SigLIP failed at %.1fs: %s", timestamp, e)
+            items.append((timestamp, "full_frame", frame))
     # embed: images of one shape go through the batched entry; the output keeps the reference's order
     out: list[dict | None] = [None] * len(items)
     by_shape: dict[tuple, list[int]] = {}
     for i, (_, _, img) in enumerate(items):
-        by_shape.setdefault(img.shape, []).append(i)
+        by_shape.setdefault(_image_shape(img), []).append(i)
     for idx in by_shape.values():
         try:
             emb = encoder.encode_images([items[i][2] for i in idx]).cpu()

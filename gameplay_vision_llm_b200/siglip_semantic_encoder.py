@@ -689,10 +689,13 @@ class SigLIPSemanticEncoder:
         m = self.encoder._model
         if m.spec.patch != 14:
             raise RuntimeError("encode_masked_regions: the reference rounds region sizes to 14-pixel patches (:131)")
+        view = _rgbx_view(frame) if hasattr(frame, "convert") else None
         if torch.is_tensor(frame):
             frame_dev = frame.to(m.device).contiguous()
+        elif view is not None:  # a PIL RGB frame: its own storage -> pinned buffer -> device, no `tobytes` packing
+            frame_dev = self.encoder._processor._upload_rgbx(view)[0]
         else:
-            frame_dev = torch.from_numpy(np.require(frame, requirements="CW")).to(m.device)  # PIL arrays are read-only
+            frame_dev = torch.from_numpy(np.require(_to_uint8_hwc(frame), requirements="CW")).to(m.device)
         if frame_dev.dtype != torch.uint8 or frame_dev.dim() != 3 or frame_dev.shape[2] != 3:
             raise ValueError("frame must be RGB uint8 (H, W, 3)")
         shape = tuple(frame_dev.shape)

@@ -311,6 +311,57 @@ def run_siglip_encoder(frames, device: str = "cuda", sam_results: list | None = 
     return [d for s in slots for d in s]
 
 
+def run_videomae_encoder(frames, device: str = "cuda", encoder=None) -> dict:
+    """Drop-in for `run_videomae_encoder` (scripts/extract_features.py:335-403): frames = [(timestamp, PIL image)] ->
+    {"num_input_frames", "num_embeddings", "embeddings": [{"start_time", "end_time", "embedding" (768,) fp32 CPU,
+    "source_frame_count"}], "embedding_dim"} — non-overlapping clips of 16 frames, the tail padded with its last frame.
+
+    `encoder`: a `VideoMAEClipEncoder` (the reference loads MCG-NJU/videomae-base from the hub on every call; there is no
+    hub here, so the caller passes one built from a local checkpoint or a state dict).  PIL frames are read through
+    Pillow's zero-copy Arrow export into a pinned buffer one batch of clips at a time; a failure returns the reference's
+    empty result (:399-403)."""
+    import logging
+
+    from .siglip_semantic_encoder import _image_shape, _rgbx_view, _to_uint8_hwc
+    log = logging.getLogger(__name__)
+    empty = {"num_input_frames": len(frames), "num_embeddings": 0, "embeddings": [], "embedding_dim": 768}
+    try:
+        if encoder is None:
+            raise RuntimeError("run_videomae_encoder needs a VideoMAEClipEncoder (no hub access to load "
+                               "MCG-NJU/videomae-base): VideoMAEClipEncoder.from_checkpoint(path, device)")
+        if not frames:
+            return dict(empty, embedding_dim=encoder.spec.hidden)
+        spec = encoder.spec
+        per_batch = encoder.clips_per_batch * spec.frames
+        shape = _image_shape(frames[0][1])
+        timestamps = [float(t) for t, _ in frames]
+        embeddings: list[dict] = []
+        stage = None
+        for start in range(0, len(frames), per_batch):
+            chunk = [f for _, f in frames[start:start + per_batch]]
+            if any(_image_shape(f) != shape for f in chunk):
+                raise ValueError("frames of one video must have one size")
+            views = [_rgbx_view(f) for f in chunk]
+            if all(v is not None for v in views):
+                if stage is None or stage.shape[0] < len(chunk):
+                    stage = torch.empty((per_batch,) + shape[:2] + (4,), dtype=torch.uint8).pin_memory()
+                host = stage.numpy()
+                for i, v in enumerate(views):
+                    np.copyto(host[i], v)
+                dev = stage[:len(chunk)].to(encoder.device, non_blocking=True)[..., :3].contiguous()
+                torch.cuda.current_stream(encoder.device).synchronize()  # the pinned buffer is refilled next iteration
+            else:
+                dev = torch.from_numpy(np.stack([_to_uint8_hwc(f) for f in chunk])).to(encoder.device)
+            part = encoder.run(dev, timestamps[start:start + len(chunk)])
+            embeddings += part["embeddings"]
+        log.info("VideoMAE: %d frames -> %d clip embeddings (%d-dim)", len(frames), len(embeddings), spec.hidden)
+        return {"num_input_frames": len(frames), "num_embeddings": len(embeddings), "embeddings": embeddings,
+                "embedding_dim": spec.hidden}
+    except Exception as e:
+        log.warning("VideoMAE failed: %s", e)
+        return empty
+
+
 def extract_siglip_embeddings(frames, device: str = "cuda", sam_results: list | None = None, encoder=None) -> list[dict]:
     """Drop-in for `extract_siglip_embeddings` of the online pipeline (scripts/realtime_inference.py:244-335): frames =
     [(timestamp, PIL image)], optional `sam_results` = [{"timestamp", "frame", "detections": [{"mask" | "bbox", "label"}]}]

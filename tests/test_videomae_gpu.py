@@ -184,3 +184,26 @@ def test_run_realtime_mirrors_stride8_windows():
         assert o["embedding"].dtype == torch.float32 and o["embedding"].device.type == "cpu"
         assert torch.equal(alone, o["embedding"])
     assert enc.run_realtime(frames[:3], ts[:3]) == []
+
+
+def test_run_videomae_encoder_caller_dropin_from_pil_frames():
+    """`pipeline.run_videomae_encoder([(ts, PIL frame)], device, encoder)` — the reference's caller-level signature
+    (scripts/extract_features.py:335-403) — returns exactly what `VideoMAEClipEncoder.run` returns for the same frames
+    as a tensor (PIL frames read through Pillow's Arrow export, several batches of clips, padded tail)."""
+    from PIL import Image
+
+    from gameplay_vision_llm_b200.pipeline import run_videomae_encoder
+    spec = VideoMAESpec.tiny()
+    enc = VideoMAEClipEncoder(synth_videomae_state_dict(spec, seed=2), spec, DEV, clips_per_batch=2)
+    n = 5 * spec.frames + 3  # 23 frames -> 6 clips over 3 batches, the last clip padded
+    frames = synth.noise_frames(n, 90, 120, seed=6)
+    ts = [i / 3.0 for i in range(n)]
+    want = enc.run(frames, ts)
+    got = run_videomae_encoder([(t, Image.fromarray(f.numpy())) for t, f in zip(ts, frames)], DEV, encoder=enc)
+    keys = ("num_input_frames", "num_embeddings", "embedding_dim")
+    assert {k: got[k] for k in keys} == {k: want[k] for k in keys} and got["num_embeddings"] == 6
+    for g, w in zip(got["embeddings"], want["embeddings"]):
+        assert (g["start_time"], g["end_time"], g["source_frame_count"]) == (w["start_time"], w["end_time"], w["source_frame_count"])
+        assert torch.equal(g["embedding"], w["embedding"])
+    # failures degrade to the reference's empty result instead of raising (:399-403)
+    assert run_videomae_encoder([(0.0, Image.fromarray(frames[0].numpy()))], DEV, encoder=None)["num_embeddings"] == 0

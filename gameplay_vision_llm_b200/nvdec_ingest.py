@@ -62,6 +62,55 @@ def usable(codec: int = CODEC_H264, device=None) -> tuple[bool, str]:
     return True, ""
 
 
+_SELF_TEST: dict = {}
+
+_SELF_TEST_SCRIPT = """
+import sys, tempfile, os, numpy as np, torch
+from gameplay_vision_llm_b200 import nvdec_ingest as nv, synth_video as sv
+dev = sys.argv[1]
+rng = np.random.default_rng(0)
+y = rng.integers(16, 236, (3, 48, 64), dtype=np.uint8)
+cb = rng.integers(16, 241, (3, 24, 32), dtype=np.uint8)
+cr = rng.integers(16, 241, (3, 24, 32), dtype=np.uint8)
+path = os.path.join(tempfile.mkdtemp(), "selftest.mp4")
+sv.write_h264_mp4(path, y, cb, cr, fps=(30, 1), skip_every=2)
+ts, frames = nv.extract_frames_nvdec(path, fps=30.0, device=dev)
+assert frames.shape == (6, 48, 64, 3), tuple(frames.shape)
+got = frames.cpu().numpy().astype(np.int16)
+Y = (255 / 219) * (y.astype(np.float64) - 16)
+Cb = cb.repeat(2, 1).repeat(2, 2).astype(np.float64) - 128
+Cr = cr.repeat(2, 1).repeat(2, 2).astype(np.float64) - 128
+k = 255 / 224
+want = np.clip(np.rint(np.stack([Y + 1.402 * k * Cr, Y - 0.344136 * k * Cb - 0.714136 * k * Cr, Y + 1.772 * k * Cb], -1)), 0, 255)
+for j in range(6):
+    assert np.abs(got[j] - want[j // 2]).max() <= 1, j
+print("nvdec self-test ok")
+"""
+
+
+def self_test(device="cuda") -> tuple[bool, str]:
+    """Power-on self-test of the hardware-decode path, once per process and device, in a CHILD process: a 64 x 48
+    known-answer H.264 clip (every macroblock I_PCM) is decoded on the engine and compared with the planes that were
+    written into it.  `embed_video(decoder="auto")` only trusts NVDEC after this passes — the binding declares the
+    driver's structs without the SDK headers (csrc/cuvid_abi.h), and a layout that did not match the installed driver
+    must cost a fallback to the software feed, not a crash or wrong pixels in the caller's process."""
+    import subprocess
+    import sys
+    dev = str(resolve_device(device))
+    if dev not in _SELF_TEST:
+        root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+        env = dict(os.environ, PYTHONPATH=root + os.pathsep + os.environ.get("PYTHONPATH", ""))
+        try:
+            r = subprocess.run([sys.executable, "-c", _SELF_TEST_SCRIPT, dev], capture_output=True, text=True, timeout=180,
+                               env=env)
+            ok = r.returncode == 0 and "nvdec self-test ok" in r.stdout
+            why = "" if ok else f"self-test failed (exit {r.returncode}): {(r.stderr or r.stdout).strip()[-300:]}"
+        except Exception as exc:  # timeout, no interpreter, ...
+            ok, why = False, f"self-test could not run: {exc}"
+        _SELF_TEST[dev] = (ok, why)
+    return _SELF_TEST[dev]
+
+
 # ------------------------------------------------------------------------------------------------ ISO-BMFF reader
 def _boxes(buf, start: int, end: int) -> Iterator[tuple[bytes, int, int]]:
     """(type, payload_start, payload_end) of the boxes in buf[start:end]."""

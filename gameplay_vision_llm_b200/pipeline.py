@@ -153,12 +153,13 @@ class EmbeddingPipeline:
         are converted to RGB in device memory and go straight into the preprocess kernel — no host frame, no H2D);
         "opencv": software decode on a background thread into pinned batches (`frame_ingest.FrameFeed`), H2D overlapped
         with compute; "auto": nvdec when the driver library, the container (MP4 / MOV) and the codec (H.264 / HEVC 8-bit
-        4:2:0) allow it, else opencv."""
+        4:2:0) allow it AND the engine has passed `nvdec_ingest.self_test` (a known-answer clip decoded in a child process,
+        once per process), else opencv."""
         if decoder not in ("auto", "nvdec", "opencv"):
             raise ValueError("decoder must be 'auto', 'nvdec' or 'opencv'")
         if decoder != "opencv":
             try:
-                return self._embed_video_nvdec(video_path, fps, index, host_out, return_pooled)
+                return self._embed_video_nvdec(video_path, fps, index, host_out, return_pooled, trust=decoder == "nvdec")
             except _NvdecUnusable as exc:
                 if decoder == "nvdec":
                     raise RuntimeError(f"hardware decode of {video_path} is not possible: {exc}") from exc
@@ -175,7 +176,7 @@ class EmbeddingPipeline:
             return feed.timestamps[:n], index[:n], pooled[:n]
         return feed.timestamps[:n], index[:n]
 
-    def _embed_video_nvdec(self, video_path, fps, index, host_out, return_pooled):
+    def _embed_video_nvdec(self, video_path, fps, index, host_out, return_pooled, trust: bool = False):
         from . import nvdec_ingest as nv
         if not nv.available():
             raise _NvdecUnusable("libnvcuvid.so.1 (GPU driver) did not load")
@@ -186,6 +187,10 @@ class EmbeddingPipeline:
         ok, why = nv.usable(track.codec, self.device)
         if not ok:
             raise _NvdecUnusable(why)
+        if not trust:  # decoder="auto": the engine must first reproduce a known-answer clip (in a child process)
+            ok, why = nv.self_test(self.device)
+            if not ok:
+                raise _NvdecUnusable(why)
         feed = nv.NvdecFeed(video_path, fps=fps, batch=self.batch, device=self.device)
         with torch.cuda.device(self.device):
             n_plan = len(feed.timestamps)

@@ -244,3 +244,12 @@ def test_real_libnvcuvid_parser_agrees_with_the_declared_struct_layouts(clip, tm
     assert num / den == 30.0
     assert "decodes=46 displays=46" in out
     assert "display #1 picture_index=0" in out
+
+
+def test_power_on_self_test_guards_the_auto_decoder():
+    """`nvdec_ingest.self_test` (a known-answer clip decoded in a child process) is what `decoder="auto"` relies on
+    before it trusts the engine."""
+    _require_nvdec()
+    ok, why = nv.self_test(DEV)
+    assert ok, why
+    assert nv.self_test(DEV) == (True, "")  # cached

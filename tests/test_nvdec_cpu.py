@@ -110,3 +110,51 @@ def test_library_reports_nvdec_absence_without_a_gpu():
         assert not ok and "libnvcuvid" in why
         with pytest.raises(RuntimeError, match="NVDEC is not available"):
             nv.NvdecFeed("whatever.mp4")
+
+
+def test_mp4_reader_parses_an_hevc_sample_entry(tmp_path):
+    """The hvcC branch (ISO/IEC 14496-15 §8.3.3): parameter-set arrays, NAL length size, 32-bit chunk offsets and a
+    multi-run sample-to-chunk table — on a hand-built file (dummy NAL payloads: only the container is under test)."""
+    import struct
+
+    from gameplay_vision_llm_b200.synth_video import _box, _full
+    vps, sps, pps = b"\x40\x01VPS", b"\x42\x01SPS-", b"\x44\x01PPS--"
+    arrays = b"".join(bytes([0x80 | t]) + struct.pack(">H", 1) + struct.pack(">H", len(n)) + n
+                      for t, n in ((32, vps), (33, sps), (34, pps)))
+    hvcc = _box(b"hvcC", bytes(21) + bytes([0xFC | 2]) + bytes([3]) + arrays)  # lengthSizeMinusOne = 2 -> 3-byte lengths
+    entry = _box(b"hvc1", b"\x00" * 6, struct.pack(">H", 1), b"\x00" * 16, struct.pack(">HH", 640, 360),
+                 struct.pack(">II", 0x00480000, 0x00480000), b"\x00" * 4, struct.pack(">H", 1), b"\x00" * 32,
+                 struct.pack(">Hh", 0x18, -1), hvcc)
+    nal = lambda payload: len(payload).to_bytes(3, "big") + payload  # noqa: E731
+    samples = [nal(b"\x26\x01" + bytes([i]) * (5 + i)) for i in range(5)]
+    sizes = [len(x) for x in samples]
+    ftyp = _box(b"ftyp", b"isom", struct.pack(">I", 0x200), b"isomiso2hvc1")
+
+    def moov(off0, off1):
+        stbl = _box(b"stbl", _full(b"stsd", 0, struct.pack(">I", 1), entry),
+                    _full(b"stts", 0, struct.pack(">IIIII", 2, 2, 1001, 3, 2002)),      # two duration runs
+                    _full(b"stsc", 0, struct.pack(">IIIIIII", 2, 1, 2, 1, 2, 3, 1)),    # chunk 1: 2 samples, chunk 2: 3
+                    _full(b"stsz", 0, struct.pack(">II", 0, 5), b"".join(struct.pack(">I", z) for z in sizes)),
+                    _full(b"stco", 0, struct.pack(">III", 2, off0, off1)))
+        minf = _box(b"minf", _full(b"vmhd", 1, b"\x00" * 8), stbl)
+        mdhd = _full(b"mdhd", 1 << 24, struct.pack(">QQIQHH", 0, 0, 24000, 8008, 0x55C4, 0))  # version 1: 64-bit times
+        hdlr = _full(b"hdlr", 0, struct.pack(">I4s", 0, b"vide"), b"\x00" * 12, b"V\x00")
+        audio = _box(b"trak", _box(b"mdia", _full(b"hdlr", 0, struct.pack(">I4s", 0, b"soun"), b"\x00" * 12, b"A\x00")))
+        return _box(b"moov", audio, _box(b"trak", _box(b"mdia", mdhd, hdlr, minf)))
+
+    gap = b"free-space"
+    head = len(ftyp) + len(moov(0, 0)) + 8
+    off0 = head
+    off1 = head + sizes[0] + sizes[1] + len(gap)
+    path = tmp_path / "h.mp4"
+    path.write_bytes(ftyp + moov(off0, off1) + struct.pack(">I4s", 8 + sum(sizes) + len(gap), b"mdat") +
+                     samples[0] + samples[1] + gap + samples[2] + samples[3] + samples[4])
+    t = nv.read_mp4_video_track(str(path))
+    assert (t.codec, t.width, t.height, t.timescale, t.n_frames, t.nal_length_size) == (nv.CODEC_HEVC, 640, 360, 24000, 5, 3)
+    assert t.parameter_sets == [vps, sps, pps]
+    assert t.sample_deltas.tolist() == [1001, 1001, 2002, 2002, 2002] and abs(t.avg_fps - 5 * 24000 / 8008) < 1e-12
+    assert t.sample_offsets.tolist() == [off0, off0 + sizes[0], off1, off1 + sizes[2], off1 + sizes[2] + sizes[3]]
+    stream = b"".join(c for c, _ in nv.annexb_chunks(str(path), t, 2))
+    start = b"\x00\x00\x00\x01"
+    want = start + vps + start + sps + start + pps + b"".join(start + b"\x26\x01" + bytes([i]) * (5 + i) for i in range(5))
+    assert stream == want

@@ -156,6 +156,40 @@ def test_attention(B, T, H, hd):
     assert rel < 1.5e-2 and mean < 2e-3  # P is rounded to bf16 before PV (as HF eager/SDPA do)
 
 
+@pytest.mark.parametrize("B,T,H,hd", [(8, 729, 16, 72), (40, 129, 8, 72), (24, 200, 8, 64), (330, 40, 1, 72)])
+def test_attention_persistent_ctas_walk_several_items(B, T, H, hd):
+    """The attention CTAs are persistent (two per SM): with more work items (query tile x head x image) than resident
+    CTAs every CTA walks several items with its mbarrier phases, K/V ring and S-buffer parity running on — even block
+    counts (12), odd ones (3: the buffer parity flips from item to item), a single block per item.  (a) against fp32
+    softmax; (b) bit-identical to the same kernel launched with one item per CTA (the tuning hook of attention_sdb.cu)."""
+    import ctypes
+
+    from gameplay_vision_llm_b200 import _lib
+    n_items = -(-T // 128) * H * B
+    sms = torch.cuda.get_device_properties(0).multi_processor_count
+    assert n_items > 2 * sms, "case does not make the CTAs loop on this device"
+    g = torch.Generator().manual_seed(B * 1000 + T)
+    D = H * hd
+    qkv = (torch.randn(B * T, 3 * D, generator=g) * 1.5).to(torch.bfloat16).to(DEV)
+    out = ops.attention(qkv, B, T, H, hd)
+    torch.cuda.synchronize()
+    ref = _attn_ref(qkv, B, T, H, hd)
+    mx, rel, mean = _rel_err(out, ref)
+    print(f"attention persistent B={B} T={T} H={H} hd={hd} ({n_items} items): max_abs={mx:.3e} rel={rel:.3e}")
+    assert torch.isfinite(out.float()).all()
+    assert rel < 1.5e-2 and mean < 2e-3
+    lib = _lib.lib()
+    lib.gvl_debug_set_attn_ctas_per_sm.argtypes = [ctypes.c_int]
+    lib.gvl_debug_set_attn_ctas_per_sm.restype = None
+    try:
+        lib.gvl_debug_set_attn_ctas_per_sm(0)
+        one = ops.attention(qkv, B, T, H, hd)
+        torch.cuda.synchronize()
+    finally:
+        lib.gvl_debug_set_attn_ctas_per_sm(2)
+    assert torch.equal(out, one)
+
+
 def _attn_ref(qkv, B, T, H, hd):
     D = H * hd
     q, k, v = qkv.float().view(B, T, 3, H, hd).permute(2, 0, 3, 1, 4)

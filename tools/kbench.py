@@ -115,6 +115,17 @@ def attn_case():
     out = torch.empty(B * T, H * hd, device=DEV, dtype=torch.bfloat16)
     ms = timeit(lambda: ops.attention(qkv, B, T, H, hd, out=out))
     print(f"attention B={B} T={T}: {ms*1e3:.1f} us  {4.0*B*H*T*T*hd/ms/1e9:.1f} TFLOP/s  (x27/step = {ms*27:.2f} ms)")
+    import ctypes
+
+    from gameplay_vision_llm_b200 import _lib
+    lib = _lib.lib()
+    lib.gvl_debug_set_attn_ctas_per_sm.argtypes = [ctypes.c_int]
+    lib.gvl_debug_set_attn_ctas_per_sm.restype = None
+    for n in (0, 1, 2, 0, 2):  # A/B in one process: 0 = one work item per CTA (round 1's launch), 2 = persistent (ships)
+        lib.gvl_debug_set_attn_ctas_per_sm(n)
+        ms = timeit(lambda: ops.attention(qkv, B, T, H, hd, out=out), reps=50)
+        print(f"attention CTAs/SM={n} ({'one item per CTA' if n == 0 else 'persistent'}): {ms*1e3:.1f} us")
+    lib.gvl_debug_set_attn_ctas_per_sm(2)
     ms, mhz, watts = sm_clock_during(lambda: ops.attention(qkv, B, T, H, hd, out=out), reps=600)
     print(f"attention sustained (600 launches): {ms*1e3:.1f} us at a median {mhz} MHz SM clock, peak {watts:.0f} W")
 

@@ -33,7 +33,9 @@
 // TMEM columns: S/P buffer u at [64 u, +64); O at [128, +DPAD); L at [128 + DPAD, +16).
 #include "common.cuh"
 
+#include <algorithm>
 #include <cstdlib>
+#include <type_traits>
 
 namespace gvl {
 
@@ -311,7 +313,12 @@ attention_sdb_kernel(const __grid_constant__ CUtensorMap tmq64, const __grid_con
             const bool rows_live = it.q0 + q * 32 < T;  // warp-uniform: at least one of the 32 rows exists
             // (prefetching S(g+1) into a second register buffer while block g is exponentiated was tried: 168
             // registers do not hold both rows, ptxas spills one and the kernel gets 2x slower)
-            for (int j = 0; j < nblk; ++j) {
+            // one key block.  PARTIAL (compile-time) = the block holds fewer than 64 keys: only an item's last block can,
+            // and only that copy of the body carries the -inf masking — as a run-time `if` inside one body the compiler
+            // if-converts it into 63 ISETP + 63 SEL per block (40 % of the block's instructions, ahead of the row max on
+            // the critical path) for every block of every item
+            auto block = [&](const int j, auto partial_tag) {
+                constexpr bool PARTIAL = decltype(partial_tag)::value;
                 const int g = g0 + j, buf = sbuf(g);
                 const uint32_t tS = tmem_base + (uint32_t)(buf * 64) + lane_off;
                 uint32_t s[2][32];
@@ -324,8 +331,8 @@ attention_sdb_kernel(const __grid_constant__ CUtensorMap tmq64, const __grid_con
                 tmem_ld_wait();
                 if (warp == 0) SDB_TRACE(j, 2);
                 if (rows_live) {
-                    const int valid = min(SDB_BKV, T - j * SDB_BKV);
-                    if (valid < SDB_BKV) {
+                    const int valid = PARTIAL ? T - j * SDB_BKV : SDB_BKV;
+                    if (PARTIAL) {
 #pragma unroll
                         for (int c = 0; c < 2; ++c)
 #pragma unroll
@@ -409,7 +416,12 @@ attention_sdb_kernel(const __grid_constant__ CUtensorMap tmq64, const __grid_con
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&p_full[buf]);
                 if (warp == 0) SDB_TRACE(j, 5);
-            }
+            };
+            for (int j = 0; j + 1 < nblk; ++j) block(j, std::false_type{});
+            if (T - (nblk - 1) * SDB_BKV < SDB_BKV)
+                block(nblk - 1, std::true_type{});
+            else
+                block(nblk - 1, std::false_type{});
             g0 += nblk;
             // ---- finalise: O / l -> bf16 -> global.  Every softmax warp observes every o_done phase (also a warp
             // without live rows: that is what keeps it from running more than one item ahead); the MMA issuer has

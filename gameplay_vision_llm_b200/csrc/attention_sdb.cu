@@ -15,10 +15,15 @@
 //   - the softmax inner loop is FFMA2 (two scores per instruction), MUFU.EX2 and F2FP only: the row sums are
 //     accumulated by the tensor cores (L += P . 1 with a constant tile of ones), so l is the sum of exactly the bf16
 //     P values the PV MMAs consume.
-// What bounds it (tools/attn_trace.py): a softmax warp alone issues one MUFU every ~13.5 cycles,
-// two per scheduler ~8.6; with ~400 cycles of fixed per-block hand-shake (mbarrier round trip, tcgen05.ld / st waits)
-// and a 6400-cycle CTA start-up the exp pipe is ~60 % busy.  Neither fewer softmax instructions, nor fewer MMAs, nor
-// more softmax warps per scheduler (NT = 3, split rows) moved the 282 us per layer.
+// What bounds it (tools/attn_trace.py, profiles/r02_attention_persistent_ncu_summary.txt): no pipe
+// is saturated (ncu: MUFU 52 %, tensor 39 %, issue slots 37 %).  A scheduler holds two softmax warps, one per resident
+// CTA; one alone issues a MUFU every ~10-13 cycles (8 is the pipe's rate), and the two drift into phase — exponentiate
+// together at half rate each, then do their ~450 cycles of non-MUFU work (barrier round trip, tcgen05.ld, max,
+// tcgen05.st, arrive) together with the pipe idle: ~1.65 k cycles per 64-key block per CTA against 1.02 k of MUFU work
+// for the pair.  Measured and not kept: more softmax warps per scheduler, fewer softmax instructions, a polynomial exp2
+// share, fewer MMAs, a leaner MMA issue path (SLOWER: bursts from one CTA delay the other's S on the shared tensor
+// pipe), dedicated read-out warps, register prefetch of S(j+1), an overlapped non-blocking s_full test
+// (profiles/r02_attention_experiments.md).  252-259 us per layer (B 64, T 729, 16 heads of 72) at 1.965 GHz.
 //
 //   warps 0-3   softmax: one thread = one query row x 64 keys; tcgen05.ld the S row,
 //               running max with lazy rescaling of O and L (only when the max grows by more than 2^8),

@@ -181,7 +181,7 @@ def main_ours(args) -> None:
     dev = torch.device("cuda", local_rank)
     _lib.check(_lib.lib().gvl_check_device(local_rank), "gvl_check_device")
     if world > 1:
-        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):  # unset: a system nccl.conf may still ask for it
+        if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
             os.environ["NCCL_DEBUG"] = "WARN"  # keep stdout to the single JSON line
         dist.init_process_group("nccl", device_id=dev)
 
@@ -521,7 +521,7 @@ def main_videomae(args) -> None:
     dev = torch.device("cuda", local_rank)
     _lib.check(_lib.lib().gvl_check_device(local_rank), "gvl_check_device")
     if world > 1:
-        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+        if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
             os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=dev)
     peaks = load_peaks()

@@ -190,6 +190,25 @@ def test_attention_persistent_ctas_walk_several_items(B, T, H, hd):
     assert torch.equal(out, one)
 
 
+@pytest.mark.parametrize("B,T,H,hd", [(1, 200, 2, 72), (3, 129, 2, 64), (1, 729, 16, 72)])
+def test_attention_never_writes_past_the_sequence(B, T, H, hd):
+    """The last query tile of an image holds rows beyond T (729 = 5 x 128 + 89): the staged read-out must not store them —
+    in a batch they are the next image's first rows, after the last image they lie outside the buffer.  Guard rows in
+    front of and behind the output keep their sentinel, and a batch equals its images attended one by one."""
+    g = torch.Generator().manual_seed(7 * T + hd)
+    D = H * hd
+    qkv = (torch.randn(B * T, 3 * D, generator=g) * 1.5).to(torch.bfloat16).to(DEV)
+    guard = 160  # more rows than a 128-row tile can overshoot
+    big = torch.full((guard + B * T + guard, D), 123.0, dtype=torch.bfloat16, device=DEV)
+    out = ops.attention(qkv, B, T, H, hd, out=big[guard:guard + B * T])
+    torch.cuda.synchronize()
+    assert torch.all(big[:guard] == 123.0) and torch.all(big[guard + B * T:] == 123.0)
+    assert torch.isfinite(out.float()).all()
+    for b in range(B):
+        one = ops.attention(qkv[b * T:(b + 1) * T].contiguous(), 1, T, H, hd)
+        assert torch.equal(out[b * T:(b + 1) * T], one), b
+
+
 def _attn_ref(qkv, B, T, H, hd):
     D = H * hd
     q, k, v = qkv.float().view(B, T, 3, H, hd).permute(2, 0, 3, 1, 4)

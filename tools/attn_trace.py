@@ -1,6 +1,14 @@
 #!/usr/bin/env python
-"""Timeline of one attention CTA (SM-clock stamps written by attention_sdb.cu when a trace buffer is set).
-python tools/attn_trace.py  -> per key block: softmax warp 0 phases, MMA thread phases, TMA refill time (cycles)."""
+"""Timeline of one attention CTA (SM-clock stamps written by attention_sdb.cu when a trace buffer is set): two consecutive
+work items of the same persistent CTA, block by block, and the O read-out between them.
+
+The stamps are compiled out of the shipped library (they cost ~10 % of the kernel).  Build a traced copy and point the
+tool at it:
+    cd gameplay_vision_llm_b200/csrc && mkdir -p /tmp/bt && for f in *.cu; do nvcc -gencode arch=compute_100a,code=sm_100a \
+        -O3 -std=c++17 -Xcompiler -fPIC --expt-relaxed-constexpr -DGVL_ATTN_TRACE -c $f -o /tmp/bt/${f%.cu}.o; done && \
+        nvcc -gencode arch=compute_100a,code=sm_100a -shared -o ../libgvl_trace.so /tmp/bt/*.o -cudart static -ldl
+    GVL_TRACE_LIB=$PWD/gameplay_vision_llm_b200/libgvl_trace.so python tools/attn_trace.py
+-> per key block: softmax warp 0 phases, MMA thread phases, TMA refill time (cycles); per item: o_done wait + read-out."""
 import ctypes
 import os
 import sys

@@ -57,3 +57,31 @@ def test_ops_refuse_cpu_tensors():
         ops.preprocess(torch.zeros(1, 8, 8, 3, dtype=torch.uint8), 4, 4)
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         ops.gemm(torch.zeros(8, 8, dtype=torch.bfloat16), torch.zeros(8, 8, dtype=torch.bfloat16))
+
+
+def test_varlen_attention_tile_table_is_built_on_the_host():
+    """gvl_attention_varlen_tiles (host only): one {first token, length, first query row, 0} entry per 128-row query tile
+    of every item of a ragged batch, longest items first (a tile's cost grows with its item's key count, so the tail of
+    the launch is short tiles), equal lengths in input order; the size query and the error path need no device."""
+    lib = _lib.lib()
+    toks = np.array([130, 729, 40, 729, 128, 257], np.int32)
+    tp = toks.ctypes.data_as(ctypes.POINTER(ctypes.c_int32))
+    n = ctypes.c_int(0)
+    assert lib.gvl_attention_varlen_tiles(len(toks), tp, None, ctypes.byref(n)) == 0
+    want_n = int(sum(-(-t // 128) for t in toks))
+    assert n.value == want_n == 2 + 6 + 1 + 6 + 1 + 3
+    table = np.full((n.value, 4), -7, np.int32)
+    assert lib.gvl_attention_varlen_tiles(len(toks), tp, table.ctypes.data_as(ctypes.POINTER(ctypes.c_int32)),
+                                          ctypes.byref(n)) == 0
+    starts = np.concatenate([[0], np.cumsum(toks)[:-1]])
+    order = sorted(range(len(toks)), key=lambda i: -int(toks[i]))  # stable: the two 729-token items keep their order
+    want = [(int(starts[i]), int(toks[i]), q0, 0) for i in order for q0 in range(0, int(toks[i]), 128)]
+    assert table.tolist() == [list(w) for w in want]
+    # every token row is covered by exactly one tile
+    covered = np.zeros(int(toks.sum()), np.int32)
+    for tok0, length, q0, _ in table.tolist():
+        covered[tok0 + q0:tok0 + min(q0 + 128, length)] += 1
+    assert (covered == 1).all()
+    bad = np.array([5, 0, 3], np.int32)
+    assert lib.gvl_attention_varlen_tiles(3, bad.ctypes.data_as(ctypes.POINTER(ctypes.c_int32)), None, ctypes.byref(n)) != 0
+    assert b"item 1" in lib.gvl_last_error()
